@@ -1,0 +1,166 @@
+"""Generate ``tests/golden/*`` by running the REFERENCE ITSELF (unmodified, AST-loaded from
+``/root/reference``) in the build container.  TEST INFRASTRUCTURE ONLY.
+
+    python -m oracle.make_golden          # from the repo root; needs /root/reference
+
+The reference ships no golden vectors; these files are what pins both the
+oracle restatement (``oracle/denoiser_oracle.py``) and the CUDA path on machines where the
+reference is not present.  Seeds follow SURVEY.md §8(d): weights ``manual_seed(0)``,
+condition ``manual_seed(1)``, noise ``manual_seed(2)``.
+"""
+from __future__ import annotations
+
+import os
+import sys
+
+import numpy as np
+import torch
+
+HERE = os.path.dirname(os.path.abspath(__file__))
+ROOT = os.path.dirname(HERE)
+sys.path.insert(0, ROOT)
+
+from oracle.reference_loader import load_reference  # noqa: E402
+
+OUT = os.path.join(ROOT, "tests", "golden")
+P, H, C, L = 29, 128, 14, 4693
+
+
+def ref_model(ref, hidden=H, seed=0):
+    torch.manual_seed(seed)
+    m = ref.ConditionalDiffusionModel(P, hidden)
+    m.eval()
+    return m
+
+
+def run_chain(model, cond, T, noise, num_steps=None, temperature=1.0):
+    ref = load_reference(noise=noise)
+    betas, alphas, alpha_bar = ref.get_diffusion_schedule(T)
+    x = ref.sample_model(model, cond, T, betas, alphas, alpha_bar, P, "cpu",
+                         num_steps=num_steps, temperature=temperature)
+    n_expected = T if num_steps is None else num_steps
+    assert ref.torch_proxy.draws == n_expected, (ref.torch_proxy.draws, n_expected)
+    return x, (betas, alphas, alpha_bar)
+
+
+def eps_trace(ref, model, cond, T, noise, at):
+    """Replay the chain step by step with the reference's model and record pred_noise."""
+    import math
+    betas, alphas, alpha_bar = ref.get_diffusion_schedule(T)
+    x = noise[0].clone()
+    draw = 1
+    out = {}
+    with torch.no_grad():
+        for t_ in reversed(range(T)):
+            tt = torch.full((cond.size(0),), t_, dtype=torch.long)
+            eps = model(x, tt, cond)
+            if t_ in at:
+                out[t_] = (x.clone(), eps.clone())
+            coef = (1 - alphas[t_]) / (math.sqrt(1 - alpha_bar[t_]) + 1e-8)
+            x = (1.0 / math.sqrt(alphas[t_])) * (x - coef * eps)
+            if t_ > 0:
+                x = x + math.sqrt(betas[t_]) * 1.0 * noise[draw]
+                draw += 1
+    return out, x
+
+
+def main():
+    os.makedirs(OUT, exist_ok=True)
+    ref = load_reference()
+    model = ref_model(ref)
+    sd = {k: v.detach().numpy().copy() for k, v in model.state_dict().items()}
+    np.savez(os.path.join(OUT, "model_seed0.npz"), **sd)
+
+    # ---- config 1: 16 members, T=50, one shared condition ---------------------------------
+    torch.manual_seed(1)
+    cond1 = torch.rand(1, C, L)
+    torch.manual_seed(2)
+    noise = torch.randn(50, 16, P)
+    cond = cond1.expand(16, C, L)
+    x0, (betas, alphas, alpha_bar) = run_chain(model, cond, 50, noise)
+    tr, x0_b = eps_trace(ref, model, cond, 50, noise, at=(49, 25, 0))
+    assert torch.equal(x0, x0_b)
+    x_tr, x0_trunc = None, None
+    x0_trunc, _ = run_chain(model, cond, 50, noise[:20], num_steps=20, temperature=0.7)
+    np.savez(os.path.join(OUT, "chain_cfg1.npz"),
+             condition=cond1.numpy(), noise=noise.numpy(), x0=x0.numpy(),
+             betas=betas.numpy(), alphas=alphas.numpy(), alpha_bar=alpha_bar.numpy(),
+             x_t49=tr[49][0].numpy(), eps_t49=tr[49][1].numpy(),
+             x_t25=tr[25][0].numpy(), eps_t25=tr[25][1].numpy(),
+             x_t0=tr[0][0].numpy(), eps_t0=tr[0][1].numpy(),
+             x0_steps20_temp07=x0_trunc.numpy())
+
+    # ---- long chains: noise regenerated from the seed (torch CPU randn is deterministic) ---
+    long = {}
+    for name, (B, T, ns, temp) in {"T1000_B4": (4, 1000, None, 1.0),
+                                   "T500_B3_steps120": (3, 500, 120, 1.0)}.items():
+        torch.manual_seed(2)
+        nz = torch.randn(T if ns is None else ns, B, P)
+        x, _ = run_chain(model, cond1.expand(B, C, L), T, nz, num_steps=ns, temperature=temp)
+        long[name] = x.numpy()
+        long[name + "_noise_head"] = nz[:2].numpy()      # guards the regeneration
+    np.savez(os.path.join(OUT, "chain_long.npz"), **long)
+
+    # ---- standalone forward: per-row t, distinct conditions, ragged lengths ---------------
+    fw = {}
+    for tag, (B, Lx) in {"L4693": (3, 4693), "L257": (5, 257), "L64": (4, 64), "L3": (2, 3),
+                         "L1": (2, 1), "L1000": (2, 1000)}.items():
+        g = torch.Generator().manual_seed(100 + Lx)
+        x = torch.randn(B, P, generator=g)
+        t = torch.randint(0, 1000, (B,), generator=g)
+        c = torch.rand(B, C, Lx, generator=g)
+        with torch.no_grad():
+            e = model(x, t, c)
+            ce = model.condition_encoder(c)
+        fw[f"{tag}_x"], fw[f"{tag}_t"], fw[f"{tag}_eps"] = x.numpy(), t.numpy(), e.numpy()
+        fw[f"{tag}_cemb"] = ce.numpy()
+        if Lx != 4693:
+            fw[f"{tag}_cond"] = c.numpy()
+        else:
+            fw[f"{tag}_cond_seed"] = np.int64(100 + Lx)
+    np.savez(os.path.join(OUT, "forward_cases.npz"), **fw)
+
+    # ---- hidden_dim=256 model (BASELINE config 5's reference-expressible widening) --------
+    m256 = ref_model(ref, hidden=256, seed=5)
+    g = torch.Generator().manual_seed(7)
+    x = torch.randn(6, P, generator=g)
+    t = torch.randint(0, 1000, (6,), generator=g)
+    c = torch.rand(6, C, 530, generator=g)
+    with torch.no_grad():
+        e = m256(x, t, c)
+    d = {"sd." + k: v.detach().numpy() for k, v in m256.state_dict().items()}
+    np.savez(os.path.join(OUT, "model_h256_case.npz"), x=x.numpy(), t=t.numpy(),
+             cond=c.numpy(), eps=e.numpy(), **d)
+
+    # ---- timestep embedding / schedule known answers -------------------------------------
+    tt = torch.tensor([0, 1, 2, 17, 499, 999], dtype=torch.long)
+    emb = ref.get_timestep_embedding(tt, 128)
+    sch = {}
+    for T in (50, 500, 1000):
+        b, a, ab = ref.get_diffusion_schedule(T)
+        sch[f"betas{T}"], sch[f"alphas{T}"], sch[f"alpha_bar{T}"] = b.numpy(), a.numpy(), ab.numpy()
+    np.savez(os.path.join(OUT, "embedding_schedule.npz"), t=tt.numpy(), emb=emb.numpy(), **sch)
+
+    # ---- statistics: numpy / scipy called exactly as the reference calls them ------------
+    from scipy import stats as sstats
+    rng = np.random.default_rng(3)
+    sim = rng.lognormal(size=(50, 12, 3))                     # (N, H, W) float64 maps
+    grid = np.linspace(np.min(sim), np.max(sim), 5000)
+    mode = np.zeros(sim.shape[1:])
+    midx = np.zeros(sim.shape[1:], dtype=np.int64)
+    for i in range(sim.shape[1]):
+        for j in range(sim.shape[2]):
+            kv = sstats.gaussian_kde(sim[:, i, j])(grid)
+            midx[i, j] = np.argmax(kv)
+            mode[i, j] = grid[midx[i, j]]
+    np.savez(os.path.join(OUT, "stats_maps.npz"), sim=sim,
+             mean=np.mean(sim, axis=0), std=np.std(sim, axis=0), var=np.var(sim, axis=0),
+             p25=np.percentile(sim, 25, axis=0), p50=np.percentile(sim, 50, axis=0),
+             p75=np.percentile(sim, 75, axis=0), mode=mode, mode_index=midx,
+             ci95=np.percentile(sim.astype(np.float32), [2.5, 97.5], axis=0))
+    sizes = {f: os.path.getsize(os.path.join(OUT, f)) for f in sorted(os.listdir(OUT))}
+    print(sizes, sum(sizes.values()))
+
+
+if __name__ == "__main__":
+    main()

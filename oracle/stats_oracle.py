@@ -1,0 +1,150 @@
+"""numpy restatement of the reference's ensemble statistics.
+
+TEST INFRASTRUCTURE ONLY (see ``oracle/__init__.py``).
+
+The reference computes its ensemble maps inline with numpy / scipy
+(``ECD.py:747-762`` KDE mode, ``ECD.py:867-872`` mean/std/var/percentiles, further
+percentile call sites ``ECD.py:612, 1126-1127, 1199-1200``).  The arithmetic lives in
+third-party code that is not under ``/root/reference``: numpy 2.3.5
+(``numpy/lib/_function_base_impl.py``: ``_quantile``, ``_lerp``; ``numpy/_core/_methods.py``:
+``_mean``, ``_var``) and scipy 1.18.1 (``scipy/stats/_kde.py`` + compiled
+``gaussian_kernel_estimate``).  Both libraries are installed wherever the tests run, so
+each restated function here is pinned by calling the library itself on the same input
+(``tests/test_stats_oracle.py``); the restatements exist to spell out the exact operation
+order the CUDA kernels must reproduce, element by element.
+
+Members are on axis 0 throughout: ``a`` has shape ``(N, Q)``.
+"""
+from __future__ import annotations
+
+import numpy as np
+
+
+# --------------------------------------------------------------------------- moments
+def seq_mean(a: np.ndarray) -> np.ndarray:
+    """``np.mean(a, axis=0)`` (ECD.py:867): for an axis-0 reduction of a C-contiguous array
+    numpy adds row after row into the output, i.e. a plain left-to-right sum per column in
+    the array's dtype, then one true-divide by N."""
+    acc = a[0].copy()
+    for i in range(1, a.shape[0]):
+        acc = acc + a[i]
+    return acc / a.dtype.type(a.shape[0])
+
+
+def seq_var(a: np.ndarray) -> np.ndarray:
+    """``np.var(a, axis=0)`` (ECD.py:869), ddof=0: mean as above, then the left-to-right sum
+    of ``(a_i - mean) * (a_i - mean)`` (separate multiply and add, no FMA), divided by N."""
+    m = seq_mean(a)
+    d = a[0] - m
+    acc = d * d
+    for i in range(1, a.shape[0]):
+        d = a[i] - m
+        acc = acc + d * d
+    return acc / a.dtype.type(a.shape[0])
+
+
+def seq_std(a: np.ndarray) -> np.ndarray:
+    """``np.std(a, axis=0)`` (ECD.py:868) = sqrt of the above."""
+    return np.sqrt(seq_var(a))
+
+
+# --------------------------------------------------------------------------- quantiles
+def percentile_index_dtype(a_dtype, q) -> np.dtype:
+    """The dtype numpy does the index arithmetic in: a python int/float
+    ``q`` is weakly typed and adopts the array's float dtype; a numpy float64 scalar, list or
+    array ``q`` stays float64."""
+    if isinstance(q, (int, float)) and not isinstance(q, np.generic):
+        return np.dtype(a_dtype) if np.issubdtype(a_dtype, np.floating) else np.dtype(np.float64)
+    return np.dtype(np.float64)
+
+
+def lerp_linear(A, Bv, gamma, out_dtype):
+    """numpy ``_lerp``: ``d = Bv - A`` in the ARRAY's dtype; then, in the result dtype,
+    ``A + d*gamma`` and, where ``gamma >= 0.5``, ``Bv - d*(1-gamma)``; separate multiply and
+    add/subtract, no FMA."""
+    d = (Bv - A).astype(out_dtype)
+    r = A.astype(out_dtype) + d * gamma
+    alt = Bv.astype(out_dtype) - d * (1 - gamma)
+    return np.where(gamma >= 0.5, alt, r)
+
+
+def percentile_linear(a: np.ndarray, q, index_dtype=None) -> np.ndarray:
+    """``np.percentile(a, q, axis=0)`` with the default ``method='linear'``
+    (ECD.py:870-872, 612, 1126-1127, 1199-1200).
+
+    ``q`` scalar -> result shape ``(Q,)``; ``q`` sequence -> ``(len(q), Q)``.
+    ``quant = q/100``; ``vi = (N-1)*quant``; ``lo = floor(vi)``, ``hi = lo+1`` (both ``N-1`` when
+    ``vi >= N-1``), ``gamma = vi - lo``, all in ``index_dtype``; the result dtype is
+    ``result_type(a, gamma)``.  Columns containing NaN give NaN.
+    """
+    N = a.shape[0]
+    idt = np.dtype(index_dtype) if index_dtype is not None else percentile_index_dtype(a.dtype, q)
+    scalar = np.ndim(q) == 0
+    qs = np.atleast_1d(np.asarray(q, dtype=idt))
+    quant = qs / idt.type(100)
+    s = np.sort(a, axis=0)
+    has_nan = np.isnan(a).any(axis=0)
+    out_dt = np.result_type(a.dtype, idt)
+    out = np.empty((len(qs),) + a.shape[1:], dtype=out_dt)
+    for k, qq in enumerate(quant):
+        vi = idt.type(N - 1) * qq
+        lo_f = np.floor(vi)
+        gamma = vi - lo_f                    # index dtype
+        lo = int(lo_f)
+        hi = lo + 1
+        if vi >= N - 1:                      # both indexes are the last element
+            lo = hi = N - 1
+        if vi < 0:
+            lo = hi = 0
+        r = lerp_linear(s[lo], s[hi], gamma, out_dt)
+        out[k] = np.where(has_nan, np.nan, r)
+    return out[0] if scalar else out
+
+
+# --------------------------------------------------------------------------- KDE mode
+def kde_grid(a: np.ndarray, n_grid: int = 5000) -> np.ndarray:
+    """ECD.py:749-751: ``np.linspace(global_min, global_max, 5000)`` over the whole array."""
+    return np.linspace(np.min(a), np.max(a), n_grid)
+
+
+def kde_pdf_closed_form(col: np.ndarray, grid: np.ndarray) -> np.ndarray:
+    """What ``scipy.stats.gaussian_kde(col)(grid)`` evaluates (ECD.py:758-759), written out:
+    Scott bandwidth ``h^2 = var_ddof1(col) * N^(-2/5)``;
+    ``pdf(g) = sum_i exp(-(g - x_i)^2 / (2 h^2)) / (N sqrt(2 pi h^2))``, float64, the sum taken
+    over members in order.  Values agree with scipy's compiled kernel to ~1e-15 relative but
+    not bit for bit (scipy whitens with a Cholesky factor first); the argmax index is the
+    contract."""
+    col = np.asarray(col, dtype=np.float64)
+    N = col.shape[0]
+    h2 = np.var(col, ddof=1) * float(N) ** (-0.4)
+    acc = np.zeros_like(grid, dtype=np.float64)
+    for xi in col:
+        acc = acc + np.exp(-((grid - xi) ** 2) / (2.0 * h2))
+    return acc / (N * np.sqrt(2.0 * np.pi * h2))
+
+
+def kde_mode(a: np.ndarray, grid: np.ndarray | None = None, n_grid: int = 5000):
+    """ECD.py:747-762: per column, ``grid[argmax(pdf)]`` (first maximum).  Returns
+    ``(mode_values (Q,), argmax_index (Q,) int64)``."""
+    a2 = a.reshape(a.shape[0], -1)
+    if grid is None:
+        grid = kde_grid(a2, n_grid)
+    idx = np.empty(a2.shape[1], dtype=np.int64)
+    for j in range(a2.shape[1]):
+        idx[j] = int(np.argmax(kde_pdf_closed_form(a2[:, j], grid)))
+    return grid[idx].reshape(a.shape[1:]), idx.reshape(a.shape[1:])
+
+
+def kde_mode_scipy(a: np.ndarray, grid: np.ndarray | None = None, n_grid: int = 5000):
+    """The reference's own call sequence (ECD.py:753-762) through scipy, for pinning."""
+    from scipy import stats
+    a2 = a.reshape(a.shape[0], -1)
+    if grid is None:
+        grid = kde_grid(a2, n_grid)
+    idx = np.empty(a2.shape[1], dtype=np.int64)
+    pdfs = []
+    for j in range(a2.shape[1]):
+        vals = stats.gaussian_kde(a2[:, j])(grid)
+        idx[j] = int(np.argmax(vals))
+        pdfs.append(vals)
+    return grid[idx].reshape(a.shape[1:]), idx.reshape(a.shape[1:]), np.stack(pdfs, axis=1)
