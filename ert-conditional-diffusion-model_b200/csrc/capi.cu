@@ -1,0 +1,532 @@
+// C ABI of libertdiff_b200.so -- see include/ertdiff_b200.h for the contract.
+#include <cmath>
+#include <cstring>
+#include <vector>
+
+#include "common.cuh"
+#include "model.cuh"
+#include "encoder.cuh"
+#include "denoiser.cuh"
+#include "stats.cuh"
+
+namespace ertdiff {
+std::string& last_error() {
+    static thread_local std::string e;
+    return e;
+}
+std::atomic<int64_t> g_launches{0};
+
+static int check_model(const ertdiff_model* m, bool need_weights = true) {
+    if (!m) return fail(ERTDIFF_ERR_ARG, "model handle is NULL");
+    if (need_weights && !m->loaded) return fail(ERTDIFF_ERR_STATE, "model weights not loaded");
+    return 0;
+}
+
+// ---- encoder ----------------------------------------------------------------------------
+static int run_encoder(ertdiff_model* m, const float* d_cond, int64_t n_cond, int64_t L,
+                       int64_t member_stride, float* d_cond_emb, float* d_cond_bias,
+                       cudaStream_t st) {
+    ERT_REQUIRE(d_cond && n_cond > 0 && L > 0, "encode_condition: bad condition/n_cond/L");
+    ERT_REQUIRE(n_cond <= 65535, "encode_condition: n_cond > 65535 per call; split the batch");
+    const int64_t L1 = conv_out_len(L), L2 = conv_out_len(L1);
+    const int n_chunks = (int)((L2 + ENC_TP - 1) / ENC_TP);
+    if (int rc = grow(m->enc_partial, m->enc_partial_n, (size_t)n_cond * n_chunks * kConv2Out)) return rc;
+    static bool attr_set = false;
+    if (!attr_set) {
+        ERT_CUDA(cudaFuncSetAttribute(k_encoder_conv, cudaFuncAttributeMaxDynamicSharedMemorySize,
+                                      (int)sizeof(EncSmem)));
+        attr_set = true;
+    }
+    dim3 grid(n_chunks, (unsigned)n_cond);
+    k_encoder_conv<<<grid, ENC_THREADS, sizeof(EncSmem), st>>>(
+        d_cond, member_stride, L, L1, L2, m->conv1_w, m->raw[1], m->conv2_w, m->raw[3],
+        m->enc_partial, n_chunks);
+    ERT_LAUNCH_CHECK("k_encoder_conv");
+    k_encoder_finish<<<(unsigned)n_cond, m->H, 0, st>>>(m->enc_partial, n_chunks, L2, m->w6T,
+                                                       m->raw[5], m->w0cT, m->raw[9], m->H,
+                                                       d_cond_emb, d_cond_bias);
+    ERT_LAUNCH_CHECK("k_encoder_finish");
+    return 0;
+}
+
+// ---- chain ------------------------------------------------------------------------------
+template <int H>
+static int launch_chain_h(const ChainParams& p, int mpb, cudaStream_t st) {
+    const unsigned grid = (unsigned)((p.B + mpb - 1) / mpb);
+    switch (mpb) {
+        case 1: k_chain<H, 1><<<grid, H, 0, st>>>(p); break;
+        case 2: k_chain<H, 2><<<grid, H, 0, st>>>(p); break;
+        case 4: k_chain<H, 4><<<grid, H, 0, st>>>(p); break;
+        default: k_chain<H, 8><<<grid, H, 0, st>>>(p); break;
+    }
+    ERT_LAUNCH_CHECK("k_chain");
+    return 0;
+}
+
+static int launch_chain(int H, const ChainParams& p, int mpb, cudaStream_t st) {
+    switch (H) {
+        case 32: return launch_chain_h<32>(p, mpb, st);
+        case 64: return launch_chain_h<64>(p, mpb, st);
+        case 128: return launch_chain_h<128>(p, mpb, st);
+        case 256: return launch_chain_h<256>(p, mpb, st);
+        case 512: return launch_chain_h<512>(p, mpb, st);
+    }
+    return fail(ERTDIFF_ERR_UNSUPPORTED, "hidden_dim must be one of 32,64,128,256,512");
+}
+
+// members per CTA: spread small ensembles over all SMs (the chain is latency-bound), pack
+// large ones so that weight registers are amortised over more members
+static int pick_mpb(int64_t B, int H) {
+    const int64_t ctas_per_sm = (H <= 128) ? 4 : (H <= 256 ? 2 : 1);
+    const int64_t slots = kNumSMs * ctas_per_sm;
+    if (B <= slots) return 1;
+    if (B <= 2 * slots) return 2;
+    if (B <= 4 * slots) return 4;
+    return 8;
+}
+
+static int run_chain(ertdiff_model* m, const ertdiff_chain_args* a, const float* d_cond_bias,
+                     cudaStream_t st) {
+    ERT_REQUIRE(a->B > 0 && a->n_cond > 0, "sample_chain: B and n_cond must be positive");
+    ERT_REQUIRE(a->T > 0 && a->num_steps > 0 && a->num_steps <= a->T,
+                "sample_chain: need 0 < num_steps <= T");
+    ERT_REQUIRE(a->d_betas && a->d_alphas && a->d_alpha_bar, "sample_chain: schedule is NULL");
+    ERT_REQUIRE(d_cond_bias, "sample_chain: cond_bias is NULL");
+    ERT_REQUIRE(a->d_x_out, "sample_chain: x_out is NULL");
+    if (a->precision != ERTDIFF_PREC_FP32)
+        return fail(ERTDIFF_ERR_UNSUPPORTED, "sample_chain: only ERTDIFF_PREC_FP32 is built");
+    const int S = a->num_steps, H = m->H, P = m->P;
+    const int64_t nstride = a->noise_member_stride_B > 0 ? a->noise_member_stride_B : a->B;
+    ERT_REQUIRE(nstride >= a->B, "sample_chain: noise_member_stride_B < B");
+
+    if (int rc = grow(m->time_table, m->time_table_n, (size_t)S * H)) return rc;
+    if (int rc = grow(m->coef_table, m->coef_table_n, (size_t)S * 4)) return rc;
+    k_time_table<<<S, H, 0, st>>>(m->freq, m->wtT, m->raw[7], m->w0tT, H, m->time_table,
+                                  a->d_betas, a->d_alphas, a->d_alpha_bar,
+                                  (double)a->temperature, m->coef_table);
+    ERT_LAUNCH_CHECK("k_time_table");
+
+    ChainParams p{};
+    p.B = a->B; p.n_cond = a->n_cond; p.S = S; p.t_hi = S - 1; p.t_count = S;
+    p.w0xT = m->w0xT; p.w2p = m->w2p; p.b2p = m->b2p; p.table = m->time_table;
+    p.coef = m->coef_table; p.cond_bias = d_cond_bias;
+    p.x_in = a->d_x_T; p.x_in_stride = P;
+    p.noise = a->d_noise; p.noise_B = nstride;
+    p.seed = a->seed; p.offset = a->offset; p.member_offset = a->member_offset;
+    p.x_out = a->d_x_out; p.eps_trace = a->d_eps_trace; p.P = P;
+    const int mpb = pick_mpb(a->B, H);
+
+    if (a->loop_mode == ERTDIFF_LOOP_PERSISTENT) {
+        if (m->profile) {
+            if (!m->ev_chain[0]) { ERT_CUDA(cudaEventCreate(&m->ev_chain[0])); ERT_CUDA(cudaEventCreate(&m->ev_chain[1])); }
+            ERT_CUDA(cudaEventRecord(m->ev_chain[0], st));
+        }
+        const int rc = launch_chain(H, p, mpb, st);
+        if (m->profile && rc == 0) { ERT_CUDA(cudaEventRecord(m->ev_chain[1], st)); m->ev_valid = true; }
+        return rc;
+    }
+
+    // ---- one kernel per timestep: plain stream launches, or the same sequence as a graph ----
+    if (int rc = grow(m->xbuf[0], m->xbuf_n[0], (size_t)a->B * P)) return rc;
+    if (int rc = grow(m->xbuf[1], m->xbuf_n[1], (size_t)a->B * P)) return rc;
+    auto enqueue_steps = [&](cudaStream_t s) -> int {
+        const float* xin = a->d_x_T;
+        for (int it = 0; it < S; ++it) {
+            ChainParams q = p;
+            q.t_hi = S - 1 - it; q.t_count = 1;
+            q.x_in = xin; q.x_in_stride = P;
+            q.x_out = (it == S - 1) ? a->d_x_out : m->xbuf[it & 1];
+            if (int rc = launch_chain(H, q, mpb, s)) return rc;
+            xin = q.x_out;
+        }
+        return 0;
+    };
+    if (a->loop_mode == ERTDIFF_LOOP_STREAM) return enqueue_steps(st);
+    if (a->loop_mode != ERTDIFF_LOOP_GRAPH) return fail(ERTDIFF_ERR_ARG, "sample_chain: bad loop_mode");
+
+    ertdiff_model::GraphKey key;
+    key.B = a->B; key.n_cond = a->n_cond; key.steps = S; key.noise = a->d_noise; key.xT = a->d_x_T;
+    key.xout = a->d_x_out; key.cb = d_cond_bias; key.seed = a->seed; key.offset = a->offset;
+    key.moff = a->member_offset; key.nstride = nstride; key.trace = a->d_eps_trace;
+    if (!(m->graph_exec && m->graph_key == key)) {
+        if (m->graph_exec) { cudaGraphExecDestroy(m->graph_exec); m->graph_exec = nullptr; }
+        cudaStream_t cap;
+        ERT_CUDA(cudaStreamCreateWithFlags(&cap, cudaStreamNonBlocking));
+        ERT_CUDA(cudaStreamBeginCapture(cap, cudaStreamCaptureModeThreadLocal));
+        const int64_t before = g_launches.load();
+        int rc = enqueue_steps(cap);
+        g_launches.store(before);                       // captured, not launched
+        cudaGraph_t graph = nullptr;
+        cudaError_t e = cudaStreamEndCapture(cap, &graph);
+        cudaStreamDestroy(cap);
+        if (rc) { if (graph) cudaGraphDestroy(graph); return rc; }
+        if (e != cudaSuccess) return fail(ERTDIFF_ERR_CUDA, std::string("graph capture: ") + cudaGetErrorString(e));
+        e = cudaGraphInstantiate(&m->graph_exec, graph, 0);
+        cudaGraphDestroy(graph);
+        if (e != cudaSuccess) { m->graph_exec = nullptr; return fail(ERTDIFF_ERR_CUDA, std::string("graph instantiate: ") + cudaGetErrorString(e)); }
+        m->graph_key = key;
+    }
+    ERT_CUDA(cudaGraphLaunch(m->graph_exec, st));
+    g_launches.fetch_add(S, std::memory_order_relaxed);
+    return 0;
+}
+
+}  // namespace ertdiff
+
+using namespace ertdiff;
+
+#pragma GCC visibility push(default)
+extern "C" {
+
+int ertdiff_abi_version(void) { return ERTDIFF_ABI_VERSION; }
+const char* ertdiff_last_error(void) { return last_error().c_str(); }
+int64_t ertdiff_launch_count(void) { return g_launches.load(); }
+void ertdiff_launch_count_reset(void) { g_launches.store(0); }
+
+int ertdiff_model_create(ertdiff_model** out, int device, int param_dim, int hidden_dim) {
+    ERT_REQUIRE(out, "model_create: out is NULL");
+    *out = nullptr;
+    ERT_REQUIRE(param_dim >= 1 && param_dim <= kPPad, "model_create: param_dim must be in [1,32]");
+    if (!(hidden_dim == 32 || hidden_dim == 64 || hidden_dim == 128 || hidden_dim == 256 ||
+          hidden_dim == 512))
+        return fail(ERTDIFF_ERR_UNSUPPORTED, "model_create: hidden_dim must be one of 32,64,128,256,512");
+    int ndev = 0;
+    ERT_CUDA(cudaGetDeviceCount(&ndev));
+    ERT_REQUIRE(device >= 0 && device < ndev, "model_create: no such CUDA device");
+    DeviceGuard g(device);
+    if (!g.ok) return fail(ERTDIFF_ERR_CUDA, "model_create: cudaSetDevice failed");
+    auto* m = new ertdiff_model();
+    m->device = device; m->P = param_dim; m->H = hidden_dim;
+    raw_shapes(m->P, m->H, m->raw_n);
+    const int H = m->H;
+    auto alloc = [&](float*& p, size_t n) -> bool { return cudaMalloc(&p, n * sizeof(float)) == cudaSuccess; };
+    bool ok = true;
+    for (int i = 0; i < 12; ++i) ok = ok && alloc(m->raw[i], m->raw_n[i]);
+    ok = ok && alloc(m->conv1_w, 32 * kInChannels * 3) && alloc(m->conv2_w, 64 * 96) &&
+         alloc(m->w6T, (size_t)64 * H) && alloc(m->wtT, (size_t)H * H) &&
+         alloc(m->w0xT, (size_t)kPPad * H) && alloc(m->w0tT, (size_t)H * H) &&
+         alloc(m->w0cT, (size_t)H * H) && alloc(m->w2p, (size_t)kPPad * H) &&
+         alloc(m->b2p, kPPad) && alloc(m->freq, H / 2);
+    if (!ok) {
+        ertdiff_model_destroy(m);
+        return fail(ERTDIFF_ERR_CUDA, "model_create: cudaMalloc failed");
+    }
+    *out = m;
+    return 0;
+}
+
+int ertdiff_model_profile(ertdiff_model* m, int enable) {
+    if (int rc = check_model(m, false)) return rc;
+    m->profile = enable != 0;
+    m->ev_valid = false;
+    return 0;
+}
+
+int ertdiff_model_last_chain_ms(ertdiff_model* m, float* h_ms) {
+    if (int rc = check_model(m, false)) return rc;
+    ERT_REQUIRE(h_ms, "last_chain_ms: h_ms is NULL");
+    if (!m->ev_valid) return fail(ERTDIFF_ERR_STATE, "last_chain_ms: no profiled persistent chain launch yet");
+    ERT_CUDA(cudaEventSynchronize(m->ev_chain[1]));
+    ERT_CUDA(cudaEventElapsedTime(h_ms, m->ev_chain[0], m->ev_chain[1]));
+    return 0;
+}
+
+int ertdiff_model_destroy(ertdiff_model* m) {
+    if (!m) return 0;
+    DeviceGuard g(m->device);
+    if (m->ev_chain[0]) { cudaEventDestroy(m->ev_chain[0]); cudaEventDestroy(m->ev_chain[1]); }
+    for (int i = 0; i < 12; ++i) cudaFree(m->raw[i]);
+    float* ptrs[] = {m->conv1_w, m->conv2_w, m->w6T, m->wtT, m->w0xT, m->w0tT, m->w0cT, m->w2p,
+                     m->b2p, m->freq, m->enc_partial, m->cond_bias, m->cond_emb, m->time_table,
+                     m->coef_table, m->xbuf[0], m->xbuf[1]};
+    for (float* p : ptrs) cudaFree(p);
+    if (m->graph_exec) cudaGraphExecDestroy(m->graph_exec);
+    delete m;
+    return 0;
+}
+
+int ertdiff_model_load(ertdiff_model* m, const float* const* tensors12, int on_device,
+                       const float* h_freq, void* stream) {
+    if (int rc = check_model(m, false)) return rc;
+    ERT_REQUIRE(tensors12 && h_freq, "model_load: tensors12 / h_freq is NULL");
+    DeviceGuard g(m->device);
+    cudaStream_t st = (cudaStream_t)stream;
+    for (int i = 0; i < 12; ++i) {
+        ERT_REQUIRE(tensors12[i], "model_load: a tensor pointer is NULL");
+        ERT_CUDA(cudaMemcpyAsync(m->raw[i], tensors12[i], m->raw_n[i] * sizeof(float),
+                                 on_device ? cudaMemcpyDeviceToDevice : cudaMemcpyHostToDevice, st));
+    }
+    ERT_CUDA(cudaMemcpyAsync(m->freq, h_freq, (m->H / 2) * sizeof(float), cudaMemcpyHostToDevice, st));
+    const int64_t nmax = (int64_t)m->H * m->H > 64 * 96 ? (int64_t)m->H * m->H : 64 * 96;
+    k_pack_weights<<<(unsigned)((nmax + 255) / 256), 256, 0, st>>>(
+        m->raw[0], m->raw[2], m->raw[4], m->raw[6], m->raw[8], m->raw[10], m->raw[11], m->P, m->H,
+        m->conv1_w, m->conv2_w, m->w6T, m->wtT, m->w0xT, m->w0tT, m->w0cT, m->w2p, m->b2p);
+    ERT_LAUNCH_CHECK("k_pack_weights");
+    ERT_CUDA(cudaStreamSynchronize(st));
+    m->loaded = true;
+    if (m->graph_exec) { cudaGraphExecDestroy(m->graph_exec); m->graph_exec = nullptr; }
+    return 0;
+}
+
+int ertdiff_model_export(ertdiff_model* m, float* const* tensors12, int on_device, void* stream) {
+    if (int rc = check_model(m)) return rc;
+    ERT_REQUIRE(tensors12, "model_export: tensors12 is NULL");
+    DeviceGuard g(m->device);
+    cudaStream_t st = (cudaStream_t)stream;
+    for (int i = 0; i < 12; ++i) {
+        ERT_REQUIRE(tensors12[i], "model_export: a tensor pointer is NULL");
+        ERT_CUDA(cudaMemcpyAsync(tensors12[i], m->raw[i], m->raw_n[i] * sizeof(float),
+                                 on_device ? cudaMemcpyDeviceToDevice : cudaMemcpyDeviceToHost, st));
+    }
+    ERT_CUDA(cudaStreamSynchronize(st));
+    return 0;
+}
+
+int ertdiff_encode_condition(ertdiff_model* m, const float* d_condition, int64_t n_cond,
+                             int64_t L, int64_t cond_member_stride, float* d_cond_emb,
+                             float* d_cond_bias, void* stream) {
+    if (int rc = check_model(m)) return rc;
+    DeviceGuard g(m->device);
+    return run_encoder(m, d_condition, n_cond, L, cond_member_stride, d_cond_emb, d_cond_bias,
+                       (cudaStream_t)stream);
+}
+
+int ertdiff_forward(ertdiff_model* m, const float* d_x, const int64_t* d_t,
+                    const float* d_condition, int64_t B, int64_t L, int64_t cond_member_stride,
+                    float* d_out, void* stream) {
+    if (int rc = check_model(m)) return rc;
+    ERT_REQUIRE(d_x && d_t && d_condition && d_out && B > 0, "forward: NULL pointer or B <= 0");
+    DeviceGuard g(m->device);
+    cudaStream_t st = (cudaStream_t)stream;
+    const int64_t n_cond = (cond_member_stride == 0) ? 1 : B;
+    if (int rc = grow(m->cond_bias, m->cond_bias_n, (size_t)n_cond * m->H)) return rc;
+    // the encoder launches with blockIdx.y = condition: at most 65535 per launch
+    for (int64_t c0 = 0; c0 < n_cond; c0 += 32768) {
+        const int64_t nc = (n_cond - c0) < 32768 ? (n_cond - c0) : 32768;
+        if (int rc = run_encoder(m, d_condition + c0 * cond_member_stride, nc, L,
+                                 cond_member_stride, nullptr, m->cond_bias + c0 * m->H, st))
+            return rc;
+    }
+    k_forward_rows<<<(unsigned)B, m->H, 0, st>>>(d_x, d_t, m->cond_bias, n_cond, m->freq, m->wtT,
+                                                 m->raw[7], m->w0tT, m->w0xT, m->w2p, m->b2p,
+                                                 m->P, m->H, d_out);
+    ERT_LAUNCH_CHECK("k_forward_rows");
+    return 0;
+}
+
+int ertdiff_sample_chain(ertdiff_model* m, const ertdiff_chain_args* args, void* stream) {
+    if (int rc = check_model(m)) return rc;
+    ERT_REQUIRE(args, "sample_chain: args is NULL");
+    DeviceGuard g(m->device);
+    return run_chain(m, args, args->d_cond_bias, (cudaStream_t)stream);
+}
+
+int ertdiff_sample_model(ertdiff_model* m, const float* d_condition, int64_t L,
+                         int64_t cond_member_stride, const ertdiff_chain_args* args,
+                         void* stream) {
+    if (int rc = check_model(m)) return rc;
+    ERT_REQUIRE(args, "sample_model: args is NULL");
+    DeviceGuard g(m->device);
+    cudaStream_t st = (cudaStream_t)stream;
+    const int64_t n_cond = args->n_cond;
+    ERT_REQUIRE(n_cond > 0, "sample_model: n_cond must be positive");
+    if (int rc = grow(m->cond_bias, m->cond_bias_n, (size_t)n_cond * m->H)) return rc;
+    for (int64_t c0 = 0; c0 < n_cond; c0 += 32768) {
+        const int64_t nc = (n_cond - c0) < 32768 ? (n_cond - c0) : 32768;
+        if (int rc = run_encoder(m, d_condition + c0 * cond_member_stride, nc, L,
+                                 cond_member_stride, nullptr, m->cond_bias + c0 * m->H, st))
+            return rc;
+    }
+    return run_chain(m, args, m->cond_bias, st);
+}
+
+int ertdiff_step_coefficients(const float* d_betas, const float* d_alphas,
+                              const float* d_alpha_bar, int32_t num_steps, double temperature,
+                              float* d_table, void* stream) {
+    ERT_REQUIRE(d_betas && d_alphas && d_alpha_bar && d_table && num_steps > 0,
+                "step_coefficients: bad arguments");
+    k_step_coefficients<<<(num_steps + 127) / 128, 128, 0, (cudaStream_t)stream>>>(
+        d_betas, d_alphas, d_alpha_bar, num_steps, temperature, d_table);
+    ERT_LAUNCH_CHECK("k_step_coefficients");
+    return 0;
+}
+
+int ertdiff_philox_normal(uint64_t seed, uint64_t offset, int64_t member_offset, int64_t B,
+                          int32_t P, int32_t draws, float* d_out, void* stream) {
+    ERT_REQUIRE(d_out && B > 0 && P > 0 && P <= kPPad && draws > 0, "philox_normal: bad arguments");
+    const int64_t n = (int64_t)((draws + 3) / 4) * B * P;
+    k_philox_fill<<<(unsigned)((n + 255) / 256), 256, 0, (cudaStream_t)stream>>>(
+        seed, offset, member_offset, B, P, draws, d_out);
+    ERT_LAUNCH_CHECK("k_philox_fill");
+    return 0;
+}
+
+int ertdiff_posterior_update(const float* d_x, const float* d_eps, const float* d_z, float coef,
+                             float c1, float sigma, int64_t n, float* d_out, void* stream) {
+    ERT_REQUIRE(d_x && d_eps && d_out && n >= 0, "posterior_update: bad arguments");
+    if (n == 0) return 0;
+    const int64_t threads = (n + 3) / 4;
+    k_posterior_update<<<(unsigned)((threads + 255) / 256), 256, 0, (cudaStream_t)stream>>>(
+        d_x, d_eps, d_z, coef, c1, sigma, n, d_out);
+    ERT_LAUNCH_CHECK("k_posterior_update");
+    return 0;
+}
+
+int ertdiff_ensemble_moments(const void* d_a, int dtype, int64_t N, int64_t Q, void* d_mean,
+                             void* d_std, void* d_var, void* stream) {
+    ERT_REQUIRE(d_a && N > 0 && Q > 0, "ensemble_moments: bad arguments");
+    cudaStream_t st = (cudaStream_t)stream;
+    const unsigned grid = (unsigned)((Q + 127) / 128);
+    if (dtype == ERTDIFF_F32)
+        k_moments<float><<<grid, 128, 0, st>>>((const float*)d_a, N, Q, (float*)d_mean,
+                                               (float*)d_std, (float*)d_var);
+    else if (dtype == ERTDIFF_F64)
+        k_moments<double><<<grid, 128, 0, st>>>((const double*)d_a, N, Q, (double*)d_mean,
+                                                (double*)d_std, (double*)d_var);
+    else
+        return fail(ERTDIFF_ERR_ARG, "ensemble_moments: bad dtype");
+    ERT_LAUNCH_CHECK("k_moments");
+    return 0;
+}
+
+int ertdiff_ensemble_percentiles(const void* d_a, int dtype, int64_t N, int64_t Q,
+                                 const double* h_q, int32_t nq, int index_dtype, void* d_out,
+                                 void* stream) {
+    ERT_REQUIRE(d_a && d_out && h_q && N > 0 && Q > 0 && nq > 0, "ensemble_percentiles: bad arguments");
+    ERT_REQUIRE(dtype == ERTDIFF_F32 || dtype == ERTDIFF_F64, "ensemble_percentiles: bad dtype");
+    ERT_REQUIRE(!(dtype == ERTDIFF_F64 && index_dtype == ERTDIFF_F32),
+                "ensemble_percentiles: float64 data always uses float64 index arithmetic");
+    cudaStream_t st = (cudaStream_t)stream;
+    // numpy's index arithmetic (function_base._quantile, method 'linear'), in index_dtype
+    std::vector<PctlQuery> qs(nq);
+    for (int k = 0; k < nq; ++k) {
+        ERT_REQUIRE(h_q[k] >= 0.0 && h_q[k] <= 100.0, "ensemble_percentiles: q outside [0,100]");
+        PctlQuery& q = qs[k];
+        if (index_dtype == ERTDIFF_F32) {
+            const float quant = (float)h_q[k] / 100.0f;
+            const float vi = (float)(N - 1) * quant;
+            const float lo = floorf(vi);
+            q.gamma_f = vi - lo; q.gamma_d = 0.0;
+            q.lo = (int32_t)lo; q.hi = q.lo + 1;
+            if (vi >= (float)(N - 1)) q.lo = q.hi = (int32_t)(N - 1);
+        } else {
+            const double quant = h_q[k] / 100.0;
+            const double vi = (double)(N - 1) * quant;
+            const double lo = floor(vi);
+            q.gamma_d = vi - lo; q.gamma_f = 0.f;
+            q.lo = (int32_t)lo; q.hi = q.lo + 1;
+            if (vi >= (double)(N - 1)) q.lo = q.hi = (int32_t)(N - 1);
+        }
+    }
+    PctlQuery* d_qs = nullptr;
+    ERT_CUDA(cudaMallocAsync(&d_qs, nq * sizeof(PctlQuery), st));
+    ERT_CUDA(cudaMemcpyAsync(d_qs, qs.data(), nq * sizeof(PctlQuery), cudaMemcpyHostToDevice, st));
+    ERT_CUDA(cudaStreamSynchronize(st));   // qs is a stack-owned vector
+    int NP = 1;
+    while (NP < N) NP <<= 1;
+    const size_t esz = dtype == ERTDIFF_F32 ? 4 : 8;
+    const size_t budget = 200 * 1024;
+    ERT_REQUIRE((size_t)NP * esz + 64 <= budget, "ensemble_percentiles: N too large for one CTA's shared memory");
+    int CT = 32;
+    while (CT > 1 && ((size_t)CT * NP * esz + CT * sizeof(int) > budget / 2 || (int64_t)CT > Q)) CT >>= 1;
+    // keep enough CTAs in flight
+    while (CT > 1 && (Q + CT - 1) / CT < 2 * kNumSMs) CT >>= 1;
+    const size_t smem = (size_t)CT * NP * esz + CT * sizeof(int);
+    const int threads = (int64_t)CT * NP / 2 >= 1024 ? 1024 : ((int64_t)CT * NP / 2 >= 256 ? 256 : 64);
+    const unsigned grid = (unsigned)((Q + CT - 1) / CT);
+    cudaError_t e = cudaSuccess;
+#define ERT_PCT_LAUNCH(T, G, O)                                                              \
+    do {                                                                                     \
+        e = cudaFuncSetAttribute(k_percentiles<T, G, O>,                                     \
+                                 cudaFuncAttributeMaxDynamicSharedMemorySize, (int)budget);  \
+        if (e == cudaSuccess)                                                                \
+            k_percentiles<T, G, O><<<grid, threads, smem, st>>>((const T*)d_a, N, Q, NP, CT, \
+                                                               d_qs, nq, (O*)d_out);         \
+    } while (0)
+    if (dtype == ERTDIFF_F32 && index_dtype == ERTDIFF_F32) ERT_PCT_LAUNCH(float, float, float);
+    else if (dtype == ERTDIFF_F32) ERT_PCT_LAUNCH(float, double, double);
+    else ERT_PCT_LAUNCH(double, double, double);
+#undef ERT_PCT_LAUNCH
+    if (e != cudaSuccess) { cudaFreeAsync(d_qs, st); return fail(ERTDIFF_ERR_CUDA, std::string("percentiles attr: ") + cudaGetErrorString(e)); }
+    ERT_LAUNCH_CHECK("k_percentiles");
+    ERT_CUDA(cudaFreeAsync(d_qs, st));
+    return 0;
+}
+
+int ertdiff_minmax(const void* d_a, int dtype, int64_t n, double* d_out2, void* stream) {
+    ERT_REQUIRE(d_a && d_out2 && n > 0, "minmax: bad arguments");
+    cudaStream_t st = (cudaStream_t)stream;
+    int blocks = (int)((n + 256 * 8 - 1) / (256 * 8));
+    if (blocks > 4 * kNumSMs) blocks = 4 * kNumSMs;
+    if (blocks < 1) blocks = 1;
+    double* part = nullptr;
+    ERT_CUDA(cudaMallocAsync(&part, (size_t)blocks * 3 * sizeof(double), st));
+    if (dtype == ERTDIFF_F32) k_minmax_partial<float><<<blocks, 256, 0, st>>>((const float*)d_a, n, part);
+    else if (dtype == ERTDIFF_F64) k_minmax_partial<double><<<blocks, 256, 0, st>>>((const double*)d_a, n, part);
+    else { cudaFreeAsync(part, st); return fail(ERTDIFF_ERR_ARG, "minmax: bad dtype"); }
+    ERT_LAUNCH_CHECK("k_minmax_partial");
+    k_minmax_final<<<1, 32, 0, st>>>(part, blocks, d_out2);
+    ERT_LAUNCH_CHECK("k_minmax_final");
+    ERT_CUDA(cudaFreeAsync(part, st));
+    return 0;
+}
+
+int ertdiff_ensemble_kde_mode(const void* d_a, int dtype, int64_t N, int64_t Q,
+                              const double* d_lohi, int32_t n_grid, double* d_mode,
+                              int64_t* d_index, void* stream) {
+    ERT_REQUIRE(d_a && d_lohi && N > 1 && Q > 0 && n_grid > 1, "ensemble_kde_mode: bad arguments");
+    ERT_REQUIRE((size_t)N * 8 <= 200 * 1024, "ensemble_kde_mode: N too large for shared memory");
+    cudaStream_t st = (cudaStream_t)stream;
+    // scipy: factor = neff**(-1/(d+4)) with d = 1, neff = N; covariance = data_cov * factor**2
+    const double factor = std::pow((double)N, -1.0 / 5.0);
+    const double f2 = factor * factor;
+    const size_t smem = (size_t)N * 8;
+    // split the grid so that Q * n_gchunks CTAs fill the machine, >= 64 grid points per CTA
+    int n_gchunks = 1;
+    while ((int64_t)Q * n_gchunks < 4 * kNumSMs && (n_grid + 2 * n_gchunks - 1) / (2 * n_gchunks) >= 64)
+        n_gchunks *= 2;
+    const int gchunk = (n_grid + n_gchunks - 1) / n_gchunks;
+    double* part_val = nullptr;
+    int* part_idx = nullptr;
+    ERT_CUDA(cudaMallocAsync(&part_val, (size_t)Q * n_gchunks * sizeof(double), st));
+    ERT_CUDA(cudaMallocAsync(&part_idx, (size_t)Q * n_gchunks * sizeof(int), st));
+    const dim3 grid((unsigned)Q, (unsigned)n_gchunks);
+    const int threads = gchunk >= 512 ? 256 : (gchunk >= 256 ? 128 : 64);
+    cudaError_t e;
+    if (dtype == ERTDIFF_F32) {
+        e = cudaFuncSetAttribute(k_kde_mode<float>, cudaFuncAttributeMaxDynamicSharedMemorySize, 200 * 1024);
+        if (e == cudaSuccess)
+            k_kde_mode<float><<<grid, threads, smem, st>>>((const float*)d_a, N, Q, d_lohi, n_grid, gchunk, f2, part_val, part_idx);
+    } else if (dtype == ERTDIFF_F64) {
+        e = cudaFuncSetAttribute(k_kde_mode<double>, cudaFuncAttributeMaxDynamicSharedMemorySize, 200 * 1024);
+        if (e == cudaSuccess)
+            k_kde_mode<double><<<grid, threads, smem, st>>>((const double*)d_a, N, Q, d_lohi, n_grid, gchunk, f2, part_val, part_idx);
+    } else {
+        cudaFreeAsync(part_val, st); cudaFreeAsync(part_idx, st);
+        return fail(ERTDIFF_ERR_ARG, "ensemble_kde_mode: bad dtype");
+    }
+    if (e != cudaSuccess) return fail(ERTDIFF_ERR_CUDA, std::string("kde attr: ") + cudaGetErrorString(e));
+    ERT_LAUNCH_CHECK("k_kde_mode");
+    k_kde_final<<<(unsigned)((Q + 127) / 128), 128, 0, st>>>(part_val, part_idx, Q, n_gchunks, d_lohi, n_grid, d_mode, d_index);
+    ERT_LAUNCH_CHECK("k_kde_final");
+    ERT_CUDA(cudaFreeAsync(part_val, st));
+    ERT_CUDA(cudaFreeAsync(part_idx, st));
+    return 0;
+}
+
+int ertdiff_untransform_bounds(const float* d_u, int64_t B, int32_t P, float a, float b,
+                               const double* d_scaler_min, const double* d_scaler_scale,
+                               const double* d_lim_lo, const double* d_lim_hi, float* d_phys,
+                               uint8_t* d_valid, int32_t* d_first_bad, void* stream) {
+    ERT_REQUIRE(d_u && B > 0 && P > 0 && P <= 32, "untransform_bounds: bad arguments");
+    ERT_REQUIRE((d_scaler_min == nullptr) == (d_scaler_scale == nullptr), "untransform_bounds: give both scaler arrays or neither");
+    ERT_REQUIRE((d_lim_lo == nullptr) == (d_lim_hi == nullptr), "untransform_bounds: give both limit arrays or neither");
+    const int64_t threads = B * 32;
+    k_untransform_bounds<<<(unsigned)((threads + 255) / 256), 256, 0, (cudaStream_t)stream>>>(
+        d_u, B, P, a, b, d_scaler_min, d_scaler_scale, d_lim_lo, d_lim_hi, d_phys, d_valid, d_first_bad);
+    ERT_LAUNCH_CHECK("k_untransform_bounds");
+    return 0;
+}
+
+}  // extern "C"
+#pragma GCC visibility pop

@@ -1,0 +1,412 @@
+// Hoisted denoiser step + DDPM posterior update + the reverse loop (ECD.py:102-119, 155-164).
+//
+// The reference evaluates, per step and per member,
+//     h   = ReLU(W0 @ [x | t_emb | c_emb] + b0),   eps = W2 @ h + b2          (ECD.py:159-163)
+// W0 @ [x|t|c] = W0x @ x + W0t @ t_emb + W0c @ c_emb.  In a chain all members share t, and a
+// member's condition never changes, so
+//     c_t[t]  = W0t @ ReLU(Wt @ emb(t) + bt)            one H-vector per step  (k_time_table)
+//     c_b[m]  = W0c @ c_emb[m] + b0                     one H-vector per member (encoder.cuh)
+//     h       = ReLU(W0x @ x + c_t[t] + c_b[m])         14,848 FLOP per member per step
+// k_chain keeps x, the weights and both tables' current rows on chip for all steps of a tile of
+// members: one launch runs the whole chain (no grid-wide dependency exists between members).
+#pragma once
+#include "common.cuh"
+
+namespace ertdiff {
+
+// ------------------------------------------------------------------------------------------
+// Posterior update, ECD.py:111-118.  Every operation is a separately rounded fp32 op (the
+// _rn intrinsics are never contracted into FMAs), in the reference's order:
+//   u = coef*eps ; v = x - u ; x' = c1*v ; [ w = sigma*z ; x' = x' + w ]
+__device__ __forceinline__ float posterior_update_rn(float x, float eps, float z, float coef,
+                                                     float c1, float sigma, bool add_noise) {
+    const float u = __fmul_rn(coef, eps);
+    const float v = __fsub_rn(x, u);
+    float xn = __fmul_rn(c1, v);
+    if (add_noise) xn = __fadd_rn(xn, __fmul_rn(sigma, z));
+    return xn;
+}
+
+__global__ void k_posterior_update(const float* __restrict__ x, const float* __restrict__ eps,
+                                   const float* __restrict__ z, float coef, float c1,
+                                   float sigma, int64_t n, float* __restrict__ out) {
+    // 4 elements per thread, 128-bit accesses when the pointers allow it
+    const int64_t i4 = ((int64_t)blockIdx.x * blockDim.x + threadIdx.x) * 4;
+    if (i4 >= n) return;
+    const bool vec = (i4 + 4 <= n) &&
+                     (((uintptr_t)x | (uintptr_t)eps | (uintptr_t)z | (uintptr_t)out) & 15) == 0;
+    if (vec) {
+        const float4 xv = *reinterpret_cast<const float4*>(x + i4);
+        const float4 ev = *reinterpret_cast<const float4*>(eps + i4);
+        float4 zv = make_float4(0.f, 0.f, 0.f, 0.f);
+        if (z) zv = *reinterpret_cast<const float4*>(z + i4);
+        float4 o;
+        o.x = posterior_update_rn(xv.x, ev.x, zv.x, coef, c1, sigma, z != nullptr);
+        o.y = posterior_update_rn(xv.y, ev.y, zv.y, coef, c1, sigma, z != nullptr);
+        o.z = posterior_update_rn(xv.z, ev.z, zv.z, coef, c1, sigma, z != nullptr);
+        o.w = posterior_update_rn(xv.w, ev.w, zv.w, coef, c1, sigma, z != nullptr);
+        *reinterpret_cast<float4*>(out + i4) = o;
+    } else {
+        for (int64_t i = i4; i < n && i < i4 + 4; ++i)
+            out[i] = posterior_update_rn(x[i], eps[i], z ? z[i] : 0.f, coef, c1, sigma,
+                                         z != nullptr);
+    }
+}
+
+// ------------------------------------------------------------------------------------------
+// Per-step scalars with the reference's rounding: (1-alpha) and (1-alpha_bar)
+// are fp32 subtractions; math.sqrt works in double; the quotient and the two other scalars are
+// rounded to fp32 once.  double sqrt and division are correctly rounded on the device, so the
+// table is bit-identical to what the reference's python arithmetic produces.
+__device__ __forceinline__ void step_coefficients(const float* betas, const float* alphas,
+                                                  const float* alpha_bar, int t,
+                                                  double temperature, float* out4) {
+    const float oma = __fsub_rn(1.0f, alphas[t]);
+    const float omab = __fsub_rn(1.0f, alpha_bar[t]);
+    const double denom = __dadd_rn(sqrt((double)omab), 1e-8);
+    out4[0] = __fdiv_rn(oma, (float)denom);
+    out4[1] = (float)(1.0 / sqrt((double)alphas[t]));
+    out4[2] = (float)__dmul_rn(sqrt((double)betas[t]), temperature);
+    out4[3] = 0.f;
+}
+
+__global__ void k_step_coefficients(const float* betas, const float* alphas,
+                                    const float* alpha_bar, int steps, double temperature,
+                                    float* table4) {
+    const int t = blockIdx.x * blockDim.x + threadIdx.x;
+    if (t < steps) step_coefficients(betas, alphas, alpha_bar, t, temperature, table4 + 4 * t);
+}
+
+// ------------------------------------------------------------------------------------------
+// Timestep embedding (ECD.py:80-88) -> time_embed Linear+ReLU (ECD.py:144-147,160) ->
+// t-block of mlp.0 : table[row] = W0t @ ReLU(Wt @ [sin(t f) | cos(t f)] + bt).
+// grid = rows, block = H.  Row r is timestep t_list[r] if given, else t = r.
+// Also fills the step-coefficient table row (thread 0) when coef_table != nullptr.
+__device__ __forceinline__ void time_embed_row(float tf, const float* __restrict__ freq,
+                                               const float* __restrict__ wtT,
+                                               const float* __restrict__ bt, int H, int tid,
+                                               float* emb /*smem H*/, float* te /*smem H*/) {
+    const int half = H >> 1;
+    if (tid < half) {
+        const float arg = __fmul_rn(tf, freq[tid]);
+        emb[tid] = sinf(arg);
+        emb[half + tid] = cosf(arg);
+    }
+    __syncthreads();
+    float a0 = bt[tid], a1 = 0.f;
+    for (int k = 0; k < H; k += 2) {
+        a0 = fmaf(wtT[(int64_t)k * H + tid], emb[k], a0);
+        a1 = fmaf(wtT[(int64_t)(k + 1) * H + tid], emb[k + 1], a1);
+    }
+    te[tid] = fmaxf(a0 + a1, 0.f);
+    __syncthreads();
+}
+
+__global__ void k_time_table(const float* __restrict__ freq, const float* __restrict__ wtT,
+                             const float* __restrict__ bt, const float* __restrict__ w0tT,
+                             int H, float* __restrict__ table, const float* betas,
+                             const float* alphas, const float* alpha_bar, double temperature,
+                             float* coef_table) {
+    __shared__ float emb[512];
+    __shared__ float te[512];
+    const int tid = threadIdx.x;
+    const int t = blockIdx.x;
+    time_embed_row((float)t, freq, wtT, bt, H, tid, emb, te);
+    float a0 = 0.f, a1 = 0.f;
+    for (int k = 0; k < H; k += 2) {
+        a0 = fmaf(w0tT[(int64_t)k * H + tid], te[k], a0);
+        a1 = fmaf(w0tT[(int64_t)(k + 1) * H + tid], te[k + 1], a1);
+    }
+    table[(int64_t)t * H + tid] = a0 + a1;
+    if (coef_table && tid == 0)
+        step_coefficients(betas, alphas, alpha_bar, t, temperature, coef_table + 4 * t);
+}
+
+// ------------------------------------------------------------------------------------------
+// Full forward for rows with their own t (ECD.py:155-164 as written; training passes random
+// t per row, ECD.py:312-315).  cond_bias already holds W0c @ c_emb + b0 for the row.
+// grid = B, block = H.
+__global__ void k_forward_rows(const float* __restrict__ x, const int64_t* __restrict__ t,
+                               const float* __restrict__ cond_bias, int64_t n_cond,
+                               const float* __restrict__ freq, const float* __restrict__ wtT,
+                               const float* __restrict__ bt, const float* __restrict__ w0tT,
+                               const float* __restrict__ w0xT, const float* __restrict__ w2p,
+                               const float* __restrict__ b2p, int P, int H,
+                               float* __restrict__ out) {
+    __shared__ float emb[512];
+    __shared__ float te[512];
+    __shared__ float xs[kPPad];
+    __shared__ float hs[512];
+    const int tid = threadIdx.x;
+    const int64_t row = blockIdx.x;
+    if (tid < kPPad) xs[tid] = (tid < P) ? x[row * P + tid] : 0.f;
+    time_embed_row((float)t[row], freq, wtT, bt, H, tid, emb, te);
+    float a0 = cond_bias[(row % n_cond) * H + tid], a1 = 0.f;
+    for (int k = 0; k < H; k += 2) {
+        a0 = fmaf(w0tT[(int64_t)k * H + tid], te[k], a0);
+        a1 = fmaf(w0tT[(int64_t)(k + 1) * H + tid], te[k + 1], a1);
+    }
+#pragma unroll
+    for (int k = 0; k < kPPad; ++k) a0 = fmaf(w0xT[k * H + tid], xs[k], a0);
+    hs[tid] = fmaxf(a0 + a1, 0.f);
+    __syncthreads();
+    // output p handled by warp (p % nwarps): lanes stride over j, then a shuffle tree
+    const int lane = tid & 31, warp = tid >> 5, nwarps = H >> 5;
+    for (int p = warp; p < P; p += nwarps) {
+        float acc = 0.f;
+        for (int j = lane; j < H; j += 32) acc = fmaf(w2p[(int64_t)p * H + j], hs[j], acc);
+#pragma unroll
+        for (int o = 16; o > 0; o >>= 1) acc += __shfl_xor_sync(0xffffffffu, acc, o);
+        if (lane == 0) out[row * P + p] = acc + b2p[p];
+    }
+}
+
+// ------------------------------------------------------------------------------------------
+// Philox4x32-10 counter RNG + Box-Muller: device-side replacement for torch.randn in
+// ECD.py:107,116 (a CPU mt19937 stream cannot be reproduced on the device; parity runs inject
+// noise instead).  Counter = (member, offset_hi, quad<<5 | p, offset_lo), key = seed; one call
+// yields the normals for 4 consecutive draws of one (member, parameter).
+__device__ __forceinline__ uint4 philox4x32_10(uint4 c, uint2 k) {
+    const uint32_t M0 = 0xD2511F53u, M1 = 0xCD9E8D57u;
+#pragma unroll
+    for (int r = 0; r < 10; ++r) {
+        const uint32_t hi0 = __umulhi(M0, c.x), lo0 = M0 * c.x;
+        const uint32_t hi1 = __umulhi(M1, c.z), lo1 = M1 * c.z;
+        c = make_uint4(hi1 ^ c.y ^ k.x, lo1, hi0 ^ c.w ^ k.y, lo0);
+        k.x += 0x9E3779B9u;
+        k.y += 0xBB67AE85u;
+    }
+    return c;
+}
+
+__device__ __forceinline__ void box_muller(uint32_t a, uint32_t b, float& n0, float& n1) {
+    const float u1 = fmaf((float)a, 2.3283064365386963e-10f, 1.1641532182693481e-10f);  // (0,1]
+    const float u2 = fmaf((float)b, 2.3283064365386963e-10f, 1.1641532182693481e-10f);
+    const float r = sqrtf(-2.0f * logf(u1));
+    float sn, cs;
+    sincospif(2.0f * u2, &sn, &cs);
+    n0 = r * cs;
+    n1 = r * sn;
+}
+
+__device__ __forceinline__ void philox_normal4(uint64_t seed, uint64_t offset, int64_t member,
+                                               int p, uint32_t quad, float out[4]) {
+    const uint4 c = make_uint4((uint32_t)member, (uint32_t)(offset >> 32) ^ (uint32_t)(member >> 32),
+                               (quad << 5) | (uint32_t)p, (uint32_t)offset);
+    const uint4 r = philox4x32_10(c, make_uint2((uint32_t)seed, (uint32_t)(seed >> 32)));
+    box_muller(r.x, r.y, out[0], out[1]);
+    box_muller(r.z, r.w, out[2], out[3]);
+}
+
+// standalone generator with the chain's stream layout (tests compare the chain in device-RNG
+// mode against the oracle fed with these very draws): out[d][m][p], d = draw index.
+__global__ void k_philox_fill(uint64_t seed, uint64_t offset, int64_t member_offset, int64_t B,
+                              int P, int draws, float* __restrict__ out) {
+    const int64_t idx = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;   // over (quad, m, p)
+    const int nquad = (draws + 3) / 4;
+    if (idx >= (int64_t)nquad * B * P) return;
+    const int p = idx % P;
+    const int64_t m = (idx / P) % B;
+    const uint32_t quad = (uint32_t)(idx / ((int64_t)P * B));
+    float z[4];
+    philox_normal4(seed, offset, member_offset + m, p, quad, z);
+#pragma unroll
+    for (int u = 0; u < 4; ++u) {
+        const int d = quad * 4 + u;
+        if (d < draws) out[((int64_t)d * B + m) * P + p] = z[u];
+    }
+}
+
+// ------------------------------------------------------------------------------------------
+struct ChainParams {
+    int64_t B;             // members handled by this launch
+    int64_t n_cond;
+    int S;                 // chain length (num_steps); draw index of step t is S - t
+    int t_hi;              // first timestep of this launch (S-1 for the whole chain)
+    int t_count;           // steps in this launch
+    const float* w0xT;     // (32,H)
+    const float* w2p;      // (32,H)
+    const float* b2p;      // (32)
+    const float* table;    // (S,H)  c_t
+    const float* coef;     // (S,4)
+    const float* cond_bias;// (n_cond,H)
+    const float* x_in;     // (B rows, P) or nullptr -> Philox draw 0
+    int64_t x_in_stride;   // elements between rows of x_in
+    const float* noise;    // (S-1, noise_B, P) or nullptr -> Philox
+    int64_t noise_B;
+    uint64_t seed, offset;
+    int64_t member_offset;
+    float* x_out;          // (B,P)
+    float* eps_trace;      // (S,B,P) indexed by t, or nullptr
+    int P;
+};
+
+constexpr int CHAIN_RING = 8;   // cp.async noise prefetch depth (steps)
+
+__device__ __forceinline__ void cp_async4(float* smem_dst, const float* gsrc) {
+    const uint32_t d = (uint32_t)__cvta_generic_to_shared(smem_dst);
+    asm volatile("cp.async.ca.shared.global [%0], [%1], 4;\n" ::"r"(d), "l"(gsrc));
+}
+__device__ __forceinline__ void cp_async_commit() { asm volatile("cp.async.commit_group;\n" ::); }
+template <int N>
+__device__ __forceinline__ void cp_async_wait() {
+    asm volatile("cp.async.wait_group %0;\n" ::"n"(N));
+}
+
+// One CTA = MPB members for all steps.  blockDim = H.
+//   layer 1: thread j owns hidden unit j (W0x row in registers, x broadcast from smem)
+//   layer 2: thread (p = tid / PARTS, part = tid % PARTS) owns a 32-wide slice of W2 row p;
+//            PARTS = H/32 partial sums are combined with xor-shuffles
+//   update : every lane of a p-group computes it (identical values); the part-0 lane owns the
+//            noise stream and writes x back to smem.
+template <int H, int MPB>
+__global__ void __launch_bounds__(H) k_chain(const ChainParams a) {
+    constexpr int PARTS = H / 32;
+    constexpr int HS_STRIDE = PARTS * 36;   // each 32-wide slice padded to 36: no bank conflicts
+    __shared__ __align__(16) float xs[MPB][kPPad];
+    __shared__ __align__(16) float hs[MPB][HS_STRIDE];
+    __shared__ float zring[CHAIN_RING][MPB][kPPad];
+
+    const int tid = threadIdx.x;
+    const int p = tid / PARTS, part = tid % PARTS;
+    const int64_t m0 = (int64_t)blockIdx.x * MPB;
+    const int P = a.P;
+    const bool owner = (part == 0) && (p < P);
+    const bool replay = a.noise != nullptr;
+
+    float w0x[kPPad], w2r[32];
+#pragma unroll
+    for (int k = 0; k < kPPad; ++k) w0x[k] = a.w0xT[k * H + tid];
+#pragma unroll
+    for (int i = 0; i < 32; ++i) w2r[i] = a.w2p[p * H + part * 32 + i];
+    const float b2 = a.b2p[p];
+    const int hidx = (tid >> 5) * 36 + (tid & 31);
+
+    float cb[MPB], x[MPB];
+    int64_t mg[MPB];      // clamped local member index
+    bool mvalid[MPB];
+#pragma unroll
+    for (int m = 0; m < MPB; ++m) {
+        mvalid[m] = (m0 + m) < a.B;
+        mg[m] = mvalid[m] ? (m0 + m) : (a.B - 1);
+        cb[m] = a.cond_bias[(mg[m] % a.n_cond) * H + tid];
+    }
+
+    float zc[MPB][4];     // Philox cache: normals of the current quad of draws
+    const int d_first = a.S - a.t_hi;          // draw index used by the first step of this launch
+    // ---- x_T -----------------------------------------------------------------------------
+    // (a launch without x_in is the start of a chain: d_first == 1, so quad 0 serves both x_T,
+    //  which is draw 0, and the first in-loop draws)
+#pragma unroll
+    for (int m = 0; m < MPB; ++m) {
+        if (!replay || !a.x_in)
+            philox_normal4(a.seed, a.offset, a.member_offset + mg[m], p & 31,
+                           a.x_in ? (uint32_t)(d_first >> 2) : 0u, zc[m]);
+        if (a.x_in) {
+            x[m] = (p < P) ? a.x_in[mg[m] * a.x_in_stride + p] : 0.f;
+        } else {
+            x[m] = (p < P) ? zc[m][0] : 0.f;
+        }
+        if (part == 0) xs[m][p] = x[m];
+    }
+
+    // ---- noise ring prologue (replay mode): rows d-1 for draws d = d0 .. d0+RING-1 ---------
+    if (replay) {
+#pragma unroll
+        for (int r = 0; r < CHAIN_RING; ++r) {
+            const int d = d_first + r;
+            if (owner && d <= a.S - 1 && r < a.t_count) {
+#pragma unroll
+                for (int m = 0; m < MPB; ++m)
+                    cp_async4(&zring[d % CHAIN_RING][m][p],
+                              a.noise + ((int64_t)(d - 1) * a.noise_B + mg[m]) * P + p);
+            }
+            cp_async_commit();
+        }
+    }
+    __syncthreads();
+
+    float ct_next = a.table[(int64_t)a.t_hi * H + tid];
+    float4 cf_next = *reinterpret_cast<const float4*>(a.coef + 4 * a.t_hi);
+
+    for (int it = 0; it < a.t_count; ++it) {
+        const int t = a.t_hi - it;
+        const int d = a.S - t;                 // draw index of this step's noise
+        const float ct = ct_next;
+        const float4 cf = cf_next;
+        if (it + 1 < a.t_count) {
+            ct_next = a.table[(int64_t)(t - 1) * H + tid];
+            cf_next = *reinterpret_cast<const float4*>(a.coef + 4 * (t - 1));
+        }
+        // ---- layer 1 ---------------------------------------------------------------------
+#pragma unroll
+        for (int m = 0; m < MPB; ++m) {
+            float a0 = cb[m] + ct, a1 = 0.f;
+#pragma unroll
+            for (int k4 = 0; k4 < kPPad / 4; ++k4) {
+                const float4 xv = *reinterpret_cast<const float4*>(&xs[m][4 * k4]);
+                a0 = fmaf(w0x[4 * k4 + 0], xv.x, a0);
+                a1 = fmaf(w0x[4 * k4 + 1], xv.y, a1);
+                a0 = fmaf(w0x[4 * k4 + 2], xv.z, a0);
+                a1 = fmaf(w0x[4 * k4 + 3], xv.w, a1);
+            }
+            hs[m][hidx] = fmaxf(a0 + a1, 0.f);
+        }
+        __syncthreads();
+        // ---- layer 2 + posterior update ------------------------------------------------------
+        if (replay) cp_async_wait<CHAIN_RING - 1>();     // this step's noise row has landed
+#pragma unroll
+        for (int m = 0; m < MPB; ++m) {
+            float e0 = 0.f, e1 = 0.f, e2 = 0.f, e3 = 0.f;
+#pragma unroll
+            for (int i4 = 0; i4 < 8; ++i4) {
+                const float4 hv = *reinterpret_cast<const float4*>(&hs[m][part * 36 + 4 * i4]);
+                e0 = fmaf(w2r[4 * i4 + 0], hv.x, e0);
+                e1 = fmaf(w2r[4 * i4 + 1], hv.y, e1);
+                e2 = fmaf(w2r[4 * i4 + 2], hv.z, e2);
+                e3 = fmaf(w2r[4 * i4 + 3], hv.w, e3);
+            }
+            float e = (e0 + e1) + (e2 + e3);
+#pragma unroll
+            for (int o = 1; o < PARTS; o <<= 1) e += __shfl_xor_sync(0xffffffffu, e, o);
+            e += b2;
+            float z = 0.f;
+            if (t > 0) {
+                if (replay) {
+                    if (owner) z = zring[d % CHAIN_RING][m][p];
+                } else {
+                    if ((d & 3) == 0)
+                        philox_normal4(a.seed, a.offset, a.member_offset + mg[m], p & 31,
+                                       (uint32_t)(d >> 2), zc[m]);
+                    const int u = d & 3;
+                    z = (u == 0) ? zc[m][0] : (u == 1) ? zc[m][1] : (u == 2) ? zc[m][2] : zc[m][3];
+                }
+            }
+            x[m] = posterior_update_rn(x[m], e, z, cf.x, cf.y, cf.z, t > 0);
+            if (owner) {
+                xs[m][p] = x[m];
+                if (a.eps_trace && mvalid[m])
+                    a.eps_trace[((int64_t)t * a.B + m0 + m) * P + p] = e;
+            }
+        }
+        if (replay) {
+            const int dn = d + CHAIN_RING;           // refill the slot just consumed
+            if (owner && dn <= a.S - 1) {
+#pragma unroll
+                for (int m = 0; m < MPB; ++m)
+                    cp_async4(&zring[dn % CHAIN_RING][m][p],
+                              a.noise + ((int64_t)(dn - 1) * a.noise_B + mg[m]) * P + p);
+            }
+            cp_async_commit();
+        }
+        __syncthreads();
+    }
+    if (replay) cp_async_wait<0>();
+    if (owner) {
+#pragma unroll
+        for (int m = 0; m < MPB; ++m)
+            if (mvalid[m]) a.x_out[(m0 + m) * P + p] = x[m];
+    }
+}
+
+}  // namespace ertdiff

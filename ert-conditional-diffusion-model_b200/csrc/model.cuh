@@ -1,0 +1,116 @@
+// Model handle: the reference's 12-tensor state_dict (ECD.py:133-153) on the device, plus the
+// re-packed copies the kernels read.
+#pragma once
+#include "common.cuh"
+
+struct ertdiff_model {
+    int device = 0;
+    int P = 0;   // param_dim
+    int H = 0;   // hidden_dim
+    bool loaded = false;
+
+    // raw tensors, reference layout/order (see ertdiff_model_load)
+    float* raw[12] = {};
+    size_t raw_n[12] = {};
+
+    // packed for the kernels (all fp32)
+    float* conv1_w = nullptr;  // [14*3][32]   conv1_w[(ci*3+k)*32 + co]
+    float* conv2_w = nullptr;  // [32*3][64]   conv2_w[(ci*3+k)*64 + co]
+    float* w6T = nullptr;      // [64][H]      condition_encoder.6.weight transposed
+    float* wtT = nullptr;      // [H][H]       time_embed.0.weight transposed (k, j)
+    float* w0xT = nullptr;     // [32][H]      mlp.0.weight[:, :P] transposed, rows >= P zero
+    float* w0tT = nullptr;     // [H][H]       mlp.0.weight[:, P:P+H] transposed
+    float* w0cT = nullptr;     // [H][H]       mlp.0.weight[:, P+H:] transposed
+    float* w2p = nullptr;      // [32][H]      mlp.2.weight, rows >= P zero
+    float* b2p = nullptr;      // [32]         mlp.2.bias padded
+    float* freq = nullptr;     // [H/2]        timestep-embedding frequencies (from the host)
+
+    // scratch, grown on demand
+    float* enc_partial = nullptr;  size_t enc_partial_n = 0;   // (n_cond, chunks, 64)
+    float* cond_bias = nullptr;    size_t cond_bias_n = 0;     // (n_cond, H)
+    float* cond_emb = nullptr;     size_t cond_emb_n = 0;      // (n_cond, H)
+    float* time_table = nullptr;   size_t time_table_n = 0;    // (steps, H)
+    float* coef_table = nullptr;   size_t coef_table_n = 0;    // (steps, 4)
+    float* xbuf[2] = {};           size_t xbuf_n[2] = {};         // graph-mode ping-pong (B,P)
+
+    // optional timing of the persistent chain kernel (bench.py's roofline figure)
+    bool profile = false, ev_valid = false;
+    cudaEvent_t ev_chain[2] = {};
+
+    // graph-mode cache
+    cudaGraphExec_t graph_exec = nullptr;
+    struct GraphKey {
+        int64_t B = -1, n_cond = -1; int steps = -1; const void* noise = nullptr;
+        const void* xT = nullptr; void* xout = nullptr; const void* cb = nullptr;
+        uint64_t seed = 0, offset = 0; int64_t moff = 0, nstride = 0; void* trace = nullptr;
+        bool operator==(const GraphKey& o) const {
+            return B == o.B && n_cond == o.n_cond && steps == o.steps && noise == o.noise &&
+                   xT == o.xT && xout == o.xout && cb == o.cb && seed == o.seed &&
+                   offset == o.offset && moff == o.moff && nstride == o.nstride &&
+                   trace == o.trace;
+        }
+    } graph_key;
+};
+
+namespace ertdiff {
+
+inline void raw_shapes(int P, int H, size_t n[12]) {
+    n[0] = 32 * kInChannels * 3; n[1] = 32;
+    n[2] = 64 * 32 * 3;          n[3] = 64;
+    n[4] = (size_t)H * 64;       n[5] = H;
+    n[6] = (size_t)H * H;        n[7] = H;
+    n[8] = (size_t)H * (P + 2 * H); n[9] = H;
+    n[10] = (size_t)P * H;       n[11] = P;
+}
+
+// One thread per packed element; tiny, runs once per load_state_dict.
+__global__ void k_pack_weights(const float* __restrict__ c1w, const float* __restrict__ c2w,
+                               const float* __restrict__ w6, const float* __restrict__ wt,
+                               const float* __restrict__ w0, const float* __restrict__ w2,
+                               const float* __restrict__ b2, int P, int H,
+                               float* __restrict__ conv1_w, float* __restrict__ conv2_w,
+                               float* __restrict__ w6T, float* __restrict__ wtT,
+                               float* __restrict__ w0xT, float* __restrict__ w0tT,
+                               float* __restrict__ w0cT, float* __restrict__ w2p,
+                               float* __restrict__ b2p) {
+    const int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+    const int K0 = P + 2 * H;
+    // conv1: src (co, ci, k) -> dst ((ci*3+k), co)
+    if (i < 32 * kInChannels * 3) {
+        int co = i % 32, r = i / 32;
+        conv1_w[i] = c1w[co * kInChannels * 3 + r];
+    }
+    if (i < 64 * 32 * 3) {
+        int co = i % 64, r = i / 64;
+        conv2_w[i] = c2w[co * 96 + r];
+    }
+    if (i < (int64_t)64 * H) {   // w6T[k][j] = w6[j][k]
+        int j = i % H, k = i / H;
+        w6T[i] = w6[j * 64 + k];
+    }
+    if (i < (int64_t)H * H) {
+        int j = i % H, k = i / H;
+        wtT[i] = wt[(int64_t)j * H + k];
+        w0tT[i] = w0[(int64_t)j * K0 + P + k];
+        w0cT[i] = w0[(int64_t)j * K0 + P + H + k];
+    }
+    if (i < (int64_t)kPPad * H) {
+        int j = i % H, k = i / H;    // w0xT[k][j]
+        w0xT[i] = (k < P) ? w0[(int64_t)j * K0 + k] : 0.f;
+        int p = i / H, jj = i % H;   // w2p[p][j]
+        w2p[i] = (p < P) ? w2[(int64_t)p * H + jj] : 0.f;
+    }
+    if (i < kPPad) b2p[i] = (i < P) ? b2[i] : 0.f;
+}
+
+template <typename T>
+inline int grow(T*& ptr, size_t& have, size_t want) {
+    if (have >= want && ptr) return 0;
+    if (ptr) cudaFree(ptr);
+    ptr = nullptr; have = 0;
+    ERT_CUDA(cudaMalloc(&ptr, want * sizeof(T)));
+    have = want;
+    return 0;
+}
+
+}  // namespace ertdiff

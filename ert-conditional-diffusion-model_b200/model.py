@@ -1,0 +1,195 @@
+"""Host-side mirror of the reference denoiser, backed by the CUDA library.
+
+``ConditionalDiffusionModel`` has the reference's constructor, call signature, attribute
+``param_dim`` and 12-key ``state_dict`` (ERT_Conditional_Diffusion.py:122-164), so the
+reference's sampling cells (``load_best_model`` -> ``model.eval()`` -> ``sample_model``,
+ECD.py:369-399) run unchanged against it.  It owns no arithmetic: ``forward`` calls
+``ertdiff_forward`` in ``libertdiff_b200.so``; parameters are ordinary ``nn.Parameter`` s that
+are mirrored into the library's device handle whenever they change.
+
+Inference only (the north-star path): outputs carry no autograd graph.
+"""
+from __future__ import annotations
+
+import ctypes as C
+import math
+
+import torch
+import torch.nn as nn
+
+from . import _lib
+
+IN_CHANNELS = 14   # ECD.py:134 hard-codes the 14 ERT surveys as conv input channels
+
+
+class _Affine(nn.Module):
+    """A weight/bias pair initialised like torch's Conv1d/Linear ``reset_parameters`` (same
+    RNG draws in the same order, so ``torch.manual_seed(s)`` gives the reference's weights)."""
+
+    def __init__(self, *weight_shape):
+        super().__init__()
+        self.weight = nn.Parameter(torch.empty(*weight_shape))
+        self.bias = nn.Parameter(torch.empty(weight_shape[0]))
+        fan_in = 1
+        for s in weight_shape[1:]:
+            fan_in *= s
+        nn.init.kaiming_uniform_(self.weight, a=math.sqrt(5))
+        bound = 1.0 / math.sqrt(fan_in) if fan_in > 0 else 0.0
+        nn.init.uniform_(self.bias, -bound, bound)
+
+
+class _Slots(nn.Module):
+    """Children registered under the integer names the reference's ``nn.Sequential`` s give
+    their parametrised layers, so ``state_dict`` keys match (``condition_encoder.0.weight`` ...)."""
+
+    def __init__(self, slots):
+        super().__init__()
+        for idx, mod in slots:
+            self.add_module(str(idx), mod)
+
+    def __getitem__(self, idx):
+        return getattr(self, str(idx))
+
+
+class ConditionalDiffusionModel(nn.Module):
+    """ECD.py:122-164.  ``model(x, t, condition) -> predicted noise``.
+
+    x ``(B, param_dim)`` f32, t ``(B,)`` int64 (per-row timesteps), condition ``(B, 14, L)`` f32.
+    All on the CUDA device the model lives on.
+    """
+
+    def __init__(self, param_dim, hidden_dim=128):
+        super().__init__()
+        self.param_dim = int(param_dim)
+        self.hidden_dim = int(hidden_dim)
+        P, H = self.param_dim, self.hidden_dim
+        # creation order == the reference's, so seeded initialisation is identical
+        self.condition_encoder = _Slots([(0, _Affine(32, IN_CHANNELS, 3)),   # Conv1d k3 s2 p1
+                                         (2, _Affine(64, 32, 3)),            # Conv1d k3 s2 p1
+                                         (6, _Affine(H, 64))])               # Linear
+        self.time_embed = _Slots([(0, _Affine(H, H))])
+        self.mlp = _Slots([(0, _Affine(H, P + 2 * H)), (2, _Affine(P, H))])
+        self._handle = None
+        self._handle_device = None
+        self._stamp = None
+
+    # ------------------------------------------------------------------ library handle
+    def _ordered_params(self):
+        ce, te, mlp = self.condition_encoder, self.time_embed, self.mlp
+        return [ce[0].weight, ce[0].bias, ce[2].weight, ce[2].bias, ce[6].weight, ce[6].bias,
+                te[0].weight, te[0].bias, mlp[0].weight, mlp[0].bias, mlp[2].weight, mlp[2].bias]
+
+    def _frequency_table(self):
+        """ECD.py:81-83, evaluated with the very torch ops the reference uses."""
+        half = self.hidden_dim // 2
+        emb = math.log(10000.0) / (half - 1)
+        return torch.exp(torch.arange(half, dtype=torch.float32) * -emb).contiguous()
+
+    def handle(self):
+        """The library's device handle, (re)loaded if parameters moved or changed."""
+        params = self._ordered_params()
+        dev = params[0].device
+        if dev.type != "cuda":
+            raise _lib.ErtdiffError(
+                "ConditionalDiffusionModel is on %s: this implementation runs on CUDA only "
+                "(call model.to('cuda')); there is no CPU path" % dev)
+        for p in params:
+            if p.device != dev or p.dtype != torch.float32:
+                raise _lib.ErtdiffError("all parameters must be float32 on one CUDA device")
+        lib = _lib.load()
+        index = dev.index if dev.index is not None else torch.cuda.current_device()
+        if self._handle is None or self._handle_device != index:
+            self._release()
+            h = C.c_void_p()
+            _lib.check(lib.ertdiff_model_create(C.byref(h), index, self.param_dim,
+                                                self.hidden_dim), "model_create")
+            self._handle, self._handle_device, self._stamp = h, index, None
+        stamp = tuple((p.data_ptr(), p._version) for p in params)
+        if stamp != self._stamp:
+            tensors = [p.detach().contiguous() for p in params]
+            arr = (C.c_void_p * 12)(*[t.data_ptr() for t in tensors])
+            freq = self._frequency_table()
+            with torch.cuda.device(index):
+                _lib.check(lib.ertdiff_model_load(self._handle, arr, 1, C.c_void_p(freq.data_ptr()),
+                                                  _lib.stream_ptr(index)), "model_load")
+            self._stamp = stamp
+        return self._handle
+
+    def _release(self):
+        if self._handle is not None:
+            try:
+                _lib.load().ertdiff_model_destroy(self._handle)
+            except Exception:
+                pass
+            self._handle = None
+
+    def __del__(self):
+        self._release()
+
+    def __getstate__(self):
+        # the device handle is not copyable/picklable; a copy re-creates its own on first use
+        d = self.__dict__.copy()
+        d["_handle"], d["_handle_device"], d["_stamp"] = None, None, None
+        return d
+
+    def profile_chain(self, enable=True):
+        """Bracket the persistent chain kernel with CUDA events (bench.py's roofline figure)."""
+        _lib.check(_lib.load().ertdiff_model_profile(self.handle(), int(bool(enable))), "model_profile")
+
+    def last_chain_ms(self):
+        ms = C.c_float()
+        _lib.check(_lib.load().ertdiff_model_last_chain_ms(self.handle(), C.byref(ms)), "last_chain_ms")
+        return float(ms.value)
+
+    @property
+    def device(self):
+        return self.mlp[2].weight.device
+
+    # ------------------------------------------------------------------ forward
+    @staticmethod
+    def _condition_layout(condition):
+        """(contiguous-per-member tensor, member stride in elements; 0 = one shared condition)."""
+        if condition.dim() != 3 or condition.size(1) != IN_CHANNELS:
+            raise ValueError(f"condition must be (B, {IN_CHANNELS}, L), got {tuple(condition.shape)}")
+        L = condition.size(2)
+        if condition.size(0) > 1 and condition.stride(0) == 0:
+            one = condition[:1].contiguous()          # an expand()ed shared condition
+            return one, 0
+        c = condition.contiguous()
+        return c, IN_CHANNELS * L
+
+    @torch.no_grad()
+    def forward(self, x, t, condition):
+        h = self.handle()
+        dev = self.device
+        x = x.to(device=dev, dtype=torch.float32).contiguous()
+        t = t.to(device=dev, dtype=torch.int64).contiguous()
+        condition = condition.to(device=dev, dtype=torch.float32)
+        B = x.size(0)
+        if x.dim() != 2 or x.size(1) != self.param_dim:
+            raise ValueError(f"x must be (B, {self.param_dim}), got {tuple(x.shape)}")
+        if t.shape != (B,) or condition.size(0) != B:
+            raise ValueError("x, t and condition disagree on the batch size")
+        cond, stride = self._condition_layout(condition)
+        out = torch.empty_like(x)
+        if B == 0:
+            return out
+        with torch.cuda.device(dev):
+            _lib.check(_lib.load().ertdiff_forward(
+                h, _lib.ptr(x), _lib.ptr(t), _lib.ptr(cond), B, cond.size(2), stride,
+                _lib.ptr(out), _lib.stream_ptr(dev)), "forward")
+        return out
+
+    @torch.no_grad()
+    def encode_condition(self, condition):
+        """``condition_encoder(condition)`` (ECD.py:133-142, 161): ``(n, 14, L) -> (n, H)``."""
+        h = self.handle()
+        dev = self.device
+        condition = condition.to(device=dev, dtype=torch.float32).contiguous()
+        n, L = condition.size(0), condition.size(2)
+        emb = torch.empty(n, self.hidden_dim, device=dev, dtype=torch.float32)
+        with torch.cuda.device(dev):
+            _lib.check(_lib.load().ertdiff_encode_condition(
+                h, _lib.ptr(condition), n, L, IN_CHANNELS * L, _lib.ptr(emb), None,
+                _lib.stream_ptr(dev)), "encode_condition")
+        return emb

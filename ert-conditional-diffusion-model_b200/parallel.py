@@ -1,0 +1,64 @@
+"""Multi-GPU ensemble: members are independent (ECD.py:106-119 has no cross-row operation), so
+each rank runs a contiguous slice of the ensemble and ONE all-gather returns the fields in
+member order (SURVEY.md §8 e).  One process per GPU, ``torch.distributed`` (NCCL) as plumbing.
+
+The slicing keeps results independent of the number of ranks: device-RNG streams are keyed by
+the GLOBAL member index (``member_offset``) and injected noise is read from the member-slice of
+the full tensor, so 1, 2, 4 or 8 ranks give bit-identical gathered fields.
+"""
+from __future__ import annotations
+
+import torch
+import torch.distributed as dist
+
+
+def member_slice(n_members: int, rank: int, world_size: int, multiple_of: int = 1):
+    """Contiguous ``[start, stop)`` of rank's members; slice sizes are multiples of
+    ``multiple_of`` (the number of distinct conditions, so ``member % n_cond`` is preserved)."""
+    if n_members % multiple_of:
+        raise ValueError("n_members must be a multiple of multiple_of")
+    groups = n_members // multiple_of
+    base, extra = divmod(groups, world_size)
+    start = rank * base + min(rank, extra)
+    stop = start + base + (1 if rank < extra else 0)
+    return start * multiple_of, stop * multiple_of
+
+
+def gather_members(x_local: torch.Tensor, n_members: int, multiple_of: int = 1,
+                   group=None) -> torch.Tensor:
+    """All-gather ``(B_local, P)`` slices into ``(n_members, P)`` in rank (= member) order.
+    Slices may differ in length by one group: each rank pads to the longest slice, one
+    equal-sized all-gather runs, and the padding is dropped."""
+    if not dist.is_available() or not dist.is_initialized() or dist.get_world_size(group) == 1:
+        return x_local
+    world = dist.get_world_size(group)
+    counts = [b - a for a, b in (member_slice(n_members, r, world, multiple_of)
+                                 for r in range(world))]
+    longest = max(counts)
+    x_local = x_local.contiguous()
+    even = min(counts) == longest
+    if not even and x_local.size(0) < longest:
+        pad = torch.zeros((longest - x_local.size(0),) + tuple(x_local.shape[1:]),
+                          device=x_local.device, dtype=x_local.dtype)
+        x_local = torch.cat([x_local, pad], dim=0)
+    if even and x_local.is_cuda:
+        out = torch.empty((n_members,) + tuple(x_local.shape[1:]), device=x_local.device,
+                          dtype=x_local.dtype)
+        dist.all_gather_into_tensor(out, x_local, group=group)     # one NCCL all-gather
+        return out
+    parts = [torch.empty_like(x_local) for _ in range(world)]
+    dist.all_gather(parts, x_local, group=group)
+    return torch.cat([p[:c] for p, c in zip(parts, counts)], dim=0)
+
+
+def sample_ensemble_sharded(chain_fn, n_members: int, n_cond: int = 1, group=None, noise=None):
+    """Run ``chain_fn(start, stop, noise_slice) -> (stop-start, P)`` on this rank's slice and
+    gather.  ``chain_fn`` is normally a closure over ``sampler.run_chain`` with
+    ``member_offset=start``; tests inject a CPU stand-in to exercise the slicing and the
+    collective on the gloo backend.  With ``n_cond`` distinct conditions slices are whole
+    realisations (multiples of ``n_cond``), so ``member % n_cond`` is the same on every rank."""
+    start, stop = member_slice(n_members, dist.get_rank(group) if dist.is_initialized() else 0,
+                               dist.get_world_size(group) if dist.is_initialized() else 1, n_cond)
+    nz = None if noise is None else noise[:, start:stop, :]
+    x_local = chain_fn(start, stop, nz)
+    return gather_members(x_local, n_members, n_cond, group)

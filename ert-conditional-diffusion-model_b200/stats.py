@@ -1,0 +1,148 @@
+"""Ensemble statistics over members (axis 0): device replacements for the numpy / scipy
+calls the reference makes inline (ERT_Conditional_Diffusion.py:747-762, 867-872, 612,
+1126-1127, 1199-1200).
+
+Every function takes an ``(N, ...)`` array -- a CUDA ``torch.Tensor`` or a ``numpy.ndarray``
+(copied to the device) -- and returns the same kind of object it was given, with the trailing
+shape.  float32 and float64 are supported; the result dtypes follow numpy's rules.
+Mean/std/var and percentiles are bit-identical to numpy for ``Q > 1`` columns; the KDE mode's
+contract is the argmax grid index.
+"""
+from __future__ import annotations
+
+import ctypes as C
+
+import numpy as np
+import torch
+
+from . import _lib
+
+_DT = {torch.float32: _lib.F32, torch.float64: _lib.F64}
+
+
+def _to_device(a, device=None):
+    """-> (2-D contiguous CUDA tensor (N, Q), trailing shape, was_numpy)."""
+    was_numpy = isinstance(a, np.ndarray)
+    if was_numpy:
+        if a.dtype not in (np.float32, np.float64):
+            a = a.astype(np.float64)
+        t = torch.from_numpy(np.ascontiguousarray(a))
+        dev = torch.device(device) if device is not None else torch.device("cuda", torch.cuda.current_device())
+        t = t.to(dev)
+    else:
+        t = a
+        if t.device.type != "cuda":
+            if device is None:
+                raise _lib.ErtdiffError("statistics run on CUDA only: pass a CUDA tensor, a numpy "
+                                        "array, or device=")
+            t = t.to(device)
+        if t.dtype not in _DT:
+            t = t.to(torch.float64)
+    if t.dim() < 1 or t.size(0) < 1:
+        raise ValueError("need an (N, ...) array with N >= 1 members on axis 0")
+    trailing = tuple(t.shape[1:])
+    t2 = t.reshape(t.size(0), -1).contiguous()
+    return t2, trailing, was_numpy
+
+
+def _finish(t, trailing, was_numpy, lead=()):
+    t = t.reshape(tuple(lead) + tuple(trailing))
+    return t.cpu().numpy() if was_numpy else t
+
+
+def ensemble_moments(a, device=None, mean=True, std=True, var=True):
+    """``np.mean / np.std / np.var (a, axis=0)`` in one pass pair (ECD.py:867-869).
+    Returns a dict with the requested keys."""
+    t, trailing, was_numpy = _to_device(a, device)
+    N, Q = t.shape
+    outs = {k: torch.empty(Q, device=t.device, dtype=t.dtype)
+            for k, want in (("mean", mean), ("std", std), ("var", var)) if want}
+    if Q > 0:
+        with torch.cuda.device(t.device):
+            _lib.check(_lib.load().ertdiff_ensemble_moments(
+                _lib.ptr(t), _DT[t.dtype], N, Q, _lib.ptr(outs.get("mean")),
+                _lib.ptr(outs.get("std")), _lib.ptr(outs.get("var")), _lib.stream_ptr(t.device)),
+                "ensemble_moments")
+    return {k: _finish(v, trailing, was_numpy) for k, v in outs.items()}
+
+
+def ensemble_mean(a, device=None):
+    return ensemble_moments(a, device, True, False, False)["mean"]
+
+
+def ensemble_std(a, device=None):
+    return ensemble_moments(a, device, False, True, False)["std"]
+
+
+def ensemble_var(a, device=None):
+    return ensemble_moments(a, device, False, False, True)["var"]
+
+
+def _index_dtype(a_dtype, q):
+    """numpy's rule (``np.percentile`` divides q by ``a.dtype.type(100)``): a python int/float q
+    is weakly typed and adopts a float32 array's dtype; numpy scalars / sequences stay float64."""
+    weak = isinstance(q, (int, float)) and not isinstance(q, np.generic)
+    return _lib.F32 if (weak and a_dtype == torch.float32) else _lib.F64
+
+
+def ensemble_percentile(a, q, device=None):
+    """``np.percentile(a, q, axis=0)`` with the default linear method
+    (ECD.py:870-872, 612, 1126-1127, 1199-1200).  Scalar q -> trailing shape; sequence q ->
+    ``(len(q),) + trailing``."""
+    t, trailing, was_numpy = _to_device(a, device)
+    N, Q = t.shape
+    scalar = np.ndim(q) == 0
+    idt = _index_dtype(t.dtype, q)
+    qs = np.atleast_1d(np.asarray(q, dtype=np.float64)).ravel()
+    if qs.size == 0:
+        raise ValueError("q is empty")
+    if np.any(qs < 0) or np.any(qs > 100) or np.any(np.isnan(qs)):
+        raise ValueError("Percentiles must be in the range [0, 100]")
+    out_dtype = torch.float32 if (t.dtype == torch.float32 and idt == _lib.F32) else torch.float64
+    out = torch.empty(qs.size, Q, device=t.device, dtype=out_dtype)
+    if Q > 0:
+        qarr = (C.c_double * qs.size)(*qs.tolist())
+        with torch.cuda.device(t.device):
+            _lib.check(_lib.load().ertdiff_ensemble_percentiles(
+                _lib.ptr(t), _DT[t.dtype], N, Q, qarr, int(qs.size), idt, _lib.ptr(out),
+                _lib.stream_ptr(t.device)), "ensemble_percentiles")
+    if scalar:
+        return _finish(out[0], trailing, was_numpy)
+    return _finish(out, trailing, was_numpy, lead=(qs.size,))
+
+
+def ensemble_kde_mode(a, n_grid=5000, grid_range=None, device=None, return_index=False):
+    """Per-column Gaussian-KDE mode on a common grid (ECD.py:747-762): ``grid =
+    linspace(a.min(), a.max(), n_grid)`` over the WHOLE array (or ``grid_range=(lo, hi)``), Scott
+    bandwidth, first argmax.  Returns float64 modes (and the int64 grid indices)."""
+    t, trailing, was_numpy = _to_device(a, device)
+    N, Q = t.shape
+    if N < 2:
+        raise ValueError("KDE needs at least 2 members")
+    lib = _lib.load()
+    lohi = torch.empty(2, device=t.device, dtype=torch.float64)
+    mode = torch.empty(Q, device=t.device, dtype=torch.float64)
+    index = torch.empty(Q, device=t.device, dtype=torch.int64)
+    with torch.cuda.device(t.device):
+        st = _lib.stream_ptr(t.device)
+        if grid_range is None:
+            _lib.check(lib.ertdiff_minmax(_lib.ptr(t), _DT[t.dtype], t.numel(), _lib.ptr(lohi), st),
+                       "minmax")
+        else:
+            lohi.copy_(torch.tensor([float(grid_range[0]), float(grid_range[1])], dtype=torch.float64))
+        if Q > 0:
+            _lib.check(lib.ertdiff_ensemble_kde_mode(_lib.ptr(t), _DT[t.dtype], N, Q, _lib.ptr(lohi),
+                                                     int(n_grid), _lib.ptr(mode), _lib.ptr(index), st),
+                       "ensemble_kde_mode")
+    m = _finish(mode, trailing, was_numpy)
+    return (m, _finish(index, trailing, was_numpy)) if return_index else m
+
+
+def ensemble_statistics(a, percentiles=(25, 50, 75), mode=True, n_grid=5000, device=None):
+    """Everything ECD.py:747-762 + 867-872 computes for an ensemble of maps, in one call:
+    ``{"mean","std","var","percentiles":{q: map},"mode","mode_index"}``."""
+    out = ensemble_moments(a, device)
+    out["percentiles"] = {q: ensemble_percentile(a, q, device) for q in percentiles}
+    if mode:
+        out["mode"], out["mode_index"] = ensemble_kde_mode(a, n_grid, None, device, True)
+    return out

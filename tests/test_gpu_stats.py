@@ -1,0 +1,111 @@
+"""GPU parity of the ensemble statistics against numpy / scipy (the reference's own calls,
+ECD.py:747-762, 867-872) and the golden maps.  Moments and percentiles: bit-exact.  KDE mode:
+exact argmax index, with the counted near-tie rule of SURVEY.md §8 a7."""
+import numpy as np
+import pytest
+import torch
+
+import ertdiff_b200 as eb
+from oracle import stats_oracle as so
+
+pytestmark = pytest.mark.gpu
+
+
+def same(a, b):
+    return a.dtype == b.dtype and a.shape == b.shape and np.array_equal(a, b, equal_nan=True)
+
+
+@pytest.mark.parametrize("dtype", [np.float32, np.float64])
+@pytest.mark.parametrize("N,Q", [(2, 2), (3, 29), (16, 29), (50, 4693 * 14), (256, 29), (1000, 257), (8192, 29), (1024, 3001)])
+def test_moments_bit_exact(cuda_dev, dtype, N, Q):
+    a = np.random.default_rng(N * 7 + Q).lognormal(size=(N, Q)).astype(dtype)
+    m = eb.ensemble_moments(a)
+    assert same(m["mean"], np.mean(a, axis=0))
+    assert same(m["var"], np.var(a, axis=0))
+    assert same(m["std"], np.std(a, axis=0))
+
+
+QS = [25, 50, 75, 0, 100, 2.5, 97.5, 33.3, np.float64(50.5), [2.5, 97.5],
+      list((1 - np.linspace(0.01, 0.99, 30)) / 2 * 100) + list((1 + np.linspace(0.01, 0.99, 30)) / 2 * 100)]
+
+
+@pytest.mark.parametrize("dtype", [np.float32, np.float64])
+@pytest.mark.parametrize("N,Q", [(2, 3), (5, 29), (16, 29), (50, 1000), (255, 64), (256, 29), (1000, 33), (1024, 29), (4096, 7), (8192, 29)])
+def test_percentiles_bit_exact(cuda_dev, dtype, N, Q):
+    a = np.random.default_rng(N + Q).normal(size=(N, Q)).astype(dtype)
+    for q in QS:
+        ref = np.percentile(a, q, axis=0)
+        got = eb.ensemble_percentile(a, q)
+        assert same(got, ref), (q, ref.dtype, got.dtype, np.abs(got - ref).max())
+
+
+def test_percentiles_edge_cases(cuda_dev):
+    rng = np.random.default_rng(1)
+    a = rng.normal(size=(1, 5))                       # one member
+    assert same(eb.ensemble_percentile(a, 50), np.percentile(a, 50, axis=0))
+    a = rng.normal(size=(20, 6))
+    a[3, 2] = np.nan                                  # NaN column -> NaN, others untouched
+    assert same(eb.ensemble_percentile(a, [10, 50]), np.percentile(a, [10, 50], axis=0))
+    a = np.repeat(rng.normal(size=(1, 9)), 40, axis=0)   # all members equal (ties)
+    assert same(eb.ensemble_percentile(a, [0, 37.5, 100]), np.percentile(a, [0, 37.5, 100], axis=0))
+    a = rng.integers(0, 4, size=(64, 11)).astype(np.float32)   # heavy ties
+    assert same(eb.ensemble_percentile(a, 30), np.percentile(a, 30, axis=0))
+    a = rng.normal(size=(50, 12, 3))                  # trailing shape is kept
+    assert eb.ensemble_percentile(a, 25).shape == (12, 3)
+    assert eb.ensemble_percentile(a, [25, 75]).shape == (2, 12, 3)
+    with pytest.raises(ValueError):
+        eb.ensemble_percentile(a, 101)
+    t = torch.from_numpy(a).to(cuda_dev)              # CUDA tensor in -> CUDA tensor out
+    r = eb.ensemble_percentile(t, 25)
+    assert r.is_cuda and same(r.cpu().numpy(), np.percentile(a, 25, axis=0))
+    a = np.where(rng.random((30, 8)) < 0.1, np.inf, rng.normal(size=(30, 8)))   # infinities
+    assert same(eb.ensemble_percentile(a, [5, 50, 99]), np.percentile(a, [5, 50, 99], axis=0))
+
+
+def test_golden_maps(cuda_dev, golden):
+    g = golden("stats_maps.npz")
+    sim = g["sim"]
+    st = eb.ensemble_statistics(sim, percentiles=(25, 50, 75))
+    assert same(st["mean"], g["mean"]) and same(st["std"], g["std"]) and same(st["var"], g["var"])
+    for q, key in ((25, "p25"), (50, "p50"), (75, "p75")):
+        assert same(st["percentiles"][q], g[key])
+    assert same(eb.ensemble_percentile(sim.astype(np.float32), [2.5, 97.5]), g["ci95"])
+    assert np.array_equal(st["mode_index"], g["mode_index"])
+    assert np.array_equal(st["mode"], g["mode"])
+
+
+@pytest.mark.parametrize("dtype", [np.float32, np.float64])
+@pytest.mark.parametrize("N", [16, 50, 256])
+def test_kde_mode_index_is_scipy(cuda_dev, dtype, N):
+    a = np.random.default_rng(N).lognormal(size=(N, 24)).astype(dtype)
+    grid = so.kde_grid(a, 5000)
+    mode, idx = eb.ensemble_kde_mode(a, 5000, return_index=True)
+    _, idx_sp, pdfs = so.kde_mode_scipy(a, grid)
+    differ = np.nonzero(idx != idx_sp)[0]
+    for j in differ:                                   # near-tie rule, counted
+        p = pdfs[:, j]
+        assert abs(p[idx[j]] - p[idx_sp[j]]) <= 1e-13 * p[idx_sp[j]], (j, idx[j], idx_sp[j])
+    assert len(differ) <= 1, f"near-tie rule invoked {len(differ)} times out of 24"
+    assert np.array_equal(mode, grid[idx])             # the grid itself is np.linspace, bit for bit
+
+
+def test_kde_mode_full_grid_pixels_property(cuda_dev):
+    # reference-sized map subsample: mode lies inside the data range and moves with a shift
+    rng = np.random.default_rng(8)
+    a = rng.lognormal(size=(50, 2000))
+    mode, idx = eb.ensemble_kde_mode(a, 5000, return_index=True)
+    assert mode.min() >= a.min() and mode.max() <= a.max()
+    lo, hi = a.min(), a.max()
+    mode2, idx2 = eb.ensemble_kde_mode(a + 3.0, 5000, grid_range=(lo + 3.0, hi + 3.0), return_index=True)
+    assert np.abs(idx2 - idx).max() <= 1               # same grid, shifted data: same argmax (+-1 ulp effects)
+
+
+def test_statistics_of_large_ensembles_properties(cuda_dev):
+    # BASELINE config 4 size: 8192 members; selection must return members of the column
+    a = torch.randn(8192, 29, device=cuda_dev, generator=torch.Generator(cuda_dev).manual_seed(0))
+    q = eb.ensemble_percentile(a, [0, 50, 100])
+    assert torch.equal(q[0].float(), a.min(dim=0).values) and torch.equal(q[2].float(), a.max(dim=0).values)
+    srt = a.sort(dim=0).values
+    assert torch.equal(q[1].float(), ((srt[4095].double() + (srt[4096] - srt[4095]).double() * 0.5)).float())
+    perm = a[torch.randperm(8192, device=cuda_dev)]
+    assert torch.equal(eb.ensemble_percentile(perm, [0, 50, 100]), q)   # order of members is irrelevant

@@ -1,0 +1,72 @@
+"""world_size-2 test of the sharding + gather host logic on the gloo backend (CPU).
+The CUDA chain is replaced by the oracle as a stand-in runner: what is tested here is
+member slicing, noise slicing and gather order -- not arithmetic."""
+import os
+import socket
+
+import numpy as np
+import pytest
+import torch
+import torch.distributed as dist
+import torch.multiprocessing as mp
+
+
+def _free_port():
+    s = socket.socket()
+    s.bind(("127.0.0.1", 0))
+    p = s.getsockname()[1]
+    s.close()
+    return p
+
+
+def _worker(rank, world, port, n_members, n_cond, out_dir):
+    os.environ["MASTER_ADDR"] = "127.0.0.1"
+    os.environ["MASTER_PORT"] = str(port)
+    dist.init_process_group("gloo", rank=rank, world_size=world)
+    import sys
+    sys.path.insert(0, os.path.dirname(os.path.dirname(os.path.abspath(__file__))))
+    from ertdiff_b200.parallel import sample_ensemble_sharded
+    from oracle import denoiser_oracle as do
+    torch.set_num_threads(1)
+    P, T, L = 29, 6, 40
+    sd = do.init_state_dict(P, 32, seed=3)
+    cond = torch.rand(n_cond, 14, L, generator=torch.Generator().manual_seed(1))
+    noise = torch.randn(T, n_members, P, generator=torch.Generator().manual_seed(2))
+    b, a, ab = do.diffusion_schedule(T)
+
+    def chain(start, stop, nz):
+        idx = torch.arange(start, stop) % n_cond
+        return do.sample_chain(sd, cond[idx], T, b, a, ab, P, nz)
+
+    x = sample_ensemble_sharded(chain, n_members, n_cond=n_cond, noise=noise)
+    np.save(os.path.join(out_dir, f"x_rank{rank}.npy"), x.numpy())
+
+    def tag(start, stop, nz):       # exact bookkeeping check: member id, condition id, noise row
+        m = torch.arange(start, stop, dtype=torch.float32)
+        return torch.stack([m, m % n_cond, nz[0, :, 0], nz[-1, :, -1]], dim=1)
+
+    tg = sample_ensemble_sharded(tag, n_members, n_cond=n_cond, noise=noise)
+    np.save(os.path.join(out_dir, f"tag_rank{rank}.npy"), tg.numpy())
+    if rank == 0:
+        m = torch.arange(n_members, dtype=torch.float32)
+        np.save(os.path.join(out_dir, "tag_full.npy"),
+                torch.stack([m, m % n_cond, noise[0, :, 0], noise[-1, :, -1]], dim=1).numpy())
+    if rank == 0:
+        full = do.sample_chain(sd, cond[torch.arange(n_members) % n_cond], T, b, a, ab, P, noise)
+        np.save(os.path.join(out_dir, "x_full.npy"), full.numpy())
+    dist.barrier()
+    dist.destroy_process_group()
+
+
+@pytest.mark.parametrize("n_members,n_cond", [(10, 1), (7, 1), (12, 3)])
+def test_two_rank_gather_equals_single_process(tmp_path, n_members, n_cond):
+    port = _free_port()
+    mp.spawn(_worker, args=(2, port, n_members, n_cond, str(tmp_path)), nprocs=2, join=True)
+    full = np.load(tmp_path / "x_full.npy")
+    for r in range(2):
+        got = np.load(tmp_path / f"x_rank{r}.npy")
+        assert got.shape == full.shape
+        # the CPU stand-in's GEMMs are batch-size dependent in the last bits; bookkeeping is
+        # checked exactly through the tags below
+        assert np.allclose(got, full, rtol=1e-5, atol=1e-5), f"rank {r}: gathered fields differ"
+        assert np.array_equal(np.load(tmp_path / f"tag_rank{r}.npy"), np.load(tmp_path / "tag_full.npy"))
