@@ -230,8 +230,10 @@ def run_ours(args):
         if world > 1:
             x = eb.parallel.gather_members(x, total)
         st = stats(x)
-        host = [x.cpu(), st["mean"].cpu(), st["std"].cpu(), st["var"].cpu(), st["pct"].cpu(), st["mode"].cpu()]
-        return host
+        # one D2H read of the step's results: fields + every statistic, packed (f64 keeps all bits)
+        packed = torch.cat([v.reshape(-1).double() for v in
+                            (x, st["mean"], st["std"], st["var"], st["pct"], st["mode"])])
+        return packed.cpu()
 
     def barrier():
         if world > 1:
@@ -284,7 +286,7 @@ def run_ours(args):
     e2e_value = total * args.steps / (ms_e2e * 1e-3)
     n_cond = members if args.distinct_conditions else 1
     h2d = cond_host.numel() * 4 + (3 * T * 4 if True else 0)
-    d2h = total * P * 4 + 3 * P * 4 + len(PERCENTILES) * P * 4 + P * 8
+    d2h = 8 * (total * P + 3 * P + len(PERCENTILES) * P + P)
 
     if rank == 0:
         peaks = load_peaks()

@@ -1,6 +1,8 @@
 // C ABI of libertdiff_b200.so -- see include/ertdiff_b200.h for the contract.
 #include <cmath>
+#include <cstdlib>
 #include <cstring>
+#include <mutex>
 #include <vector>
 
 #include "common.cuh"
@@ -19,6 +21,32 @@ std::atomic<int64_t> g_launches{0};
 static int check_model(const ertdiff_model* m, bool need_weights = true) {
     if (!m) return fail(ERTDIFF_ERR_ARG, "model handle is NULL");
     if (need_weights && !m->loaded) return fail(ERTDIFF_ERR_STATE, "model weights not loaded");
+    return 0;
+}
+
+// ---- per-device scratch for the statistics entry points (they take no model handle) --------
+// Grown on demand, kept for the life of the process: no allocation on the hot path.  Calls on
+// one device are expected to come from one stream at a time.
+struct Workspace {
+    void* ptr = nullptr;
+    size_t bytes = 0;
+};
+static Workspace g_ws[64];
+static std::mutex g_ws_mutex;
+
+static int workspace(size_t bytes, void** out) {
+    int dev = 0;
+    ERT_CUDA(cudaGetDevice(&dev));
+    if (dev < 0 || dev >= 64) return fail(ERTDIFF_ERR_ARG, "workspace: device index out of range");
+    std::lock_guard<std::mutex> lock(g_ws_mutex);
+    Workspace& w = g_ws[dev];
+    if (w.bytes < bytes) {
+        if (w.ptr) { ERT_CUDA(cudaDeviceSynchronize()); cudaFree(w.ptr); w.ptr = nullptr; w.bytes = 0; }
+        size_t want = bytes < (1u << 20) ? (1u << 20) : bytes;
+        ERT_CUDA(cudaMalloc(&w.ptr, want));
+        w.bytes = want;
+    }
+    *out = w.ptr;
     return 0;
 }
 
@@ -77,6 +105,10 @@ static int launch_chain(int H, const ChainParams& p, int mpb, cudaStream_t st) {
 // members per CTA: spread small ensembles over all SMs (the chain is latency-bound), pack
 // large ones so that weight registers are amortised over more members
 static int pick_mpb(int64_t B, int H) {
+    if (const char* e = std::getenv("ERTDIFF_CHAIN_MPB")) {      // tuning override
+        const int v = std::atoi(e);
+        if (v == 1 || v == 2 || v == 4 || v == 8) return v;
+    }
     const int64_t ctas_per_sm = (H <= 128) ? 4 : (H <= 256 ? 2 : 1);
     const int64_t slots = kNumSMs * ctas_per_sm;
     if (B <= slots) return 1;
@@ -418,10 +450,6 @@ int ertdiff_ensemble_percentiles(const void* d_a, int dtype, int64_t N, int64_t 
             if (vi >= (double)(N - 1)) q.lo = q.hi = (int32_t)(N - 1);
         }
     }
-    PctlQuery* d_qs = nullptr;
-    ERT_CUDA(cudaMallocAsync(&d_qs, nq * sizeof(PctlQuery), st));
-    ERT_CUDA(cudaMemcpyAsync(d_qs, qs.data(), nq * sizeof(PctlQuery), cudaMemcpyHostToDevice, st));
-    ERT_CUDA(cudaStreamSynchronize(st));   // qs is a stack-owned vector
     int NP = 1;
     while (NP < N) NP <<= 1;
     const size_t esz = dtype == ERTDIFF_F32 ? 4 : 8;
@@ -435,21 +463,26 @@ int ertdiff_ensemble_percentiles(const void* d_a, int dtype, int64_t N, int64_t 
     const int threads = (int64_t)CT * NP / 2 >= 1024 ? 1024 : ((int64_t)CT * NP / 2 >= 256 ? 256 : 64);
     const unsigned grid = (unsigned)((Q + CT - 1) / CT);
     cudaError_t e = cudaSuccess;
+    // queries travel as a by-value kernel argument, kMaxPctlQueries per launch
+    for (int k0 = 0; k0 < nq && e == cudaSuccess; k0 += kMaxPctlQueries) {
+        PctlQueryPack pack{};
+        pack.n = (nq - k0) < kMaxPctlQueries ? (nq - k0) : kMaxPctlQueries;
+        for (int k = 0; k < pack.n; ++k) pack.q[k] = qs[k0 + k];
 #define ERT_PCT_LAUNCH(T, G, O)                                                              \
     do {                                                                                     \
         e = cudaFuncSetAttribute(k_percentiles<T, G, O>,                                     \
                                  cudaFuncAttributeMaxDynamicSharedMemorySize, (int)budget);  \
         if (e == cudaSuccess)                                                                \
             k_percentiles<T, G, O><<<grid, threads, smem, st>>>((const T*)d_a, N, Q, NP, CT, \
-                                                               d_qs, nq, (O*)d_out);         \
+                                                               pack, (O*)d_out + (size_t)k0 * Q); \
     } while (0)
-    if (dtype == ERTDIFF_F32 && index_dtype == ERTDIFF_F32) ERT_PCT_LAUNCH(float, float, float);
-    else if (dtype == ERTDIFF_F32) ERT_PCT_LAUNCH(float, double, double);
-    else ERT_PCT_LAUNCH(double, double, double);
+        if (dtype == ERTDIFF_F32 && index_dtype == ERTDIFF_F32) ERT_PCT_LAUNCH(float, float, float);
+        else if (dtype == ERTDIFF_F32) ERT_PCT_LAUNCH(float, double, double);
+        else ERT_PCT_LAUNCH(double, double, double);
 #undef ERT_PCT_LAUNCH
-    if (e != cudaSuccess) { cudaFreeAsync(d_qs, st); return fail(ERTDIFF_ERR_CUDA, std::string("percentiles attr: ") + cudaGetErrorString(e)); }
-    ERT_LAUNCH_CHECK("k_percentiles");
-    ERT_CUDA(cudaFreeAsync(d_qs, st));
+        if (e != cudaSuccess) return fail(ERTDIFF_ERR_CUDA, std::string("percentiles attr: ") + cudaGetErrorString(e));
+        ERT_LAUNCH_CHECK("k_percentiles");
+    }
     return 0;
 }
 
@@ -460,14 +493,13 @@ int ertdiff_minmax(const void* d_a, int dtype, int64_t n, double* d_out2, void* 
     if (blocks > 4 * kNumSMs) blocks = 4 * kNumSMs;
     if (blocks < 1) blocks = 1;
     double* part = nullptr;
-    ERT_CUDA(cudaMallocAsync(&part, (size_t)blocks * 3 * sizeof(double), st));
+    if (int rc = workspace((size_t)blocks * 3 * sizeof(double), (void**)&part)) return rc;
     if (dtype == ERTDIFF_F32) k_minmax_partial<float><<<blocks, 256, 0, st>>>((const float*)d_a, n, part);
     else if (dtype == ERTDIFF_F64) k_minmax_partial<double><<<blocks, 256, 0, st>>>((const double*)d_a, n, part);
-    else { cudaFreeAsync(part, st); return fail(ERTDIFF_ERR_ARG, "minmax: bad dtype"); }
+    else return fail(ERTDIFF_ERR_ARG, "minmax: bad dtype");
     ERT_LAUNCH_CHECK("k_minmax_partial");
     k_minmax_final<<<1, 32, 0, st>>>(part, blocks, d_out2);
     ERT_LAUNCH_CHECK("k_minmax_final");
-    ERT_CUDA(cudaFreeAsync(part, st));
     return 0;
 }
 
@@ -488,8 +520,13 @@ int ertdiff_ensemble_kde_mode(const void* d_a, int dtype, int64_t N, int64_t Q,
     const int gchunk = (n_grid + n_gchunks - 1) / n_gchunks;
     double* part_val = nullptr;
     int* part_idx = nullptr;
-    ERT_CUDA(cudaMallocAsync(&part_val, (size_t)Q * n_gchunks * sizeof(double), st));
-    ERT_CUDA(cudaMallocAsync(&part_idx, (size_t)Q * n_gchunks * sizeof(int), st));
+    {   // (minmax's scratch is consumed by k_minmax_final before this kernel starts: same stream)
+        void* ws = nullptr;
+        const size_t nv = (size_t)Q * n_gchunks;
+        if (int rc = workspace(nv * (sizeof(double) + sizeof(int)), &ws)) return rc;
+        part_val = (double*)ws;
+        part_idx = (int*)(part_val + nv);
+    }
     const dim3 grid((unsigned)Q, (unsigned)n_gchunks);
     const int threads = gchunk >= 512 ? 256 : (gchunk >= 256 ? 128 : 64);
     cudaError_t e;
@@ -502,15 +539,12 @@ int ertdiff_ensemble_kde_mode(const void* d_a, int dtype, int64_t N, int64_t Q,
         if (e == cudaSuccess)
             k_kde_mode<double><<<grid, threads, smem, st>>>((const double*)d_a, N, Q, d_lohi, n_grid, gchunk, f2, part_val, part_idx);
     } else {
-        cudaFreeAsync(part_val, st); cudaFreeAsync(part_idx, st);
         return fail(ERTDIFF_ERR_ARG, "ensemble_kde_mode: bad dtype");
     }
     if (e != cudaSuccess) return fail(ERTDIFF_ERR_CUDA, std::string("kde attr: ") + cudaGetErrorString(e));
     ERT_LAUNCH_CHECK("k_kde_mode");
     k_kde_final<<<(unsigned)((Q + 127) / 128), 128, 0, st>>>(part_val, part_idx, Q, n_gchunks, d_lohi, n_grid, d_mode, d_index);
     ERT_LAUNCH_CHECK("k_kde_final");
-    ERT_CUDA(cudaFreeAsync(part_val, st));
-    ERT_CUDA(cudaFreeAsync(part_idx, st));
     return 0;
 }
 

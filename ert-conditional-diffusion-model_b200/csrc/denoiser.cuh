@@ -241,11 +241,15 @@ struct ChainParams {
     int P;
 };
 
-constexpr int CHAIN_RING = 8;   // cp.async noise prefetch depth (steps)
+constexpr int CHAIN_RING = 8;   // cp.async prefetch depth (steps) for c_t, coefficients, noise
 
 __device__ __forceinline__ void cp_async4(float* smem_dst, const float* gsrc) {
     const uint32_t d = (uint32_t)__cvta_generic_to_shared(smem_dst);
     asm volatile("cp.async.ca.shared.global [%0], [%1], 4;\n" ::"r"(d), "l"(gsrc));
+}
+__device__ __forceinline__ void cp_async16(float* smem_dst, const float* gsrc) {
+    const uint32_t d = (uint32_t)__cvta_generic_to_shared(smem_dst);
+    asm volatile("cp.async.ca.shared.global [%0], [%1], 16;\n" ::"r"(d), "l"(gsrc));
 }
 __device__ __forceinline__ void cp_async_commit() { asm volatile("cp.async.commit_group;\n" ::); }
 template <int N>
@@ -257,18 +261,25 @@ __device__ __forceinline__ void cp_async_wait() {
 //   layer 1: thread j owns hidden unit j (W0x row in registers, x broadcast from smem)
 //   layer 2: thread (p = tid / PARTS, part = tid % PARTS) owns a 32-wide slice of W2 row p;
 //            PARTS = H/32 partial sums are combined with xor-shuffles
-//   update : every lane of a p-group computes it (identical values); the part-0 lane owns the
-//            noise stream and writes x back to smem.
+//   update : every lane of a p-group computes it; the part-0 lane ("owner") writes x back.
+// Everything a step reads from global memory -- the c_t row, the three step scalars and (replay
+// mode) the injected noise row -- is staged CHAIN_RING steps ahead into a shared-memory ring with
+// cp.async, so the dependent chain of a step never waits on L2/HBM latency.
+// Device RNG: the PARTS lanes of a p-group each run Philox once per 4*PARTS draws (lane `part`
+// generates quad blk*PARTS+part) and hand the normal of the current draw over with one shuffle.
 template <int H, int MPB>
 __global__ void __launch_bounds__(H) k_chain(const ChainParams a) {
     constexpr int PARTS = H / 32;
     constexpr int HS_STRIDE = PARTS * 36;   // each 32-wide slice padded to 36: no bank conflicts
+    constexpr int CT_STRIDE = H + 4;        // c_t row + [coef, c1, sigma, 0]
     __shared__ __align__(16) float xs[MPB][kPPad];
     __shared__ __align__(16) float hs[MPB][HS_STRIDE];
+    __shared__ __align__(16) float ctring[CHAIN_RING][CT_STRIDE];
     __shared__ float zring[CHAIN_RING][MPB][kPPad];
 
     const int tid = threadIdx.x;
     const int p = tid / PARTS, part = tid % PARTS;
+    const int lane = tid & 31;
     const int64_t m0 = (int64_t)blockIdx.x * MPB;
     const int P = a.P;
     const bool owner = (part == 0) && (p < P);
@@ -292,96 +303,122 @@ __global__ void __launch_bounds__(H) k_chain(const ChainParams a) {
         cb[m] = a.cond_bias[(mg[m] % a.n_cond) * H + tid];
     }
 
-    float zc[MPB][4];     // Philox cache: normals of the current quad of draws
-    const int d_first = a.S - a.t_hi;          // draw index used by the first step of this launch
-    // ---- x_T -----------------------------------------------------------------------------
-    // (a launch without x_in is the start of a chain: d_first == 1, so quad 0 serves both x_T,
-    //  which is draw 0, and the first in-loop draws)
+    // ---- staging ring ------------------------------------------------------------------------
+    // running source pointers of the NEXT iteration to stage (iteration j is timestep t_hi - j)
+    const float* tab_s = a.table + (int64_t)a.t_hi * H + tid;
+    const float* coef_s = a.coef + 4 * (int64_t)a.t_hi;
+    const int64_t noise_step = a.noise_B * P;
+    const float* noise_s[MPB];
+#pragma unroll
+    for (int m = 0; m < MPB; ++m)
+        noise_s[m] = replay ? a.noise + ((int64_t)(a.S - a.t_hi - 1) * a.noise_B + mg[m]) * P + p
+                            : nullptr;
+    int js = 0;                          // next iteration to stage
+    int t_s = a.t_hi;                    // its timestep
+    auto stage = [&]() {
+        if (js < a.t_count) {
+            const int slot = js & (CHAIN_RING - 1);
+            cp_async4(&ctring[slot][tid], tab_s);
+            if (tid == 0) cp_async16(&ctring[slot][H], coef_s);
+            if (replay && owner && t_s > 0) {
+#pragma unroll
+                for (int m = 0; m < MPB; ++m) cp_async4(&zring[slot][m][p], noise_s[m]);
+            }
+        }
+        cp_async_commit();
+        tab_s -= H;
+        coef_s -= 4;
+#pragma unroll
+        for (int m = 0; m < MPB; ++m) noise_s[m] += noise_step;
+        ++js;
+        --t_s;
+    };
+#pragma unroll
+    for (int j = 0; j < CHAIN_RING - 1; ++j) stage();
+
+    // ---- device RNG state ----------------------------------------------------------------------
+    float zc[MPB][4];     // normals of quad (blk*PARTS + part) for each member
+    const int d_first = a.S - a.t_hi;       // draw index used by the first step of this launch
+    auto refill_rng = [&](int d) {
+        const uint32_t blk = (uint32_t)(d >> 2) / PARTS;
+#pragma unroll
+        for (int m = 0; m < MPB; ++m)
+            philox_normal4(a.seed, a.offset, a.member_offset + mg[m], p & 31,
+                           blk * PARTS + part, zc[m]);
+    };
+    auto rng_draw = [&](int d, int m) -> float {   // normal of draw d for (member m, parameter p)
+        const int u = d & 3;
+        const float v = (u == 0) ? zc[m][0] : (u == 1) ? zc[m][1] : (u == 2) ? zc[m][2] : zc[m][3];
+        const int src = (lane - part) + ((d >> 2) % PARTS);
+        return __shfl_sync(0xffffffffu, v, src);
+    };
+    // (a launch without x_in starts a chain: d_first == 1, and draw 0 = x_T sits in the same block)
+    if (!replay || !a.x_in) refill_rng(a.x_in ? d_first : 0);
+
+    // ---- x_T -----------------------------------------------------------------------------------
 #pragma unroll
     for (int m = 0; m < MPB; ++m) {
-        if (!replay || !a.x_in)
-            philox_normal4(a.seed, a.offset, a.member_offset + mg[m], p & 31,
-                           a.x_in ? (uint32_t)(d_first >> 2) : 0u, zc[m]);
         if (a.x_in) {
             x[m] = (p < P) ? a.x_in[mg[m] * a.x_in_stride + p] : 0.f;
         } else {
-            x[m] = (p < P) ? zc[m][0] : 0.f;
+            const float z0 = rng_draw(0, m);
+            x[m] = (p < P) ? z0 : 0.f;
         }
         if (part == 0) xs[m][p] = x[m];
     }
-
-    // ---- noise ring prologue (replay mode): rows d-1 for draws d = d0 .. d0+RING-1 ---------
-    if (replay) {
-#pragma unroll
-        for (int r = 0; r < CHAIN_RING; ++r) {
-            const int d = d_first + r;
-            if (owner && d <= a.S - 1 && r < a.t_count) {
-#pragma unroll
-                for (int m = 0; m < MPB; ++m)
-                    cp_async4(&zring[d % CHAIN_RING][m][p],
-                              a.noise + ((int64_t)(d - 1) * a.noise_B + mg[m]) * P + p);
-            }
-            cp_async_commit();
-        }
-    }
     __syncthreads();
-
-    float ct_next = a.table[(int64_t)a.t_hi * H + tid];
-    float4 cf_next = *reinterpret_cast<const float4*>(a.coef + 4 * a.t_hi);
 
     for (int it = 0; it < a.t_count; ++it) {
         const int t = a.t_hi - it;
-        const int d = a.S - t;                 // draw index of this step's noise
-        const float ct = ct_next;
-        const float4 cf = cf_next;
-        if (it + 1 < a.t_count) {
-            ct_next = a.table[(int64_t)(t - 1) * H + tid];
-            cf_next = *reinterpret_cast<const float4*>(a.coef + 4 * (t - 1));
-        }
+        const int d = a.S - t;
+        const int slot = it & (CHAIN_RING - 1);
+        stage();                                  // iteration it+RING-1, into the slot iteration it-1 used
+        cp_async_wait<CHAIN_RING - 1>();          // this thread's copies for iteration `it` landed
+        const float ct = ctring[slot][tid];
         // ---- layer 1 ---------------------------------------------------------------------
 #pragma unroll
         for (int m = 0; m < MPB; ++m) {
-            float a0 = cb[m] + ct, a1 = 0.f;
+            float4 xv[kPPad / 4];
+#pragma unroll
+            for (int k4 = 0; k4 < kPPad / 4; ++k4)
+                xv[k4] = *reinterpret_cast<const float4*>(&xs[m][4 * k4]);
+            float a0 = cb[m] + ct, a1 = 0.f, a2 = 0.f, a3 = 0.f;
 #pragma unroll
             for (int k4 = 0; k4 < kPPad / 4; ++k4) {
-                const float4 xv = *reinterpret_cast<const float4*>(&xs[m][4 * k4]);
-                a0 = fmaf(w0x[4 * k4 + 0], xv.x, a0);
-                a1 = fmaf(w0x[4 * k4 + 1], xv.y, a1);
-                a0 = fmaf(w0x[4 * k4 + 2], xv.z, a0);
-                a1 = fmaf(w0x[4 * k4 + 3], xv.w, a1);
+                a0 = fmaf(w0x[4 * k4 + 0], xv[k4].x, a0);
+                a1 = fmaf(w0x[4 * k4 + 1], xv[k4].y, a1);
+                a2 = fmaf(w0x[4 * k4 + 2], xv[k4].z, a2);
+                a3 = fmaf(w0x[4 * k4 + 3], xv[k4].w, a3);
             }
-            hs[m][hidx] = fmaxf(a0 + a1, 0.f);
+            hs[m][hidx] = fmaxf((a0 + a1) + (a2 + a3), 0.f);
         }
-        __syncthreads();
+        __syncthreads();        // hs complete; thread 0's coefficient copy is now visible to all
+        const float4 cf = *reinterpret_cast<const float4*>(&ctring[slot][H]);
+        if (!replay && t > 0 && (d & (4 * PARTS - 1)) == 0) refill_rng(d);
         // ---- layer 2 + posterior update ------------------------------------------------------
-        if (replay) cp_async_wait<CHAIN_RING - 1>();     // this step's noise row has landed
 #pragma unroll
         for (int m = 0; m < MPB; ++m) {
+            float4 hv[8];
+#pragma unroll
+            for (int i4 = 0; i4 < 8; ++i4)
+                hv[i4] = *reinterpret_cast<const float4*>(&hs[m][part * 36 + 4 * i4]);
+            float z = 0.f;
+            if (t > 0) {
+                if (replay) { if (owner) z = zring[slot][m][p]; }
+                else z = rng_draw(d, m);
+            }
             float e0 = 0.f, e1 = 0.f, e2 = 0.f, e3 = 0.f;
 #pragma unroll
             for (int i4 = 0; i4 < 8; ++i4) {
-                const float4 hv = *reinterpret_cast<const float4*>(&hs[m][part * 36 + 4 * i4]);
-                e0 = fmaf(w2r[4 * i4 + 0], hv.x, e0);
-                e1 = fmaf(w2r[4 * i4 + 1], hv.y, e1);
-                e2 = fmaf(w2r[4 * i4 + 2], hv.z, e2);
-                e3 = fmaf(w2r[4 * i4 + 3], hv.w, e3);
+                e0 = fmaf(w2r[4 * i4 + 0], hv[i4].x, e0);
+                e1 = fmaf(w2r[4 * i4 + 1], hv[i4].y, e1);
+                e2 = fmaf(w2r[4 * i4 + 2], hv[i4].z, e2);
+                e3 = fmaf(w2r[4 * i4 + 3], hv[i4].w, e3);
             }
             float e = (e0 + e1) + (e2 + e3);
 #pragma unroll
             for (int o = 1; o < PARTS; o <<= 1) e += __shfl_xor_sync(0xffffffffu, e, o);
             e += b2;
-            float z = 0.f;
-            if (t > 0) {
-                if (replay) {
-                    if (owner) z = zring[d % CHAIN_RING][m][p];
-                } else {
-                    if ((d & 3) == 0)
-                        philox_normal4(a.seed, a.offset, a.member_offset + mg[m], p & 31,
-                                       (uint32_t)(d >> 2), zc[m]);
-                    const int u = d & 3;
-                    z = (u == 0) ? zc[m][0] : (u == 1) ? zc[m][1] : (u == 2) ? zc[m][2] : zc[m][3];
-                }
-            }
             x[m] = posterior_update_rn(x[m], e, z, cf.x, cf.y, cf.z, t > 0);
             if (owner) {
                 xs[m][p] = x[m];
@@ -389,19 +426,9 @@ __global__ void __launch_bounds__(H) k_chain(const ChainParams a) {
                     a.eps_trace[((int64_t)t * a.B + m0 + m) * P + p] = e;
             }
         }
-        if (replay) {
-            const int dn = d + CHAIN_RING;           // refill the slot just consumed
-            if (owner && dn <= a.S - 1) {
-#pragma unroll
-                for (int m = 0; m < MPB; ++m)
-                    cp_async4(&zring[dn % CHAIN_RING][m][p],
-                              a.noise + ((int64_t)(dn - 1) * a.noise_B + mg[m]) * P + p);
-            }
-            cp_async_commit();
-        }
         __syncthreads();
     }
-    if (replay) cp_async_wait<0>();
+    cp_async_wait<0>();
     if (owner) {
 #pragma unroll
         for (int m = 0; m < MPB; ++m)

@@ -136,6 +136,12 @@ struct PctlQuery {
     double gamma_d;   // index dtype f64
 };
 
+constexpr int kMaxPctlQueries = 96;     // by-value kernel argument: 96 * 24 B
+struct PctlQueryPack {
+    int32_t n;
+    PctlQuery q[kMaxPctlQueries];
+};
+
 template <typename T, typename G, typename O>
 __device__ __forceinline__ O lerp_numpy(T A, T Bv, G gamma) {
     const T d = RN<T>::sub(Bv, A);            // subtract(b, a) in the array's dtype
@@ -148,7 +154,7 @@ __device__ __forceinline__ O lerp_numpy(T A, T Bv, G gamma) {
 
 template <typename T, typename G, typename O>
 __global__ void k_percentiles(const T* __restrict__ a, int64_t N, int64_t Q, int NP /*pow2>=N*/,
-                              int CT, const PctlQuery* __restrict__ qs, int nq,
+                              int CT, const __grid_constant__ PctlQueryPack qs,
                               O* __restrict__ out) {
     extern __shared__ __align__(16) unsigned char pct_smem_raw[];
     T* sm = reinterpret_cast<T*>(pct_smem_raw);               // [CT][NP]
@@ -188,11 +194,12 @@ __global__ void k_percentiles(const T* __restrict__ a, int64_t N, int64_t Q, int
             __syncthreads();
         }
     }
+    const int nq = qs.n;
     for (int idx = tid; idx < nq * CT; idx += nthr) {
         const int c = idx % CT, k = idx / CT;
         if (c0 + c >= Q) continue;
         const T* colp = sm + (size_t)c * NP;
-        const PctlQuery qq = qs[k];
+        const PctlQuery qq = qs.q[k];
         O r;
         if (nanflag[c]) {
             r = RN<O>::nan();

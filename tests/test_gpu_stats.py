@@ -78,9 +78,11 @@ def test_golden_maps(cuda_dev, golden):
 @pytest.mark.parametrize("N", [16, 50, 256])
 def test_kde_mode_index_is_scipy(cuda_dev, dtype, N):
     a = np.random.default_rng(N).lognormal(size=(N, 24)).astype(dtype)
-    grid = so.kde_grid(a, 5000)
+    # the reference's maps are float64 (ECD.py:716); float32 input is defined as promoted first
+    a64 = a.astype(np.float64)
+    grid = so.kde_grid(a64, 5000)
     mode, idx = eb.ensemble_kde_mode(a, 5000, return_index=True)
-    _, idx_sp, pdfs = so.kde_mode_scipy(a, grid)
+    _, idx_sp, pdfs = so.kde_mode_scipy(a64, grid)
     differ = np.nonzero(idx != idx_sp)[0]
     for j in differ:                                   # near-tie rule, counted
         p = pdfs[:, j]

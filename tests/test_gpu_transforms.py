@@ -25,8 +25,11 @@ def test_untransform_and_bounds(cuda_dev):
                           for row in phys_ref])
     phys, valid, first_bad = eb.untransform_and_check(u.to(cuda_dev), 0.0, 1.0, scaler.min_, scaler.scale_, limits)
     assert phys.dtype == torch.float32 and phys_ref.dtype == np.float32
-    # sigmoid differs from torch's CPU kernel by <= 2 ulp of fp32; everything after it is exact
-    np.testing.assert_allclose(phys.cpu().numpy(), phys_ref, rtol=3e-6, atol=0)
+    # sigmoid differs from torch's CPU kernel by <= 2 ulp of fp32 (|ds| <= 2.4e-7); the scaler
+    # then maps ds to ds/scale_ and rounds once more, so the bound is per parameter, in units of
+    # its data range -- not relative to the value (values near zero are differences of large terms)
+    tol = 3e-7 / scaler.scale_ + 2e-7 * np.abs(phys_ref).max(axis=0)
+    assert (np.abs(phys.cpu().numpy().astype(np.float64) - phys_ref) <= tol[None, :]).all()
     agree = valid.cpu().numpy() == valid_ref
     assert agree.mean() > 0.995          # rows sitting within 1 ulp of a limit may flip
     assert (first_bad.cpu().numpy()[agree] == first_ref[agree]).all()
