@@ -57,18 +57,28 @@ static int run_encoder(ertdiff_model* m, const float* d_cond, int64_t n_cond, in
     ERT_REQUIRE(d_cond && n_cond > 0 && L > 0, "encode_condition: bad condition/n_cond/L");
     ERT_REQUIRE(n_cond <= 65535, "encode_condition: n_cond > 65535 per call; split the batch");
     const int64_t L1 = conv_out_len(L), L2 = conv_out_len(L1);
-    const int n_chunks = (int)((L2 + ENC_TP - 1) / ENC_TP);
+    // few conditions: 32 positions per CTA so that one condition still spreads over ~37 SMs
+    const bool small = n_cond * ((L2 + 127) / 128) < 2 * kNumSMs;
+    const int tp = small ? 32 : 128;
+    const int n_chunks = (int)((L2 + tp - 1) / tp);
     if (int rc = grow(m->enc_partial, m->enc_partial_n, (size_t)n_cond * n_chunks * kConv2Out)) return rc;
     static bool attr_set = false;
     if (!attr_set) {
-        ERT_CUDA(cudaFuncSetAttribute(k_encoder_conv, cudaFuncAttributeMaxDynamicSharedMemorySize,
-                                      (int)sizeof(EncSmem)));
+        ERT_CUDA(cudaFuncSetAttribute(k_encoder_conv<4>, cudaFuncAttributeMaxDynamicSharedMemorySize,
+                                      (int)sizeof(EncSmem<4>)));
+        ERT_CUDA(cudaFuncSetAttribute(k_encoder_conv<1>, cudaFuncAttributeMaxDynamicSharedMemorySize,
+                                      (int)sizeof(EncSmem<1>)));
         attr_set = true;
     }
     dim3 grid(n_chunks, (unsigned)n_cond);
-    k_encoder_conv<<<grid, ENC_THREADS, sizeof(EncSmem), st>>>(
-        d_cond, member_stride, L, L1, L2, m->conv1_w, m->raw[1], m->conv2_w, m->raw[3],
-        m->enc_partial, n_chunks);
+    if (small)
+        k_encoder_conv<1><<<grid, ENC_THREADS, sizeof(EncSmem<1>), st>>>(
+            d_cond, member_stride, L, L1, L2, m->conv1_w, m->raw[1], m->conv2_w, m->raw[3],
+            m->enc_partial, n_chunks);
+    else
+        k_encoder_conv<4><<<grid, ENC_THREADS, sizeof(EncSmem<4>), st>>>(
+            d_cond, member_stride, L, L1, L2, m->conv1_w, m->raw[1], m->conv2_w, m->raw[3],
+            m->enc_partial, n_chunks);
     ERT_LAUNCH_CHECK("k_encoder_conv");
     k_encoder_finish<<<(unsigned)n_cond, m->H, 0, st>>>(m->enc_partial, n_chunks, L2, m->w6T,
                                                        m->raw[5], m->w0cT, m->raw[9], m->H,
@@ -78,15 +88,26 @@ static int run_encoder(ertdiff_model* m, const float* d_cond, int64_t n_cond, in
 }
 
 // ---- chain ------------------------------------------------------------------------------
+template <int H, int MPB>
+static void launch_chain_hm(const ChainParams& p, unsigned grid, cudaStream_t st) {
+    const bool replay = p.noise != nullptr, trace = p.eps_trace != nullptr;
+    if (replay) {
+        if (trace) k_chain<H, MPB, true, true><<<grid, H, 0, st>>>(p);
+        else k_chain<H, MPB, true, false><<<grid, H, 0, st>>>(p);
+    } else {
+        if (trace) k_chain<H, MPB, false, true><<<grid, H, 0, st>>>(p);
+        else k_chain<H, MPB, false, false><<<grid, H, 0, st>>>(p);
+    }
+}
+
 template <int H>
 static int launch_chain_h(const ChainParams& p, int mpb, cudaStream_t st) {
+    if (H >= 512 && mpb > 4) mpb = 4;            // static shared memory budget
     const unsigned grid = (unsigned)((p.B + mpb - 1) / mpb);
-    switch (mpb) {
-        case 1: k_chain<H, 1><<<grid, H, 0, st>>>(p); break;
-        case 2: k_chain<H, 2><<<grid, H, 0, st>>>(p); break;
-        case 4: k_chain<H, 4><<<grid, H, 0, st>>>(p); break;
-        default: k_chain<H, 8><<<grid, H, 0, st>>>(p); break;
-    }
+    if (mpb == 1) launch_chain_hm<H, 1>(p, grid, st);
+    else if (mpb == 2) launch_chain_hm<H, 2>(p, grid, st);
+    else if (mpb == 4 || H >= 512) launch_chain_hm<H, 4>(p, grid, st);
+    else launch_chain_hm<H, (H >= 512 ? 4 : 8)>(p, grid, st);
     ERT_LAUNCH_CHECK("k_chain");
     return 0;
 }
@@ -125,18 +146,28 @@ static int run_chain(ertdiff_model* m, const ertdiff_chain_args* a, const float*
     ERT_REQUIRE(a->d_betas && a->d_alphas && a->d_alpha_bar, "sample_chain: schedule is NULL");
     ERT_REQUIRE(d_cond_bias, "sample_chain: cond_bias is NULL");
     ERT_REQUIRE(a->d_x_out, "sample_chain: x_out is NULL");
+    ERT_REQUIRE(!(a->d_noise && !a->d_x_T), "sample_chain: injected noise needs d_x_T as well (row 0 of the draws)");
     if (a->precision != ERTDIFF_PREC_FP32)
         return fail(ERTDIFF_ERR_UNSUPPORTED, "sample_chain: only ERTDIFF_PREC_FP32 is built");
     const int S = a->num_steps, H = m->H, P = m->P;
     const int64_t nstride = a->noise_member_stride_B > 0 ? a->noise_member_stride_B : a->B;
     ERT_REQUIRE(nstride >= a->B, "sample_chain: noise_member_stride_B < B");
 
-    if (int rc = grow(m->time_table, m->time_table_n, (size_t)S * H)) return rc;
+    // c_t rows depend only on the weights: computed once per load_state_dict, extended on demand
+    if (m->time_table_n < (size_t)S * H) {
+        if (int rc = grow(m->time_table, m->time_table_n, (size_t)S * H)) return rc;
+        m->time_rows_valid = 0;
+    }
     if (int rc = grow(m->coef_table, m->coef_table_n, (size_t)S * 4)) return rc;
-    k_time_table<<<S, H, 0, st>>>(m->freq, m->wtT, m->raw[7], m->w0tT, H, m->time_table,
-                                  a->d_betas, a->d_alphas, a->d_alpha_bar,
-                                  (double)a->temperature, m->coef_table);
-    ERT_LAUNCH_CHECK("k_time_table");
+    if (m->time_rows_valid < S) {
+        const int t0 = m->time_rows_valid;
+        k_time_table<<<S - t0, H, 0, st>>>(m->freq, m->wtT, m->raw[7], m->w0tT, H, t0, m->time_table);
+        ERT_LAUNCH_CHECK("k_time_table");
+        m->time_rows_valid = S;
+    }
+    k_step_coefficients<<<(S + 127) / 128, 128, 0, st>>>(a->d_betas, a->d_alphas, a->d_alpha_bar, S,
+                                                        (double)a->temperature, m->coef_table);
+    ERT_LAUNCH_CHECK("k_step_coefficients");
 
     ChainParams p{};
     p.B = a->B; p.n_cond = a->n_cond; p.S = S; p.t_hi = S - 1; p.t_count = S;
@@ -296,6 +327,7 @@ int ertdiff_model_load(ertdiff_model* m, const float* const* tensors12, int on_d
     ERT_LAUNCH_CHECK("k_pack_weights");
     ERT_CUDA(cudaStreamSynchronize(st));
     m->loaded = true;
+    m->time_rows_valid = 0;
     if (m->graph_exec) { cudaGraphExecDestroy(m->graph_exec); m->graph_exec = nullptr; }
     return 0;
 }
@@ -507,44 +539,58 @@ int ertdiff_ensemble_kde_mode(const void* d_a, int dtype, int64_t N, int64_t Q,
                               const double* d_lohi, int32_t n_grid, double* d_mode,
                               int64_t* d_index, void* stream) {
     ERT_REQUIRE(d_a && d_lohi && N > 1 && Q > 0 && n_grid > 1, "ensemble_kde_mode: bad arguments");
+    ERT_REQUIRE(dtype == ERTDIFF_F32 || dtype == ERTDIFF_F64, "ensemble_kde_mode: bad dtype");
     ERT_REQUIRE((size_t)N * 8 <= 200 * 1024, "ensemble_kde_mode: N too large for shared memory");
     cudaStream_t st = (cudaStream_t)stream;
+    const int G = n_grid;
     // scipy: factor = neff**(-1/(d+4)) with d = 1, neff = N; covariance = data_cov * factor**2
     const double factor = std::pow((double)N, -1.0 / 5.0);
     const double f2 = factor * factor;
-    const size_t smem = (size_t)N * 8;
-    // split the grid so that Q * n_gchunks CTAs fill the machine, >= 64 grid points per CTA
-    int n_gchunks = 1;
-    while ((int64_t)Q * n_gchunks < 4 * kNumSMs && (n_grid + 2 * n_gchunks - 1) / (2 * n_gchunks) >= 64)
-        n_gchunks *= 2;
-    const int gchunk = (n_grid + n_gchunks - 1) / n_gchunks;
-    double* part_val = nullptr;
-    int* part_idx = nullptr;
-    {   // (minmax's scratch is consumed by k_minmax_final before this kernel starts: same stream)
-        void* ws = nullptr;
-        const size_t nv = (size_t)Q * n_gchunks;
-        if (int rc = workspace(nv * (sizeof(double) + sizeof(int)), &ws)) return rc;
-        part_val = (double*)ws;
-        part_idx = (int*)(part_val + nv);
+    // columns per batch: the fp32 scan of a batch lives in the workspace (<= 128 MiB)
+    int64_t qb = (int64_t)((128u << 20) / ((size_t)G * sizeof(float)));
+    if (qb < 1) qb = 1;
+    if (qb > Q) qb = Q;
+    if (qb > 65535 * 16) qb = 65535 * 16;
+    void* ws = nullptr;
+    const size_t cols_bytes = ((size_t)Q * sizeof(KdeColumn) + 255) & ~(size_t)255;
+    if (int rc = workspace(cols_bytes + (size_t)qb * G * sizeof(float), &ws)) return rc;
+    KdeColumn* cols = (KdeColumn*)ws;
+    float* s32 = (float*)((char*)ws + cols_bytes);
+    const bool f32in = dtype == ERTDIFF_F32;
+    {
+        const unsigned grid = (unsigned)((Q * 32 + 255) / 256);
+        if (f32in) k_kde_prepare<float><<<grid, 256, 0, st>>>((const float*)d_a, N, Q, f2, cols);
+        else k_kde_prepare<double><<<grid, 256, 0, st>>>((const double*)d_a, N, Q, f2, cols);
+        ERT_LAUNCH_CHECK("k_kde_prepare");
     }
-    const dim3 grid((unsigned)Q, (unsigned)n_gchunks);
-    const int threads = gchunk >= 512 ? 256 : (gchunk >= 256 ? 128 : 64);
-    cudaError_t e;
-    if (dtype == ERTDIFF_F32) {
-        e = cudaFuncSetAttribute(k_kde_mode<float>, cudaFuncAttributeMaxDynamicSharedMemorySize, 200 * 1024);
-        if (e == cudaSuccess)
-            k_kde_mode<float><<<grid, threads, smem, st>>>((const float*)d_a, N, Q, d_lohi, n_grid, gchunk, f2, part_val, part_idx);
-    } else if (dtype == ERTDIFF_F64) {
-        e = cudaFuncSetAttribute(k_kde_mode<double>, cudaFuncAttributeMaxDynamicSharedMemorySize, 200 * 1024);
-        if (e == cudaSuccess)
-            k_kde_mode<double><<<grid, threads, smem, st>>>((const double*)d_a, N, Q, d_lohi, n_grid, gchunk, f2, part_val, part_idx);
-    } else {
-        return fail(ERTDIFF_ERR_ARG, "ensemble_kde_mode: bad dtype");
+    static bool attr_set = false;
+    if (!attr_set) {
+        ERT_CUDA(cudaFuncSetAttribute(k_kde_scan32<float>, cudaFuncAttributeMaxDynamicSharedMemorySize, 200 * 1024));
+        ERT_CUDA(cudaFuncSetAttribute(k_kde_scan32<double>, cudaFuncAttributeMaxDynamicSharedMemorySize, 200 * 1024));
+        ERT_CUDA(cudaFuncSetAttribute(k_kde_select64<float>, cudaFuncAttributeMaxDynamicSharedMemorySize, 200 * 1024));
+        ERT_CUDA(cudaFuncSetAttribute(k_kde_select64<double>, cudaFuncAttributeMaxDynamicSharedMemorySize, 200 * 1024));
+        attr_set = true;
     }
-    if (e != cudaSuccess) return fail(ERTDIFF_ERR_CUDA, std::string("kde attr: ") + cudaGetErrorString(e));
-    ERT_LAUNCH_CHECK("k_kde_mode");
-    k_kde_final<<<(unsigned)((Q + 127) / 128), 128, 0, st>>>(part_val, part_idx, Q, n_gchunks, d_lohi, n_grid, d_mode, d_index);
-    ERT_LAUNCH_CHECK("k_kde_final");
+    for (int64_t c0 = 0; c0 < Q; c0 += qb) {
+        const int64_t nc = (Q - c0) < qb ? (Q - c0) : qb;
+        // split the grid so that nc * n_gchunks CTAs fill the machine, >= 128 grid points per CTA
+        int n_gchunks = 1;
+        while (nc * n_gchunks < 4 * kNumSMs && (G + 2 * n_gchunks - 1) / (2 * n_gchunks) >= 128 && n_gchunks < 64)
+            n_gchunks *= 2;
+        const int gchunk = (G + n_gchunks - 1) / n_gchunks;
+        const int threads = gchunk >= 512 ? 256 : (gchunk >= 256 ? 128 : 64);
+        const dim3 grid((unsigned)nc, (unsigned)n_gchunks);
+        if (f32in) {
+            k_kde_scan32<float><<<grid, threads, (size_t)N * 4, st>>>((const float*)d_a, N, Q, c0, d_lohi, G, gchunk, cols, s32);
+            ERT_LAUNCH_CHECK("k_kde_scan32");
+            k_kde_select64<float><<<(unsigned)nc, 256, (size_t)N * 8, st>>>((const float*)d_a, N, Q, c0, d_lohi, G, cols, s32, d_mode, d_index);
+        } else {
+            k_kde_scan32<double><<<grid, threads, (size_t)N * 4, st>>>((const double*)d_a, N, Q, c0, d_lohi, G, gchunk, cols, s32);
+            ERT_LAUNCH_CHECK("k_kde_scan32");
+            k_kde_select64<double><<<(unsigned)nc, 256, (size_t)N * 8, st>>>((const double*)d_a, N, Q, c0, d_lohi, G, cols, s32, d_mode, d_index);
+        }
+        ERT_LAUNCH_CHECK("k_kde_select64");
+    }
     return 0;
 }
 

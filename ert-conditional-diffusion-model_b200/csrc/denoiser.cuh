@@ -80,8 +80,7 @@ __global__ void k_step_coefficients(const float* betas, const float* alphas,
 // ------------------------------------------------------------------------------------------
 // Timestep embedding (ECD.py:80-88) -> time_embed Linear+ReLU (ECD.py:144-147,160) ->
 // t-block of mlp.0 : table[row] = W0t @ ReLU(Wt @ [sin(t f) | cos(t f)] + bt).
-// grid = rows, block = H.  Row r is timestep t_list[r] if given, else t = r.
-// Also fills the step-coefficient table row (thread 0) when coef_table != nullptr.
+// grid = rows, block = H.  Row r is timestep t0 + r.
 __device__ __forceinline__ void time_embed_row(float tf, const float* __restrict__ freq,
                                                const float* __restrict__ wtT,
                                                const float* __restrict__ bt, int H, int tid,
@@ -104,22 +103,21 @@ __device__ __forceinline__ void time_embed_row(float tf, const float* __restrict
 
 __global__ void k_time_table(const float* __restrict__ freq, const float* __restrict__ wtT,
                              const float* __restrict__ bt, const float* __restrict__ w0tT,
-                             int H, float* __restrict__ table, const float* betas,
-                             const float* alphas, const float* alpha_bar, double temperature,
-                             float* coef_table) {
+                             int H, int t0, float* __restrict__ table) {
     __shared__ float emb[512];
     __shared__ float te[512];
     const int tid = threadIdx.x;
-    const int t = blockIdx.x;
+    const int t = t0 + blockIdx.x;
     time_embed_row((float)t, freq, wtT, bt, H, tid, emb, te);
-    float a0 = 0.f, a1 = 0.f;
-    for (int k = 0; k < H; k += 2) {
-        a0 = fmaf(w0tT[(int64_t)k * H + tid], te[k], a0);
+    float a0 = 0.f, a1 = 0.f, a2 = 0.f, a3 = 0.f;
+#pragma unroll 4
+    for (int k = 0; k < H; k += 4) {
+        a0 = fmaf(w0tT[(int64_t)(k + 0) * H + tid], te[k + 0], a0);
         a1 = fmaf(w0tT[(int64_t)(k + 1) * H + tid], te[k + 1], a1);
+        a2 = fmaf(w0tT[(int64_t)(k + 2) * H + tid], te[k + 2], a2);
+        a3 = fmaf(w0tT[(int64_t)(k + 3) * H + tid], te[k + 3], a3);
     }
-    table[(int64_t)t * H + tid] = a0 + a1;
-    if (coef_table && tid == 0)
-        step_coefficients(betas, alphas, alpha_bar, t, temperature, coef_table + 4 * t);
+    table[(int64_t)t * H + tid] = (a0 + a1) + (a2 + a3);
 }
 
 // ------------------------------------------------------------------------------------------
@@ -241,21 +239,48 @@ struct ChainParams {
     int P;
 };
 
-constexpr int CHAIN_RING = 8;   // cp.async prefetch depth (steps) for c_t, coefficients, noise
-
-__device__ __forceinline__ void cp_async4(float* smem_dst, const float* gsrc) {
-    const uint32_t d = (uint32_t)__cvta_generic_to_shared(smem_dst);
-    asm volatile("cp.async.ca.shared.global [%0], [%1], 4;\n" ::"r"(d), "l"(gsrc));
+// ---- small PTX helpers for the chain kernel ----------------------------------------------------
+__device__ __forceinline__ void cp_async4(uint32_t smem_dst, const float* gsrc) {
+    asm volatile("cp.async.ca.shared.global [%0], [%1], 4;\n" ::"r"(smem_dst), "l"(gsrc) : "memory");
 }
-__device__ __forceinline__ void cp_async16(float* smem_dst, const float* gsrc) {
-    const uint32_t d = (uint32_t)__cvta_generic_to_shared(smem_dst);
-    asm volatile("cp.async.ca.shared.global [%0], [%1], 16;\n" ::"r"(d), "l"(gsrc));
+__device__ __forceinline__ void cp_async16(uint32_t smem_dst, const float* gsrc) {
+    asm volatile("cp.async.cg.shared.global [%0], [%1], 16;\n" ::"r"(smem_dst), "l"(gsrc) : "memory");
 }
-__device__ __forceinline__ void cp_async_commit() { asm volatile("cp.async.commit_group;\n" ::); }
+__device__ __forceinline__ void cp_async_commit() { asm volatile("cp.async.commit_group;\n" ::: "memory"); }
 template <int N>
 __device__ __forceinline__ void cp_async_wait() {
-    asm volatile("cp.async.wait_group %0;\n" ::"n"(N));
+    asm volatile("cp.async.wait_group %0;\n" ::"n"(N) : "memory");
 }
+__device__ __forceinline__ float4 lds128(uint32_t addr) {
+    float4 v;
+    asm volatile("ld.shared.v4.f32 {%0, %1, %2, %3}, [%4];\n"
+                 : "=f"(v.x), "=f"(v.y), "=f"(v.z), "=f"(v.w) : "r"(addr) : "memory");
+    return v;
+}
+__device__ __forceinline__ float lds32(uint32_t addr) {
+    float v;
+    asm volatile("ld.shared.f32 %0, [%1];\n" : "=f"(v) : "r"(addr) : "memory");
+    return v;
+}
+__device__ __forceinline__ void sts32(uint32_t addr, float v) {
+    asm volatile("st.shared.f32 [%0], %1;\n" ::"r"(addr), "f"(v) : "memory");
+}
+__device__ __forceinline__ void sts128(uint32_t addr, float4 v) {
+    asm volatile("st.shared.v4.f32 [%0], {%1, %2, %3, %4};\n"
+                 ::"r"(addr), "f"(v.x), "f"(v.y), "f"(v.z), "f"(v.w) : "memory");
+}
+// packed fp32x2 FMA (sm_100: one instruction, two IEEE fp32 FMAs) -- halves the issue slots of the
+// two matrix-vector products; each lane of the pair is an ordinary fma.rn.f32
+__device__ __forceinline__ float2 ffma2(float2 a, float2 b, float2 c) {
+    unsigned long long d;
+    asm("fma.rn.f32x2 %0, %1, %2, %3;\n"
+        : "=l"(d)
+        : "l"(*reinterpret_cast<unsigned long long*>(&a)), "l"(*reinterpret_cast<unsigned long long*>(&b)),
+          "l"(*reinterpret_cast<unsigned long long*>(&c)));
+    return *reinterpret_cast<float2*>(&d);
+}
+
+constexpr int CHAIN_NB = 4;     // steps per staging block (double-buffered, cp.async one block ahead)
 
 // One CTA = MPB members for all steps.  blockDim = H.
 //   layer 1: thread j owns hidden unit j (W0x row in registers, x broadcast from smem)
@@ -263,35 +288,48 @@ __device__ __forceinline__ void cp_async_wait() {
 //            PARTS = H/32 partial sums are combined with xor-shuffles
 //   update : every lane of a p-group computes it; the part-0 lane ("owner") writes x back.
 // Everything a step reads from global memory -- the c_t row, the three step scalars and (replay
-// mode) the injected noise row -- is staged CHAIN_RING steps ahead into a shared-memory ring with
-// cp.async, so the dependent chain of a step never waits on L2/HBM latency.
-// Device RNG: the PARTS lanes of a p-group each run Philox once per 4*PARTS draws (lane `part`
-// generates quad blk*PARTS+part) and hand the normal of the current draw over with one shuffle.
-template <int H, int MPB>
+// mode) the injected noise row -- is staged one block of CHAIN_NB steps ahead into shared memory
+// with cp.async (one 16-byte copy per thread per block for the c_t rows), so the dependent chain
+// of a step never waits on L2/HBM latency.
+// Device RNG: RG = min(PARTS,4) lanes of a p-group each run Philox once per 4*RG draws (lane
+// `part` generates quad blk*RG+part) and park the normals in shared memory for the owner lane.
+template <int H, int MPB, bool REPLAY, bool TRACE>
 __global__ void __launch_bounds__(H) k_chain(const ChainParams a) {
     constexpr int PARTS = H / 32;
+    constexpr int RG = PARTS < 4 ? PARTS : 4;
     constexpr int HS_STRIDE = PARTS * 36;   // each 32-wide slice padded to 36: no bank conflicts
     constexpr int CT_STRIDE = H + 4;        // c_t row + [coef, c1, sigma, 0]
+    constexpr int ZB = REPLAY ? 1 : 0;
     __shared__ __align__(16) float xs[MPB][kPPad];
     __shared__ __align__(16) float hs[MPB][HS_STRIDE];
-    __shared__ __align__(16) float ctring[CHAIN_RING][CT_STRIDE];
-    __shared__ float zring[CHAIN_RING][MPB][kPPad];
+    __shared__ __align__(16) float ctbuf[2][CHAIN_NB][CT_STRIDE];
+    __shared__ __align__(16) float zbuf[ZB ? 2 : 1][ZB ? CHAIN_NB : 1][ZB ? MPB : 1][kPPad];
+    __shared__ __align__(16) float znorm[ZB ? 1 : MPB][kPPad][ZB ? 4 : 4 * RG];
 
     const int tid = threadIdx.x;
     const int p = tid / PARTS, part = tid % PARTS;
-    const int lane = tid & 31;
     const int64_t m0 = (int64_t)blockIdx.x * MPB;
     const int P = a.P;
     const bool owner = (part == 0) && (p < P);
-    const bool replay = a.noise != nullptr;
 
-    float w0x[kPPad], w2r[32];
+    float2 w0x[kPPad / 2], w2r[16];
 #pragma unroll
-    for (int k = 0; k < kPPad; ++k) w0x[k] = a.w0xT[k * H + tid];
+    for (int k = 0; k < kPPad / 2; ++k)
+        w0x[k] = make_float2(a.w0xT[(2 * k) * H + tid], a.w0xT[(2 * k + 1) * H + tid]);
 #pragma unroll
-    for (int i = 0; i < 32; ++i) w2r[i] = a.w2p[p * H + part * 32 + i];
+    for (int i = 0; i < 16; ++i)
+        w2r[i] = make_float2(a.w2p[p * H + part * 32 + 2 * i], a.w2p[p * H + part * 32 + 2 * i + 1]);
     const float b2 = a.b2p[p];
-    const int hidx = (tid >> 5) * 36 + (tid & 31);
+
+    // 32-bit shared-window addresses, computed once
+    const uint32_t xs_a = (uint32_t)__cvta_generic_to_shared(&xs[0][0]);
+    const uint32_t hs_a = (uint32_t)__cvta_generic_to_shared(&hs[0][0]);
+    const uint32_t ct_a = (uint32_t)__cvta_generic_to_shared(&ctbuf[0][0][0]);
+    const uint32_t zb_a = (uint32_t)__cvta_generic_to_shared(&zbuf[0][0][0][0]);
+    const uint32_t zn_a = (uint32_t)__cvta_generic_to_shared(&znorm[0][0][0]);
+    const uint32_t hs_w = hs_a + 4u * ((tid >> 5) * 36 + (tid & 31));   // this thread's h slot (member 0)
+    const uint32_t hs_r = hs_a + 4u * (part * 36);                      // this thread's W2 slice of h
+    const uint32_t xs_w = xs_a + 4u * p;
 
     float cb[MPB], x[MPB];
     int64_t mg[MPB];      // clamped local member index
@@ -303,130 +341,136 @@ __global__ void __launch_bounds__(H) k_chain(const ChainParams a) {
         cb[m] = a.cond_bias[(mg[m] % a.n_cond) * H + tid];
     }
 
-    // ---- staging ring ------------------------------------------------------------------------
-    // running source pointers of the NEXT iteration to stage (iteration j is timestep t_hi - j)
-    const float* tab_s = a.table + (int64_t)a.t_hi * H + tid;
-    const float* coef_s = a.coef + 4 * (int64_t)a.t_hi;
-    const int64_t noise_step = a.noise_B * P;
-    const float* noise_s[MPB];
+    // ---- block staging ---------------------------------------------------------------------
+    const int nblocks = (a.t_count + CHAIN_NB - 1) / CHAIN_NB;
+    const int d_first = a.S - a.t_hi;        // draw index used by the first step of this launch
+    auto stage_block = [&](int b) {          // iterations [NB*b, NB*b+NB): t = t_hi - it
+        if (b < nblocks) {
+            const int buf = b & 1;
+            const int it0 = b * CHAIN_NB;
+            {   // c_t rows: H/4 16-byte chunks per row, NB rows -> exactly one chunk per thread
+                const int r = tid / (H / 4), c4 = tid % (H / 4);
+                if (it0 + r < a.t_count)
+                    cp_async16(ct_a + 4u * ((buf * CHAIN_NB + r) * CT_STRIDE + 4 * c4),
+                               a.table + (int64_t)(a.t_hi - it0 - r) * H + 4 * c4);
+            }
+            if (tid < CHAIN_NB && it0 + tid < a.t_count)
+                cp_async16(ct_a + 4u * ((buf * CHAIN_NB + tid) * CT_STRIDE + H),
+                           a.coef + 4 * (int64_t)(a.t_hi - it0 - tid));
+            if (REPLAY && owner) {
 #pragma unroll
-    for (int m = 0; m < MPB; ++m)
-        noise_s[m] = replay ? a.noise + ((int64_t)(a.S - a.t_hi - 1) * a.noise_B + mg[m]) * P + p
-                            : nullptr;
-    int js = 0;                          // next iteration to stage
-    int t_s = a.t_hi;                    // its timestep
-    auto stage = [&]() {
-        if (js < a.t_count) {
-            const int slot = js & (CHAIN_RING - 1);
-            cp_async4(&ctring[slot][tid], tab_s);
-            if (tid == 0) cp_async16(&ctring[slot][H], coef_s);
-            if (replay && owner && t_s > 0) {
+                for (int r = 0; r < CHAIN_NB; ++r) {
+                    const int it = it0 + r;
+                    if (it < a.t_count && a.t_hi - it > 0) {
+                        const int64_t row = (int64_t)(d_first + it - 1) * a.noise_B;
 #pragma unroll
-                for (int m = 0; m < MPB; ++m) cp_async4(&zring[slot][m][p], noise_s[m]);
+                        for (int m = 0; m < MPB; ++m)
+                            cp_async4(zb_a + 4u * (((buf * CHAIN_NB + r) * MPB + m) * kPPad + p),
+                                      a.noise + (row + mg[m]) * P + p);
+                    }
+                }
             }
         }
         cp_async_commit();
-        tab_s -= H;
-        coef_s -= 4;
-#pragma unroll
-        for (int m = 0; m < MPB; ++m) noise_s[m] += noise_step;
-        ++js;
-        --t_s;
     };
-#pragma unroll
-    for (int j = 0; j < CHAIN_RING - 1; ++j) stage();
+    stage_block(0);
 
-    // ---- device RNG state ----------------------------------------------------------------------
-    float zc[MPB][4];     // normals of quad (blk*PARTS + part) for each member
-    const int d_first = a.S - a.t_hi;       // draw index used by the first step of this launch
+    // ---- device RNG ----------------------------------------------------------------------------
+    // draw d of (member m, parameter p) = normal number (d % (4*RG)) of block d / (4*RG); lane
+    // `part` < RG generates quad blk*RG + part and parks its 4 normals at znorm[m][p][4*part..]
     auto refill_rng = [&](int d) {
-        const uint32_t blk = (uint32_t)(d >> 2) / PARTS;
+        const uint32_t blk = (uint32_t)(d >> 2) / RG;
+        if (part < RG) {
 #pragma unroll
-        for (int m = 0; m < MPB; ++m)
-            philox_normal4(a.seed, a.offset, a.member_offset + mg[m], p & 31,
-                           blk * PARTS + part, zc[m]);
+            for (int m = 0; m < MPB; ++m) {
+                float z4[4];
+                philox_normal4(a.seed, a.offset, a.member_offset + mg[m], p & 31, blk * RG + part, z4);
+                sts128(zn_a + 4u * ((m * kPPad + p) * (4 * RG) + 4 * part),
+                       make_float4(z4[0], z4[1], z4[2], z4[3]));
+            }
+        }
+        __syncwarp();
     };
-    auto rng_draw = [&](int d, int m) -> float {   // normal of draw d for (member m, parameter p)
-        const int u = d & 3;
-        const float v = (u == 0) ? zc[m][0] : (u == 1) ? zc[m][1] : (u == 2) ? zc[m][2] : zc[m][3];
-        const int src = (lane - part) + ((d >> 2) % PARTS);
-        return __shfl_sync(0xffffffffu, v, src);
+    auto rng_draw = [&](int d, int m) -> float {
+        return lds32(zn_a + 4u * ((m * kPPad + p) * (4 * RG) + (d & (4 * RG - 1))));
     };
     // (a launch without x_in starts a chain: d_first == 1, and draw 0 = x_T sits in the same block)
-    if (!replay || !a.x_in) refill_rng(a.x_in ? d_first : 0);
+    if (!REPLAY) refill_rng(a.x_in ? d_first : 0);
 
     // ---- x_T -----------------------------------------------------------------------------------
 #pragma unroll
     for (int m = 0; m < MPB; ++m) {
         if (a.x_in) {
             x[m] = (p < P) ? a.x_in[mg[m] * a.x_in_stride + p] : 0.f;
-        } else {
+        } else if (!REPLAY) {
             const float z0 = rng_draw(0, m);
             x[m] = (p < P) ? z0 : 0.f;
+        } else {
+            x[m] = 0.f;       // replay launches always carry x_in
         }
-        if (part == 0) xs[m][p] = x[m];
+        if (part == 0) sts32(xs_w + 4u * (m * kPPad), x[m]);
     }
+    cp_async_wait<0>();
     __syncthreads();
 
-    for (int it = 0; it < a.t_count; ++it) {
-        const int t = a.t_hi - it;
-        const int d = a.S - t;
-        const int slot = it & (CHAIN_RING - 1);
-        stage();                                  // iteration it+RING-1, into the slot iteration it-1 used
-        cp_async_wait<CHAIN_RING - 1>();          // this thread's copies for iteration `it` landed
-        const float ct = ctring[slot][tid];
-        // ---- layer 1 ---------------------------------------------------------------------
+    for (int b = 0; b < nblocks; ++b) {
+        const int buf = b & 1;
+        stage_block(b + 1);           // into the buffer block b-1 used (all its readers are past the barrier)
 #pragma unroll
-        for (int m = 0; m < MPB; ++m) {
-            float4 xv[kPPad / 4];
+        for (int r = 0; r < CHAIN_NB; ++r) {
+            const int it = b * CHAIN_NB + r;
+            if (it >= a.t_count) break;
+            const int t = a.t_hi - it;
+            const int d = d_first + it;          // draw index of this step's noise
+            const uint32_t row_a = ct_a + 4u * ((buf * CHAIN_NB + r) * CT_STRIDE);
+            const float ct = lds32(row_a + 4u * tid);
+            // ---- layer 1 -----------------------------------------------------------------
 #pragma unroll
-            for (int k4 = 0; k4 < kPPad / 4; ++k4)
-                xv[k4] = *reinterpret_cast<const float4*>(&xs[m][4 * k4]);
-            float a0 = cb[m] + ct, a1 = 0.f, a2 = 0.f, a3 = 0.f;
+            for (int m = 0; m < MPB; ++m) {
+                float4 xv[kPPad / 4];
 #pragma unroll
-            for (int k4 = 0; k4 < kPPad / 4; ++k4) {
-                a0 = fmaf(w0x[4 * k4 + 0], xv[k4].x, a0);
-                a1 = fmaf(w0x[4 * k4 + 1], xv[k4].y, a1);
-                a2 = fmaf(w0x[4 * k4 + 2], xv[k4].z, a2);
-                a3 = fmaf(w0x[4 * k4 + 3], xv[k4].w, a3);
+                for (int k4 = 0; k4 < kPPad / 4; ++k4) xv[k4] = lds128(xs_a + 16u * (m * (kPPad / 4) + k4));
+                float2 A01 = make_float2(cb[m] + ct, 0.f), A23 = make_float2(0.f, 0.f);
+#pragma unroll
+                for (int k4 = 0; k4 < kPPad / 4; ++k4) {
+                    A01 = ffma2(w0x[2 * k4], make_float2(xv[k4].x, xv[k4].y), A01);
+                    A23 = ffma2(w0x[2 * k4 + 1], make_float2(xv[k4].z, xv[k4].w), A23);
+                }
+                sts32(hs_w + 4u * (m * HS_STRIDE), fmaxf((A01.x + A01.y) + (A23.x + A23.y), 0.f));
             }
-            hs[m][hidx] = fmaxf((a0 + a1) + (a2 + a3), 0.f);
+            __syncthreads();          // hs complete (and, at block starts, staged rows are visible)
+            const float4 cf = lds128(row_a + 4u * H);
+            if (!REPLAY && t > 0 && (d & (4 * RG - 1)) == 0) refill_rng(d);
+            // ---- layer 2 + posterior update --------------------------------------------------
+#pragma unroll
+            for (int m = 0; m < MPB; ++m) {
+                float4 hv[8];
+#pragma unroll
+                for (int i4 = 0; i4 < 8; ++i4) hv[i4] = lds128(hs_r + 4u * (m * HS_STRIDE + 4 * i4));
+                float z = 0.f;
+                if (t > 0) {
+                    if (REPLAY) { if (owner) z = lds32(zb_a + 4u * (((buf * CHAIN_NB + r) * MPB + m) * kPPad + p)); }
+                    else z = rng_draw(d, m);
+                }
+                float2 E01 = make_float2(0.f, 0.f), E23 = make_float2(0.f, 0.f);
+#pragma unroll
+                for (int i4 = 0; i4 < 8; ++i4) {
+                    E01 = ffma2(w2r[2 * i4], make_float2(hv[i4].x, hv[i4].y), E01);
+                    E23 = ffma2(w2r[2 * i4 + 1], make_float2(hv[i4].z, hv[i4].w), E23);
+                }
+                float e = (E01.x + E01.y) + (E23.x + E23.y);
+#pragma unroll
+                for (int o = 1; o < PARTS; o <<= 1) e += __shfl_xor_sync(0xffffffffu, e, o);
+                e += b2;
+                x[m] = posterior_update_rn(x[m], e, z, cf.x, cf.y, cf.z, t > 0);
+                if (owner) {
+                    sts32(xs_w + 4u * (m * kPPad), x[m]);
+                    if (TRACE && mvalid[m]) a.eps_trace[((int64_t)t * a.B + m0 + m) * P + p] = e;
+                }
+            }
+            if (r == CHAIN_NB - 1) cp_async_wait<0>();   // next block's rows landed (this thread's)
+            __syncthreads();
         }
-        __syncthreads();        // hs complete; thread 0's coefficient copy is now visible to all
-        const float4 cf = *reinterpret_cast<const float4*>(&ctring[slot][H]);
-        if (!replay && t > 0 && (d & (4 * PARTS - 1)) == 0) refill_rng(d);
-        // ---- layer 2 + posterior update ------------------------------------------------------
-#pragma unroll
-        for (int m = 0; m < MPB; ++m) {
-            float4 hv[8];
-#pragma unroll
-            for (int i4 = 0; i4 < 8; ++i4)
-                hv[i4] = *reinterpret_cast<const float4*>(&hs[m][part * 36 + 4 * i4]);
-            float z = 0.f;
-            if (t > 0) {
-                if (replay) { if (owner) z = zring[slot][m][p]; }
-                else z = rng_draw(d, m);
-            }
-            float e0 = 0.f, e1 = 0.f, e2 = 0.f, e3 = 0.f;
-#pragma unroll
-            for (int i4 = 0; i4 < 8; ++i4) {
-                e0 = fmaf(w2r[4 * i4 + 0], hv[i4].x, e0);
-                e1 = fmaf(w2r[4 * i4 + 1], hv[i4].y, e1);
-                e2 = fmaf(w2r[4 * i4 + 2], hv[i4].z, e2);
-                e3 = fmaf(w2r[4 * i4 + 3], hv[i4].w, e3);
-            }
-            float e = (e0 + e1) + (e2 + e3);
-#pragma unroll
-            for (int o = 1; o < PARTS; o <<= 1) e += __shfl_xor_sync(0xffffffffu, e, o);
-            e += b2;
-            x[m] = posterior_update_rn(x[m], e, z, cf.x, cf.y, cf.z, t > 0);
-            if (owner) {
-                xs[m][p] = x[m];
-                if (a.eps_trace && mvalid[m])
-                    a.eps_trace[((int64_t)t * a.B + m0 + m) * P + p] = e;
-            }
-        }
-        __syncthreads();
     }
     cp_async_wait<0>();
     if (owner) {

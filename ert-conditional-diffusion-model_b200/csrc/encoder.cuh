@@ -23,28 +23,32 @@
 
 namespace ertdiff {
 
-constexpr int ENC_TP = 128;          // conv2 output positions per CTA
 constexpr int ENC_THREADS = 256;     // 8 warps
-constexpr int ENC_IN_STRIDE = 132;   // >= ENC_TP + 1
-constexpr int ENC_H1O_STRIDE = 132;  // >= ENC_TP + 1
 
+// NJ = conv2 positions per lane; a CTA owns ENC_TP = 32*NJ positions.  NJ = 4 for throughput
+// (many conditions), NJ = 1 to spread a single condition over ~37 CTAs instead of 10.
+template <int NJ>
 struct EncSmem {
-    float in_ph[4][kInChannels][ENC_IN_STRIDE];  // in_ph[r][ci][i] = in[ci][4*(p0-1+i) + r]
-    float h1e[kConv1Out][ENC_TP];                // h1e[c][i] = h1[c][2*(p0+i)]
-    float h1o[kConv1Out][ENC_H1O_STRIDE];        // h1o[c][i] = h1[c][2*(p0-1+i)+1]
+    static constexpr int TP = 32 * NJ;
+    static constexpr int STRIDE = TP + 4;        // >= TP + 1, keeps rows 16-byte aligned
+    float in_ph[4][kInChannels][STRIDE];         // in_ph[r][ci][i] = in[ci][4*(p0-1+i) + r]
+    float h1e[kConv1Out][TP];                    // h1e[c][i] = h1[c][2*(p0+i)]
+    float h1o[kConv1Out][STRIDE];                // h1o[c][i] = h1[c][2*(p0-1+i)+1]
     float w1[kInChannels * 3][kConv1Out];        // [(ci*3+k)][co]
     float w2[kConv1Out * 3][kConv2Out];          // [(ci*3+k)][co]
     float b1[kConv1Out];
     float b2[kConv2Out];
 };
 
+template <int NJ>
 __global__ void __launch_bounds__(ENC_THREADS, 2)
 k_encoder_conv(const float* __restrict__ cond, int64_t member_stride, int64_t L, int64_t L1,
                int64_t L2, const float* __restrict__ conv1_w, const float* __restrict__ b1g,
                const float* __restrict__ conv2_w, const float* __restrict__ b2g,
                float* __restrict__ partial, int n_chunks) {
     extern __shared__ __align__(16) unsigned char enc_smem_raw[];
-    EncSmem& s = *reinterpret_cast<EncSmem*>(enc_smem_raw);
+    constexpr int ENC_TP = 32 * NJ;
+    EncSmem<NJ>& s = *reinterpret_cast<EncSmem<NJ>*>(enc_smem_raw);
     const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
     const int chunk = blockIdx.x;
     const int64_t member = blockIdx.y;
@@ -82,9 +86,9 @@ k_encoder_conv(const float* __restrict__ cond, int64_t member_stride, int64_t L,
         const int co0 = warp * 4;   // 8 warps x 4 = 32 output channels
         // even phase: h1e[i], i = lane + 32 j ; m = p0 + i ; q = 2m
         {
-            float acc[4][4];
+            float acc[NJ][4];
 #pragma unroll
-            for (int j = 0; j < 4; ++j)
+            for (int j = 0; j < NJ; ++j)
 #pragma unroll
                 for (int c = 0; c < 4; ++c) acc[j][c] = s.b1[co0 + c];
 #pragma unroll 2
@@ -93,7 +97,7 @@ k_encoder_conv(const float* __restrict__ cond, int64_t member_stride, int64_t L,
                 const float4 wb = *reinterpret_cast<const float4*>(&s.w1[ci * 3 + 1][co0]);
                 const float4 wc = *reinterpret_cast<const float4*>(&s.w1[ci * 3 + 2][co0]);
 #pragma unroll
-                for (int j = 0; j < 4; ++j) {
+                for (int j = 0; j < NJ; ++j) {
                     const int i = lane + 32 * j;
                     const float a = s.in_ph[3][ci][i];       // in[4m-1]
                     const float b = s.in_ph[0][ci][i + 1];   // in[4m]
@@ -107,7 +111,7 @@ k_encoder_conv(const float* __restrict__ cond, int64_t member_stride, int64_t L,
                 }
             }
 #pragma unroll
-            for (int j = 0; j < 4; ++j) {
+            for (int j = 0; j < NJ; ++j) {
                 const int i = lane + 32 * j;
                 const int64_t q = 2 * (p0 + i);
                 const bool ok = q < L1;                       // conv2 zero padding beyond L1
@@ -117,9 +121,9 @@ k_encoder_conv(const float* __restrict__ cond, int64_t member_stride, int64_t L,
         }
         // odd phase: h1o[i], i in [0, ENC_TP) ; m = p0 - 1 + i ; q = 2m + 1
         {
-            float acc[4][4];
+            float acc[NJ][4];
 #pragma unroll
-            for (int j = 0; j < 4; ++j)
+            for (int j = 0; j < NJ; ++j)
 #pragma unroll
                 for (int c = 0; c < 4; ++c) acc[j][c] = s.b1[co0 + c];
 #pragma unroll 2
@@ -128,7 +132,7 @@ k_encoder_conv(const float* __restrict__ cond, int64_t member_stride, int64_t L,
                 const float4 wb = *reinterpret_cast<const float4*>(&s.w1[ci * 3 + 1][co0]);
                 const float4 wc = *reinterpret_cast<const float4*>(&s.w1[ci * 3 + 2][co0]);
 #pragma unroll
-                for (int j = 0; j < 4; ++j) {
+                for (int j = 0; j < NJ; ++j) {
                     const int i = lane + 32 * j;
                     const float a = s.in_ph[1][ci][i];   // in[4m+1]
                     const float b = s.in_ph[2][ci][i];   // in[4m+2]
@@ -142,7 +146,7 @@ k_encoder_conv(const float* __restrict__ cond, int64_t member_stride, int64_t L,
                 }
             }
 #pragma unroll
-            for (int j = 0; j < 4; ++j) {
+            for (int j = 0; j < NJ; ++j) {
                 const int i = lane + 32 * j;
                 const int64_t q = 2 * (p0 - 1 + i) + 1;
                 const bool ok = q >= 0 && q < L1;
@@ -169,16 +173,16 @@ k_encoder_conv(const float* __restrict__ cond, int64_t member_stride, int64_t L,
     // ---- conv2 + ReLU + pooled partial sum --------------------------------------------
     {
         const int co0 = warp * 8;   // 8 warps x 8 = 64 output channels
-        float acc[4][8];
+        float acc[NJ][8];
 #pragma unroll
-        for (int j = 0; j < 4; ++j)
+        for (int j = 0; j < NJ; ++j)
 #pragma unroll
             for (int c = 0; c < 8; ++c) acc[j][c] = s.b2[co0 + c];
 #pragma unroll 2
         for (int ci = 0; ci < kConv1Out; ++ci) {
-            float hv[3][4];
+            float hv[3][NJ];
 #pragma unroll
-            for (int j = 0; j < 4; ++j) {
+            for (int j = 0; j < NJ; ++j) {
                 const int i = lane + 32 * j;
                 hv[0][j] = s.h1o[ci][i];       // h1[2p-1]
                 hv[1][j] = s.h1e[ci][i];       // h1[2p]
@@ -189,7 +193,7 @@ k_encoder_conv(const float* __restrict__ cond, int64_t member_stride, int64_t L,
                 const float4 wlo = *reinterpret_cast<const float4*>(&s.w2[ci * 3 + k][co0]);
                 const float4 whi = *reinterpret_cast<const float4*>(&s.w2[ci * 3 + k][co0 + 4]);
 #pragma unroll
-                for (int j = 0; j < 4; ++j) {
+                for (int j = 0; j < NJ; ++j) {
                     const float h = hv[k][j];
                     acc[j][0] = fmaf(wlo.x, h, acc[j][0]); acc[j][1] = fmaf(wlo.y, h, acc[j][1]);
                     acc[j][2] = fmaf(wlo.z, h, acc[j][2]); acc[j][3] = fmaf(wlo.w, h, acc[j][3]);
@@ -202,7 +206,7 @@ k_encoder_conv(const float* __restrict__ cond, int64_t member_stride, int64_t L,
 #pragma unroll
         for (int c = 0; c < 8; ++c) part[c] = 0.f;
 #pragma unroll
-        for (int j = 0; j < 4; ++j) {
+        for (int j = 0; j < NJ; ++j) {
             const bool ok = (p0 + lane + 32 * j) < L2;
 #pragma unroll
             for (int c = 0; c < 8; ++c) part[c] += ok ? fmaxf(acc[j][c], 0.f) : 0.f;
@@ -238,20 +242,28 @@ __global__ void k_encoder_finish(const float* __restrict__ partial, int n_chunks
         pooled[co] = sum / (float)L2;
     }
     __syncthreads();
-    float a = b6[tid];
-#pragma unroll 8
-    for (int k = 0; k < kConv2Out; ++k) a = fmaf(w6T[k * H + tid], pooled[k], a);
-    a = fmaxf(a, 0.f);
+    float a0 = b6[tid], a1 = 0.f, a2 = 0.f, a3 = 0.f;
+#pragma unroll
+    for (int k = 0; k < kConv2Out; k += 4) {
+        a0 = fmaf(w6T[(k + 0) * H + tid], pooled[k + 0], a0);
+        a1 = fmaf(w6T[(k + 1) * H + tid], pooled[k + 1], a1);
+        a2 = fmaf(w6T[(k + 2) * H + tid], pooled[k + 2], a2);
+        a3 = fmaf(w6T[(k + 3) * H + tid], pooled[k + 3], a3);
+    }
+    const float a = fmaxf((a0 + a1) + (a2 + a3), 0.f);
     cemb[tid] = a;
     if (cond_emb) cond_emb[member * H + tid] = a;
     __syncthreads();
     if (cond_bias) {
-        float acc0 = b0[tid], acc1 = 0.f;
-        for (int k = 0; k < H; k += 2) {
-            acc0 = fmaf(w0cT[(int64_t)k * H + tid], cemb[k], acc0);
+        float acc0 = b0[tid], acc1 = 0.f, acc2 = 0.f, acc3 = 0.f;
+#pragma unroll 8
+        for (int k = 0; k < H; k += 4) {
+            acc0 = fmaf(w0cT[(int64_t)(k + 0) * H + tid], cemb[k + 0], acc0);
             acc1 = fmaf(w0cT[(int64_t)(k + 1) * H + tid], cemb[k + 1], acc1);
+            acc2 = fmaf(w0cT[(int64_t)(k + 2) * H + tid], cemb[k + 2], acc2);
+            acc3 = fmaf(w0cT[(int64_t)(k + 3) * H + tid], cemb[k + 3], acc3);
         }
-        cond_bias[member * H + tid] = acc0 + acc1;
+        cond_bias[member * H + tid] = (acc0 + acc1) + (acc2 + acc3);
     }
 }
 

@@ -30,6 +30,7 @@ struct ertdiff_model {
     float* cond_bias = nullptr;    size_t cond_bias_n = 0;     // (n_cond, H)
     float* cond_emb = nullptr;     size_t cond_emb_n = 0;      // (n_cond, H)
     float* time_table = nullptr;   size_t time_table_n = 0;    // (steps, H)
+    int time_rows_valid = 0;       // rows of time_table computed for the current weights
     float* coef_table = nullptr;   size_t coef_table_n = 0;    // (steps, 4)
     float* xbuf[2] = {};           size_t xbuf_n[2] = {};         // graph-mode ping-pong (B,P)
 

@@ -213,124 +213,180 @@ __global__ void k_percentiles(const T* __restrict__ a, int64_t N, int64_t Q, int
 }
 
 // ------------------------------------------------------------------------------------------
-// Gaussian-KDE mode, ECD.py:751-762.  One CTA per column: the N members sit in shared memory
-// as float64, every thread evaluates pdf(g) = sum_i exp(-(g - x_i)^2 / (2 h^2)) for a strided
-// set of grid points (members in order, float64 throughout, as scipy does), and the CTA reduces
-// to the FIRST maximum.  h^2 = var_ddof1 * N^(-2/5) (Scott).  The normalisation constant is
-// common to all grid points of a column and does not change the argmax, so it is skipped.
-// grid[i] = lo + i*step (separately rounded multiply and add, as np.linspace), grid[G-1] = hi.
+// Gaussian-KDE mode, ECD.py:751-762: per column, argmax over a common grid of
+//   pdf(g) = sum_i exp(-(g - x_i)^2 / (2 h^2)),   h^2 = var_ddof1 * N^(-2/5)   (Scott),
+// first maximum.  (The normalisation constant is common to a column's grid points and is
+// skipped.)  grid[i] = lo + i*step with separately rounded multiply and add, grid[G-1] = hi,
+// exactly as np.linspace builds it.
 //
-// Launch: grid = (Q, n_gchunks); CTA (col, gc) scans grid points [gc*gchunk, (gc+1)*gchunk) and
-// writes its (best value, best index) to part_val/part_idx[col*n_gchunks + gc]; k_kde_final
-// picks the first maximum per column.  Splitting the grid keeps all SMs busy when Q is small
-// (the (N, 29) parameter posteriors); for map-shaped inputs n_gchunks = 1.
+// The argmax is decided in float64, but float64 exp is only evaluated where it can matter:
+//   k_kde_scan32   every (column, grid point) in fp32 on data centred at the column mean
+//                  (ex2.approx, 64-term fp32 partial sums added up in fp64): N*G cheap terms.
+//   k_kde_select64 per column: the fp32 maximum M; every grid point whose fp32 value reaches
+//                  M*(1 - KDE_TOL) is re-evaluated in float64 (members summed lane-strided in
+//                  order, then a fixed shuffle tree) and the first float64 maximum wins.
+// KDE_TOL = 1e-3 is ~50x the worst-case relative error of the fp32 scan (centred arguments:
+// <= 2e-5), so the true float64 maximum -- and every exact tie with it -- is always among the
+// candidates; typically a few dozen of the 5000 grid points are re-evaluated.
+// Columns with zero variance have no KDE (scipy raises): mode = NaN, index = -1.
+constexpr float KDE_TOL = 1e-3f;
+constexpr int KDE_MAX_CAND = 2048;
+
+struct KdeColumn {          // per-column constants, written by k_kde_prepare
+    double mean;
+    double neg_inv_2h2;     // -1 / (2 h^2)
+};
+
+// one warp per column: mean, ddof-1 variance, bandwidth
 template <typename T>
-__global__ void __launch_bounds__(256)
-k_kde_mode(const T* __restrict__ a, int64_t N, int64_t Q, const double* __restrict__ lohi,
-           int G, int gchunk, double scott_factor_sq, double* __restrict__ part_val,
-           int* __restrict__ part_idx) {
-    extern __shared__ __align__(16) unsigned char kde_smem_raw[];
-    double* xs = reinterpret_cast<double*>(kde_smem_raw);    // [N]
-    __shared__ double red[32];
-    __shared__ int redi[32];
-    __shared__ double s_bcast[2];
-    const int tid = threadIdx.x, nthr = blockDim.x, lane = tid & 31, warp = tid >> 5;
-    const int nwarps = nthr >> 5;
-    const int64_t col = blockIdx.x;
-    const int g_begin = blockIdx.y * gchunk;
-    const int g_end = min(G, g_begin + gchunk);
-
-    double lsum = 0.0;
-    for (int64_t i = tid; i < N; i += nthr) {
-        const double v = (double)a[i * Q + col];
-        xs[i] = v;
-        lsum += v;
+__global__ void k_kde_prepare(const T* __restrict__ a, int64_t N, int64_t Q,
+                              double scott_factor_sq, KdeColumn* __restrict__ cols) {
+    const int lane = threadIdx.x & 31;
+    const int64_t col = ((int64_t)blockIdx.x * blockDim.x + threadIdx.x) >> 5;
+    if (col >= Q) return;
+    double s = 0.0;
+    for (int64_t i = lane; i < N; i += 32) s += (double)a[i * Q + col];
+#pragma unroll
+    for (int o = 16; o > 0; o >>= 1) s += __shfl_xor_sync(0xffffffffu, s, o);
+    const double mean = s / (double)N;
+    double ss = 0.0;
+    for (int64_t i = lane; i < N; i += 32) {
+        const double d = (double)a[i * Q + col] - mean;
+        ss += d * d;
     }
 #pragma unroll
-    for (int o = 16; o > 0; o >>= 1) lsum += __shfl_xor_sync(0xffffffffu, lsum, o);
-    if (lane == 0) red[warp] = lsum;
-    __syncthreads();
-    if (tid == 0) {
-        double s = 0.0;
-        for (int w = 0; w < nwarps; ++w) s += red[w];
-        s_bcast[0] = s / (double)N;
-    }
-    __syncthreads();
-    const double mean = s_bcast[0];
-    double lss = 0.0;
-    for (int64_t i = tid; i < N; i += nthr) {
-        const double d = xs[i] - mean;
-        lss += d * d;
-    }
-#pragma unroll
-    for (int o = 16; o > 0; o >>= 1) lss += __shfl_xor_sync(0xffffffffu, lss, o);
-    __syncthreads();
-    if (lane == 0) red[warp] = lss;
-    __syncthreads();
-    if (tid == 0) {
-        double s = 0.0;
-        for (int w = 0; w < nwarps; ++w) s += red[w];
-        const double h2 = (s / (double)(N - 1)) * scott_factor_sq;
-        s_bcast[1] = -0.5 / h2;
-    }
-    __syncthreads();
-    const double neg_inv_2h2 = s_bcast[1];
-
-    const double lo = lohi[0], hi = lohi[1];
-    const double step = (hi - lo) / (double)(G - 1);
-    double best = -1.0;
-    int besti = 0x7fffffff;
-    // two grid points per thread per pass: independent exp chains
-    for (int g0 = g_begin + tid; g0 < g_end; g0 += 2 * nthr) {
-        const int g1 = g0 + nthr;
-        const double ga = (g0 == G - 1) ? hi : __dadd_rn(__dmul_rn((double)g0, step), lo);
-        const double gb = (g1 >= g_end) ? ga : (g1 == G - 1) ? hi
-                                                              : __dadd_rn(__dmul_rn((double)g1, step), lo);
-        double pa = 0.0, pb = 0.0;
-        for (int64_t i = 0; i < N; ++i) {
-            const double xi = xs[i];
-            const double da = ga - xi, db = gb - xi;
-            pa += exp(da * da * neg_inv_2h2);
-            pb += exp(db * db * neg_inv_2h2);
-        }
-        if (pa > best) { best = pa; besti = g0; }
-        if (g1 < g_end && pb > best) { best = pb; besti = g1; }
-    }
-    // first maximum: larger value wins, ties go to the smaller index
-#pragma unroll
-    for (int o = 16; o > 0; o >>= 1) {
-        const double ov = __shfl_xor_sync(0xffffffffu, best, o);
-        const int oi = __shfl_xor_sync(0xffffffffu, besti, o);
-        if (ov > best || (ov == best && oi < besti)) { best = ov; besti = oi; }
-    }
-    __syncthreads();
-    if (lane == 0) { red[warp] = best; redi[warp] = besti; }
-    __syncthreads();
-    if (tid == 0) {
-        for (int w = 1; w < nwarps; ++w)
-            if (red[w] > best || (red[w] == best && redi[w] < besti)) { best = red[w]; besti = redi[w]; }
-        part_val[col * gridDim.y + blockIdx.y] = best;
-        part_idx[col * gridDim.y + blockIdx.y] = besti;
+    for (int o = 16; o > 0; o >>= 1) ss += __shfl_xor_sync(0xffffffffu, ss, o);
+    if (lane == 0) {
+        const double h2 = (ss / (double)(N - 1)) * scott_factor_sq;
+        cols[col].mean = mean;
+        cols[col].neg_inv_2h2 = -0.5 / h2;        // -inf when the column is constant
     }
 }
 
-__global__ void k_kde_final(const double* __restrict__ part_val, const int* __restrict__ part_idx,
-                            int64_t Q, int n_gchunks, const double* __restrict__ lohi, int G,
-                            double* __restrict__ mode_out, int64_t* __restrict__ index_out) {
-    const int64_t col = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
-    if (col >= Q) return;
-    double best = -1.0;
-    int besti = 0x7fffffff;
-    for (int c = 0; c < n_gchunks; ++c) {            // chunks are in grid order: strict > keeps the first
-        const double v = part_val[col * n_gchunks + c];
-        const int i = part_idx[col * n_gchunks + c];
-        if (v > best || (v == best && i < besti)) { best = v; besti = i; }
-    }
+__device__ __forceinline__ float ex2_approx(float x) {
+    float y;
+    asm("ex2.approx.ftz.f32 %0, %1;" : "=f"(y) : "f"(x));
+    return y;
+}
+
+__device__ __forceinline__ double kde_grid_point(int g, int G, double lo, double hi, double step) {
+    return (g == G - 1) ? hi : __dadd_rn(__dmul_rn((double)g, step), lo);
+}
+
+// grid = (columns of this batch, n_gchunks); CTA (c, gc) scans grid points
+// [gc*gchunk, (gc+1)*gchunk) of column col0 + c and writes s32[c*G + g].
+template <typename T>
+__global__ void __launch_bounds__(256)
+k_kde_scan32(const T* __restrict__ a, int64_t N, int64_t Q, int64_t col0,
+             const double* __restrict__ lohi, int G, int gchunk,
+             const KdeColumn* __restrict__ cols, float* __restrict__ s32) {
+    extern __shared__ __align__(16) unsigned char kde_smem_raw[];
+    float* xs = reinterpret_cast<float*>(kde_smem_raw);        // [N] centred members, fp32
+    const int tid = threadIdx.x, nthr = blockDim.x;
+    const int64_t col = col0 + blockIdx.x;
+    const KdeColumn kc = cols[col];
+    for (int64_t i = tid; i < N; i += nthr) xs[i] = (float)((double)a[i * Q + col] - kc.mean);
+    __syncthreads();
     const double lo = lohi[0], hi = lohi[1];
     const double step = (hi - lo) / (double)(G - 1);
-    if (index_out) index_out[col] = besti;
-    if (mode_out)
-        mode_out[col] = (besti == G - 1) ? hi : __dadd_rn(__dmul_rn((double)besti, step), lo);
+    const float c2 = (float)(kc.neg_inv_2h2 * 1.4426950408889634);   // exponent in base 2
+    const int g_begin = blockIdx.y * gchunk;
+    const int g_end = min(G, g_begin + gchunk);
+    float* out = s32 + (int64_t)blockIdx.x * G;
+    for (int g0 = g_begin + tid; g0 < g_end; g0 += 2 * nthr) {
+        const int g1 = g0 + nthr;
+        const float ga = (float)(kde_grid_point(g0, G, lo, hi, step) - kc.mean);
+        const float gb = (float)(kde_grid_point(min(g1, G - 1), G, lo, hi, step) - kc.mean);
+        double sa = 0.0, sb = 0.0;
+        for (int64_t i0 = 0; i0 < N; i0 += 64) {
+            const int64_t i1 = (i0 + 64 < N) ? i0 + 64 : N;
+            float pa = 0.f, pb = 0.f;
+            for (int64_t i = i0; i < i1; ++i) {
+                const float xi = xs[i];
+                const float da = ga - xi, db = gb - xi;
+                pa += ex2_approx(da * da * c2);
+                pb += ex2_approx(db * db * c2);
+            }
+            sa += (double)pa;
+            sb += (double)pb;
+        }
+        out[g0] = (float)sa;
+        if (g1 < g_end) out[g1] = (float)sb;
+    }
+}
+
+// grid = columns of this batch, 256 threads.
+template <typename T>
+__global__ void __launch_bounds__(256)
+k_kde_select64(const T* __restrict__ a, int64_t N, int64_t Q, int64_t col0,
+               const double* __restrict__ lohi, int G, const KdeColumn* __restrict__ cols,
+               const float* __restrict__ s32, double* __restrict__ mode_out,
+               int64_t* __restrict__ index_out) {
+    extern __shared__ __align__(16) unsigned char kde_smem_raw[];
+    double* xs = reinterpret_cast<double*>(kde_smem_raw);      // [N] members, float64
+    __shared__ float redf[8];
+    __shared__ double redv[8];
+    __shared__ int redi[8];
+    __shared__ int cand[KDE_MAX_CAND];
+    __shared__ int ncand;
+    const int tid = threadIdx.x, nthr = blockDim.x, lane = tid & 31, warp = tid >> 5;
+    const int nwarps = nthr >> 5;
+    const int64_t col = col0 + blockIdx.x;
+    const KdeColumn kc = cols[col];
+    const float* row = s32 + (int64_t)blockIdx.x * G;
+    if (tid == 0) ncand = 0;
+    for (int64_t i = tid; i < N; i += nthr) xs[i] = (double)a[i * Q + col];
+    // fp32 maximum of the column's scan
+    float mx = 0.f;
+    for (int g = tid; g < G; g += nthr) mx = fmaxf(mx, row[g]);
+#pragma unroll
+    for (int o = 16; o > 0; o >>= 1) mx = fmaxf(mx, __shfl_xor_sync(0xffffffffu, mx, o));
+    if (lane == 0) redf[warp] = mx;
+    __syncthreads();
+    mx = redf[0];
+    for (int w = 1; w < nwarps; ++w) mx = fmaxf(mx, redf[w]);
+    const bool degenerate = !(kc.neg_inv_2h2 > -CUDART_INF) || !(kc.neg_inv_2h2 == kc.neg_inv_2h2);
+    const float thr = mx * (1.0f - KDE_TOL);
+    for (int g = tid; g < G; g += nthr) {
+        if (row[g] >= thr) {
+            const int k = atomicAdd(&ncand, 1);
+            if (k < KDE_MAX_CAND) cand[k] = g;
+        }
+    }
+    __syncthreads();
+    // a flat scan (more candidates than the list holds, or an all-zero scan) falls back to
+    // evaluating every grid point in float64
+    const bool all = ncand > KDE_MAX_CAND || !(mx > 0.f);
+    const int n_eval = all ? G : ncand;
+    const double lo = lohi[0], hi = lohi[1];
+    const double step = (hi - lo) / (double)(G - 1);
+    double best = -1.0;
+    int besti = 0x7fffffff;
+    for (int k = warp; k < n_eval; k += nwarps) {
+        const int g = all ? k : cand[k];
+        const double gv = kde_grid_point(g, G, lo, hi, step);
+        double acc = 0.0;
+        for (int64_t i = lane; i < N; i += 32) {
+            const double d = gv - xs[i];
+            acc += exp(d * d * kc.neg_inv_2h2);
+        }
+#pragma unroll
+        for (int o = 16; o > 0; o >>= 1) acc += __shfl_xor_sync(0xffffffffu, acc, o);
+        if (acc > best || (acc == best && g < besti)) { best = acc; besti = g; }
+    }
+    if (lane == 0) { redv[warp] = best; redi[warp] = besti; }
+    __syncthreads();
+    if (tid == 0) {
+        for (int w = 1; w < nwarps; ++w)
+            if (redv[w] > best || (redv[w] == best && redi[w] < besti)) { best = redv[w]; besti = redi[w]; }
+        if (degenerate) {
+            if (index_out) index_out[col] = -1;
+            if (mode_out) mode_out[col] = CUDART_NAN;
+        } else {
+            if (index_out) index_out[col] = besti;
+            if (mode_out) mode_out[col] = kde_grid_point(besti, G, lo, hi, step);
+        }
+    }
 }
 
 // ------------------------------------------------------------------------------------------

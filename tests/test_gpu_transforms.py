@@ -30,9 +30,12 @@ def test_untransform_and_bounds(cuda_dev):
     # its data range -- not relative to the value (values near zero are differences of large terms)
     tol = 3e-7 / scaler.scale_ + 2e-7 * np.abs(phys_ref).max(axis=0)
     assert (np.abs(phys.cpu().numpy().astype(np.float64) - phys_ref) <= tol[None, :]).all()
-    agree = valid.cpu().numpy() == valid_ref
-    assert agree.mean() > 0.995          # rows sitting within 1 ulp of a limit may flip
-    assert (first_bad.cpu().numpy()[agree] == first_ref[agree]).all()
+    # rows with a parameter sitting within the sigmoid tolerance of a limit may flip
+    near = (np.minimum(np.abs(phys_ref - limits[None, :, 0]), np.abs(phys_ref - limits[None, :, 1]))
+            <= tol[None, :]).any(axis=1)
+    assert near.mean() < 0.02
+    assert (valid.cpu().numpy()[~near] == valid_ref[~near]).all()
+    assert (first_bad.cpu().numpy()[~near] == first_ref[~near]).all()
     assert valid_ref.sum() > 0 and (~valid_ref).sum() > 0
     # sigmoid only
     s_gpu = eb.inverse_transform(u.to(cuda_dev), 0.0, 1.0)
