@@ -322,11 +322,14 @@ __global__ void __launch_bounds__(H) k_chain(const ChainParams a) {
     const float b2 = a.b2p[p];
 
     // 32-bit shared-window addresses, computed once
-    const uint32_t xs_a = (uint32_t)__cvta_generic_to_shared(&xs[0][0]);
-    const uint32_t hs_a = (uint32_t)__cvta_generic_to_shared(&hs[0][0]);
-    const uint32_t ct_a = (uint32_t)__cvta_generic_to_shared(&ctbuf[0][0][0]);
-    const uint32_t zb_a = (uint32_t)__cvta_generic_to_shared(&zbuf[0][0][0][0]);
-    const uint32_t zn_a = (uint32_t)__cvta_generic_to_shared(&znorm[0][0][0]);
+    uint32_t xs_a = (uint32_t)__cvta_generic_to_shared(&xs[0][0]);
+    uint32_t hs_a = (uint32_t)__cvta_generic_to_shared(&hs[0][0]);
+    uint32_t ct_a = (uint32_t)__cvta_generic_to_shared(&ctbuf[0][0][0]);
+    uint32_t zb_a = (uint32_t)__cvta_generic_to_shared(&zbuf[0][0][0][0]);
+    uint32_t zn_a = (uint32_t)__cvta_generic_to_shared(&znorm[0][0][0]);
+    // make the bases opaque: otherwise the compiler re-derives them (S2UR SR_CgaCtaId + ULEA,
+    // a long-latency special-register read) inside every step
+    asm volatile("" : "+r"(xs_a), "+r"(hs_a), "+r"(ct_a), "+r"(zb_a), "+r"(zn_a));
     const uint32_t hs_w = hs_a + 4u * ((tid >> 5) * 36 + (tid & 31));   // this thread's h slot (member 0)
     const uint32_t hs_r = hs_a + 4u * (part * 36);                      // this thread's W2 slice of h
     const uint32_t xs_w = xs_a + 4u * p;
@@ -439,9 +442,10 @@ __global__ void __launch_bounds__(H) k_chain(const ChainParams a) {
                 sts32(hs_w + 4u * (m * HS_STRIDE), fmaxf((A01.x + A01.y) + (A23.x + A23.y), 0.f));
             }
             __syncthreads();          // hs complete (and, at block starts, staged rows are visible)
-            const float4 cf = lds128(row_a + 4u * H);
             if (!REPLAY && t > 0 && (d & (4 * RG - 1)) == 0) refill_rng(d);
             // ---- layer 2 + posterior update --------------------------------------------------
+            // (loads are issued in the order their consumers need them: h first, scalars last)
+            float cf_coef, cf_c1, cf_sigma;
 #pragma unroll
             for (int m = 0; m < MPB; ++m) {
                 float4 hv[8];
@@ -451,6 +455,11 @@ __global__ void __launch_bounds__(H) k_chain(const ChainParams a) {
                 if (t > 0) {
                     if (REPLAY) { if (owner) z = lds32(zb_a + 4u * (((buf * CHAIN_NB + r) * MPB + m) * kPPad + p)); }
                     else z = rng_draw(d, m);
+                }
+                if (m == 0) {
+                    cf_coef = lds32(row_a + 4u * H);
+                    cf_c1 = lds32(row_a + 4u * H + 4u);
+                    cf_sigma = lds32(row_a + 4u * H + 8u);
                 }
                 float2 E01 = make_float2(0.f, 0.f), E23 = make_float2(0.f, 0.f);
 #pragma unroll
@@ -462,7 +471,7 @@ __global__ void __launch_bounds__(H) k_chain(const ChainParams a) {
 #pragma unroll
                 for (int o = 1; o < PARTS; o <<= 1) e += __shfl_xor_sync(0xffffffffu, e, o);
                 e += b2;
-                x[m] = posterior_update_rn(x[m], e, z, cf.x, cf.y, cf.z, t > 0);
+                x[m] = posterior_update_rn(x[m], e, z, cf_coef, cf_c1, cf_sigma, t > 0);
                 if (owner) {
                     sts32(xs_w + 4u * (m * kPPad), x[m]);
                     if (TRACE && mvalid[m]) a.eps_trace[((int64_t)t * a.B + m0 + m) * P + p] = e;
