@@ -14,7 +14,7 @@ from ._lib import ErtdiffError, LIB_PATH
 from .model import ConditionalDiffusionModel
 from .sampler import (get_diffusion_schedule, get_timestep_embedding, sample_model,
                       sample_ensemble, run_chain, step_coefficients, posterior_update,
-                      philox_normal)
+                      philox_normal, debug_umma_gemm)
 from .stats import (ensemble_moments, ensemble_mean, ensemble_std, ensemble_var,
                     ensemble_percentile, ensemble_kde_mode, ensemble_statistics)
 from .transforms import untransform_and_check, inverse_transform, check_param_bounds

@@ -10,6 +10,7 @@
 #include "encoder.cuh"
 #include "denoiser.cuh"
 #include "stats.cuh"
+#include "umma.cuh"
 
 namespace ertdiff {
 std::string& last_error() {
@@ -231,6 +232,22 @@ static int run_chain(ertdiff_model* m, const ertdiff_chain_args* a, const float*
     }
     ERT_CUDA(cudaGraphLaunch(m->graph_exec, st));
     g_launches.fetch_add(S, std::memory_order_relaxed);
+    return 0;
+}
+
+template <int N, int K>
+static int run_umma_selftest(const float* A, const float* B, float* D, cudaStream_t st) {
+    int* d_status = nullptr;
+    if (int rc = workspace(256, (void**)&d_status)) return rc;
+    ERT_CUDA(cudaMemsetAsync(d_status, 0, sizeof(int), st));
+    const size_t smem = umma::tile_bytes(128, K) + umma::tile_bytes(N, K);
+    ERT_CUDA(cudaFuncSetAttribute(umma::k_umma_selftest<N, K>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+    umma::k_umma_selftest<N, K><<<1, 128, smem, st>>>(A, B, D, d_status);
+    ERT_LAUNCH_CHECK("k_umma_selftest");
+    int h = 0;
+    ERT_CUDA(cudaMemcpyAsync(&h, d_status, sizeof(int), cudaMemcpyDeviceToHost, st));
+    ERT_CUDA(cudaStreamSynchronize(st));
+    if (h) return fail(ERTDIFF_ERR_CUDA, "umma selftest: mbarrier wait timed out (MMA never completed)");
     return 0;
 }
 
@@ -592,6 +609,17 @@ int ertdiff_ensemble_kde_mode(const void* d_a, int dtype, int64_t N, int64_t Q,
         ERT_LAUNCH_CHECK("k_kde_select64");
     }
     return 0;
+}
+
+int ertdiff_debug_umma_gemm(const float* d_A, const float* d_B, int32_t N, int32_t K, float* d_D,
+                            void* stream) {
+    ERT_REQUIRE(d_A && d_B && d_D, "debug_umma_gemm: NULL pointer");
+    cudaStream_t st = (cudaStream_t)stream;
+    if (N == 128 && K == 32) return run_umma_selftest<128, 32>(d_A, d_B, d_D, st);
+    if (N == 32 && K == 128) return run_umma_selftest<32, 128>(d_A, d_B, d_D, st);
+    if (N == 128 && K == 128) return run_umma_selftest<128, 128>(d_A, d_B, d_D, st);
+    if (N == 64 && K == 96) return run_umma_selftest<64, 96>(d_A, d_B, d_D, st);
+    return fail(ERTDIFF_ERR_UNSUPPORTED, "debug_umma_gemm: (N,K) must be (128,32), (32,128), (128,128) or (64,96)");
 }
 
 int ertdiff_untransform_bounds(const float* d_u, int64_t B, int32_t P, float a, float b,

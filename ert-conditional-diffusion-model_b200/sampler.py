@@ -236,3 +236,16 @@ def philox_normal(seed, offset, n_members, param_dim, draws, device="cuda", memb
             int(seed) & 0xFFFFFFFFFFFFFFFF, int(offset), int(member_offset), n_members, param_dim,
             draws, _lib.ptr(out), _lib.stream_ptr(device)), "philox_normal")
     return out
+
+
+def debug_umma_gemm(a, b):
+    """Self-test of the tcgen05 path: ``a (128,K) @ b (N,K)^T`` with bf16 operands on the tensor
+    cores (``ertdiff_debug_umma_gemm``)."""
+    a = a.contiguous().float()
+    b = b.contiguous().float()
+    out = torch.empty(128, b.size(0), device=a.device, dtype=torch.float32)
+    with torch.cuda.device(a.device):
+        _lib.check(_lib.load().ertdiff_debug_umma_gemm(_lib.ptr(a), _lib.ptr(b), b.size(0), a.size(1),
+                                                       _lib.ptr(out), _lib.stream_ptr(a.device)),
+                   "debug_umma_gemm")
+    return out

@@ -197,6 +197,13 @@ int ertdiff_untransform_bounds(const float* d_u, int64_t B, int32_t P, float a, 
                                const double* d_lim_lo, const double* d_lim_hi, float* d_phys,
                                uint8_t* d_valid, int32_t* d_first_bad, void* stream);
 
+/* ---- self-test of the tcgen05 building blocks -------------------------------------------------
+ * D (128,N) = A (128,K) @ B (N,K)^T on the tensor cores (bf16 operands, fp32 accumulate in TMEM),
+ * one CTA; (N,K) in {(128,32), (32,128), (128,128), (64,96)}.  Row-major fp32 in and out.
+ * Synchronises the stream; fails with ERTDIFF_ERR_CUDA if the MMA never signals completion. */
+int ertdiff_debug_umma_gemm(const float* d_A, const float* d_B, int32_t N, int32_t K, float* d_D,
+                            void* stream);
+
 #ifdef __cplusplus
 }
 #endif
