@@ -45,6 +45,7 @@ SIGNATURES = {
     "ertdiff_model_destroy": (C.c_int, [C.c_void_p]),
     "ertdiff_model_profile": (C.c_int, [C.c_void_p, C.c_int]),
     "ertdiff_model_last_chain_ms": (C.c_int, [C.c_void_p, C.POINTER(C.c_float)]),
+    "ertdiff_model_umma_status": (C.c_int, [C.c_void_p, C.POINTER(C.c_int)]),
     "ertdiff_model_load": (C.c_int, [C.c_void_p, C.POINTER(C.c_void_p), C.c_int, C.c_void_p, C.c_void_p]),
     "ertdiff_model_export": (C.c_int, [C.c_void_p, C.POINTER(C.c_void_p), C.c_int, C.c_void_p]),
     "ertdiff_forward": (C.c_int, [C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p, C.c_int64,

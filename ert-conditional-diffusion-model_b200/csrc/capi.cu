@@ -11,6 +11,7 @@
 #include "denoiser.cuh"
 #include "stats.cuh"
 #include "umma.cuh"
+#include "chain_umma.cuh"
 
 namespace ertdiff {
 std::string& last_error() {
@@ -148,8 +149,10 @@ static int run_chain(ertdiff_model* m, const ertdiff_chain_args* a, const float*
     ERT_REQUIRE(d_cond_bias, "sample_chain: cond_bias is NULL");
     ERT_REQUIRE(a->d_x_out, "sample_chain: x_out is NULL");
     ERT_REQUIRE(!(a->d_noise && !a->d_x_T), "sample_chain: injected noise needs d_x_T as well (row 0 of the draws)");
-    if (a->precision != ERTDIFF_PREC_FP32)
-        return fail(ERTDIFF_ERR_UNSUPPORTED, "sample_chain: only ERTDIFF_PREC_FP32 is built");
+    const bool use_umma = a->precision == ERTDIFF_PREC_BF16;
+    if (a->precision != ERTDIFF_PREC_FP32 && !use_umma) return fail(ERTDIFF_ERR_ARG, "sample_chain: bad precision");
+    if (use_umma && !(m->H == UC_H && m->P <= 29 && m->w1_pk))
+        return fail(ERTDIFF_ERR_UNSUPPORTED, "sample_chain: the bf16 tensor-core chain is built for hidden_dim = 128, param_dim <= 29");
     const int S = a->num_steps, H = m->H, P = m->P;
     const int64_t nstride = a->noise_member_stride_B > 0 ? a->noise_member_stride_B : a->B;
     ERT_REQUIRE(nstride >= a->B, "sample_chain: noise_member_stride_B < B");
@@ -180,12 +183,37 @@ static int run_chain(ertdiff_model* m, const ertdiff_chain_args* a, const float*
     p.x_out = a->d_x_out; p.eps_trace = a->d_eps_trace; p.P = P;
     const int mpb = pick_mpb(a->B, H);
 
+    auto launch_any = [&](const ChainParams& q, cudaStream_t s2) -> int {
+        if (!use_umma) return launch_chain(H, q, mpb, s2);
+        static bool attr_set = false;
+        if (!attr_set) {
+            ERT_CUDA(cudaFuncSetAttribute(k_chain_umma<false, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)sizeof(UmmaChainSmem)));
+            ERT_CUDA(cudaFuncSetAttribute(k_chain_umma<false, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)sizeof(UmmaChainSmem)));
+            ERT_CUDA(cudaFuncSetAttribute(k_chain_umma<true, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)sizeof(UmmaChainSmem)));
+            ERT_CUDA(cudaFuncSetAttribute(k_chain_umma<true, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)sizeof(UmmaChainSmem)));
+            attr_set = true;
+        }
+        UmmaChainExtra ex{reinterpret_cast<const uint4*>(m->w1_pk), reinterpret_cast<const uint4*>(m->w2_pk), m->umma_status};
+        const unsigned grid = (unsigned)((q.B + UC_M - 1) / UC_M);
+        const bool replay = q.noise != nullptr, trace = q.eps_trace != nullptr;
+        const size_t smem = sizeof(UmmaChainSmem);
+        if (replay) {
+            if (trace) k_chain_umma<true, true><<<grid, UC_M, smem, s2>>>(q, ex);
+            else k_chain_umma<true, false><<<grid, UC_M, smem, s2>>>(q, ex);
+        } else {
+            if (trace) k_chain_umma<false, true><<<grid, UC_M, smem, s2>>>(q, ex);
+            else k_chain_umma<false, false><<<grid, UC_M, smem, s2>>>(q, ex);
+        }
+        ERT_LAUNCH_CHECK("k_chain_umma");
+        return 0;
+    };
+
     if (a->loop_mode == ERTDIFF_LOOP_PERSISTENT) {
         if (m->profile) {
             if (!m->ev_chain[0]) { ERT_CUDA(cudaEventCreate(&m->ev_chain[0])); ERT_CUDA(cudaEventCreate(&m->ev_chain[1])); }
             ERT_CUDA(cudaEventRecord(m->ev_chain[0], st));
         }
-        const int rc = launch_chain(H, p, mpb, st);
+        const int rc = launch_any(p, st);
         if (m->profile && rc == 0) { ERT_CUDA(cudaEventRecord(m->ev_chain[1], st)); m->ev_valid = true; }
         return rc;
     }
@@ -200,7 +228,7 @@ static int run_chain(ertdiff_model* m, const ertdiff_chain_args* a, const float*
             q.t_hi = S - 1 - it; q.t_count = 1;
             q.x_in = xin; q.x_in_stride = P;
             q.x_out = (it == S - 1) ? a->d_x_out : m->xbuf[it & 1];
-            if (int rc = launch_chain(H, q, mpb, s)) return rc;
+            if (int rc = launch_any(q, s)) return rc;
             xin = q.x_out;
         }
         return 0;
@@ -287,6 +315,10 @@ int ertdiff_model_create(ertdiff_model** out, int device, int param_dim, int hid
          alloc(m->w0xT, (size_t)kPPad * H) && alloc(m->w0tT, (size_t)H * H) &&
          alloc(m->w0cT, (size_t)H * H) && alloc(m->w2p, (size_t)kPPad * H) &&
          alloc(m->b2p, kPPad) && alloc(m->freq, H / 2);
+    if (ok && H == UC_H) {
+        ok = cudaMalloc(&m->w1_pk, UC_H * UC_K1 * 2) == cudaSuccess && cudaMalloc(&m->w2_pk, UC_N2 * UC_H * 2) == cudaSuccess &&
+             cudaMalloc(&m->umma_status, sizeof(int)) == cudaSuccess;
+    }
     if (!ok) {
         ertdiff_model_destroy(m);
         return fail(ERTDIFF_ERR_CUDA, "model_create: cudaMalloc failed");
@@ -311,6 +343,16 @@ int ertdiff_model_last_chain_ms(ertdiff_model* m, float* h_ms) {
     return 0;
 }
 
+int ertdiff_model_umma_status(ertdiff_model* m, int* h_status) {
+    if (int rc = check_model(m, false)) return rc;
+    ERT_REQUIRE(h_status, "umma_status: h_status is NULL");
+    *h_status = 0;
+    if (!m->umma_status) return 0;
+    DeviceGuard g(m->device);
+    ERT_CUDA(cudaMemcpy(h_status, m->umma_status, sizeof(int), cudaMemcpyDeviceToHost));
+    return 0;
+}
+
 int ertdiff_model_destroy(ertdiff_model* m) {
     if (!m) return 0;
     DeviceGuard g(m->device);
@@ -320,6 +362,7 @@ int ertdiff_model_destroy(ertdiff_model* m) {
                      m->b2p, m->freq, m->enc_partial, m->cond_bias, m->cond_emb, m->time_table,
                      m->coef_table, m->xbuf[0], m->xbuf[1]};
     for (float* p : ptrs) cudaFree(p);
+    cudaFree(m->w1_pk); cudaFree(m->w2_pk); cudaFree(m->umma_status);
     if (m->graph_exec) cudaGraphExecDestroy(m->graph_exec);
     delete m;
     return 0;
@@ -342,6 +385,11 @@ int ertdiff_model_load(ertdiff_model* m, const float* const* tensors12, int on_d
         m->raw[0], m->raw[2], m->raw[4], m->raw[6], m->raw[8], m->raw[10], m->raw[11], m->P, m->H,
         m->conv1_w, m->conv2_w, m->w6T, m->wtT, m->w0xT, m->w0tT, m->w0cT, m->w2p, m->b2p);
     ERT_LAUNCH_CHECK("k_pack_weights");
+    if (m->w1_pk) {
+        k_pack_umma_weights<<<(UC_H * UC_K1 + 255) / 256, 256, 0, st>>>(m->w0xT, m->w2p, m->P, m->w1_pk, m->w2_pk);
+        ERT_LAUNCH_CHECK("k_pack_umma_weights");
+        ERT_CUDA(cudaMemsetAsync(m->umma_status, 0, sizeof(int), st));
+    }
     ERT_CUDA(cudaStreamSynchronize(st));
     m->loaded = true;
     m->time_rows_valid = 0;
@@ -435,7 +483,7 @@ int ertdiff_step_coefficients(const float* d_betas, const float* d_alphas,
 int ertdiff_philox_normal(uint64_t seed, uint64_t offset, int64_t member_offset, int64_t B,
                           int32_t P, int32_t draws, float* d_out, void* stream) {
     ERT_REQUIRE(d_out && B > 0 && P > 0 && P <= kPPad && draws > 0, "philox_normal: bad arguments");
-    const int64_t n = (int64_t)((draws + 3) / 4) * B * P;
+    const int64_t n = (int64_t)draws * B * 8;
     k_philox_fill<<<(unsigned)((n + 255) / 256), 256, 0, (cudaStream_t)stream>>>(
         seed, offset, member_offset, B, P, draws, d_out);
     ERT_LAUNCH_CHECK("k_philox_fill");

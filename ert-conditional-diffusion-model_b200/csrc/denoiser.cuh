@@ -162,8 +162,11 @@ __global__ void k_forward_rows(const float* __restrict__ x, const int64_t* __res
 // ------------------------------------------------------------------------------------------
 // Philox4x32-10 counter RNG + Box-Muller: device-side replacement for torch.randn in
 // ECD.py:107,116 (a CPU mt19937 stream cannot be reproduced on the device; parity runs inject
-// noise instead).  Counter = (member, offset_hi, quad<<5 | p, offset_lo), key = seed; one call
-// yields the normals for 4 consecutive draws of one (member, parameter).
+// noise instead).  Stream layout: one Philox call yields the normals of ONE draw (draw 0 = x_T,
+// draw k = k-th in-loop draw) for FOUR consecutive parameters of one member:
+//     counter = (member_lo, offset_hi ^ member_hi, draw * 8 + pquad, offset_lo), key = seed
+// so every kernel -- whatever its thread-to-work mapping -- and any sharding of the members
+// draws identical numbers for (member, draw, parameter).
 __device__ __forceinline__ uint4 philox4x32_10(uint4 c, uint2 k) {
     const uint32_t M0 = 0xD2511F53u, M1 = 0xCD9E8D57u;
 #pragma unroll
@@ -187,10 +190,11 @@ __device__ __forceinline__ void box_muller(uint32_t a, uint32_t b, float& n0, fl
     n1 = r * sn;
 }
 
+// normals of draw `draw` for parameters 4*pquad .. 4*pquad+3 of `member`
 __device__ __forceinline__ void philox_normal4(uint64_t seed, uint64_t offset, int64_t member,
-                                               int p, uint32_t quad, float out[4]) {
+                                               uint32_t draw, uint32_t pquad, float out[4]) {
     const uint4 c = make_uint4((uint32_t)member, (uint32_t)(offset >> 32) ^ (uint32_t)(member >> 32),
-                               (quad << 5) | (uint32_t)p, (uint32_t)offset);
+                               (draw << 3) | pquad, (uint32_t)offset);
     const uint4 r = philox4x32_10(c, make_uint2((uint32_t)seed, (uint32_t)(seed >> 32)));
     box_muller(r.x, r.y, out[0], out[1]);
     box_muller(r.z, r.w, out[2], out[3]);
@@ -200,18 +204,17 @@ __device__ __forceinline__ void philox_normal4(uint64_t seed, uint64_t offset, i
 // mode against the oracle fed with these very draws): out[d][m][p], d = draw index.
 __global__ void k_philox_fill(uint64_t seed, uint64_t offset, int64_t member_offset, int64_t B,
                               int P, int draws, float* __restrict__ out) {
-    const int64_t idx = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;   // over (quad, m, p)
-    const int nquad = (draws + 3) / 4;
-    if (idx >= (int64_t)nquad * B * P) return;
-    const int p = idx % P;
-    const int64_t m = (idx / P) % B;
-    const uint32_t quad = (uint32_t)(idx / ((int64_t)P * B));
+    const int64_t idx = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;   // over (d, m, pquad)
+    if (idx >= (int64_t)draws * B * 8) return;
+    const uint32_t q = (uint32_t)(idx & 7);
+    const int64_t m = (idx >> 3) % B;
+    const uint32_t d = (uint32_t)((idx >> 3) / B);
     float z[4];
-    philox_normal4(seed, offset, member_offset + m, p, quad, z);
+    philox_normal4(seed, offset, member_offset + m, d, q, z);
 #pragma unroll
     for (int u = 0; u < 4; ++u) {
-        const int d = quad * 4 + u;
-        if (d < draws) out[((int64_t)d * B + m) * P + p] = z[u];
+        const int p = 4 * q + u;
+        if (p < P) out[((int64_t)d * B + m) * P + p] = z[u];
     }
 }
 
@@ -291,12 +294,13 @@ constexpr int CHAIN_NB = 4;     // steps per staging block (double-buffered, cp.
 // mode) the injected noise row -- is staged one block of CHAIN_NB steps ahead into shared memory
 // with cp.async (one 16-byte copy per thread per block for the c_t rows), so the dependent chain
 // of a step never waits on L2/HBM latency.
-// Device RNG: RG = min(PARTS,4) lanes of a p-group each run Philox once per 4*RG draws (lane
-// `part` generates quad blk*RG+part) and park the normals in shared memory for the owner lane.
+// Device RNG: every RP = min(H,128)/8 steps the first 8*RP threads run Philox once per member
+// (thread -> (draw within the block, parameter quad)) and park the normals of the next RP draws
+// in shared memory, where the owner lanes pick them up.
 template <int H, int MPB, bool REPLAY, bool TRACE>
 __global__ void __launch_bounds__(H) k_chain(const ChainParams a) {
     constexpr int PARTS = H / 32;
-    constexpr int RG = PARTS < 4 ? PARTS : 4;
+    constexpr int RP = (H >= 128 ? 128 : H) / 8;   // draws per RNG refill
     constexpr int HS_STRIDE = PARTS * 36;   // each 32-wide slice padded to 36: no bank conflicts
     constexpr int CT_STRIDE = H + 4;        // c_t row + [coef, c1, sigma, 0]
     constexpr int ZB = REPLAY ? 1 : 0;
@@ -304,7 +308,7 @@ __global__ void __launch_bounds__(H) k_chain(const ChainParams a) {
     __shared__ __align__(16) float hs[MPB][HS_STRIDE];
     __shared__ __align__(16) float ctbuf[2][CHAIN_NB][CT_STRIDE];
     __shared__ __align__(16) float zbuf[ZB ? 2 : 1][ZB ? CHAIN_NB : 1][ZB ? MPB : 1][kPPad];
-    __shared__ __align__(16) float znorm[ZB ? 1 : MPB][kPPad][ZB ? 4 : 4 * RG];
+    __shared__ __align__(16) float znorm[ZB ? 1 : MPB][ZB ? 1 : RP][kPPad];
 
     const int tid = threadIdx.x;
     const int p = tid / PARTS, part = tid % PARTS;
@@ -379,26 +383,28 @@ __global__ void __launch_bounds__(H) k_chain(const ChainParams a) {
     stage_block(0);
 
     // ---- device RNG ----------------------------------------------------------------------------
-    // draw d of (member m, parameter p) = normal number (d % (4*RG)) of block d / (4*RG); lane
-    // `part` < RG generates quad blk*RG + part and parks its 4 normals at znorm[m][p][4*part..]
+    // draws [blk*RP, blk*RP + RP): thread (dd = tid / 8, q = tid % 8) generates draw blk*RP + dd
+    // for parameters 4q..4q+3 of every member of the CTA -> znorm[m][dd][4q..4q+3]
     auto refill_rng = [&](int d) {
-        const uint32_t blk = (uint32_t)(d >> 2) / RG;
-        if (part < RG) {
+        const uint32_t d0 = ((uint32_t)d / RP) * RP;
+        if (tid < 8 * RP) {
+            const uint32_t dd = tid >> 3, q = tid & 7;
 #pragma unroll
             for (int m = 0; m < MPB; ++m) {
                 float z4[4];
-                philox_normal4(a.seed, a.offset, a.member_offset + mg[m], p & 31, blk * RG + part, z4);
-                sts128(zn_a + 4u * ((m * kPPad + p) * (4 * RG) + 4 * part),
-                       make_float4(z4[0], z4[1], z4[2], z4[3]));
+                philox_normal4(a.seed, a.offset, a.member_offset + mg[m], d0 + dd, q, z4);
+                sts128(zn_a + 4u * ((m * RP + dd) * kPPad + 4 * q), make_float4(z4[0], z4[1], z4[2], z4[3]));
             }
         }
-        __syncwarp();
     };
     auto rng_draw = [&](int d, int m) -> float {
-        return lds32(zn_a + 4u * ((m * kPPad + p) * (4 * RG) + (d & (4 * RG - 1))));
+        return lds32(zn_a + 4u * ((m * RP + (d % RP)) * kPPad + (p & 31)));
     };
     // (a launch without x_in starts a chain: d_first == 1, and draw 0 = x_T sits in the same block)
-    if (!REPLAY) refill_rng(a.x_in ? d_first : 0);
+    if (!REPLAY) {
+        refill_rng(a.x_in ? d_first : 0);
+        __syncthreads();
+    }
 
     // ---- x_T -----------------------------------------------------------------------------------
 #pragma unroll
@@ -427,6 +433,9 @@ __global__ void __launch_bounds__(H) k_chain(const ChainParams a) {
             const int d = d_first + it;          // draw index of this step's noise
             const uint32_t row_a = ct_a + 4u * ((buf * CHAIN_NB + r) * CT_STRIDE);
             const float ct = lds32(row_a + 4u * tid);
+            // next block of normals: written here, published by the barrier after layer 1, first
+            // read after it (the previous block's last reader finished before the last barrier)
+            if (!REPLAY && t > 0 && (d % RP) == 0 && it > 0) refill_rng(d);
             // ---- layer 1 -----------------------------------------------------------------
 #pragma unroll
             for (int m = 0; m < MPB; ++m) {
@@ -442,7 +451,6 @@ __global__ void __launch_bounds__(H) k_chain(const ChainParams a) {
                 sts32(hs_w + 4u * (m * HS_STRIDE), fmaxf((A01.x + A01.y) + (A23.x + A23.y), 0.f));
             }
             __syncthreads();          // hs complete (and, at block starts, staged rows are visible)
-            if (!REPLAY && t > 0 && (d & (4 * RG - 1)) == 0) refill_rng(d);
             // ---- layer 2 + posterior update --------------------------------------------------
             // (loads are issued in the order their consumers need them: h first, scalars last)
             float cf_coef, cf_c1, cf_sigma;

@@ -24,6 +24,9 @@ struct ertdiff_model {
     float* w2p = nullptr;      // [32][H]      mlp.2.weight, rows >= P zero
     float* b2p = nullptr;      // [32]         mlp.2.bias padded
     float* freq = nullptr;     // [H/2]        timestep-embedding frequencies (from the host)
+    unsigned short* w1_pk = nullptr;   // bf16 B operand of GEMM1 (tcgen05 chain, H == 128): 8 KB
+    unsigned short* w2_pk = nullptr;   // bf16 B operand of GEMM2: 8 KB
+    int* umma_status = nullptr;        // device flag: a tcgen05 chain tile timed out
 
     // scratch, grown on demand
     float* enc_partial = nullptr;  size_t enc_partial_n = 0;   // (n_cond, chunks, 64)

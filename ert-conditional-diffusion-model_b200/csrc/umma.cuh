@@ -57,11 +57,11 @@ __device__ __forceinline__ void mbar_init(uint32_t bar, uint32_t count) {
 __device__ __forceinline__ void fence_mbar_init() {
     asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
 }
-// bounded spin: a kernel bug must not hang the GPU -- after ~2^26 polls the wait gives up and
-// reports through *timeout (the host turns it into an error)
+// bounded spin: a kernel bug must not hang the GPU -- after 2^20 polls (each may sleep inside
+// try_wait; a healthy MMA completes within a few polls) the wait gives up and the caller flags it
 __device__ __forceinline__ bool mbar_wait(uint32_t bar, uint32_t parity) {
     uint32_t ok = 0;
-    for (uint32_t spin = 0; spin < (1u << 26); ++spin) {
+    for (uint32_t spin = 0; spin < (1u << 20); ++spin) {
         asm volatile(
             "{\n\t.reg .pred p;\n\t"
             "mbarrier.try_wait.parity.shared::cta.b64 p, [%1], %2;\n\t"

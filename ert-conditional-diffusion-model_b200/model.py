@@ -136,6 +136,12 @@ class ConditionalDiffusionModel(nn.Module):
         """Bracket the persistent chain kernel with CUDA events (bench.py's roofline figure)."""
         _lib.check(_lib.load().ertdiff_model_profile(self.handle(), int(bool(enable))), "model_profile")
 
+    def umma_status(self):
+        """0 unless a tile of the tensor-core chain timed out (its output is NaN)."""
+        st = C.c_int()
+        _lib.check(_lib.load().ertdiff_model_umma_status(self.handle(), C.byref(st)), "umma_status")
+        return int(st.value)
+
     def last_chain_ms(self):
         ms = C.c_float()
         _lib.check(_lib.load().ertdiff_model_last_chain_ms(self.handle(), C.byref(ms)), "last_chain_ms")

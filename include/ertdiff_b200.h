@@ -52,7 +52,8 @@ typedef enum ertdiff_loop_mode {
 /* arithmetic of the denoiser contractions */
 typedef enum ertdiff_precision {
     ERTDIFF_PREC_FP32 = 0,        /* fp32 FFMA everywhere (BASELINE config 2)               */
-    ERTDIFF_PREC_BF16 = 1         /* bf16 operands, fp32 accumulate on tcgen05 (config 3)   */
+    ERTDIFF_PREC_BF16 = 1         /* bf16 operands, fp32 accumulate on tcgen05 (configs 3/4); */
+                                  /* hidden_dim = 128, param_dim <= 29                        */
 } ertdiff_precision;
 
 typedef struct ertdiff_model ertdiff_model;
@@ -75,6 +76,9 @@ int ertdiff_model_destroy(ertdiff_model* m);
  * returns that kernel's duration in milliseconds. */
 int ertdiff_model_profile(ertdiff_model* m, int enable);
 int ertdiff_model_last_chain_ms(ertdiff_model* m, float* h_ms);
+/* diagnostics of the tensor-core chain: *h_status != 0 if a tile's MMA never signalled completion
+ * (that tile's output was filled with NaN).  Synchronises the device. */
+int ertdiff_model_umma_status(ertdiff_model* m, int* h_status);
 /* The 12 tensors in the reference's state_dict order:
  *  0 condition_encoder.0.weight (32,14,3)   1 condition_encoder.0.bias (32)
  *  2 condition_encoder.2.weight (64,32,3)   3 condition_encoder.2.bias (64)

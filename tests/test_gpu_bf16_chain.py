@@ -1,0 +1,116 @@
+"""The tcgen05 (bf16 operands, fp32 accumulate) reverse chain, `precision="bf16"`.
+
+Two references:
+  * an emulation of the kernel's own rounding points (x, W0x, W2, h rounded to bf16; c_t split
+    into bf16 hi+lo; everything else fp32) built from the oracle's pieces -- tight tolerance,
+    this is what validates the kernel's data flow;
+  * the fp32 oracle itself -- loose tolerance, stated below, this is the precision cost of bf16.
+"""
+import numpy as np
+import pytest
+import torch
+import torch.nn.functional as F
+
+import ertdiff_b200 as eb
+from oracle import denoiser_oracle as do
+
+pytestmark = pytest.mark.gpu
+P, C = 29, 14
+
+
+def bf(t):
+    return t.to(torch.bfloat16).to(torch.float64)
+
+
+def emulate_bf16_chain(sd, cond, T, betas, alphas, alpha_bar, noise, num_steps=None, temperature=1.0):
+    """The chain with the tensor-core kernel's rounding points, in float64 arithmetic."""
+    num_steps = T if num_steps is None else num_steps
+    H = sd["time_embed.0.weight"].shape[1]
+    W0 = sd["mlp.0.weight"]
+    W0x, W0t, W0c = W0[:, :P], W0[:, P:P + H], W0[:, P + H:]
+    cemb = do.encode_condition(sd, cond)
+    cb = (F.linear(cemb, W0c) + sd["mlp.0.bias"]).double()
+    x = noise[0].clone()
+    draw = 1
+    eps_trace = {}
+    for t_ in reversed(range(num_steps)):
+        temb = F.relu(F.linear(do.timestep_embedding(torch.tensor([t_]), H), sd["time_embed.0.weight"],
+                               sd["time_embed.0.bias"]))
+        ct = F.linear(temb, W0t)[0]
+        ct_hi = ct.to(torch.bfloat16).float()
+        ct_lo = (ct - ct_hi).to(torch.bfloat16).float()
+        pre = bf(x) @ bf(W0x).t() + (ct_hi.double() + ct_lo.double()) + cb
+        h = torch.relu(pre.float())                       # fp32 accumulator + fp32 c_b add
+        eps = (bf(h) @ bf(sd["mlp.2.weight"]).t()).float() + sd["mlp.2.bias"]
+        eps_trace[t_] = eps
+        coef, c1, sigma = do.step_coefficients(betas, alphas, alpha_bar, t_, temperature)
+        z = None
+        if t_ > 0:
+            z = noise[draw]
+            draw += 1
+        x = do.posterior_update(x, eps, z, coef, c1, sigma)
+    return x, eps_trace
+
+
+@pytest.mark.parametrize("B,distinct", [(128, False), (200, False), (37, True), (300, True)])
+def test_bf16_chain_matches_its_emulation(gpu_model, ref_state_dict, cuda_dev, B, distinct):
+    T = 24
+    g = torch.Generator().manual_seed(B)
+    cond = torch.rand(B if distinct else 1, C, 400, generator=g)
+    cond_b = cond if distinct else cond.expand(B, C, 400)
+    noise = torch.randn(T, B, P, generator=g)
+    b, a, ab = do.diffusion_schedule(T)
+    x_gpu, eps_gpu = eb.run_chain(gpu_model, cond_b.to(cuda_dev), T, b, a, ab, cuda_dev, noise=noise.to(cuda_dev),
+                                  precision="bf16", return_eps=True)
+    assert gpu_model.umma_status() == 0
+    x_emu, eps_emu = emulate_bf16_chain(ref_state_dict, cond_b, T, b, a, ab, noise)
+    # first step: identical inputs, so only fp32 accumulation order differs
+    e0 = eps_gpu[T - 1].cpu()
+    assert (e0 - eps_emu[T - 1]).abs().max() <= 2e-5 * eps_emu[T - 1].abs().max() + 2e-6
+    # whole chain: a 1-ulp difference can flip a bf16 rounding of x or h now and then
+    scale = x_emu.abs().max().item()
+    assert (x_gpu.cpu() - x_emu).abs().max().item() <= 2e-3 * scale, (x_gpu.cpu() - x_emu).abs().max().item() / scale
+
+
+def test_bf16_chain_vs_fp32_oracle_tolerance(gpu_model, ref_state_dict, cuda_dev, golden):
+    # BASELINE config 1 inputs.  bf16 operands carry 8 mantissa bits: predicted noise is off by up to
+    # ~1e-2 of its scale per step, and the final fields by a few percent of theirs after 50 steps.
+    c = golden("chain_cfg1.npz")
+    cond = torch.from_numpy(c["condition"]).to(cuda_dev).expand(16, C, 4693)
+    noise = torch.from_numpy(c["noise"]).to(cuda_dev)
+    b, a, ab = eb.get_diffusion_schedule(50)
+    x, eps = eb.run_chain(gpu_model, cond, 50, b, a, ab, cuda_dev, noise=noise, precision="bf16", return_eps=True)
+    e49 = eps[49].cpu().numpy()
+    assert np.abs(e49 - c["eps_t49"]).max() <= 2e-2 * np.abs(c["eps_t49"]).max()
+    assert np.abs(x.cpu().numpy() - c["x0"]).max() <= 5e-2 * np.abs(c["x0"]).max()
+    x32 = eb.run_chain(gpu_model, cond, 50, b, a, ab, cuda_dev, noise=noise)
+    assert np.abs(x32.cpu().numpy() - c["x0"]).max() <= 1e-4 + 1e-3 * np.abs(c["x0"]).max()
+
+
+def test_bf16_chain_rng_modes_and_loop_modes(gpu_model, cuda_dev):
+    B, T = 260, 21
+    cond = torch.rand(1, C, 300, generator=torch.Generator().manual_seed(3)).to(cuda_dev).expand(B, C, 300)
+    b, a, ab = eb.get_diffusion_schedule(T)
+    x_rng = eb.run_chain(gpu_model, cond, T, b, a, ab, cuda_dev, seed=11, offset=0, precision="bf16")
+    draws = eb.philox_normal(11, 0, B, P, T, cuda_dev)
+    x_rep = eb.run_chain(gpu_model, cond, T, b, a, ab, cuda_dev, noise=draws, precision="bf16")
+    assert torch.equal(x_rng, x_rep)                 # device RNG == replay of the very same draws
+    for mode in ("graph", "stream"):
+        assert torch.equal(x_rng, eb.run_chain(gpu_model, cond, T, b, a, ab, cuda_dev, seed=11, offset=0,
+                                               precision="bf16", loop_mode=mode)), mode
+    # the fp32 kernel draws the same numbers for (member, draw, parameter)
+    x32_rng = eb.run_chain(gpu_model, cond, T, b, a, ab, cuda_dev, seed=11, offset=0)
+    x32_rep = eb.run_chain(gpu_model, cond, T, b, a, ab, cuda_dev, noise=draws)
+    assert torch.equal(x32_rng, x32_rep)
+    # shards see the same streams
+    part = eb.run_chain(gpu_model, cond[:100], T, b, a, ab, cuda_dev, seed=11, offset=0, precision="bf16",
+                        member_offset=160)
+    assert torch.equal(part, x_rng[160:260])
+    assert gpu_model.umma_status() == 0
+
+
+def test_bf16_unsupported_shapes_fail_loudly(cuda_dev):
+    m = eb.ConditionalDiffusionModel(29, 256).to(cuda_dev)
+    b, a, ab = eb.get_diffusion_schedule(5)
+    with pytest.raises(eb.ErtdiffError, match="hidden_dim = 128"):
+        eb.run_chain(m, torch.rand(2, C, 50, device=cuda_dev), 5, b, a, ab, cuda_dev, seed=1, precision="bf16")
