@@ -168,7 +168,7 @@ def run_reference(args):
 
 def workload_config(args, members_per_gpu):
     return {"workload": f"BASELINE configs[1]: {members_per_gpu} members/GPU, T={args.T} full DDPM chain, "
-                        f"fp32, grid 14x{L}, {'distinct' if args.distinct_conditions else 'one shared'} "
+                        f"{args.precision}, grid 14x{L}, {'distinct' if args.distinct_conditions else 'one shared'} "
                         "condition, + ensemble mean/std/var, 5 percentiles, KDE mode",
             "members_per_gpu": members_per_gpu, "T": args.T, "param_dim": P, "hidden_dim": H,
             "loop_mode": args.loop_mode, "rng": "device Philox4x32-10",
@@ -214,7 +214,7 @@ def run_ours(args):
     def step_device(i):
         """inputs resident in HBM"""
         x = eb.run_chain(model, cond_dev_b, T, *sched_dev, dev, seed=1234, offset=4 * i,
-                         member_offset=rank * members, loop_mode=args.loop_mode)
+                         member_offset=rank * members, loop_mode=args.loop_mode, precision=args.precision)
         if world > 1:
             x = eb.parallel.gather_members(x, total)
         return x, stats(x)
@@ -224,9 +224,9 @@ def run_ours(args):
         c = cond_pinned.to(dev, non_blocking=True)
         c = c if args.distinct_conditions else c.expand(members, C, L)
         x = eb.sample_model(model, c, T, betas, alphas, alpha_bar, P, dev, seed=1234 + i,
-                            loop_mode=args.loop_mode) if world == 1 else \
+                            loop_mode=args.loop_mode, precision=args.precision) if world == 1 else \
             eb.run_chain(model, c, T, betas, alphas, alpha_bar, dev, seed=1234, offset=4 * i,
-                         member_offset=rank * members, loop_mode=args.loop_mode)
+                         member_offset=rank * members, loop_mode=args.loop_mode, precision=args.precision)
         if world > 1:
             x = eb.parallel.gather_members(x, total)
         st = stats(x)
@@ -294,7 +294,7 @@ def run_ours(args):
             "metric": "posterior_samples_per_sec_full_chain", "value": value, "unit": "samples/s",
             "n_gpus": world, "steps": args.steps, "warmup": args.warmup,
             "ms_per_step": ms_dev / args.steps, "higher_is_better": True, "scaling": "weak",
-            "vs_baseline": None, "dtype": "f32", "data": "synthetic",
+            "vs_baseline": None, "dtype": "f32" if args.precision == "fp32" else "bf16", "data": "synthetic",
             "config": workload_config(args, members),
             "ms_per_denoiser_step": (float(np.mean(chain_ms)) / T) if chain_ms else ms_dev / args.steps / T,
             "e2e": {"value": e2e_value, "unit": "samples/s", "h2d_bytes_per_step": int(h2d),
@@ -310,7 +310,8 @@ def run_ours(args):
             peak = peaks["bf16_tflops_sustained"]
             fp32_peak = 148 * 128 * 2 * (clocks["sm_mhz"] or 1965.0) * 1e6 / 1e12 if clocks else None
             line["roofline"] = {
-                "kernel": "k_chain (persistent reverse loop, fp32 FFMA)", "bound": "tensor",
+                "kernel": "k_chain (persistent reverse loop, fp32 FFMA2)" if args.precision == "fp32"
+                          else "k_chain_umma (persistent reverse loop, tcgen05 bf16)", "bound": "tensor",
                 "achieved": achieved, "peak": peak, "unit": "TFLOP/s", "frac": achieved / peak,
                 "traffic": None, "peak_source": peaks["source"] + ", sustained bf16",
                 "kernel_ms": k_ms, "flop_per_launch": flops,
@@ -348,6 +349,8 @@ def main():
     ap.add_argument("--T", type=int, default=1000)
     ap.add_argument("--loop-mode", default="persistent", choices=["persistent", "graph", "stream"])
     ap.add_argument("--distinct-conditions", action="store_true")
+    ap.add_argument("--precision", default="fp32", choices=["fp32", "bf16"],
+                    help="fp32 = CUDA-core FFMA chain (BASELINE config 2); bf16 = tcgen05 chain (configs 3/4)")
     ap.add_argument("--ref-sample-steps", type=int, default=10,
                     help="steps of the T-step chain the CPU arm actually runs per sample")
     ap.add_argument("--no-cpu-baseline", action="store_true")
