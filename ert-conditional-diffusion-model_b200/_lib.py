@@ -9,7 +9,8 @@ import ctypes as C
 import os
 
 _HERE = os.path.dirname(os.path.abspath(__file__))
-LIB_PATH = os.path.join(_HERE, "libertdiff_b200.so")
+# ERTDIFF_B200_LIB: development override (e.g. the -DUC_TIMING=1 build of scripts/gpu_umma_quick.sh)
+LIB_PATH = os.environ.get("ERTDIFF_B200_LIB") or os.path.join(_HERE, "libertdiff_b200.so")
 
 F32, F64 = 0, 1
 LOOP_PERSISTENT, LOOP_GRAPH, LOOP_STREAM = 0, 1, 2
@@ -46,6 +47,7 @@ SIGNATURES = {
     "ertdiff_model_profile": (C.c_int, [C.c_void_p, C.c_int]),
     "ertdiff_model_last_chain_ms": (C.c_int, [C.c_void_p, C.POINTER(C.c_float)]),
     "ertdiff_model_umma_status": (C.c_int, [C.c_void_p, C.POINTER(C.c_int)]),
+    "ertdiff_debug_umma_timing": (C.c_int, [C.c_void_p, C.c_int, C.POINTER(C.c_int64)]),
     "ertdiff_model_load": (C.c_int, [C.c_void_p, C.POINTER(C.c_void_p), C.c_int, C.c_void_p, C.c_void_p]),
     "ertdiff_model_export": (C.c_int, [C.c_void_p, C.POINTER(C.c_void_p), C.c_int, C.c_void_p]),
     "ertdiff_forward": (C.c_int, [C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p, C.c_int64,

@@ -179,31 +179,30 @@ static int run_chain(ertdiff_model* m, const ertdiff_chain_args* a, const float*
     p.coef = m->coef_table; p.cond_bias = d_cond_bias;
     p.x_in = a->d_x_T; p.x_in_stride = P;
     p.noise = a->d_noise; p.noise_B = nstride;
-    p.seed = a->seed; p.offset = a->offset; p.member_offset = a->member_offset;
+    p.keys = make_philox_keys(a->seed); p.offset = a->offset; p.member_offset = a->member_offset;
     p.x_out = a->d_x_out; p.eps_trace = a->d_eps_trace; p.P = P;
     const int mpb = pick_mpb(a->B, H);
 
     auto launch_any = [&](const ChainParams& q, cudaStream_t s2) -> int {
         if (!use_umma) return launch_chain(H, q, mpb, s2);
+        UmmaChainExtra ex{reinterpret_cast<const uint4*>(m->w1_pk), reinterpret_cast<const uint4*>(m->w2_pk), m->umma_status,
+                          m->umma_timing_on ? m->umma_timing : nullptr};
+        const unsigned grid = (unsigned)((q.B + UC_M - 1) / UC_M);
+        const size_t smem = sizeof(UmmaChainSmem);
+        const int variant = (q.noise != nullptr ? 4 : 0) | (q.eps_trace != nullptr ? 2 : 0) | (q.n_cond == 1 ? 1 : 0);
+        using Kern = void (*)(const ChainParams, const UmmaChainExtra);
+        static const Kern kerns[8] = {
+            k_chain_umma<false, false, false>, k_chain_umma<false, false, true>,
+            k_chain_umma<false, true, false>,  k_chain_umma<false, true, true>,
+            k_chain_umma<true, false, false>,  k_chain_umma<true, false, true>,
+            k_chain_umma<true, true, false>,   k_chain_umma<true, true, true>};
         static bool attr_set = false;
         if (!attr_set) {
-            ERT_CUDA(cudaFuncSetAttribute(k_chain_umma<false, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)sizeof(UmmaChainSmem)));
-            ERT_CUDA(cudaFuncSetAttribute(k_chain_umma<false, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)sizeof(UmmaChainSmem)));
-            ERT_CUDA(cudaFuncSetAttribute(k_chain_umma<true, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)sizeof(UmmaChainSmem)));
-            ERT_CUDA(cudaFuncSetAttribute(k_chain_umma<true, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)sizeof(UmmaChainSmem)));
+            for (Kern k : kerns)
+                ERT_CUDA(cudaFuncSetAttribute(k, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
             attr_set = true;
         }
-        UmmaChainExtra ex{reinterpret_cast<const uint4*>(m->w1_pk), reinterpret_cast<const uint4*>(m->w2_pk), m->umma_status};
-        const unsigned grid = (unsigned)((q.B + UC_M - 1) / UC_M);
-        const bool replay = q.noise != nullptr, trace = q.eps_trace != nullptr;
-        const size_t smem = sizeof(UmmaChainSmem);
-        if (replay) {
-            if (trace) k_chain_umma<true, true><<<grid, UC_M, smem, s2>>>(q, ex);
-            else k_chain_umma<true, false><<<grid, UC_M, smem, s2>>>(q, ex);
-        } else {
-            if (trace) k_chain_umma<false, true><<<grid, UC_M, smem, s2>>>(q, ex);
-            else k_chain_umma<false, false><<<grid, UC_M, smem, s2>>>(q, ex);
-        }
+        kerns[variant]<<<grid, UC_THREADS, smem, s2>>>(q, ex);
         ERT_LAUNCH_CHECK("k_chain_umma");
         return 0;
     };
@@ -317,7 +316,8 @@ int ertdiff_model_create(ertdiff_model** out, int device, int param_dim, int hid
          alloc(m->b2p, kPPad) && alloc(m->freq, H / 2);
     if (ok && H == UC_H) {
         ok = cudaMalloc(&m->w1_pk, UC_H * UC_K1 * 2) == cudaSuccess && cudaMalloc(&m->w2_pk, UC_N2 * UC_H * 2) == cudaSuccess &&
-             cudaMalloc(&m->umma_status, sizeof(int)) == cudaSuccess;
+             cudaMalloc(&m->umma_status, sizeof(int)) == cudaSuccess &&
+             cudaMalloc(&m->umma_timing, 16 * sizeof(long long)) == cudaSuccess;
     }
     if (!ok) {
         ertdiff_model_destroy(m);
@@ -353,6 +353,16 @@ int ertdiff_model_umma_status(ertdiff_model* m, int* h_status) {
     return 0;
 }
 
+int ertdiff_debug_umma_timing(ertdiff_model* m, int enable, int64_t* h_out16) {
+    if (int rc = check_model(m, false)) return rc;
+    if (!m->umma_timing) return fail(ERTDIFF_ERR_UNSUPPORTED, "debug_umma_timing: the tcgen05 chain needs hidden_dim = 128");
+    DeviceGuard g(m->device);
+    if (h_out16) ERT_CUDA(cudaMemcpy(h_out16, m->umma_timing, 16 * sizeof(long long), cudaMemcpyDeviceToHost));
+    m->umma_timing_on = enable != 0;
+    if (enable) ERT_CUDA(cudaMemset(m->umma_timing, 0, 16 * sizeof(long long)));
+    return 0;
+}
+
 int ertdiff_model_destroy(ertdiff_model* m) {
     if (!m) return 0;
     DeviceGuard g(m->device);
@@ -362,7 +372,7 @@ int ertdiff_model_destroy(ertdiff_model* m) {
                      m->b2p, m->freq, m->enc_partial, m->cond_bias, m->cond_emb, m->time_table,
                      m->coef_table, m->xbuf[0], m->xbuf[1]};
     for (float* p : ptrs) cudaFree(p);
-    cudaFree(m->w1_pk); cudaFree(m->w2_pk); cudaFree(m->umma_status);
+    cudaFree(m->w1_pk); cudaFree(m->w2_pk); cudaFree(m->umma_status); cudaFree(m->umma_timing);
     if (m->graph_exec) cudaGraphExecDestroy(m->graph_exec);
     delete m;
     return 0;
@@ -485,7 +495,7 @@ int ertdiff_philox_normal(uint64_t seed, uint64_t offset, int64_t member_offset,
     ERT_REQUIRE(d_out && B > 0 && P > 0 && P <= kPPad && draws > 0, "philox_normal: bad arguments");
     const int64_t n = (int64_t)draws * B * 8;
     k_philox_fill<<<(unsigned)((n + 255) / 256), 256, 0, (cudaStream_t)stream>>>(
-        seed, offset, member_offset, B, P, draws, d_out);
+        make_philox_keys(seed), offset, member_offset, B, P, draws, d_out);
     ERT_LAUNCH_CHECK("k_philox_fill");
     return 0;
 }

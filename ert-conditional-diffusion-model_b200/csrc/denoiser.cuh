@@ -167,42 +167,81 @@ __global__ void k_forward_rows(const float* __restrict__ x, const int64_t* __res
 //     counter = (member_lo, offset_hi ^ member_hi, draw * 8 + pquad, offset_lo), key = seed
 // so every kernel -- whatever its thread-to-work mapping -- and any sharding of the members
 // draws identical numbers for (member, draw, parameter).
-__device__ __forceinline__ uint4 philox4x32_10(uint4 c, uint2 k) {
+__device__ __forceinline__ void mul_wide_u32(uint32_t a, uint32_t b, uint32_t& hi, uint32_t& lo) {
+    // one IMAD.WIDE.U32 for both halves of the product
+    asm("{\n\t.reg .u64 p;\n\tmul.wide.u32 p, %2, %3;\n\tmov.b64 {%0, %1}, p;\n\t}"
+        : "=r"(lo), "=r"(hi) : "r"(a), "r"(b));
+}
+
+// The ten round keys of a stream depend only on the seed: the host expands them once and they
+// travel as kernel parameters, so every round reads its key straight from the constant bank.
+struct PhiloxKeys {
+    uint32_t k[20];
+};
+inline PhiloxKeys make_philox_keys(uint64_t seed) {
+    PhiloxKeys ks;
+    uint32_t k0 = (uint32_t)seed, k1 = (uint32_t)(seed >> 32);
+    for (int r = 0; r < 10; ++r) {
+        ks.k[2 * r] = k0; ks.k[2 * r + 1] = k1;
+        k0 += 0x9E3779B9u; k1 += 0xBB67AE85u;
+    }
+    return ks;
+}
+
+__device__ __forceinline__ uint4 philox4x32_10(uint4 c, const PhiloxKeys& ks) {
     const uint32_t M0 = 0xD2511F53u, M1 = 0xCD9E8D57u;
 #pragma unroll
     for (int r = 0; r < 10; ++r) {
-        const uint32_t hi0 = __umulhi(M0, c.x), lo0 = M0 * c.x;
-        const uint32_t hi1 = __umulhi(M1, c.z), lo1 = M1 * c.z;
-        c = make_uint4(hi1 ^ c.y ^ k.x, lo1, hi0 ^ c.w ^ k.y, lo0);
-        k.x += 0x9E3779B9u;
-        k.y += 0xBB67AE85u;
+        uint32_t hi0, lo0, hi1, lo1;
+        mul_wide_u32(M0, c.x, hi0, lo0);
+        mul_wide_u32(M1, c.z, hi1, lo1);
+        c = make_uint4(hi1 ^ c.y ^ ks.k[2 * r], lo1, hi0 ^ c.w ^ ks.k[2 * r + 1], lo0);
     }
     return c;
 }
 
+// Box-Muller on the special-function unit: lg2 / sqrt / sin / cos are single MUFU instructions
+// (abs. error ~1e-6 on a N(0,1) variate, far below what any statistic of the chain resolves).
+// The generator runs once per member, step and parameter, so its instruction count -- not its
+// last bit -- is what the chain kernels pay for.  Every kernel calls this one function, hence all
+// of them (and k_philox_fill, which the parity tests replay) produce bit-identical draws.
 __device__ __forceinline__ void box_muller(uint32_t a, uint32_t b, float& n0, float& n1) {
     const float u1 = fmaf((float)a, 2.3283064365386963e-10f, 1.1641532182693481e-10f);  // (0,1]
-    const float u2 = fmaf((float)b, 2.3283064365386963e-10f, 1.1641532182693481e-10f);
-    const float r = sqrtf(-2.0f * logf(u1));
-    float sn, cs;
-    sincospif(2.0f * u2, &sn, &cs);
+    // angle = 2*pi*u2 - pi in (-pi, pi]: the MUFU sin/cos need no further range reduction
+    const float ang = fmaf((float)b, 1.4629180792671596e-09f, -3.1415926528583304f);
+    float lg, r, sn, cs;
+    asm("lg2.approx.ftz.f32 %0, %1;" : "=f"(lg) : "f"(u1));            // u1 >= 2^-33: never denormal
+    asm("sqrt.approx.ftz.f32 %0, %1;" : "=f"(r) : "f"(-1.3862943611198906f * lg));
+    asm("sin.approx.ftz.f32 %0, %1;" : "=f"(sn) : "f"(ang));
+    asm("cos.approx.ftz.f32 %0, %1;" : "=f"(cs) : "f"(ang));
     n0 = r * cs;
     n1 = r * sn;
 }
 
 // normals of draw `draw` for parameters 4*pquad .. 4*pquad+3 of `member`
-__device__ __forceinline__ void philox_normal4(uint64_t seed, uint64_t offset, int64_t member,
+__device__ __forceinline__ void philox_normal4(const PhiloxKeys& ks, uint64_t offset, int64_t member,
                                                uint32_t draw, uint32_t pquad, float out[4]) {
     const uint4 c = make_uint4((uint32_t)member, (uint32_t)(offset >> 32) ^ (uint32_t)(member >> 32),
                                (draw << 3) | pquad, (uint32_t)offset);
-    const uint4 r = philox4x32_10(c, make_uint2((uint32_t)seed, (uint32_t)(seed >> 32)));
+    const uint4 r = philox4x32_10(c, ks);
     box_muller(r.x, r.y, out[0], out[1]);
     box_muller(r.z, r.w, out[2], out[3]);
+}
+// two neighbouring quads at once: four independent multiply chains keep the pipes busy
+__device__ __forceinline__ void philox_normal8(const PhiloxKeys& ks, uint64_t offset, int64_t member,
+                                               uint32_t draw, uint32_t pquad0, float out[8]) {
+    const uint32_t cy = (uint32_t)(offset >> 32) ^ (uint32_t)(member >> 32);
+    const uint4 ra = philox4x32_10(make_uint4((uint32_t)member, cy, (draw << 3) | pquad0, (uint32_t)offset), ks);
+    const uint4 rb = philox4x32_10(make_uint4((uint32_t)member, cy, (draw << 3) | (pquad0 + 1), (uint32_t)offset), ks);
+    box_muller(ra.x, ra.y, out[0], out[1]);
+    box_muller(ra.z, ra.w, out[2], out[3]);
+    box_muller(rb.x, rb.y, out[4], out[5]);
+    box_muller(rb.z, rb.w, out[6], out[7]);
 }
 
 // standalone generator with the chain's stream layout (tests compare the chain in device-RNG
 // mode against the oracle fed with these very draws): out[d][m][p], d = draw index.
-__global__ void k_philox_fill(uint64_t seed, uint64_t offset, int64_t member_offset, int64_t B,
+__global__ void k_philox_fill(const PhiloxKeys keys, uint64_t offset, int64_t member_offset, int64_t B,
                               int P, int draws, float* __restrict__ out) {
     const int64_t idx = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;   // over (d, m, pquad)
     if (idx >= (int64_t)draws * B * 8) return;
@@ -210,7 +249,7 @@ __global__ void k_philox_fill(uint64_t seed, uint64_t offset, int64_t member_off
     const int64_t m = (idx >> 3) % B;
     const uint32_t d = (uint32_t)((idx >> 3) / B);
     float z[4];
-    philox_normal4(seed, offset, member_offset + m, d, q, z);
+    philox_normal4(keys, offset, member_offset + m, d, q, z);
 #pragma unroll
     for (int u = 0; u < 4; ++u) {
         const int p = 4 * q + u;
@@ -235,7 +274,8 @@ struct ChainParams {
     int64_t x_in_stride;   // elements between rows of x_in
     const float* noise;    // (S-1, noise_B, P) or nullptr -> Philox
     int64_t noise_B;
-    uint64_t seed, offset;
+    PhiloxKeys keys;       // round keys of the device RNG stream (make_philox_keys(seed))
+    uint64_t offset;
     int64_t member_offset;
     float* x_out;          // (B,P)
     float* eps_trace;      // (S,B,P) indexed by t, or nullptr
@@ -392,7 +432,7 @@ __global__ void __launch_bounds__(H) k_chain(const ChainParams a) {
 #pragma unroll
             for (int m = 0; m < MPB; ++m) {
                 float z4[4];
-                philox_normal4(a.seed, a.offset, a.member_offset + mg[m], d0 + dd, q, z4);
+                philox_normal4(a.keys, a.offset, a.member_offset + mg[m], d0 + dd, q, z4);
                 sts128(zn_a + 4u * ((m * RP + dd) * kPPad + 4 * q), make_float4(z4[0], z4[1], z4[2], z4[3]));
             }
         }

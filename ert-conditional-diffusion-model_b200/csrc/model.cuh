@@ -27,6 +27,8 @@ struct ertdiff_model {
     unsigned short* w1_pk = nullptr;   // bf16 B operand of GEMM1 (tcgen05 chain, H == 128): 8 KB
     unsigned short* w2_pk = nullptr;   // bf16 B operand of GEMM2: 8 KB
     int* umma_status = nullptr;        // device flag: a tcgen05 chain tile timed out
+    long long* umma_timing = nullptr;  // 16 int64: phase cycle sums of CTA 0 (debug aid)
+    bool umma_timing_on = false;
 
     // scratch, grown on demand
     float* enc_partial = nullptr;  size_t enc_partial_n = 0;   // (n_cond, chunks, 64)

@@ -121,10 +121,15 @@ class ConditionalDiffusionModel(nn.Module):
                 _lib.load().ertdiff_model_destroy(self._handle)
             except Exception:
                 pass
-            self._handle = None
+            # object.__setattr__: nn.Module.__setattr__ touches module globals that are already
+            # gone when this runs from __del__ at interpreter shutdown
+            object.__setattr__(self, "_handle", None)
 
     def __del__(self):
-        self._release()
+        try:
+            self._release()
+        except Exception:
+            pass
 
     def __getstate__(self):
         # the device handle is not copyable/picklable; a copy re-creates its own on first use
@@ -141,6 +146,13 @@ class ConditionalDiffusionModel(nn.Module):
         st = C.c_int()
         _lib.check(_lib.load().ertdiff_model_umma_status(self.handle(), C.byref(st)), "umma_status")
         return int(st.value)
+
+    def umma_timing(self, enable=True):
+        """Development aid (``ertdiff_debug_umma_timing``): returns the 16 cycle sums recorded by
+        CTA 0 of the last tensor-core chain launch, then switches the recording on/off."""
+        out = (C.c_int64 * 16)()
+        _lib.check(_lib.load().ertdiff_debug_umma_timing(self.handle(), int(bool(enable)), out), "umma_timing")
+        return [int(v) for v in out]
 
     def last_chain_ms(self):
         ms = C.c_float()

@@ -79,6 +79,12 @@ int ertdiff_model_last_chain_ms(ertdiff_model* m, float* h_ms);
 /* diagnostics of the tensor-core chain: *h_status != 0 if a tile's MMA never signalled completion
  * (that tile's output was filled with NaN).  Synchronises the device. */
 int ertdiff_model_umma_status(ertdiff_model* m, int* h_status);
+/* development aid for the tensor-core chain: reads (if h_out16 != NULL) the 16 int64 cycle sums
+ * CTA 0 recorded during the last chain launch -- worker thread 0: [0] noise half 1, [1] wait D,
+ * [2] epilogue 1, [3] noise half 2, [4] wait E, [5] epilogue 2 + operand publish; MMA thread:
+ * [8] wait X, [9] GEMM1 issue, [10] waits on H + GEMM2 issue; [15] steps -- then enables or
+ * disables the recording for the following launches.  Synchronises the device. */
+int ertdiff_debug_umma_timing(ertdiff_model* m, int enable, int64_t* h_out16);
 /* The 12 tensors in the reference's state_dict order:
  *  0 condition_encoder.0.weight (32,14,3)   1 condition_encoder.0.bias (32)
  *  2 condition_encoder.2.weight (64,32,3)   3 condition_encoder.2.bias (64)

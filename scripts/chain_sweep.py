@@ -1,0 +1,49 @@
+#!/usr/bin/env python
+"""Chain-kernel sweep on one GPU: per (members, precision) the persistent kernel's duration (CUDA
+events inside the library), ms per denoiser step and the FLOP rate.  Development aid, not a bench
+line:  python scripts/chain_sweep.py [--T 1000] [--members 256,1024,...] [--distinct]"""
+import argparse
+import os
+import sys
+
+import torch
+
+sys.path.insert(0, os.path.dirname(os.path.dirname(os.path.abspath(__file__))))
+import ertdiff_b200 as eb  # noqa: E402
+
+ap = argparse.ArgumentParser()
+ap.add_argument("--T", type=int, default=1000)
+ap.add_argument("--members", default="256,1024,4096,8192,18944,37888")
+ap.add_argument("--precisions", default="fp32,bf16")
+ap.add_argument("--distinct", action="store_true")
+ap.add_argument("--reps", type=int, default=3)
+ap.add_argument("--timing", action="store_true")
+a = ap.parse_args()
+dev = torch.device("cuda", 0)
+P, H, C, L = 29, 128, 14, 4693
+torch.manual_seed(0)
+model = eb.ConditionalDiffusionModel(P, H).to(dev).eval()
+sched = [t.to(dev) for t in eb.get_diffusion_schedule(a.T)]
+model.profile_chain(True)
+for B in [int(v) for v in a.members.split(",")]:
+    n = min(B, 512) if a.distinct else 1
+    cond = torch.rand(n, C, L if not a.distinct else 256, device=dev)
+    cond_b = cond.expand(B, C, cond.size(2)) if n == 1 else cond
+    for prec in a.precisions.split(","):
+        ms = []
+        for i in range(a.reps + 1):
+            x = eb.run_chain(model, cond_b, a.T, *sched, dev, seed=7, offset=i, precision=prec,
+                             n_members=B)
+            ms.append(model.last_chain_ms())
+        assert torch.isfinite(x).all()
+        best = min(ms[1:])
+        if prec == "bf16" and a.timing:
+            model.umma_timing(True)
+            eb.run_chain(model, cond_b, a.T, *sched, dev, seed=7, offset=0, precision=prec, n_members=B)
+            tm = model.umma_timing(False)
+            n = max(tm[15], 1)
+            names = ["rng1", "waitD", "epi1", "rng2", "waitE", "epi2+pub", "", "", "mma:waitX", "mma:gemm1", "mma:waitH+gemm2"]
+            print("   cycles/step:", {k: round(tm[i] / n) for i, k in enumerate(names) if k}, flush=True)
+        print(f"B {B:6d} {prec} chain_ms {best:8.3f} us/step {best / a.T * 1e3:7.3f} "
+              f"samples/s {B / best * 1e3:12.0f} TFLOP/s {B * a.T * 14848 / best / 1e9:7.2f} "
+              f"|x|max {x.abs().max().item():.2f} umma_status {model.umma_status()}", flush=True)

@@ -22,14 +22,26 @@ def bf(t):
     return t.to(torch.bfloat16).to(torch.float64)
 
 
-def emulate_bf16_chain(sd, cond, T, betas, alphas, alpha_bar, noise, num_steps=None, temperature=1.0):
-    """The chain with the tensor-core kernel's rounding points, in float64 arithmetic."""
+def split3(v):
+    """v (fp32) as the sum of three bf16 terms, the way the kernel feeds it to the MMA."""
+    hi = v.to(torch.bfloat16).float()
+    r1 = v - hi
+    mid = r1.to(torch.bfloat16).float()
+    lo = (r1 - mid).to(torch.bfloat16).float()
+    return hi.double() + mid.double() + lo.double()
+
+
+def emulate_bf16_chain(sd, cond, T, betas, alphas, alpha_bar, noise, num_steps=None, temperature=1.0,
+                       shared=False):
+    """The chain with the tensor-core kernel's rounding points, in float64 arithmetic.
+    shared=True: one condition for all members -- c_b is added to c_t in fp32 and rides through the
+    MMA with it; otherwise c_b is added to the fp32 accumulator in the epilogue."""
     num_steps = T if num_steps is None else num_steps
     H = sd["time_embed.0.weight"].shape[1]
     W0 = sd["mlp.0.weight"]
     W0x, W0t, W0c = W0[:, :P], W0[:, P:P + H], W0[:, P + H:]
     cemb = do.encode_condition(sd, cond)
-    cb = (F.linear(cemb, W0c) + sd["mlp.0.bias"]).double()
+    cb = F.linear(cemb, W0c) + sd["mlp.0.bias"]
     x = noise[0].clone()
     draw = 1
     eps_trace = {}
@@ -37,10 +49,11 @@ def emulate_bf16_chain(sd, cond, T, betas, alphas, alpha_bar, noise, num_steps=N
         temb = F.relu(F.linear(do.timestep_embedding(torch.tensor([t_]), H), sd["time_embed.0.weight"],
                                sd["time_embed.0.bias"]))
         ct = F.linear(temb, W0t)[0]
-        ct_hi = ct.to(torch.bfloat16).float()
-        ct_lo = (ct - ct_hi).to(torch.bfloat16).float()
-        pre = bf(x) @ bf(W0x).t() + (ct_hi.double() + ct_lo.double()) + cb
-        h = torch.relu(pre.float())                       # fp32 accumulator + fp32 c_b add
+        if shared:
+            pre = (bf(x) @ bf(W0x).t() + split3(ct + cb[0])).float()
+        else:
+            pre = (bf(x) @ bf(W0x).t() + split3(ct)).float() + cb
+        h = torch.relu(pre)
         eps = (bf(h) @ bf(sd["mlp.2.weight"]).t()).float() + sd["mlp.2.bias"]
         eps_trace[t_] = eps
         coef, c1, sigma = do.step_coefficients(betas, alphas, alpha_bar, t_, temperature)
@@ -63,7 +76,7 @@ def test_bf16_chain_matches_its_emulation(gpu_model, ref_state_dict, cuda_dev, B
     x_gpu, eps_gpu = eb.run_chain(gpu_model, cond_b.to(cuda_dev), T, b, a, ab, cuda_dev, noise=noise.to(cuda_dev),
                                   precision="bf16", return_eps=True)
     assert gpu_model.umma_status() == 0
-    x_emu, eps_emu = emulate_bf16_chain(ref_state_dict, cond_b, T, b, a, ab, noise)
+    x_emu, eps_emu = emulate_bf16_chain(ref_state_dict, cond_b, T, b, a, ab, noise, shared=not distinct)
     # first step: identical inputs, so only fp32 accumulation order differs
     e0 = eps_gpu[T - 1].cpu()
     assert (e0 - eps_emu[T - 1]).abs().max() <= 2e-5 * eps_emu[T - 1].abs().max() + 2e-6
