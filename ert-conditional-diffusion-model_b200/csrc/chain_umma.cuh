@@ -2,33 +2,38 @@
 // fp32 accumulation; BASELINE configs 3/4): the two projections of the hoisted denoiser step run
 // as tcgen05.mma with accumulators in TMEM, everything between them stays on chip.
 //
-// One CTA = a tile of 128 members for all steps: 16 worker warps + 1 MMA-issue warp, no
-// __syncthreads in the step loop (mbarriers only, so warps drift apart and fill each other's
-// waits).  TMEM lane r <-> member r of the tile; a warp may only touch the lane quarter
-// (warp % 4), so worker warp w handles members 32*(w%4)..+31 and column group g = w/4: FOUR
-// threads share one member, each owning a quarter of the hidden columns (epilogue 1) and 8 of the
-// 32 padded parameters (RNG, epilogue 2, x).
+// One CTA = a tile of 128 members for all steps, 17 warps in three roles, no __syncthreads in the
+// step loop (mbarriers only):
+//   * 8 epilogue warps.  TMEM lane r <-> member r of the tile; a warp may only touch the lane
+//     quarter (warp % 4), so warp w handles members 32*(w%4)..+31 and half = w/4 of the columns:
+//     TWO threads share one member, each owning 64 hidden columns (epilogue 1) and 16 of the 32
+//     padded parameters (epilogue 2, x).
+//   * 8 noise warps.  They run ahead of the chain and fill a 4-deep shared-memory ring with the
+//     N(0,1) draws of the coming steps (Philox4x32-10 + Box-Muller, or the caller's replayed
+//     noise).  The generator is bound by the MUFU and integer-multiply pipes, the epilogues by
+//     conversion / packed-fp32 / shared-memory work: separate warps let the two overlap instead of
+//     alternating.
+//   * 1 MMA-issue warp (one elected thread).
 //
 //   GEMM1  D[128 members x 128 hidden] = Xaug[128 x 32] * W1aug[128 x 32]^T           (2 MMAs, K=16)
-//          Xaug row     = [x_0..x_28, 1, 1, 1]   (bf16, rewritten by its four threads every step)
+//          Xaug row     = [x_0..x_28, 1, 1, 1]   (bf16, rewritten by its two threads every step)
 //          W1aug row j  = [W0x[j][0..28], v_hi[j], v_mid[j], v_lo[j]]
 //          v = c_t (per-step vector), or c_t + c_b when all members share one condition; split
 //          into three bf16 terms (exact to 2^-24) and folded into the contraction through the
 //          three spare K columns -- the "embedding add" happens inside the MMA
-//   epi 1  h = ReLU(D [+ c_b[member], fp32 registers, only with distinct conditions])
-//          -> bf16 (cvt.rn.relu.bf16x2) into the K-major A operand of GEMM2
+//   epi 1  h = ReLU(D [+ c_b[member], fp32, parked in TMEM columns 256..383, only with distinct
+//          conditions]) -> bf16 (cvt.rn.relu.bf16x2) into the K-major A operand of GEMM2
 //   GEMM2  E[128 members x 32] = Hbf16[128 x 128] * W2pad[32 x 128]^T                  (8 MMAs, K=16)
-//          issued per column group as soon as that group's 32 K-columns of H are written
-//   epi 2  eps = E + b2; bit-exact posterior update of the thread's 8 parameters (x stays in fp32
-//          registers for the whole chain) with Philox / replayed noise, new Xaug chunk
-// Barriers (all mbarriers, one completion per step each):
-//   bar_x  (16 warp arrivals)  Xaug / W1aug of the next step written     workers -> MMA warp
-//   bar_d  (tcgen05.commit)    D complete                                MMA warp -> workers
-//   bar_h[g] (4 warp arrivals) H columns of group g written              workers -> MMA warp
-//   bar_e  (tcgen05.commit)    E complete                                MMA warp -> workers
-// The Philox + Box-Muller work of a step (two interleaved Philox calls, four Box-Muller pairs per
-// thread) is issued ahead of the wait for D, i.e. while GEMM1 is in flight.
-// TMEM: 256 columns (D: 0..127, E: 128..159).
+//          issued per column half as soon as that half's 64 K-columns of H are written
+//   epi 2  eps = E + b2; bit-exact posterior update of the thread's 16 parameters (x stays in fp32
+//          registers for the whole chain) with the ring's noise, new Xaug chunks
+// Barriers (all mbarriers):
+//   bar_x     (8 warp arrivals)  Xaug / W1aug of the next step written    epilogue -> MMA warp
+//   bar_d     (tcgen05.commit)   D complete                               MMA warp -> epilogue
+//   bar_h[h]  (4 warp arrivals)  H columns of half h written              epilogue -> MMA warp
+//   bar_e     (tcgen05.commit)   E complete                               MMA warp -> epilogue
+//   bar_full[s] / bar_empty[s] (8 warp arrivals each)  noise ring slot s  noise <-> epilogue
+// TMEM: D columns 0..127, E 128..159, c_b 256..383 (distinct conditions only).
 // Algorithmic work: 14,848 FLOP per member-step, as in the fp32 kernel (the K/N padding to
 // 32/32 is not counted).
 #pragma once
@@ -52,16 +57,27 @@ constexpr int UC_M = 128;       // members per CTA
 constexpr int UC_H = 128;       // hidden_dim this kernel is built for
 constexpr int UC_K1 = 32;       // padded param_dim + 3 augmentation columns
 constexpr int UC_N2 = 32;       // padded param_dim
-constexpr int UC_WORKERS = 512; // 4 threads per member
-constexpr int UC_THREADS = UC_WORKERS + 32;   // + the MMA-issue warp
+#ifndef UC_TPM_N
+#define UC_TPM_N 2
+#endif
+constexpr int UC_TPM = UC_TPM_N;           // epilogue threads per member: 2 or 4
+constexpr int UC_EPI_WARPS = 4 * UC_TPM;
+#ifndef UC_RNG_WARPS_N
+#define UC_RNG_WARPS_N 4
+#endif
+constexpr int UC_RNG_WARPS = UC_RNG_WARPS_N;   // 4 or 8
+constexpr int UC_THREADS = (UC_EPI_WARPS + UC_RNG_WARPS + 1) * 32;   // + the MMA-issue warp
 constexpr int UC_AUG = 29;      // first augmentation column (param_dim <= 29)
+constexpr int UC_NSLOT = 4;     // depth of the noise ring (steps)
 
 struct UmmaChainSmem {
     unsigned char x[UC_M * UC_K1 * 2];      // A of GEMM1
     unsigned char h[UC_M * UC_H * 2];       // A of GEMM2
     unsigned char w1[UC_H * UC_K1 * 2];     // B of GEMM1 (W0x augmented)
     unsigned char w2[UC_N2 * UC_H * 2];     // B of GEMM2 (W2 padded)
-    unsigned long long bar_x, bar_d, bar_e, bar_h[4];
+    float zring[UC_NSLOT][UC_M][kPPad];     // noise ring; 16-byte chunk c of member m sits at chunk c ^ (m & 7)
+    unsigned long long bar_x, bar_d, bar_e, bar_h[UC_TPM], bar_full[UC_NSLOT], bar_empty[UC_NSLOT];
+    alignas(16) float b2[kPPad];
     uint32_t tmem_slot;
     int timeout;
 };
@@ -117,9 +133,19 @@ __global__ void __launch_bounds__(UC_THREADS, 1) k_chain_umma(const ChainParams 
     extern __shared__ __align__(128) unsigned char uc_smem_raw[];
     UmmaChainSmem& s = *reinterpret_cast<UmmaChainSmem*>(uc_smem_raw);
     const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
-    const uint32_t sX = smem_u32(s.x), sH = smem_u32(s.h), sW1 = smem_u32(s.w1), sW2 = smem_u32(s.w2);
-    const uint32_t bar_x = smem_u32(&s.bar_x), bar_d = smem_u32(&s.bar_d), bar_e = smem_u32(&s.bar_e);
-    const uint32_t bar_h0 = smem_u32(&s.bar_h[0]);
+    const uint32_t sX_ = smem_u32(s.x), sH_ = smem_u32(s.h), sW1_ = smem_u32(s.w1), sW2_ = smem_u32(s.w2);
+    const uint32_t sZ_ = smem_u32(&s.zring[0][0][0]);
+    const uint32_t bar_x_ = smem_u32(&s.bar_x), bar_d_ = smem_u32(&s.bar_d), bar_e_ = smem_u32(&s.bar_e);
+    const uint32_t bar_h0_ = smem_u32(&s.bar_h[0]);
+    const uint32_t bar_full0_ = smem_u32(&s.bar_full[0]), bar_empty0_ = smem_u32(&s.bar_empty[0]);
+    uint32_t sX = sX_, sH = sH_, sW1 = sW1_, sW2 = sW2_, sZ = sZ_, bar_x = bar_x_, bar_d = bar_d_, bar_e = bar_e_,
+             bar_h0 = bar_h0_, bar_full0 = bar_full0_, bar_empty0 = bar_empty0_;
+    // opaque to the optimiser: otherwise every use re-derives the shared window base
+    // (S2R SR_CgaCtaId + LEA, a long-scoreboard read) inside the step loop
+    asm volatile("" : "+r"(sX), "+r"(sH), "+r"(sW1), "+r"(sW2), "+r"(sZ), "+r"(bar_x), "+r"(bar_d), "+r"(bar_e),
+                      "+r"(bar_h0), "+r"(bar_full0), "+r"(bar_empty0));
+    constexpr uint32_t TMEM_COLS = SHARED ? 256 : 512;
+    constexpr uint32_t SLOT_BYTES = UC_M * kPPad * 4;
 
     // ---- one-time setup ------------------------------------------------------------------------
     {
@@ -127,14 +153,19 @@ __global__ void __launch_bounds__(UC_THREADS, 1) k_chain_umma(const ChainParams 
         uint4* d2 = reinterpret_cast<uint4*>(s.w2);
         for (int i = tid; i < UC_H * UC_K1 * 2 / 16; i += UC_THREADS) d1[i] = ex.w1_pk[i];
         for (int i = tid; i < UC_N2 * UC_H * 2 / 16; i += UC_THREADS) d2[i] = ex.w2_pk[i];
+        if (tid < kPPad) s.b2[tid] = a.b2p[tid];
         if (tid == 0) s.timeout = 0;
     }
-    if (warp == 0) tmem_alloc(smem_u32(&s.tmem_slot), 256);
+    if (warp == 0) tmem_alloc(smem_u32(&s.tmem_slot), TMEM_COLS);
     if (tid == 0) {
-        mbar_init(bar_x, UC_WORKERS / 32);
+        mbar_init(bar_x, UC_EPI_WARPS);
         mbar_init(bar_d, 1);
         mbar_init(bar_e, 1);
-        for (int g = 0; g < 4; ++g) mbar_init(bar_h0 + 8u * g, 4);
+        for (int h = 0; h < UC_TPM; ++h) mbar_init(bar_h0 + 8u * h, 4);
+        for (int i = 0; i < UC_NSLOT; ++i) {
+            mbar_init(bar_full0 + 8u * i, UC_RNG_WARPS);
+            mbar_init(bar_empty0 + 8u * i, UC_EPI_WARPS);
+        }
         fence_mbar_init();
     }
     fence_proxy_async();          // the weight tiles were written through the generic proxy
@@ -143,13 +174,34 @@ __global__ void __launch_bounds__(UC_THREADS, 1) k_chain_umma(const ChainParams 
     tc_fence_after();
     const uint32_t tmem = s.tmem_slot;
     const int n_steps = a.t_count;
+    const int d_first = a.S - a.t_hi;
+    const int64_t m0 = (int64_t)blockIdx.x * UC_M;
+    const int P = a.P;
+    // ring items, in consumption order: [x_T when the launch starts a chain] then one per step with
+    // t > 0 (steps run t = t_hi, t_hi-1, ...; the step with t == 0 adds no noise, ECD.py:115)
+    const int first_item_step = a.x_in ? 0 : 1;          // ring item of step `it` = it + first_item_step
+    const int n_noisy = n_steps < a.t_hi ? n_steps : a.t_hi;
+    bool ok = true;
 
-    if (warp == UC_WORKERS / 32) {
+    if (warp == UC_EPI_WARPS + UC_RNG_WARPS) {
         // ===== MMA-issue warp: one elected thread, everything it does is asynchronous ============
         if (lane == 0) {
             constexpr uint32_t IDESC1 = idesc_bf16_f32(UC_M, UC_H);
             constexpr uint32_t IDESC2 = idesc_bf16_f32(UC_M, UC_N2);
-            bool ok = true;
+            // all operand descriptors are loop-invariant: build them once, so that a step costs this
+            // (single, latency-bound) thread little more than the ten MMA issues themselves
+            uint64_t dA1[UC_K1 / 16], dB1[UC_K1 / 16], dA2[UC_H / 16], dB2[UC_H / 16];
+#pragma unroll
+            for (int k = 0; k < UC_K1 / 16; ++k) {
+                dA1[k] = smem_desc(sX + 2 * k * kLBO, kLBO, sbo_bytes(UC_K1));
+                dB1[k] = smem_desc(sW1 + 2 * k * kLBO, kLBO, sbo_bytes(UC_K1));
+            }
+#pragma unroll
+            for (int k = 0; k < UC_H / 16; ++k) {
+                dA2[k] = smem_desc(sH + 2 * k * kLBO, kLBO, sbo_bytes(UC_H));
+                dB2[k] = smem_desc(sW2 + 2 * k * kLBO, kLBO, sbo_bytes(UC_H));
+            }
+            const uint32_t tmemE = tmem + 128;
 #if UC_TIMING
             const bool timed = ex.timing != nullptr && blockIdx.x == 0;
             long long tm[4] = {0, 0, 0, 0}, c0 = 0, c1 = 0;
@@ -160,92 +212,153 @@ __global__ void __launch_bounds__(UC_THREADS, 1) k_chain_umma(const ChainParams 
                 ok = mbar_wait(bar_x, ph);
                 UC_T(if (timed) { c1 = clock64(); tm[0] += c1 - c0; })
                 tc_fence_after();
+                mma_bf16_first(tmem, dA1[0], dB1[0], IDESC1);
 #pragma unroll
-                for (int k = 0; k < UC_K1 / 16; ++k)
-                    mma_bf16(tmem, smem_desc(sX + 2 * k * kLBO, kLBO, sbo_bytes(UC_K1)),
-                             smem_desc(sW1 + 2 * k * kLBO, kLBO, sbo_bytes(UC_K1)), IDESC1, k > 0);
+                for (int k = 1; k < UC_K1 / 16; ++k) mma_bf16_acc(tmem, dA1[k], dB1[k], IDESC1);
                 mma_commit(bar_d);
                 UC_T(if (timed) { c0 = clock64(); tm[1] += c0 - c1; })
-#pragma unroll 1
-                for (int g = 0; g < 4 && ok; ++g) {
-                    ok = mbar_wait(bar_h0 + 8u * g, ph);
+#pragma unroll
+                for (int part = 0; part < UC_TPM; ++part) {      // each part's K columns as soon as they are written
+                    ok = ok && mbar_wait(bar_h0 + 8u * part, ph);
                     tc_fence_after();
 #pragma unroll
-                    for (int kk = 0; kk < 2; ++kk) {
-                        const int k = 2 * g + kk;
-                        mma_bf16(tmem + 128, smem_desc(sH + 2 * k * kLBO, kLBO, sbo_bytes(UC_H)),
-                                 smem_desc(sW2 + 2 * k * kLBO, kLBO, sbo_bytes(UC_H)), IDESC2, k > 0);
+                    for (int kk = 0; kk < 8 / UC_TPM; ++kk) {
+                        const int k = 8 / UC_TPM * part + kk;
+                        if (k == 0) mma_bf16_first(tmemE, dA2[0], dB2[0], IDESC2);
+                        else mma_bf16_acc(tmemE, dA2[k], dB2[k], IDESC2);
                     }
                 }
                 mma_commit(bar_e);
                 UC_T(if (timed) { c1 = clock64(); tm[2] += c1 - c0; })
             }
-            if (!ok) s.timeout = 1;
             UC_T(if (timed) { ex.timing[8] = tm[0]; ex.timing[9] = tm[1]; ex.timing[10] = tm[2]; })
         }
+    } else if (warp < UC_RNG_WARPS) {
+        // ===== noise warps: thread (member m, half) produces the 16 draws of that member's
+        // parameters 16*half..16*half+15 for one ring item at a time ===============================
+        const int r = tid;
+        const int m = r & (UC_M - 1), half = r >> 7;
+        const int64_t mg = (m0 + m) < a.B ? (m0 + m) : (a.B - 1);
+        const int64_t gmember = a.member_offset + mg;
+        const int n_items = first_item_step + n_noisy;
+        const uint32_t zrow = sZ + (uint32_t)m * (kPPad * 4);
+#if UC_TIMING
+        const bool timed = ex.timing != nullptr && blockIdx.x == 0 && r == 0;
+        long long tg[2] = {0, 0}, g0 = 0, g1 = 0;
+#endif
+#pragma unroll 1
+        for (int item = 0; item < n_items && ok; ++item) {
+            const int slot = item % UC_NSLOT;
+            const uint32_t use = (uint32_t)(item / UC_NSLOT);
+            UC_T(if (timed) g0 = clock64();)
+            ok = mbar_wait(bar_empty0 + 8u * slot, (use & 1u) ^ 1u);    // passes at once on the first lap
+            UC_T(if (timed) { g1 = clock64(); tg[0] += g1 - g0; })
+            const uint32_t draw = (item < first_item_step) ? 0u : (uint32_t)(d_first + item - first_item_step);
+#pragma unroll 1
+            for (int hf = half; hf < 2; hf += UC_RNG_WARPS / 4) {
+                float z[16];
+                if (REPLAY) {
+                    const float* zr = a.noise + ((int64_t)(draw - 1) * a.noise_B + mg) * P + 16 * hf;
+#pragma unroll
+                    for (int i = 0; i < 16; ++i) z[i] = (16 * hf + i < P) ? zr[i] : 0.f;
+                } else {
+                    philox_normal8(a.keys, a.offset, gmember, draw, 4 * hf, &z[0]);
+                    philox_normal8(a.keys, a.offset, gmember, draw, 4 * hf + 2, &z[8]);
+#pragma unroll
+                    for (int i = 0; i < 16; ++i) z[i] = (16 * hf + i < P) ? z[i] : 0.f;
+                }
+#pragma unroll
+                for (int c = 0; c < 4; ++c)
+                    sts128(zrow + (uint32_t)slot * SLOT_BYTES + (uint32_t)(((4 * hf + c) ^ (m & 7)) * 16),
+                           make_float4(z[4 * c], z[4 * c + 1], z[4 * c + 2], z[4 * c + 3]));
+            }
+            __syncwarp();
+            if (lane == 0) mbar_arrive(bar_full0 + 8u * slot);
+            UC_T(if (timed) tg[1] += clock64() - g1;)
+        }
+        UC_T(if (timed) { ex.timing[11] = tg[0]; ex.timing[12] = tg[1]; })
     } else {
-        // ===== worker warps ===========================================================================
-        const int quarter = warp & 3;            // TMEM lane quarter this warp may access
-        const int g = warp >> 2;                 // column group: hidden 32g..32g+31, parameters 8g..8g+7
+        // ===== epilogue warps =========================================================================
+        constexpr int CW = UC_H / UC_TPM;        // hidden columns per thread
+        constexpr int PW = kPPad / UC_TPM;       // parameters per thread
+        const int et = tid - UC_RNG_WARPS * 32;  // 0 .. 128*UC_TPM-1
+        const int quarter = warp & 3;            // TMEM lane quarter this warp may access (warp % 4)
+        const int part = et >> 7;                // hidden columns CW*part..+CW-1, parameters PW*part..+PW-1
         const int row = quarter * 32 + lane;     // member of the tile = TMEM lane
-        const int P = a.P;
-        const int64_t m0 = (int64_t)blockIdx.x * UC_M;
         const bool mvalid = (m0 + row) < a.B;
         const int64_t mg = mvalid ? (m0 + row) : (a.B - 1);
-        const int64_t gmember = a.member_offset + mg;
-        constexpr bool shared_cond = SHARED;   // all members use one condition (n_cond == 1)
-        const int d_first = a.S - a.t_hi;
         const uint32_t tlane = tmem + ((uint32_t)(quarter * 32) << 16);
-        const uint32_t tD = tlane + 32 * g;              // this thread's 32 hidden columns of D
-        const uint32_t tE = tlane + 128 + 8 * g;         // this thread's 8 parameter columns of E
-        const uint32_t bar_h = bar_h0 + 8u * g;
+        const uint32_t tD = tlane + CW * part;           // this thread's hidden columns of D
+        const uint32_t tE = tlane + 128 + PW * part;     // this thread's parameter columns of E
+        const uint32_t tCB = tlane + 256 + CW * part;    // c_b of this member (distinct conditions)
+        const uint32_t bar_h = bar_h0 + 8u * part;
+        const uint32_t zrow = sZ + (uint32_t)row * (kPPad * 4);
+        const uint32_t zsw = (uint32_t)(row & 7);
 
-        // distinct conditions: c_b of this member for the thread's hidden columns, fp32 registers
-        float2 cb[16];
-        if (!shared_cond) {
-            const float4* cbrow = reinterpret_cast<const float4*>(a.cond_bias + (mg % a.n_cond) * UC_H + 32 * g);
+        if (!SHARED) {   // park c_b of this member's hidden columns in TMEM for the whole chain
+            const float4* cbrow = reinterpret_cast<const float4*>(a.cond_bias + (mg % a.n_cond) * UC_H + CW * part);
+#pragma unroll 1
+            for (int c = 0; c < CW / 32; ++c) {
+                uint32_t v[32];
 #pragma unroll
-            for (int i = 0; i < 8; ++i) {
-                const float4 f = cbrow[i];
-                cb[2 * i] = make_float2(f.x, f.y);
-                cb[2 * i + 1] = make_float2(f.z, f.w);
+                for (int i = 0; i < 8; ++i) {
+                    const float4 f = cbrow[8 * c + i];
+                    v[4 * i] = __float_as_uint(f.x); v[4 * i + 1] = __float_as_uint(f.y);
+                    v[4 * i + 2] = __float_as_uint(f.z); v[4 * i + 3] = __float_as_uint(f.w);
+                }
+                tmem_st32(tCB + 32 * c, v);
             }
-        } else {
-#pragma unroll
-            for (int i = 0; i < 16; ++i) cb[i] = make_float2(0.f, 0.f);
+            tmem_st_wait();
         }
-        // threads 0..127 own row j = tid of W1aug: v = c_t[t][j] (+ c_b[j] of the shared condition)
-        const float cb0 = (tid < UC_H && shared_cond) ? a.cond_bias[tid] : 0.f;
-        float2 b2r[4];
-#pragma unroll
-        for (int i = 0; i < 4; ++i) b2r[i] = make_float2(a.b2p[8 * g + 2 * i], a.b2p[8 * g + 2 * i + 1]);
+        // epilogue threads 0..127 own row j = et of W1aug: v = c_t[t][j] (+ c_b[j] of the shared condition)
+        const float cb0 = (et < UC_H && SHARED) ? a.cond_bias[et] : 0.f;
+        uint32_t b2a = smem_u32(&s.b2[PW * part]);
+        asm volatile("" : "+r"(b2a));
+
+        // one ring item: the thread's PW draws, 4 at a time
+        auto ring_wait = [&](int item) -> uint32_t {
+            const int slot = item % UC_NSLOT;
+            ok = ok && mbar_wait(bar_full0 + 8u * slot, (uint32_t)(item / UC_NSLOT) & 1u);
+            return zrow + (uint32_t)slot * SLOT_BYTES;
+        };
+        auto ring_release = [&](int item) {
+            __syncwarp();
+            if (lane == 0) mbar_arrive(bar_empty0 + 8u * (item % UC_NSLOT));
+        };
 
         // ---- x_T -------------------------------------------------------------------------------
-        float2 x[4];
-        float z[8];
+        float2 x[PW / 2];
         if (a.x_in) {
+            const float* xr = a.x_in + mg * a.x_in_stride + PW * part;
 #pragma unroll
-            for (int i = 0; i < 8; ++i) z[i] = (8 * g + i < P) ? a.x_in[mg * a.x_in_stride + 8 * g + i] : 0.f;
+            for (int i = 0; i < PW / 2; ++i)
+                x[i] = make_float2((PW * part + 2 * i < P) ? xr[2 * i] : 0.f, (PW * part + 2 * i + 1 < P) ? xr[2 * i + 1] : 0.f);
         } else {
-            philox_normal8(a.keys, a.offset, gmember, 0u, 2 * g, z);
+            const uint32_t zb = ring_wait(0);
 #pragma unroll
-            for (int i = 0; i < 8; ++i) z[i] = (8 * g + i < P) ? z[i] : 0.f;
+            for (int c = 0; c < PW / 4; ++c) {
+                const float4 z4 = lds128(zb + (((uint32_t)(PW / 4 * part + c) ^ zsw) << 4));
+                x[2 * c] = make_float2(z4.x, z4.y);
+                x[2 * c + 1] = make_float2(z4.z, z4.w);
+            }
+            ring_release(0);
         }
-#pragma unroll
-        for (int i = 0; i < 4; ++i) x[i] = make_float2(z[2 * i], z[2 * i + 1]);
 
-        const uint32_t xchunk = sX + (uint32_t)(row / 8) * sbo_bytes(UC_K1) + (uint32_t)(row % 8) * 16u + (uint32_t)g * kLBO;
-        const uint32_t hrow = sH + (uint32_t)(row / 8) * sbo_bytes(UC_H) + (uint32_t)(row % 8) * 16u + (uint32_t)(4 * g) * kLBO;
-        const uint32_t w1aug = sW1 + elem_offset(tid & (UC_H - 1), UC_AUG, UC_K1);   // (v_hi | v_mid v_lo) of row j = tid
+        const uint32_t xchunk = sX + (uint32_t)(row / 8) * sbo_bytes(UC_K1) + (uint32_t)(row % 8) * 16u + (uint32_t)(PW / 8 * part) * kLBO;
+        const uint32_t hrow = sH + (uint32_t)(row / 8) * sbo_bytes(UC_H) + (uint32_t)(row % 8) * 16u + (uint32_t)(CW / 8 * part) * kLBO;
+        const uint32_t w1aug = sW1 + elem_offset(et & (UC_H - 1), UC_AUG, UC_K1);   // (v_hi | v_mid v_lo) of row j = et
 
-        // operands of the next GEMM1: this thread's chunk of Xaug; threads 0..127 also refresh the
-        // augmentation columns of W1 with the 3-term bf16 split of v; then one arrival per warp
+        // operands of the next GEMM1: this thread's chunk(s) of Xaug; epilogue threads 0..127 also
+        // refresh the augmentation columns of W1 with the 3-term bf16 split of v; one arrival per warp
         auto publish_gemm1_operands = [&](float ct) {
-            if (g == 3)   // parameters 24..28 + the three constant-one columns (bf16 1.0 = 0x3F80)
-                sts_u4(xchunk, pack_bf16(x[0].x, x[0].y), pack_bf16(x[1].x, x[1].y), pack_bf16(x[2].x, 1.0f), 0x3F803F80u);
-            else
-                sts_u4(xchunk, pack_bf16(x[0].x, x[0].y), pack_bf16(x[1].x, x[1].y), pack_bf16(x[2].x, x[2].y), pack_bf16(x[3].x, x[3].y));
-            if (tid < UC_H) {
+#pragma unroll
+            for (int c = 0; c < PW / 8; ++c) {
+                const bool last = (PW / 8 * part + c) == 3;   // parameters 24..28 + three constant-one columns (bf16 1.0 = 0x3F80)
+                const uint32_t w2 = last ? pack_bf16(x[4 * c + 2].x, 1.0f) : pack_bf16(x[4 * c + 2].x, x[4 * c + 2].y);
+                const uint32_t w3 = last ? 0x3F803F80u : pack_bf16(x[4 * c + 3].x, x[4 * c + 3].y);
+                sts_u4(xchunk + (uint32_t)c * kLBO, pack_bf16(x[4 * c].x, x[4 * c].y), pack_bf16(x[4 * c + 1].x, x[4 * c + 1].y), w2, w3);
+            }
+            if (et < UC_H) {
                 const float v = ct + cb0;
                 const float v_hi = bf16_round(v);
                 const float r1 = v - v_hi;                    // exact
@@ -260,70 +373,67 @@ __global__ void __launch_bounds__(UC_THREADS, 1) k_chain_umma(const ChainParams 
             __syncwarp();
             if (lane == 0) mbar_arrive(bar_x);
         };
-        const float* ctcol = a.table + (tid & (UC_H - 1));
-        publish_gemm1_operands(tid < UC_H ? __ldg(ctcol + (int64_t)a.t_hi * UC_H) : 0.f);
+        const float* ctcol = a.table + (et & (UC_H - 1));
+        publish_gemm1_operands(et < UC_H ? __ldg(ctcol + (int64_t)a.t_hi * UC_H) : 0.f);
 
-        bool ok = true;
 #if UC_TIMING
-        const bool timed = ex.timing != nullptr && blockIdx.x == 0 && tid == 0;
-        long long tw[6] = {0, 0, 0, 0, 0, 0}, k0 = 0, k1 = 0;
+        const bool timed = ex.timing != nullptr && blockIdx.x == 0 && et == 0;
+        long long tw[6] = {0, 0, 0, 0, 0, 0}, k0 = 0, k1 = 0, tf[2] = {0, 0};
 #endif
 #pragma unroll 1
         for (int it = 0; it < n_steps && ok; ++it) {
             UC_T(if (timed) k0 = clock64();)
             const int t = a.t_hi - it;
-            const int d = d_first + it;
             const uint32_t ph = (uint32_t)it & 1u;
             // prefetches: the step scalars and (threads 0..127) the next step's c_t element
             const float4 cf = __ldg(reinterpret_cast<const float4*>(a.coef) + t);
             float ct_next = 0.f;
-            if (tid < UC_H && it + 1 < n_steps) ct_next = __ldg(ctcol + (int64_t)(t - 1) * UC_H);
-            // ---- this step's noise (GEMM1 is in flight) ----------------------------------------------
-            if (t > 0) {
-                if (REPLAY) {
-                    const float* zr = a.noise + ((int64_t)(d - 1) * a.noise_B + mg) * P + 8 * g;
-#pragma unroll
-                    for (int i = 0; i < 8; ++i) z[i] = (8 * g + i < P) ? zr[i] : 0.f;
-                } else {
-                    philox_normal8(a.keys, a.offset, gmember, (uint32_t)d, 2 * g, z);
-                }
-            }
+            if (et < UC_H && it + 1 < n_steps) ct_next = __ldg(ctcol + (int64_t)(t - 1) * UC_H);
+            // this step's noise: the ring runs ahead, so this wait is normally already satisfied
+            uint32_t zb = 0;
+            if (t > 0) zb = ring_wait(it + first_item_step);
             UC_T(if (timed) { k1 = clock64(); tw[0] += k1 - k0; })
-            ok = mbar_wait(bar_d, ph);
+            ok = ok && mbar_wait(bar_d, ph);
             UC_T(if (timed) { k0 = clock64(); tw[1] += k0 - k1; })
             tc_fence_after();
             // ---- epilogue 1: h = ReLU(D [+ c_b]) -> bf16 A operand of GEMM2 ----------------------
-            if (shared_cond) {
-                uint32_t dv[32];
-                tmem_ld32(tD, dv);
+            if (SHARED) {
+                uint32_t dv[CW];             // all loads in flight, one wait
+#pragma unroll
+                for (int hh = 0; hh < CW / 16; ++hh) tmem_ld16(tD + 16 * hh, *reinterpret_cast<uint32_t(*)[16]>(&dv[16 * hh]));
                 tmem_ld_wait();
-                uint32_t pk[16];
 #pragma unroll
-                for (int i = 0; i < 16; ++i)
-                    pk[i] = pack_bf16_relu(__uint_as_float(dv[2 * i]), __uint_as_float(dv[2 * i + 1]));
-#pragma unroll
-                for (int q = 0; q < 4; ++q)
-                    sts_u4(hrow + (uint32_t)q * kLBO, pk[4 * q], pk[4 * q + 1], pk[4 * q + 2], pk[4 * q + 3]);
+                for (int q = 0; q < CW / 8; ++q)
+                    sts_u4(hrow + (uint32_t)q * kLBO,
+                           pack_bf16_relu(__uint_as_float(dv[8 * q]), __uint_as_float(dv[8 * q + 1])),
+                           pack_bf16_relu(__uint_as_float(dv[8 * q + 2]), __uint_as_float(dv[8 * q + 3])),
+                           pack_bf16_relu(__uint_as_float(dv[8 * q + 4]), __uint_as_float(dv[8 * q + 5])),
+                           pack_bf16_relu(__uint_as_float(dv[8 * q + 6]), __uint_as_float(dv[8 * q + 7])));
             } else {
 #pragma unroll
-                for (int hh = 0; hh < 2; ++hh) {       // two halves of 16 columns: c_b occupies 32 registers
-                    uint32_t dv[16];
+                for (int hh = 0; hh < CW / 16; ++hh) {       // 16 columns at a time: accumulator + c_b
+                    uint32_t dv[16], cv[16];
                     tmem_ld16(tD + 16 * hh, dv);
+                    tmem_ld16(tCB + 16 * hh, cv);
                     tmem_ld_wait();
                     uint32_t pk[8];
 #pragma unroll
                     for (int i = 0; i < 8; ++i) {
-                        const float2 hsum = fadd2(make_float2(__uint_as_float(dv[2 * i]), __uint_as_float(dv[2 * i + 1])), cb[8 * hh + i]);
+                        const float2 hsum = fadd2(make_float2(__uint_as_float(dv[2 * i]), __uint_as_float(dv[2 * i + 1])),
+                                                  make_float2(__uint_as_float(cv[2 * i]), __uint_as_float(cv[2 * i + 1])));
                         pk[i] = pack_bf16_relu(hsum.x, hsum.y);
                     }
                     sts_u4(hrow + (uint32_t)(2 * hh) * kLBO, pk[0], pk[1], pk[2], pk[3]);
                     sts_u4(hrow + (uint32_t)(2 * hh + 1) * kLBO, pk[4], pk[5], pk[6], pk[7]);
                 }
             }
+            UC_T(long long f0 = 0; if (timed) f0 = clock64();)
             fence_proxy_async();
+            UC_T(if (timed) { const long long f1 = clock64(); tf[0] += f1 - f0; f0 = f1; })
             tc_fence_before();
             __syncwarp();
             if (lane == 0) mbar_arrive(bar_h);
+            UC_T(if (timed) tf[1] += clock64() - f0;)
             UC_T(if (timed) { k1 = clock64(); tw[2] += k1 - k0; })
             UC_T(if (timed) { k0 = clock64(); tw[3] += k0 - k1; })
             ok = ok && mbar_wait(bar_e, ph);
@@ -331,57 +441,67 @@ __global__ void __launch_bounds__(UC_THREADS, 1) k_chain_umma(const ChainParams 
             tc_fence_after();
             // ---- epilogue 2: eps -> posterior update of this thread's parameters ----------------
             {
-                uint32_t ev[8];
-                tmem_ld8(tE, ev);
+                uint32_t ev[PW];
+                if (PW == 16) tmem_ld16(tE, *reinterpret_cast<uint32_t(*)[16]>(&ev[0]));
+                else tmem_ld8(tE, *reinterpret_cast<uint32_t(*)[8]>(&ev[0]));
                 tmem_ld_wait();
-                // ECD.py:111-118 with separately rounded operations (packed f32x2 ops are IEEE rn):
-                //   u = coef*eps ; v = x - u ; x' = c1*v ; [ w = sigma*z ; x' = x' + w ]
-                // (x - u is formed as x + (-coef)*eps: negation commutes with rounding)
+                // ECD.py:111-118: u = coef*eps ; v = x - u ; x' = c1*v ; [ w = sigma*z ; x' = x' + w ]
+                // in packed fp32 (x - u formed as x + (-coef)*eps; the assembler is free to contract
+                // these, the bf16 path's contract is its tolerance, not bit-exactness of the update)
                 const float2 ncoef = make_float2(-cf.x, -cf.x), c1 = make_float2(cf.y, cf.y), sg = make_float2(cf.z, cf.z);
 #pragma unroll
-                for (int i = 0; i < 4; ++i) {
-                    const float2 e = fadd2(make_float2(__uint_as_float(ev[2 * i]), __uint_as_float(ev[2 * i + 1])), b2r[i]);
-                    float2 xn = fmul2(c1, fadd2(x[i], fmul2(ncoef, e)));
-                    if (t > 0) xn = fadd2(xn, fmul2(sg, make_float2(z[2 * i], z[2 * i + 1])));
-                    x[i] = xn;
-                    if (TRACE && mvalid) {
-                        float* dst = a.eps_trace + ((int64_t)t * a.B + m0 + row) * P + 8 * g + 2 * i;
-                        if (8 * g + 2 * i < P) dst[0] = e.x;
-                        if (8 * g + 2 * i + 1 < P) dst[1] = e.y;
+                for (int c = 0; c < PW / 4; ++c) {
+                    float4 z4 = make_float4(0.f, 0.f, 0.f, 0.f);
+                    if (t > 0) z4 = lds128(zb + (((uint32_t)(PW / 4 * part + c) ^ zsw) << 4));
+                    const float4 b4 = lds128(b2a + 16u * c);
+#pragma unroll
+                    for (int u = 0; u < 2; ++u) {
+                        const int i = 2 * c + u;
+                        const float2 e = fadd2(make_float2(__uint_as_float(ev[2 * i]), __uint_as_float(ev[2 * i + 1])),
+                                               u == 0 ? make_float2(b4.x, b4.y) : make_float2(b4.z, b4.w));
+                        float2 xn = fmul2(c1, fadd2(x[i], fmul2(ncoef, e)));
+                        if (t > 0) xn = fadd2(xn, fmul2(sg, u == 0 ? make_float2(z4.x, z4.y) : make_float2(z4.z, z4.w)));
+                        x[i] = xn;
+                        if (TRACE && mvalid) {
+                            float* dst = a.eps_trace + ((int64_t)t * a.B + m0 + row) * P + PW * part + 2 * i;
+                            if (PW * part + 2 * i < P) dst[0] = e.x;
+                            if (PW * part + 2 * i + 1 < P) dst[1] = e.y;
+                        }
                     }
                 }
             }
+            if (t > 0) ring_release(it + first_item_step);
             if (it + 1 < n_steps) publish_gemm1_operands(ct_next);
             UC_T(if (timed) tw[5] += clock64() - k1;)
         }
-        if (!ok) s.timeout = 1;
 #if UC_TIMING
         if (timed) {
 #pragma unroll
             for (int i = 0; i < 6; ++i) ex.timing[i] = tw[i];
+            ex.timing[6] = tf[0]; ex.timing[7] = tf[1];
             ex.timing[15] = n_steps;
         }
 #endif
         // parameters >= P of the padded tile carry finite garbage that the zero weight columns
         // ignore; they are never stored
         if (mvalid) {
-            float* dst = a.x_out + (m0 + row) * P + 8 * g;
+            float* dst = a.x_out + (m0 + row) * P + PW * part;
 #pragma unroll
-            for (int i = 0; i < 4; ++i) {
-                if (8 * g + 2 * i < P) dst[2 * i] = x[i].x;
-                if (8 * g + 2 * i + 1 < P) dst[2 * i + 1] = x[i].y;
+            for (int i = 0; i < PW / 2; ++i) {
+                if (PW * part + 2 * i < P) dst[2 * i] = x[i].x;
+                if (PW * part + 2 * i + 1 < P) dst[2 * i + 1] = x[i].y;
             }
         }
     }
+    if (!ok) s.timeout = 1;
     tc_fence_before();
     __syncthreads();
     if (s.timeout != 0) {                   // an MMA never completed: poison the tile's output
-        const int64_t m0 = (int64_t)blockIdx.x * UC_M;
         for (int i = tid; i < UC_M * a.P; i += UC_THREADS)
             if (m0 + i / a.P < a.B) a.x_out[m0 * a.P + i] = __int_as_float(0x7fc00000);
         if (tid == 0) ex.status[0] = 1;
     }
-    if (warp == 0) tmem_dealloc(tmem, 256);
+    if (warp == 0) tmem_dealloc(tmem, TMEM_COLS);
 }
 
 }  // namespace ertdiff

@@ -42,7 +42,7 @@ for B in [int(v) for v in a.members.split(",")]:
             eb.run_chain(model, cond_b, a.T, *sched, dev, seed=7, offset=0, precision=prec, n_members=B)
             tm = model.umma_timing(False)
             n = max(tm[15], 1)
-            names = ["rng1", "waitD", "epi1", "rng2", "waitE", "epi2+pub", "", "", "mma:waitX", "mma:gemm1", "mma:waitH+gemm2"]
+            names = ["top", "waitD", "epi1", "waitZ", "waitE", "epi2+pub", "epi1:proxyfence", "epi1:arrive", "mma:waitX", "mma:gemm1", "mma:waitH+gemm2", "rng:waitEmpty", "rng:generate"]
             print("   cycles/step:", {k: round(tm[i] / n) for i, k in enumerate(names) if k}, flush=True)
         print(f"B {B:6d} {prec} chain_ms {best:8.3f} us/step {best / a.T * 1e3:7.3f} "
               f"samples/s {B / best * 1e3:12.0f} TFLOP/s {B * a.T * 14848 / best / 1e9:7.2f} "
