@@ -54,6 +54,8 @@ SIGNATURES = {
                                   C.c_int64, C.c_int64, C.c_void_p, C.c_void_p]),
     "ertdiff_encode_condition": (C.c_int, [C.c_void_p, C.c_void_p, C.c_int64, C.c_int64, C.c_int64,
                                            C.c_void_p, C.c_void_p, C.c_void_p]),
+    "ertdiff_encode_condition_prec": (C.c_int, [C.c_void_p, C.c_void_p, C.c_int64, C.c_int64, C.c_int64,
+                                           C.c_void_p, C.c_void_p, C.c_int32, C.c_void_p]),
     "ertdiff_sample_chain": (C.c_int, [C.c_void_p, C.POINTER(ChainArgs), C.c_void_p]),
     "ertdiff_sample_model": (C.c_int, [C.c_void_p, C.c_void_p, C.c_int64, C.c_int64,
                                        C.POINTER(ChainArgs), C.c_void_p]),

@@ -12,6 +12,7 @@
 #include "stats.cuh"
 #include "umma.cuh"
 #include "chain_umma.cuh"
+#include "encoder_umma.cuh"
 
 namespace ertdiff {
 std::string& last_error() {
@@ -85,6 +86,43 @@ static int run_encoder(ertdiff_model* m, const float* d_cond, int64_t n_cond, in
     k_encoder_finish<<<(unsigned)n_cond, m->H, 0, st>>>(m->enc_partial, n_chunks, L2, m->w6T,
                                                        m->raw[5], m->w0cT, m->raw[9], m->H,
                                                        d_cond_emb, d_cond_bias);
+    ERT_LAUNCH_CHECK("k_encoder_finish");
+    return 0;
+}
+
+// ---- tensor-core encoder (precision = bf16) ---------------------------------------------
+static int run_encoder_umma(ertdiff_model* m, const float* d_cond, int64_t n_cond, int64_t L,
+                            int64_t member_stride, float* d_cond_emb, float* d_cond_bias, cudaStream_t st) {
+    ERT_REQUIRE(d_cond && n_cond > 0 && L > 0, "encode_condition: bad condition/n_cond/L");
+    ERT_REQUIRE(m->enc_w1_pk, "encode_condition: tensor-core encoder weights missing");
+    const int64_t L1 = conv_out_len(L), L2 = conv_out_len(L1);
+    ERT_REQUIRE(4 * (L2 + 128) + 16 < (int64_t)1 << 30, "encode_condition: L too large");
+    const int n_chunks = (int)((L2 + EU_TPC * 128 - 1) / (EU_TPC * 128));
+    if (int rc = grow(m->enc_partial, m->enc_partial_n, (size_t)n_cond * n_chunks * kConv2Out)) return rc;
+    static bool attr_set = false;
+    if (!attr_set) {
+        ERT_CUDA(cudaFuncSetAttribute(k_encoder_umma, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)sizeof(EncUmmaSmem)));
+        attr_set = true;
+    }
+    const int64_t batch = 32768;               // blockIdx.y
+    for (int64_t c0 = 0; c0 < n_cond; c0 += batch) {
+        const int64_t nc = (n_cond - c0) < batch ? (n_cond - c0) : batch;
+        const float* first = d_cond + c0 * member_stride;
+        const uintptr_t addr = (uintptr_t)first, base = addr & ~(uintptr_t)15;     // bulk copies need 16-byte aligned sources
+        const int64_t elem0 = (int64_t)((addr - base) / 4);
+        EncUmmaParams p{};
+        p.base = (const float*)base; p.elem0 = elem0; p.member_stride = member_stride;
+        p.total = (elem0 + (nc - 1) * member_stride + kInChannels * L + 3) & ~(int64_t)3; p.L = (int)L; p.L1 = (int)L1; p.L2 = (int)L2;
+        p.n_chunks = n_chunks;
+        p.w1_pk = reinterpret_cast<const uint4*>(m->enc_w1_pk); p.w2_pk = reinterpret_cast<const uint4*>(m->enc_w2_pk);
+        p.b1 = m->raw[1]; p.b2 = m->raw[3]; p.conv1_w = m->conv1_w;
+        p.partial = m->enc_partial + (size_t)c0 * n_chunks * kConv2Out; p.status = m->umma_status;
+        p.timing = m->umma_timing_on ? m->umma_timing : nullptr;
+        k_encoder_umma<<<dim3(n_chunks, (unsigned)nc), EU_THREADS, sizeof(EncUmmaSmem), st>>>(p);
+        ERT_LAUNCH_CHECK("k_encoder_umma");
+    }
+    k_encoder_finish<<<(unsigned)n_cond, m->H, 0, st>>>(m->enc_partial, n_chunks, L2, m->w6T, m->raw[5], m->w0cT,
+                                                       m->raw[9], m->H, d_cond_emb, d_cond_bias);
     ERT_LAUNCH_CHECK("k_encoder_finish");
     return 0;
 }
@@ -314,10 +352,12 @@ int ertdiff_model_create(ertdiff_model** out, int device, int param_dim, int hid
          alloc(m->w0xT, (size_t)kPPad * H) && alloc(m->w0tT, (size_t)H * H) &&
          alloc(m->w0cT, (size_t)H * H) && alloc(m->w2p, (size_t)kPPad * H) &&
          alloc(m->b2p, kPPad) && alloc(m->freq, H / 2);
+    ok = ok && cudaMalloc(&m->enc_w1_pk, kConv1Out * EU_K1 * 2) == cudaSuccess &&
+         cudaMalloc(&m->enc_w2_pk, kConv2Out * EU_K2 * 2) == cudaSuccess;
+    if (ok && !m->umma_status) ok = cudaMalloc(&m->umma_status, sizeof(int)) == cudaSuccess &&
+                                    cudaMalloc(&m->umma_timing, 16 * sizeof(long long)) == cudaSuccess;
     if (ok && H == UC_H) {
-        ok = cudaMalloc(&m->w1_pk, UC_H * UC_K1 * 2) == cudaSuccess && cudaMalloc(&m->w2_pk, UC_N2 * UC_H * 2) == cudaSuccess &&
-             cudaMalloc(&m->umma_status, sizeof(int)) == cudaSuccess &&
-             cudaMalloc(&m->umma_timing, 16 * sizeof(long long)) == cudaSuccess;
+        ok = cudaMalloc(&m->w1_pk, UC_H * UC_K1 * 2) == cudaSuccess && cudaMalloc(&m->w2_pk, UC_N2 * UC_H * 2) == cudaSuccess;
     }
     if (!ok) {
         ertdiff_model_destroy(m);
@@ -355,7 +395,6 @@ int ertdiff_model_umma_status(ertdiff_model* m, int* h_status) {
 
 int ertdiff_debug_umma_timing(ertdiff_model* m, int enable, int64_t* h_out16) {
     if (int rc = check_model(m, false)) return rc;
-    if (!m->umma_timing) return fail(ERTDIFF_ERR_UNSUPPORTED, "debug_umma_timing: the tcgen05 chain needs hidden_dim = 128");
     DeviceGuard g(m->device);
     if (h_out16) ERT_CUDA(cudaMemcpy(h_out16, m->umma_timing, 16 * sizeof(long long), cudaMemcpyDeviceToHost));
     m->umma_timing_on = enable != 0;
@@ -373,6 +412,7 @@ int ertdiff_model_destroy(ertdiff_model* m) {
                      m->coef_table, m->xbuf[0], m->xbuf[1]};
     for (float* p : ptrs) cudaFree(p);
     cudaFree(m->w1_pk); cudaFree(m->w2_pk); cudaFree(m->umma_status); cudaFree(m->umma_timing);
+    cudaFree(m->enc_w1_pk); cudaFree(m->enc_w2_pk);
     if (m->graph_exec) cudaGraphExecDestroy(m->graph_exec);
     delete m;
     return 0;
@@ -395,6 +435,9 @@ int ertdiff_model_load(ertdiff_model* m, const float* const* tensors12, int on_d
         m->raw[0], m->raw[2], m->raw[4], m->raw[6], m->raw[8], m->raw[10], m->raw[11], m->P, m->H,
         m->conv1_w, m->conv2_w, m->w6T, m->wtT, m->w0xT, m->w0tT, m->w0cT, m->w2p, m->b2p);
     ERT_LAUNCH_CHECK("k_pack_weights");
+    k_pack_encoder_umma<<<(kConv2Out * EU_K2 + 255) / 256, 256, 0, st>>>(m->raw[0], m->raw[2], m->enc_w1_pk, m->enc_w2_pk);
+    ERT_LAUNCH_CHECK("k_pack_encoder_umma");
+    ERT_CUDA(cudaMemsetAsync(m->umma_status, 0, sizeof(int), st));
     if (m->w1_pk) {
         k_pack_umma_weights<<<(UC_H * UC_K1 + 255) / 256, 256, 0, st>>>(m->w0xT, m->w2p, m->P, m->w1_pk, m->w2_pk);
         ERT_LAUNCH_CHECK("k_pack_umma_weights");
@@ -426,6 +469,19 @@ int ertdiff_encode_condition(ertdiff_model* m, const float* d_condition, int64_t
                              float* d_cond_bias, void* stream) {
     if (int rc = check_model(m)) return rc;
     DeviceGuard g(m->device);
+    return run_encoder(m, d_condition, n_cond, L, cond_member_stride, d_cond_emb, d_cond_bias,
+                       (cudaStream_t)stream);
+}
+
+int ertdiff_encode_condition_prec(ertdiff_model* m, const float* d_condition, int64_t n_cond,
+                                  int64_t L, int64_t cond_member_stride, float* d_cond_emb,
+                                  float* d_cond_bias, int32_t precision, void* stream) {
+    if (int rc = check_model(m)) return rc;
+    DeviceGuard g(m->device);
+    if (precision == ERTDIFF_PREC_BF16)
+        return run_encoder_umma(m, d_condition, n_cond, L, cond_member_stride, d_cond_emb, d_cond_bias,
+                                (cudaStream_t)stream);
+    if (precision != ERTDIFF_PREC_FP32) return fail(ERTDIFF_ERR_ARG, "encode_condition: bad precision");
     return run_encoder(m, d_condition, n_cond, L, cond_member_stride, d_cond_emb, d_cond_bias,
                        (cudaStream_t)stream);
 }
@@ -470,11 +526,16 @@ int ertdiff_sample_model(ertdiff_model* m, const float* d_condition, int64_t L,
     const int64_t n_cond = args->n_cond;
     ERT_REQUIRE(n_cond > 0, "sample_model: n_cond must be positive");
     if (int rc = grow(m->cond_bias, m->cond_bias_n, (size_t)n_cond * m->H)) return rc;
-    for (int64_t c0 = 0; c0 < n_cond; c0 += 32768) {
-        const int64_t nc = (n_cond - c0) < 32768 ? (n_cond - c0) : 32768;
-        if (int rc = run_encoder(m, d_condition + c0 * cond_member_stride, nc, L,
-                                 cond_member_stride, nullptr, m->cond_bias + c0 * m->H, st))
+    if (args->precision == ERTDIFF_PREC_BF16) {      // tensor-core encoder (batches internally)
+        if (int rc = run_encoder_umma(m, d_condition, n_cond, L, cond_member_stride, nullptr, m->cond_bias, st))
             return rc;
+    } else {
+        for (int64_t c0 = 0; c0 < n_cond; c0 += 32768) {
+            const int64_t nc = (n_cond - c0) < 32768 ? (n_cond - c0) : 32768;
+            if (int rc = run_encoder(m, d_condition + c0 * cond_member_stride, nc, L,
+                                     cond_member_stride, nullptr, m->cond_bias + c0 * m->H, st))
+                return rc;
+        }
     }
     return run_chain(m, args, m->cond_bias, st);
 }

@@ -107,26 +107,6 @@ struct UmmaChainExtra {
     long long* timing;      // optional (16 int64): phase cycle sums of CTA 0, see ertdiff_debug_umma_timing
 };
 
-// packed fp32x2 add / mul (sm_100): two IEEE-rn operations per instruction
-__device__ __forceinline__ float2 fadd2(float2 a, float2 b) {
-    unsigned long long d;
-    asm("add.rn.f32x2 %0, %1, %2;" : "=l"(d)
-        : "l"(*reinterpret_cast<unsigned long long*>(&a)), "l"(*reinterpret_cast<unsigned long long*>(&b)));
-    return *reinterpret_cast<float2*>(&d);
-}
-__device__ __forceinline__ float2 fmul2(float2 a, float2 b) {
-    unsigned long long d;
-    asm("mul.rn.f32x2 %0, %1, %2;" : "=l"(d)
-        : "l"(*reinterpret_cast<unsigned long long*>(&a)), "l"(*reinterpret_cast<unsigned long long*>(&b)));
-    return *reinterpret_cast<float2*>(&d);
-}
-// {lo, hi} -> bf16x2 with ReLU folded into the conversion
-__device__ __forceinline__ uint32_t pack_bf16_relu(float lo, float hi) {
-    uint32_t d;
-    asm("cvt.rn.relu.bf16x2.f32 %0, %1, %2;" : "=r"(d) : "f"(hi), "f"(lo));
-    return d;
-}
-
 template <bool REPLAY, bool TRACE, bool SHARED>
 __global__ void __launch_bounds__(UC_THREADS, 1) k_chain_umma(const ChainParams a, const UmmaChainExtra ex) {
     using namespace umma;

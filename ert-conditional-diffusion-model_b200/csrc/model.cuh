@@ -26,6 +26,8 @@ struct ertdiff_model {
     float* freq = nullptr;     // [H/2]        timestep-embedding frequencies (from the host)
     unsigned short* w1_pk = nullptr;   // bf16 B operand of GEMM1 (tcgen05 chain, H == 128): 8 KB
     unsigned short* w2_pk = nullptr;   // bf16 B operand of GEMM2: 8 KB
+    unsigned short* enc_w1_pk = nullptr;   // bf16 B operands of the tensor-core encoder (conv1: 3 KB, conv2: 12 KB)
+    unsigned short* enc_w2_pk = nullptr;
     int* umma_status = nullptr;        // device flag: a tcgen05 chain tile timed out
     long long* umma_timing = nullptr;  // 16 int64: phase cycle sums of CTA 0 (debug aid)
     bool umma_timing_on = false;

@@ -199,15 +199,20 @@ class ConditionalDiffusionModel(nn.Module):
         return out
 
     @torch.no_grad()
-    def encode_condition(self, condition):
-        """``condition_encoder(condition)`` (ECD.py:133-142, 161): ``(n, 14, L) -> (n, H)``."""
+    def encode_condition(self, condition, precision="fp32", return_bias=False):
+        """``condition_encoder(condition)`` (ECD.py:133-142, 161): ``(n, 14, L) -> (n, H)``.
+        ``precision="bf16"`` runs both convolutions on the tensor cores (bf16 operands, fp32
+        accumulation).  ``return_bias`` also returns ``mlp.0.weight[:, P+H:] @ emb + mlp.0.bias``,
+        the per-condition constant the chain consumes."""
         h = self.handle()
         dev = self.device
         condition = condition.to(device=dev, dtype=torch.float32).contiguous()
         n, L = condition.size(0), condition.size(2)
         emb = torch.empty(n, self.hidden_dim, device=dev, dtype=torch.float32)
+        bias = torch.empty(n, self.hidden_dim, device=dev, dtype=torch.float32) if return_bias else None
         with torch.cuda.device(dev):
-            _lib.check(_lib.load().ertdiff_encode_condition(
-                h, _lib.ptr(condition), n, L, IN_CHANNELS * L, _lib.ptr(emb), None,
+            _lib.check(_lib.load().ertdiff_encode_condition_prec(
+                h, _lib.ptr(condition), n, L, IN_CHANNELS * L, _lib.ptr(emb),
+                _lib.ptr(bias) if bias is not None else None, _lib.PRECISIONS[precision],
                 _lib.stream_ptr(dev)), "encode_condition")
-        return emb
+        return (emb, bias) if return_bias else emb

@@ -116,6 +116,13 @@ int ertdiff_forward(ertdiff_model* m, const float* d_x, const int64_t* d_t,
 int ertdiff_encode_condition(ertdiff_model* m, const float* d_condition, int64_t n_cond,
                              int64_t L, int64_t cond_member_stride, float* d_cond_emb,
                              float* d_cond_bias, void* stream);
+/* the same with the arithmetic selectable: ERTDIFF_PREC_FP32 = the call above (CUDA-core FFMA);
+ * ERTDIFF_PREC_BF16 = both convolutions as implicit GEMMs on the tensor cores (tcgen05, bf16
+ * operands, fp32 accumulation, input fed by TMA), which is also what ertdiff_sample_model uses when
+ * args->precision is ERTDIFF_PREC_BF16. */
+int ertdiff_encode_condition_prec(ertdiff_model* m, const float* d_condition, int64_t n_cond,
+                                  int64_t L, int64_t cond_member_stride, float* d_cond_emb,
+                                  float* d_cond_bias, int32_t precision, void* stream);
 
 /* ---- reverse chain: sample_model (ECD.py:102-119) --------------------------------------- */
 typedef struct ertdiff_chain_args {

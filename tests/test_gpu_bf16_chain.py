@@ -13,6 +13,7 @@ import torch.nn.functional as F
 
 import ertdiff_b200 as eb
 from oracle import denoiser_oracle as do
+from bf16_emulation import emulate_encoder
 
 pytestmark = pytest.mark.gpu
 P, C = 29, 14
@@ -40,7 +41,7 @@ def emulate_bf16_chain(sd, cond, T, betas, alphas, alpha_bar, noise, num_steps=N
     H = sd["time_embed.0.weight"].shape[1]
     W0 = sd["mlp.0.weight"]
     W0x, W0t, W0c = W0[:, :P], W0[:, P:P + H], W0[:, P + H:]
-    cemb = do.encode_condition(sd, cond)
+    cemb = emulate_encoder(sd, cond)          # precision="bf16" also selects the tensor-core encoder
     cb = F.linear(cemb, W0c) + sd["mlp.0.bias"]
     x = noise[0].clone()
     draw = 1
