@@ -53,6 +53,18 @@ static int workspace(size_t bytes, void** out) {
     return 0;
 }
 
+static int colstats_attr() {
+    static bool done = false;
+    if (!done) {
+        ERT_CUDA(cudaFuncSetAttribute(k_colstats_smallq<float, 0>, cudaFuncAttributeMaxDynamicSharedMemorySize, SQ_SMEM_BYTES));
+        ERT_CUDA(cudaFuncSetAttribute(k_colstats_smallq<double, 0>, cudaFuncAttributeMaxDynamicSharedMemorySize, SQ_SMEM_BYTES));
+        ERT_CUDA(cudaFuncSetAttribute(k_colstats_smallq<float, 1>, cudaFuncAttributeMaxDynamicSharedMemorySize, SQ_SMEM_BYTES));
+        ERT_CUDA(cudaFuncSetAttribute(k_colstats_smallq<double, 1>, cudaFuncAttributeMaxDynamicSharedMemorySize, SQ_SMEM_BYTES));
+        done = true;
+    }
+    return 0;
+}
+
 // ---- encoder ----------------------------------------------------------------------------
 static int run_encoder(ertdiff_model* m, const float* d_cond, int64_t n_cond, int64_t L,
                        int64_t member_stride, float* d_cond_emb, float* d_cond_bias,
@@ -577,6 +589,18 @@ int ertdiff_ensemble_moments(const void* d_a, int dtype, int64_t N, int64_t Q, v
     ERT_REQUIRE(d_a && N > 0 && Q > 0, "ensemble_moments: bad arguments");
     cudaStream_t st = (cudaStream_t)stream;
     const unsigned grid = (unsigned)((Q + 127) / 128);
+    if (Q <= SQ_MAXQ && N >= 64 && (dtype == ERTDIFF_F32 || dtype == ERTDIFF_F64)) {
+        // few columns: one CTA streams the rows through shared memory (see k_colstats_smallq)
+        const size_t esz = dtype == ERTDIFF_F32 ? 4 : 8;
+        const size_t smem = (size_t)N * esz < (size_t)SQ_SMEM_BYTES ? (size_t)N * esz : (size_t)SQ_SMEM_BYTES;
+        if (int rc = colstats_attr()) return rc;
+        if (dtype == ERTDIFF_F32)
+            k_colstats_smallq<float, 0><<<(unsigned)Q, 256, smem, st>>>((const float*)d_a, N, Q, (float*)d_mean, (float*)d_std, (float*)d_var, 0.0, nullptr);
+        else
+            k_colstats_smallq<double, 0><<<(unsigned)Q, 256, smem, st>>>((const double*)d_a, N, Q, (double*)d_mean, (double*)d_std, (double*)d_var, 0.0, nullptr);
+        ERT_LAUNCH_CHECK("k_colstats_smallq");
+        return 0;
+    }
     if (dtype == ERTDIFF_F32)
         k_moments<float><<<grid, 128, 0, st>>>((const float*)d_a, N, Q, (float*)d_mean,
                                                (float*)d_std, (float*)d_var);
@@ -693,7 +717,15 @@ int ertdiff_ensemble_kde_mode(const void* d_a, int dtype, int64_t N, int64_t Q,
     KdeColumn* cols = (KdeColumn*)ws;
     float* s32 = (float*)((char*)ws + cols_bytes);
     const bool f32in = dtype == ERTDIFF_F32;
-    {
+    if (Q <= SQ_MAXQ && N >= 64) {
+        static_assert(sizeof(KdeColumn) == 2 * sizeof(double), "KdeColumn is written as two doubles");
+        const size_t esz = f32in ? 4 : 8;
+        const size_t smem = (size_t)N * esz < (size_t)SQ_SMEM_BYTES ? (size_t)N * esz : (size_t)SQ_SMEM_BYTES;
+        if (int rc = colstats_attr()) return rc;
+        if (f32in) k_colstats_smallq<float, 1><<<(unsigned)Q, 256, smem, st>>>((const float*)d_a, N, Q, nullptr, nullptr, nullptr, f2, (double*)cols);
+        else k_colstats_smallq<double, 1><<<(unsigned)Q, 256, smem, st>>>((const double*)d_a, N, Q, nullptr, nullptr, nullptr, f2, (double*)cols);
+        ERT_LAUNCH_CHECK("k_colstats_smallq");
+    } else {
         const unsigned grid = (unsigned)((Q * 32 + 255) / 256);
         if (f32in) k_kde_prepare<float><<<grid, 256, 0, st>>>((const float*)d_a, N, Q, f2, cols);
         else k_kde_prepare<double><<<grid, 256, 0, st>>>((const double*)d_a, N, Q, f2, cols);

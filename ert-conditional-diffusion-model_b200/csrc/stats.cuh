@@ -80,6 +80,106 @@ k_moments(const T* __restrict__ a, int64_t N, int64_t Q, T* __restrict__ mean,
 }
 
 // ------------------------------------------------------------------------------------------
+// Few columns, many members (the chain's own output: Q = 29 parameters, N up to 10^5 members): one
+// thread per column leaves the machine to 29 threads waiting on strided loads.  Here one CTA owns
+// one column: all its threads gather the column into shared memory (every load in flight at once),
+// then a single thread runs numpy's left-to-right chain out of shared memory with 128-bit reads, so
+// the dependent fp add -- 4 cycles per member -- is all that is left.  The second pass (variance)
+// re-reads shared memory, not HBM.  MODE 0: numpy mean / var / std (bit-exact order).  MODE 1: the
+// KDE column constants (double sums, any order: all threads).
+constexpr int SQ_MAXQ = 256;
+constexpr int SQ_SMEM_BYTES = 192 * 1024;     // column chunk held in shared memory
+
+struct KdeColumn;
+template <typename T, int MODE>
+__global__ void __launch_bounds__(256)
+k_colstats_smallq(const T* __restrict__ a, int64_t N, int64_t Q, T* __restrict__ mean, T* __restrict__ stdv,
+                  T* __restrict__ var, double scott_factor_sq, double* __restrict__ kde_cols /* (Q,2) */) {
+    extern __shared__ __align__(16) unsigned char sq_smem_raw[];
+    T* xs = reinterpret_cast<T*>(sq_smem_raw);
+    __shared__ double red[8];
+    const int tid = threadIdx.x;
+    const int64_t j = blockIdx.x;
+    constexpr int64_t CH = SQ_SMEM_BYTES / (int64_t)sizeof(T);
+    const bool second = MODE == 1 || stdv != nullptr || var != nullptr;
+    const bool resident = N <= CH;               // the whole column stays in shared memory for pass 2
+    T acc = (T)0, m = (T)0;
+    double dacc = 0.0, dmean = 0.0;
+    for (int pass = 0; pass < (second ? 2 : 1); ++pass) {
+        for (int64_t c0 = 0; c0 < N; c0 += CH) {
+            const int n = (int)(N - c0 < CH ? N - c0 : CH);
+            if (pass == 0 || !resident) {
+                __syncthreads();
+                for (int i = tid; i < n; i += 256) xs[i] = a[(c0 + i) * Q + j];
+                __syncthreads();
+            }
+            if (MODE == 0) {
+                if (tid == 0) {
+                    int i = 0;
+                    if (c0 == 0) {
+                        if (pass == 0) acc = xs[0];
+                        else { const T d0 = RN<T>::sub(xs[0], m); acc = RN<T>::mul(d0, d0); }
+                        i = 1;
+                    }
+                    for (; i < n && (i & 3); ++i) {           // up to a 16-byte boundary (fp32) / 32-byte (fp64)
+                        if (pass == 0) acc = RN<T>::add(acc, xs[i]);
+                        else { const T d = RN<T>::sub(xs[i], m); acc = RN<T>::add(acc, RN<T>::mul(d, d)); }
+                    }
+#pragma unroll 4
+                    for (; i + 4 <= n; i += 4) {
+                        T v[4];
+                        if (sizeof(T) == 4) *reinterpret_cast<float4*>(v) = *reinterpret_cast<const float4*>(xs + i);
+                        else { *reinterpret_cast<double2*>(v) = *reinterpret_cast<const double2*>(xs + i);
+                               *reinterpret_cast<double2*>(v + 2) = *reinterpret_cast<const double2*>(xs + i + 2); }
+#pragma unroll
+                        for (int u = 0; u < 4; ++u) {
+                            if (pass == 0) acc = RN<T>::add(acc, v[u]);
+                            else { const T d = RN<T>::sub(v[u], m); acc = RN<T>::add(acc, RN<T>::mul(d, d)); }
+                        }
+                    }
+                    for (; i < n; ++i) {
+                        if (pass == 0) acc = RN<T>::add(acc, xs[i]);
+                        else { const T d = RN<T>::sub(xs[i], m); acc = RN<T>::add(acc, RN<T>::mul(d, d)); }
+                    }
+                }
+            } else {
+                for (int i = tid; i < n; i += 256) {
+                    const double d = (double)xs[i] - dmean;      // dmean == 0 in pass 0
+                    dacc += pass == 0 ? d : d * d;
+                }
+            }
+        }
+        if (MODE == 0) {
+            if (tid == 0) {
+                if (pass == 0) {
+                    m = RN<T>::div(acc, (T)N);
+                    if (mean) mean[j] = m;
+                } else {
+                    const T vv = RN<T>::div(acc, (T)N);
+                    if (var) var[j] = vv;
+                    if (stdv) stdv[j] = RN<T>::sqrt(vv);
+                }
+            }
+        } else {
+#pragma unroll
+            for (int o = 16; o > 0; o >>= 1) dacc += __shfl_xor_sync(0xffffffffu, dacc, o);
+            __syncthreads();
+            if ((tid & 31) == 0) red[tid >> 5] = dacc;
+            __syncthreads();
+            double tot = 0.0;
+#pragma unroll
+            for (int w = 0; w < 8; ++w) tot += red[w];
+            if (pass == 0) { dmean = tot / (double)N; dacc = 0.0; }
+            else if (tid == 0) {
+                const double h2 = (tot / (double)(N - 1)) * scott_factor_sq;
+                kde_cols[2 * j] = dmean;
+                kde_cols[2 * j + 1] = -0.5 / h2;        // -inf when the column is constant
+            }
+        }
+    }
+}
+
+// ------------------------------------------------------------------------------------------
 // Global min / max (ECD.py:749-750).  NaN propagates like np.min/np.max.
 template <typename T>
 __global__ void k_minmax_partial(const T* __restrict__ a, int64_t n, double* __restrict__ part) {
