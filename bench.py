@@ -50,6 +50,15 @@ def load_peaks():
             "source": "fallback (B200_PROFILING.md)"}
 
 
+def ncu_traffic(kernel):
+    """DRAM bytes of one launch of `kernel` from the committed `ncu --set full` summary (or None)."""
+    path = os.path.join(ROOT, "profiles", "r01_ncu_kernels.json")
+    try:
+        return json.load(open(path))[kernel]["traffic_bytes_per_launch"]
+    except Exception:
+        return None
+
+
 class ClockSampler:
     """nvidia-smi clocks / throttle reasons sampled DURING the timed region."""
     Q = ("clocks.sm,clocks.max.sm,power.draw,clocks_event_reasons.hw_slowdown,"
@@ -309,18 +318,27 @@ def run_ours(args):
             achieved = flops / (k_ms * 1e-3) / 1e12
             peak = peaks["bf16_tflops_sustained"]
             fp32_peak = 148 * 128 * 2 * (clocks["sm_mhz"] or 1965.0) * 1e6 / 1e12 if clocks else None
+            fp32 = args.precision == "fp32"
             line["roofline"] = {
-                "kernel": "k_chain (persistent reverse loop, fp32 FFMA2)" if args.precision == "fp32"
-                          else "k_chain_umma (persistent reverse loop, tcgen05 bf16)", "bound": "tensor",
+                "kernel": "k_chain (persistent reverse loop, fp32 FFMA2)" if fp32
+                          else "k_chain_umma (persistent reverse loop, tcgen05 bf16, TMEM accumulators)",
+                "bound": "tensor",
                 "achieved": achieved, "peak": peak, "unit": "TFLOP/s", "frac": achieved / peak,
-                "traffic": None, "peak_source": peaks["source"] + ", sustained bf16",
+                "traffic": ncu_traffic("chain_fp32" if fp32 else "chain_umma"),
+                "peak_source": peaks["source"] + ", sustained bf16",
                 "kernel_ms": k_ms, "flop_per_launch": flops,
                 "share_of_step": k_ms / (ms_dev / args.steps),
-                "note": "structurally latency-bound: T dependent steps per member, 14,848 FLOP each; "
-                        "fp32 CUDA-core kernel, so also quoted against the fp32 FFMA peak",
+                "note": ("structurally latency-bound: T dependent steps per member, 14,848 FLOP each, no HBM traffic "
+                         "beyond the tables (device RNG); fp32 CUDA-core kernel, so also quoted against the fp32 FFMA peak"
+                         if fp32 else
+                         "T dependent steps per member; per step and 128-member tile the tensor pipe needs ~0.13 us, the "
+                         "Philox/Box-Muller generator ~0.5 us of MUFU + integer-multiply pipe time (measured, "
+                         "scripts/microbench/rng_bench.cu): the kernel is bound by issue slots / those pipes, not by the MMAs"),
                 "fp32_ffma_peak_tflops": fp32_peak,
-                "fp32_ffma_frac": (achieved / fp32_peak) if fp32_peak else None,
+                "fp32_ffma_frac": (achieved / fp32_peak) if (fp32_peak and fp32) else None,
                 "as_written_equivalent_tflops": members * T * FLOP_AS_WRITTEN / (k_ms * 1e-3) / 1e12,
+                "traffic_note": "dram__bytes_read+write of one launch from the committed ncu capture "
+                                "(profiles/r01_ncu_kernels.json; its workload is stated there), null if absent",
             }
         # CPU baseline on a bounded sample (rank 0, N=1 only)
         if world == 1 and not args.no_cpu_baseline:

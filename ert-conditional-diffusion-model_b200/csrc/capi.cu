@@ -678,6 +678,16 @@ int ertdiff_ensemble_percentiles(const void* d_a, int dtype, int64_t N, int64_t 
     return 0;
 }
 
+int ertdiff_interval_coverage(const double* d_low, const double* d_upp, const double* d_truth,
+                              int32_t n_intervals, int64_t Q, int32_t P, int32_t* d_counts, void* stream) {
+    ERT_REQUIRE(d_low && d_upp && d_truth && d_counts, "interval_coverage: NULL pointer");
+    ERT_REQUIRE(n_intervals > 0 && Q > 0 && P > 0 && P <= kPPad && Q % P == 0,
+                "interval_coverage: need n_intervals > 0, 0 < P <= 32 and Q a multiple of P");
+    k_interval_coverage<<<(unsigned)n_intervals, 256, 0, (cudaStream_t)stream>>>(d_low, d_upp, d_truth, Q, P, d_counts);
+    ERT_LAUNCH_CHECK("k_interval_coverage");
+    return 0;
+}
+
 int ertdiff_minmax(const void* d_a, int dtype, int64_t n, double* d_out2, void* stream) {
     ERT_REQUIRE(d_a && d_out2 && n > 0, "minmax: bad arguments");
     cudaStream_t st = (cudaStream_t)stream;

@@ -180,6 +180,32 @@ k_colstats_smallq(const T* __restrict__ a, int64_t N, int64_t Q, T* __restrict__
 }
 
 // ------------------------------------------------------------------------------------------
+// Coverage of K nested probability intervals (ECD.py:1121-1132, 1195-1206): for interval k and
+// column c (= condition m, parameter c % P), indicator = (low[k][c] < truth[c]) & (truth[c] <= upp[k][c]).
+// counts[k][0] = number of ones over all columns, counts[k][1 + j] = over the columns of parameter j.
+// grid = K, block = 256.  Integer counts: the means the reference takes are exact quotients of them.
+__global__ void __launch_bounds__(256)
+k_interval_coverage(const double* __restrict__ low, const double* __restrict__ upp,
+                    const double* __restrict__ truth, int64_t Q, int P, int32_t* __restrict__ counts) {
+    __shared__ int cnt[kPPad + 1];
+    const int tid = threadIdx.x;
+    const int64_t k = blockIdx.x;
+    if (tid <= kPPad) cnt[tid] = 0;
+    __syncthreads();
+    const double* lo = low + k * Q;
+    const double* up = upp + k * Q;
+    for (int64_t c = tid; c < Q; c += 256) {
+        const double t = truth[c];
+        if (lo[c] < t && t <= up[c]) {
+            atomicAdd(&cnt[0], 1);
+            atomicAdd(&cnt[1 + (int)(c % P)], 1);
+        }
+    }
+    __syncthreads();
+    if (tid <= P) counts[k * (P + 1) + tid] = cnt[tid];
+}
+
+// ------------------------------------------------------------------------------------------
 // Global min / max (ECD.py:749-750).  NaN propagates like np.min/np.max.
 template <typename T>
 __global__ void k_minmax_partial(const T* __restrict__ a, int64_t n, double* __restrict__ part) {

@@ -146,3 +146,57 @@ def ensemble_statistics(a, percentiles=(25, 50, 75), mode=True, n_grid=5000, dev
     if mode:
         out["mode"], out["mode_index"] = ensemble_kde_mode(a, n_grid, None, device, True)
     return out
+
+
+# ---------------------------------------------------------------------------------------------
+# UQ calibration metrics (ECD.py:1089-1137 pooled over the parameters, ECD.py:1191-1214 per parameter)
+def _trapezoid(y, x):
+    # np.trapz(y, x, dx=...) (ECD.py:1099, 1107, 1112): with x given, dx is ignored
+    d = np.diff(x)
+    return float(np.sum(d * (y[1:] + y[:-1]) / 2.0))
+
+
+def _calibration_scores(avg, prob):
+    a_p = (avg >= prob).astype(np.int64)                                  # ECD.py:1089-1096
+    accuracy = _trapezoid(a_p.astype(np.float64), prob)                   # ECD.py:1098-1100
+    precision = 0.0 if accuracy == 0 else 1 - 2 * _trapezoid(a_p * (avg - prob), prob)   # ECD.py:1102-1109
+    goodness = 1 - _trapezoid((3 * a_p - 2) * (avg - prob), prob)         # ECD.py:1111-1115
+    return accuracy, precision, goodness
+
+
+def uq_calibration(generated, true, n_prob=30, device=None):
+    """The reference's uncertainty-calibration metrics for an ensemble ``generated (N, M, P)``
+    against ``true (M, P)`` (ECD.py:1115-1137 and 1191-1214): for ``n_prob`` nested probability
+    intervals p, the 2*n_prob ensemble percentiles ``(1 -/+ p)/2*100`` over the members and the
+    coverage counts run on the device (one multi-quantile selection pass + one counting kernel);
+    the 30-point trapezoid integrals are host arithmetic.  Returns numpy values:
+    ``prob_array, avg_proportion, accuracy, precision, goodness`` and ``param_*`` per parameter."""
+    t = generated if isinstance(generated, torch.Tensor) else np.asarray(generated)
+    if t.ndim != 3:
+        raise ValueError("generated must be (N, M, P)")
+    N, M, P = t.shape
+    tr = true if isinstance(true, torch.Tensor) else torch.from_numpy(np.ascontiguousarray(np.asarray(true)))
+    if tuple(tr.shape) != (M, P):
+        raise ValueError(f"true must be ({M}, {P})")
+    if P > 32:
+        raise _lib.ErtdiffError("uq_calibration: at most 32 parameters")
+    prob = np.linspace(0.01, 0.99, int(n_prob))                           # ECD.py:1119
+    q = np.concatenate([(1 - prob) / 2 * 100, (1 + prob) / 2 * 100])      # ECD.py:1123-1126 (float64 scalars)
+    flat, _, _ = _to_device(t.reshape(N, M * P), device)
+    bounds = ensemble_percentile(flat, list(q))                           # (2K, M*P) float64 on the device
+    truth = tr.to(device=flat.device, dtype=torch.float64).reshape(-1).contiguous()
+    K = int(n_prob)
+    counts = torch.empty(K, P + 1, device=flat.device, dtype=torch.int32)
+    with torch.cuda.device(flat.device):
+        _lib.check(_lib.load().ertdiff_interval_coverage(
+            _lib.ptr(bounds[:K]), _lib.ptr(bounds[K:]), _lib.ptr(truth), K, M * P, P, _lib.ptr(counts),
+            _lib.stream_ptr(flat.device)), "interval_coverage")
+    c = counts.cpu().numpy().astype(np.float64)
+    avg = c[:, 0] / (M * P)
+    pavg = (c[:, 1:] / M).T.copy()                                        # (P, K)
+    out = {"prob_array": prob, "avg_proportion": avg}
+    out["accuracy"], out["precision"], out["goodness"] = _calibration_scores(avg, prob)
+    scores = np.array([_calibration_scores(pavg[j], prob) for j in range(P)])
+    out.update(param_avg_proportion=pavg, param_accuracy=scores[:, 0], param_precision=scores[:, 1],
+               param_goodness=scores[:, 2])
+    return out

@@ -190,6 +190,13 @@ int ertdiff_ensemble_moments(const void* d_a, int dtype, int64_t N, int64_t Q, v
 int ertdiff_ensemble_percentiles(const void* d_a, int dtype, int64_t N, int64_t Q,
                                  const double* h_q, int32_t nq, int index_dtype, void* d_out,
                                  void* stream);
+/* UQ calibration, the coverage step (ECD.py:1121-1132, 1195-1206): d_low / d_upp are
+ * (n_intervals, Q) float64 lower / upper bounds (rows of ertdiff_ensemble_percentiles), d_truth (Q)
+ * float64, column c belongs to parameter c % P.  d_counts (n_intervals, P + 1) int32:
+ * [k][0] = #{c : low < truth <= upp}, [k][1 + j] = the same over the columns of parameter j. */
+int ertdiff_interval_coverage(const double* d_low, const double* d_upp, const double* d_truth,
+                              int32_t n_intervals, int64_t Q, int32_t P, int32_t* d_counts, void* stream);
+
 /* global min and max of n elements (the KDE grid's end points, ECD.py:749-750) -> d_out[2]
  * as float64. */
 int ertdiff_minmax(const void* d_a, int dtype, int64_t n, double* d_out2, void* stream);

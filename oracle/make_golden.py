@@ -158,6 +158,38 @@ def main():
              p25=np.percentile(sim, 25, axis=0), p50=np.percentile(sim, 50, axis=0),
              p75=np.percentile(sim, 75, axis=0), mode=mode, mode_index=midx,
              ci95=np.percentile(sim.astype(np.float32), [2.5, 97.5], axis=0))
+    # ---- UQ calibration (ECD.py:1089-1137, 1191-1214): the reference's four helper functions run
+    # unmodified; its inline percentile loop is replayed around them with numpy, as written there
+    import warnings
+    warnings.simplefilter("ignore", DeprecationWarning)          # np.trapz
+    rng = np.random.default_rng(8)
+    truth = rng.normal(size=(8, P)).astype(np.float32)
+    gen = (truth[None] * 0.9 + rng.normal(scale=0.8, size=(50, 8, P))).astype(np.float32)
+    prob_array = np.linspace(0.01, 0.99, 30)
+
+    def curve(dist, true):
+        avg = np.zeros(len(prob_array))
+        for prob in enumerate(prob_array):
+            p_low = (1 - prob[1]) / 2
+            p_upp = (1 + prob[1]) / 2
+            low_bound = np.percentile(dist, p_low * 100, axis=0)
+            upp_bound = np.percentile(dist, p_upp * 100, axis=0)
+            indicator_matrix = ((low_bound < true) & (true <= upp_bound)).astype(int)
+            avg[prob[0]] = np.mean(indicator_matrix)
+        return avg
+
+    def metrics(avg):
+        a_p = ref.avg_prop_indicator_function(avg, prob_array)
+        acc = ref.accuracy_score(a_p, prob_array)
+        return acc, ref.preccision_score(acc, avg, prob_array, a_p), ref.goodness_score(a_p, avg, prob_array)
+
+    avg = curve(gen, truth)
+    acc, prec, good = metrics(avg)
+    pavg = np.stack([curve(gen[:, :, j], truth[:, j]) for j in range(P)])
+    pm = np.array([metrics(pavg[j]) for j in range(P)])
+    np.savez(os.path.join(OUT, "uq_calibration.npz"), generated=gen, true=truth, prob_array=prob_array,
+             avg_proportion=avg, accuracy=acc, precision=prec, goodness=good, param_avg_proportion=pavg,
+             param_accuracy=pm[:, 0], param_precision=pm[:, 1], param_goodness=pm[:, 2])
     sizes = {f: os.path.getsize(os.path.join(OUT, f)) for f in sorted(os.listdir(OUT))}
     print(sizes, sum(sizes.values()))
 

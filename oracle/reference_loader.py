@@ -44,6 +44,10 @@ WANTED = (
     "mode_kde_calculation",         # :166-181
     "check_param_bounds",           # :183-218
     "load_best_model",              # :369-377
+    "avg_prop_indicator_function",  # :1089-1096
+    "accuracy_score",               # :1098-1100
+    "preccision_score",             # :1102-1109
+    "goodness_score",               # :1111-1115
 )
 
 

@@ -148,3 +148,68 @@ def kde_mode_scipy(a: np.ndarray, grid: np.ndarray | None = None, n_grid: int = 
         idx[j] = int(np.argmax(vals))
         pdfs.append(vals)
     return grid[idx].reshape(a.shape[1:]), idx.reshape(a.shape[1:]), np.stack(pdfs, axis=1)
+
+
+# ---------------------------------------------------------------------------------------------
+# UQ calibration metrics (ECD.py:1089-1137 for all parameters pooled, ECD.py:1191-1214 per
+# parameter).  `generated` is (N realisations, M conditions, P) -- Uncertainty_params.npy at
+# ECD.py:1082 -- and `true` is (M, P).
+def _trapezoid(y, x):
+    # np.trapz(y, x, dx=...) at ECD.py:1099, 1107, 1112: with x given, dx is ignored
+    y = np.asarray(y, dtype=np.float64)
+    d = np.diff(np.asarray(x, dtype=np.float64))
+    return float(np.sum(d * (y[1:] + y[:-1]) / 2.0))
+
+
+def avg_prop_indicator(avg_proportion, prob_array):          # ECD.py:1089-1096
+    return np.array([1 if avg_proportion[i] >= prob_array[i] else 0 for i in range(prob_array.shape[0])])
+
+
+def accuracy_score(a_p, prob_array):                         # ECD.py:1098-1100
+    return _trapezoid(a_p, prob_array)
+
+
+def precision_score(accuracy, avg_proportion, prob_array, a_p):   # ECD.py:1102-1109
+    if accuracy == 0:
+        return 0.0
+    return 1 - 2 * _trapezoid(a_p * (avg_proportion - prob_array), prob_array)
+
+
+def goodness_score(a_p, avg_proportion, prob_array):         # ECD.py:1111-1115
+    return 1 - _trapezoid((3 * a_p - 2) * (avg_proportion - prob_array), prob_array)
+
+
+def coverage_curve(dist, true, prob_array):
+    """avg_proportion[k] = mean over the trailing axes of (low < true) & (true <= upp), with
+    low/upp = np.percentile(dist, (1 -/+ p_k)/2 * 100, axis=0) (ECD.py:1121-1132, 1195-1206; the
+    percentile argument is an np.float64, so the index arithmetic runs in float64)."""
+    avg = np.zeros(len(prob_array))
+    for k, p in enumerate(prob_array):
+        p_low, p_upp = (1 - p) / 2, (1 + p) / 2
+        low = np.percentile(dist, p_low * 100, axis=0)
+        upp = np.percentile(dist, p_upp * 100, axis=0)
+        avg[k] = np.mean(((low < true) & (true <= upp)).astype(int))
+    return avg
+
+
+def uq_calibration(generated, true, n_prob=30):
+    """Returns {"prob_array", "avg_proportion", "accuracy", "precision", "goodness"} for the pooled
+    parameters and the same keys with a ``param_`` prefix holding one entry per parameter."""
+    prob = np.linspace(0.01, 0.99, n_prob)                   # ECD.py:1119
+    out = {"prob_array": prob}
+    avg = coverage_curve(generated, true, prob)
+    a_p = avg_prop_indicator(avg, prob)
+    acc = accuracy_score(a_p, prob)
+    out.update(avg_proportion=avg, accuracy=acc, precision=precision_score(acc, avg, prob, a_p),
+               goodness=goodness_score(a_p, avg, prob))
+    P = generated.shape[2]
+    pavg = np.zeros((P, n_prob))
+    pacc, pprec, pgood = np.zeros(P), np.zeros(P), np.zeros(P)
+    for j in range(P):                                        # ECD.py:1191-1214
+        pavg[j] = coverage_curve(generated[:, :, j], true[:, j], prob)
+        a_p = avg_prop_indicator(pavg[j], prob)
+        pacc[j] = accuracy_score(a_p, prob)
+        pprec[j] = precision_score(pacc[j], pavg[j], prob, a_p)
+        pgood[j] = goodness_score(a_p, pavg[j], prob)
+    out.update(param_avg_proportion=pavg, param_accuracy=pacc, param_precision=pprec, param_goodness=pgood)
+    return out

@@ -1,0 +1,1 @@
+python -m pytest tests/test_uq_calibration.py tests/test_gpu_stats.py -q 2>&1 | tail -n 6
