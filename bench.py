@@ -182,7 +182,8 @@ def workload_config(args, members_per_gpu):
             "members_per_gpu": members_per_gpu, "T": args.T, "param_dim": P, "hidden_dim": H,
             "loop_mode": args.loop_mode, "rng": "device Philox4x32-10",
             "l2": "flushed between steps (256 MiB memset outside the per-step event pairs)",
-            "parallelism": f"members sharded over {args.gpus} GPU(s), one all-gather of (B/G,29) f32"}
+            "parallelism": f"members sharded over {args.gpus} GPU(s), one all-gather of (B/G,29) f32; statistics "
+                           "columns sharded over the ranks, one all-gather of the maps"}
 
 
 # ------------------------------------------------------------------------------------------
@@ -215,6 +216,8 @@ def run_ours(args):
     stream = torch.cuda.current_stream(dev)
 
     def stats(x):
+        if world > 1:                       # per-column statistics: columns split over the ranks
+            return eb.parallel.sharded_statistics(x, PERCENTILES, KDE_GRID)
         out = eb.ensemble_moments(x)
         out["pct"] = eb.ensemble_percentile(x, PERCENTILES)
         out["mode"] = eb.ensemble_kde_mode(x, KDE_GRID)

@@ -62,3 +62,46 @@ def sample_ensemble_sharded(chain_fn, n_members: int, n_cond: int = 1, group=Non
     nz = None if noise is None else noise[:, start:stop, :]
     x_local = chain_fn(start, stop, nz)
     return gather_members(x_local, n_members, n_cond, group)
+
+
+def column_slice(n_columns: int, rank: int, world_size: int):
+    """Contiguous ``[start, stop)`` of the columns (pixels / parameters) whose statistics this rank
+    computes."""
+    return member_slice(n_columns, rank, world_size, 1)
+
+
+def sharded_statistics(x: torch.Tensor, percentiles=(25, 50, 75), n_grid: int = 5000, group=None,
+                       stats_fn=None):
+    """Ensemble statistics of the gathered fields ``x (N, Q)`` with the COLUMNS split over the ranks:
+    every statistic of the path is per column (ECD.py:747-762, 867-872), so rank r computes columns
+    ``column_slice(Q, r, world)`` over all N members and one small all-gather returns every map to
+    every rank.  The KDE grid spans the global min/max of the whole array (ECD.py:749-751), which each
+    rank takes from its own copy of ``x`` -- so the result is bit-identical to the unsharded call for
+    any number of ranks.  Returns ``{"mean","std","var","pct" (len(percentiles), Q),"mode","mode_index"}``
+    (float64 except as noted by the unsharded functions; packed and gathered as float64).
+    ``stats_fn(x_cols, lohi) -> (rows, q_local)`` float64 replaces the device kernels in CPU tests."""
+    from . import stats as st
+    world = dist.get_world_size(group) if dist.is_initialized() else 1
+    rank = dist.get_rank(group) if dist.is_initialized() else 0
+    N, Q = x.shape
+    a, b = column_slice(Q, rank, world)
+    nq = len(percentiles)
+    if stats_fn is None:
+        def stats_fn(cols, lohi):
+            m = st.ensemble_moments(cols)
+            pct = st.ensemble_percentile(cols, list(percentiles)).double()
+            mode, idx = st.ensemble_kde_mode(cols, n_grid, grid_range=lohi, return_index=True)
+            return torch.cat([m["mean"].double()[None], m["std"].double()[None], m["var"].double()[None],
+                              pct, mode[None], idx.double()[None]], dim=0)
+        lohi = st.global_minmax(x)
+    else:
+        lohi = None
+    rows = 5 + nq
+    local = stats_fn(x[:, a:b].contiguous(), lohi) if b > a else torch.zeros(rows, 0, device=x.device, dtype=torch.float64)
+    if world > 1:
+        # columns on axis 0 so that gather_members' (uneven) row gather applies
+        full = gather_members(local.t().contiguous(), Q, 1, group).t().contiguous()
+    else:
+        full = local
+    return {"mean": full[0], "std": full[1], "var": full[2], "pct": full[3:3 + nq], "mode": full[3 + nq],
+            "mode_index": full[4 + nq].to(torch.int64)}

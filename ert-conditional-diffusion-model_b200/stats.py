@@ -128,6 +128,8 @@ def ensemble_kde_mode(a, n_grid=5000, grid_range=None, device=None, return_index
         if grid_range is None:
             _lib.check(lib.ertdiff_minmax(_lib.ptr(t), _DT[t.dtype], t.numel(), _lib.ptr(lohi), st),
                        "minmax")
+        elif isinstance(grid_range, torch.Tensor):       # (lo, hi) already on the device: no host round trip
+            lohi.copy_(grid_range.to(device=t.device, dtype=torch.float64).reshape(2))
         else:
             lohi.copy_(torch.tensor([float(grid_range[0]), float(grid_range[1])], dtype=torch.float64))
         if Q > 0:
@@ -136,6 +138,17 @@ def ensemble_kde_mode(a, n_grid=5000, grid_range=None, device=None, return_index
                        "ensemble_kde_mode")
     m = _finish(mode, trailing, was_numpy)
     return (m, _finish(index, trailing, was_numpy)) if return_index else m
+
+
+def global_minmax(a, device=None):
+    """``(np.min(a), np.max(a))`` over the whole array as a 2-element float64 CUDA tensor: the range
+    of the KDE grid (ECD.py:749-750)."""
+    t, _, _ = _to_device(a, device)
+    lohi = torch.empty(2, device=t.device, dtype=torch.float64)
+    with torch.cuda.device(t.device):
+        _lib.check(_lib.load().ertdiff_minmax(_lib.ptr(t), _DT[t.dtype], t.numel(), _lib.ptr(lohi),
+                                              _lib.stream_ptr(t.device)), "minmax")
+    return lohi
 
 
 def ensemble_statistics(a, percentiles=(25, 50, 75), mode=True, n_grid=5000, device=None):

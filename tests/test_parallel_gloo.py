@@ -70,3 +70,48 @@ def test_two_rank_gather_equals_single_process(tmp_path, n_members, n_cond):
         # checked exactly through the tags below
         assert np.allclose(got, full, rtol=1e-5, atol=1e-5), f"rank {r}: gathered fields differ"
         assert np.array_equal(np.load(tmp_path / f"tag_rank{r}.npy"), np.load(tmp_path / "tag_full.npy"))
+
+
+def _stats_worker(rank, world, port, n_members, n_cols, out_dir):
+    os.environ["MASTER_ADDR"] = "127.0.0.1"
+    os.environ["MASTER_PORT"] = str(port)
+    dist.init_process_group("gloo", rank=rank, world_size=world)
+    import sys
+    sys.path.insert(0, os.path.dirname(os.path.dirname(os.path.abspath(__file__))))
+    from ertdiff_b200.parallel import sharded_statistics, column_slice
+    from oracle import stats_oracle as so
+    x = torch.from_numpy(np.random.default_rng(4).lognormal(size=(n_members, n_cols)))
+    lo, hi = float(x.min()), float(x.max())
+    qs = (25.0, 50.0, 97.5)
+
+    def numpy_stats(cols, lohi):        # CPU stand-in for the device kernels, same row layout
+        a = cols.numpy()
+        grid = np.linspace(lo, hi, 64)                  # the GLOBAL range, as ECD.py:749-751
+        mode, idx = so.kde_mode(a, grid)
+        rows = [np.mean(a, 0), np.std(a, 0), np.var(a, 0)] + [np.percentile(a, q, axis=0) for q in qs] + \
+               [mode, idx.astype(np.float64)]
+        return torch.from_numpy(np.stack(rows))
+
+    out = sharded_statistics(x, qs, 64, stats_fn=numpy_stats)
+    np.savez(os.path.join(out_dir, f"stats_rank{rank}.npz"), **{k: v.numpy() for k, v in out.items()},
+             slice=np.array(column_slice(n_cols, rank, world)))
+    if rank == 0:
+        full = numpy_stats(x, None)
+        np.save(os.path.join(out_dir, "stats_full.npy"), full.numpy())
+    dist.barrier()
+    dist.destroy_process_group()
+
+
+@pytest.mark.parametrize("n_cols", [29, 8, 1])
+def test_two_rank_column_sharded_statistics(tmp_path, n_cols):
+    port = _free_port()
+    mp.spawn(_stats_worker, args=(2, port, 40, n_cols, str(tmp_path)), nprocs=2, join=True)
+    full = np.load(tmp_path / "stats_full.npy")
+    slices = []
+    for r in range(2):
+        got = np.load(tmp_path / f"stats_rank{r}.npz")
+        slices.append(tuple(got["slice"]))
+        assert np.array_equal(got["mean"], full[0]) and np.array_equal(got["std"], full[1])
+        assert np.array_equal(got["var"], full[2]) and np.array_equal(got["pct"], full[3:6])
+        assert np.array_equal(got["mode"], full[6]) and np.array_equal(got["mode_index"], full[7].astype(np.int64))
+    assert slices[0][0] == 0 and slices[0][1] == slices[1][0] and slices[1][1] == n_cols
