@@ -33,7 +33,8 @@ KEYS = ["gpu__time_duration.sum", "dram__bytes_read.sum", "dram__bytes_write.sum
         "launch__grid_size", "launch__block_size", "dram__throughput.avg.pct_of_peak_sustained_elapsed",
         "sm__throughput.avg.pct_of_peak_sustained_elapsed", "l1tex__data_bank_conflicts_pipe_lsu_mem_shared.sum"]
 SCALE = {"byte": 1, "Kbyte": 1e3, "Mbyte": 1e6, "Gbyte": 1e9, "ns": 1e-3, "us": 1, "ms": 1e3}
-summary = {}
+jpath = os.path.join(out, f"{rnd}_ncu_kernels.json")
+summary = json.load(open(jpath)) if os.path.isfile(jpath) else {}      # captures arrive one per gpurun call
 for name, what in (("chain_fp32", "k_chain, 256 members, T=1000 (chain_sweep.py)"),
                    ("chain_umma", "k_chain_umma, 18,944 members, T=200 (chain_sweep.py)"),
                    ("encoder_umma", "k_encoder_umma, 1024 conditions of 14x4693 (encoder_bench.py)")):
@@ -67,5 +68,5 @@ for name, what in (("chain_fp32", "k_chain, 256 members, T=1000 (chain_sweep.py)
             if isinstance(v, dict):
                 f.write(f"- `{k}` = {v['value']:.6g} {v['unit']}\n")
         f.write(f"- DRAM traffic per launch = {m['traffic_bytes_per_launch']:.6g} bytes\n\n```\n{txt}```\n")
-json.dump(summary, open(os.path.join(out, f"{rnd}_ncu_kernels.json"), "w"), indent=1)
+json.dump(summary, open(jpath, "w"), indent=1)
 print("wrote", sorted(os.listdir(out)))
