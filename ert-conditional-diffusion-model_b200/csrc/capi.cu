@@ -184,7 +184,8 @@ static int pick_mpb(int64_t B, int H) {
     }
     const int64_t ctas_per_sm = (H <= 128) ? 4 : (H <= 256 ? 2 : 1);
     const int64_t slots = kNumSMs * ctas_per_sm;
-    if (B <= slots) return 1;
+    // the one-member variant trades registers for latency (see k_chain): 3 CTAs per SM at H <= 128
+    if (B <= kNumSMs * ((H <= 128) ? 3 : ctas_per_sm)) return 1;
     if (B <= 2 * slots) return 2;
     if (B <= 4 * slots) return 4;
     return 8;
