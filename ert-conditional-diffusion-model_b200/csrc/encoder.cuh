@@ -238,17 +238,30 @@ __global__ void k_encoder_finish(const float* __restrict__ partial, int n_chunks
     for (int co = tid; co < kConv2Out; co += blockDim.x) {
         const float* src = partial + member * n_chunks * kConv2Out + co;
         float sum = 0.f;
-        for (int c = 0; c < n_chunks; ++c) sum += src[(int64_t)c * kConv2Out];
+        int c = 0;
+        for (; c + 8 <= n_chunks; c += 8) {        // loads in flight together, adds in chunk order
+            float v[8];
+#pragma unroll
+            for (int u = 0; u < 8; ++u) v[u] = src[(int64_t)(c + u) * kConv2Out];
+#pragma unroll
+            for (int u = 0; u < 8; ++u) sum += v[u];
+        }
+        for (; c < n_chunks; ++c) sum += src[(int64_t)c * kConv2Out];
         pooled[co] = sum / (float)L2;
     }
     __syncthreads();
+    // both matrix-vector products read their weight column with every load in flight at once (the
+    // weights are cold after an L2 flush: a rolled loop would pay one DRAM latency per iteration)
+    float w6c[kConv2Out];
+#pragma unroll
+    for (int k = 0; k < kConv2Out; ++k) w6c[k] = w6T[k * H + tid];
     float a0 = b6[tid], a1 = 0.f, a2 = 0.f, a3 = 0.f;
 #pragma unroll
     for (int k = 0; k < kConv2Out; k += 4) {
-        a0 = fmaf(w6T[(k + 0) * H + tid], pooled[k + 0], a0);
-        a1 = fmaf(w6T[(k + 1) * H + tid], pooled[k + 1], a1);
-        a2 = fmaf(w6T[(k + 2) * H + tid], pooled[k + 2], a2);
-        a3 = fmaf(w6T[(k + 3) * H + tid], pooled[k + 3], a3);
+        a0 = fmaf(w6c[k + 0], pooled[k + 0], a0);
+        a1 = fmaf(w6c[k + 1], pooled[k + 1], a1);
+        a2 = fmaf(w6c[k + 2], pooled[k + 2], a2);
+        a3 = fmaf(w6c[k + 3], pooled[k + 3], a3);
     }
     const float a = fmaxf((a0 + a1) + (a2 + a3), 0.f);
     cemb[tid] = a;
@@ -256,12 +269,17 @@ __global__ void k_encoder_finish(const float* __restrict__ partial, int n_chunks
     __syncthreads();
     if (cond_bias) {
         float acc0 = b0[tid], acc1 = 0.f, acc2 = 0.f, acc3 = 0.f;
-#pragma unroll 8
-        for (int k = 0; k < H; k += 4) {
-            acc0 = fmaf(w0cT[(int64_t)(k + 0) * H + tid], cemb[k + 0], acc0);
-            acc1 = fmaf(w0cT[(int64_t)(k + 1) * H + tid], cemb[k + 1], acc1);
-            acc2 = fmaf(w0cT[(int64_t)(k + 2) * H + tid], cemb[k + 2], acc2);
-            acc3 = fmaf(w0cT[(int64_t)(k + 3) * H + tid], cemb[k + 3], acc3);
+        for (int k0 = 0; k0 < H; k0 += 32) {          // H is a multiple of 32
+            float wc[32];
+#pragma unroll
+            for (int k = 0; k < 32; ++k) wc[k] = w0cT[(int64_t)(k0 + k) * H + tid];
+#pragma unroll
+            for (int k = 0; k < 32; k += 4) {
+                acc0 = fmaf(wc[k + 0], cemb[k0 + k + 0], acc0);
+                acc1 = fmaf(wc[k + 1], cemb[k0 + k + 1], acc1);
+                acc2 = fmaf(wc[k + 2], cemb[k0 + k + 2], acc2);
+                acc3 = fmaf(wc[k + 3], cemb[k0 + k + 3], acc3);
+            }
         }
         cond_bias[member * H + tid] = (acc0 + acc1) + (acc2 + acc3);
     }
