@@ -73,6 +73,8 @@ SIGNATURES = {
     "ertdiff_minmax": (C.c_int, [C.c_void_p, C.c_int, C.c_int64, C.c_void_p, C.c_void_p]),
     "ertdiff_ensemble_kde_mode": (C.c_int, [C.c_void_p, C.c_int, C.c_int64, C.c_int64, C.c_void_p,
                                             C.c_int32, C.c_void_p, C.c_void_p, C.c_void_p]),
+    "ertdiff_ensemble_kde_mode_auto": (C.c_int, [C.c_void_p, C.c_int, C.c_int64, C.c_int64, C.c_int32, C.c_void_p,
+                                                 C.c_void_p, C.c_void_p, C.c_void_p]),
     "ertdiff_interval_coverage": (C.c_int, [C.c_void_p, C.c_void_p, C.c_void_p, C.c_int32, C.c_int64, C.c_int32,
                                             C.c_void_p, C.c_void_p]),
     "ertdiff_debug_umma_gemm": (C.c_int, [C.c_void_p, C.c_void_p, C.c_int32, C.c_int32, C.c_void_p, C.c_void_p]),

@@ -53,8 +53,20 @@ static int workspace(size_t bytes, void** out) {
     return 0;
 }
 
+// cudaFuncSetAttribute is per device: every "set the dynamic shared memory limit once" site keeps one
+// flag per device (a process may drive several GPUs through several handles)
+struct PerDeviceOnce {
+    bool done[64] = {};
+    bool* slot() {
+        int dev = 0;
+        if (cudaGetDevice(&dev) != cudaSuccess || dev < 0 || dev >= 64) dev = 0;
+        return &done[dev];
+    }
+};
+
 static int colstats_attr() {
-    static bool done = false;
+    static PerDeviceOnce once;
+    bool& done = *once.slot();
     if (!done) {
         ERT_CUDA(cudaFuncSetAttribute(k_colstats_smallq<float, 0>, cudaFuncAttributeMaxDynamicSharedMemorySize, SQ_SMEM_BYTES));
         ERT_CUDA(cudaFuncSetAttribute(k_colstats_smallq<double, 0>, cudaFuncAttributeMaxDynamicSharedMemorySize, SQ_SMEM_BYTES));
@@ -77,7 +89,8 @@ static int run_encoder(ertdiff_model* m, const float* d_cond, int64_t n_cond, in
     const int tp = small ? 32 : 128;
     const int n_chunks = (int)((L2 + tp - 1) / tp);
     if (int rc = grow(m->enc_partial, m->enc_partial_n, (size_t)n_cond * n_chunks * kConv2Out)) return rc;
-    static bool attr_set = false;
+    static PerDeviceOnce once;
+    bool& attr_set = *once.slot();
     if (!attr_set) {
         ERT_CUDA(cudaFuncSetAttribute(k_encoder_conv<4>, cudaFuncAttributeMaxDynamicSharedMemorySize,
                                       (int)sizeof(EncSmem<4>)));
@@ -111,7 +124,8 @@ static int run_encoder_umma(ertdiff_model* m, const float* d_cond, int64_t n_con
     ERT_REQUIRE(4 * (L2 + 128) + 16 < (int64_t)1 << 30, "encode_condition: L too large");
     const int n_chunks = (int)((L2 + EU_TPC * 128 - 1) / (EU_TPC * 128));
     if (int rc = grow(m->enc_partial, m->enc_partial_n, (size_t)n_cond * n_chunks * kConv2Out)) return rc;
-    static bool attr_set = false;
+    static PerDeviceOnce once;
+    bool& attr_set = *once.slot();
     if (!attr_set) {
         ERT_CUDA(cudaFuncSetAttribute(k_encoder_umma, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)sizeof(EncUmmaSmem)));
         attr_set = true;
@@ -247,7 +261,8 @@ static int run_chain(ertdiff_model* m, const ertdiff_chain_args* a, const float*
             k_chain_umma<false, true, false>,  k_chain_umma<false, true, true>,
             k_chain_umma<true, false, false>,  k_chain_umma<true, false, true>,
             k_chain_umma<true, true, false>,   k_chain_umma<true, true, true>};
-        static bool attr_set = false;
+        static PerDeviceOnce once;
+        bool& attr_set = *once.slot();
         if (!attr_set) {
             for (Kern k : kerns)
                 ERT_CUDA(cudaFuncSetAttribute(k, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
@@ -742,7 +757,8 @@ int ertdiff_ensemble_kde_mode(const void* d_a, int dtype, int64_t N, int64_t Q,
         else k_kde_prepare<double><<<grid, 256, 0, st>>>((const double*)d_a, N, Q, f2, cols);
         ERT_LAUNCH_CHECK("k_kde_prepare");
     }
-    static bool attr_set = false;
+    static PerDeviceOnce once;
+    bool& attr_set = *once.slot();
     if (!attr_set) {
         ERT_CUDA(cudaFuncSetAttribute(k_kde_scan32<float>, cudaFuncAttributeMaxDynamicSharedMemorySize, 200 * 1024));
         ERT_CUDA(cudaFuncSetAttribute(k_kde_scan32<double>, cudaFuncAttributeMaxDynamicSharedMemorySize, 200 * 1024));
@@ -770,6 +786,48 @@ int ertdiff_ensemble_kde_mode(const void* d_a, int dtype, int64_t N, int64_t Q,
         }
         ERT_LAUNCH_CHECK("k_kde_select64");
     }
+    return 0;
+}
+
+int ertdiff_ensemble_kde_mode_auto(const void* d_a, int dtype, int64_t N, int64_t Q, int32_t n_grid,
+                                   double* d_lohi, double* d_mode, int64_t* d_index, void* stream) {
+    ERT_REQUIRE(d_a && d_lohi && N > 1 && Q > 0 && n_grid > 1, "ensemble_kde_mode_auto: bad arguments");
+    ERT_REQUIRE(dtype == ERTDIFF_F32 || dtype == ERTDIFF_F64, "ensemble_kde_mode_auto: bad dtype");
+    cudaStream_t st = (cudaStream_t)stream;
+    const bool small = N * Q <= 65536 && (size_t)N * 12 <= 48 * 1024 && Q <= 4096;
+    if (!small) {
+        if (int rc = ertdiff_minmax(d_a, dtype, N * Q, d_lohi, stream)) return rc;
+        return ertdiff_ensemble_kde_mode(d_a, dtype, N, Q, d_lohi, n_grid, d_mode, d_index, stream);
+    }
+    // one fused launch (k_kde_small); tickets: a persistent, self-cleaning counter per column
+    static unsigned int* tickets[64] = {};
+    int dev = 0;
+    ERT_CUDA(cudaGetDevice(&dev));
+    ERT_REQUIRE(dev >= 0 && dev < 64, "ensemble_kde_mode_auto: device index out of range");
+    if (!tickets[dev]) {
+        std::lock_guard<std::mutex> lock(g_ws_mutex);
+        if (!tickets[dev]) {
+            ERT_CUDA(cudaMalloc(&tickets[dev], 4096 * sizeof(unsigned int)));
+            ERT_CUDA(cudaMemset(tickets[dev], 0, 4096 * sizeof(unsigned int)));
+        }
+    }
+    const int G = n_grid;
+    void* ws = nullptr;
+    if (int rc = workspace((size_t)Q * G * sizeof(float), &ws)) return rc;
+    int n_gchunks = 1;
+    while (Q * n_gchunks < 4 * kNumSMs && (G + 2 * n_gchunks - 1) / (2 * n_gchunks) >= 128 && n_gchunks < 64)
+        n_gchunks *= 2;
+    const int gchunk = (G + n_gchunks - 1) / n_gchunks;
+    const double factor = std::pow((double)N, -1.0 / 5.0);
+    const dim3 grid((unsigned)Q, (unsigned)n_gchunks);
+    const size_t smem = (size_t)N * 12;
+    if (dtype == ERTDIFF_F32)
+        k_kde_small<float><<<grid, 256, smem, st>>>((const float*)d_a, N, Q, 1, d_lohi, G, gchunk, factor * factor,
+                                                    (float*)ws, tickets[dev], d_mode, d_index);
+    else
+        k_kde_small<double><<<grid, 256, smem, st>>>((const double*)d_a, N, Q, 1, d_lohi, G, gchunk, factor * factor,
+                                                     (float*)ws, tickets[dev], d_mode, d_index);
+    ERT_LAUNCH_CHECK("k_kde_small");
     return 0;
 }
 

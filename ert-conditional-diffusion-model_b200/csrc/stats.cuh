@@ -441,15 +441,12 @@ k_kde_scan32(const T* __restrict__ a, int64_t N, int64_t Q, int64_t col0,
     }
 }
 
-// grid = columns of this batch, 256 threads.
-template <typename T>
-__global__ void __launch_bounds__(256)
-k_kde_select64(const T* __restrict__ a, int64_t N, int64_t Q, int64_t col0,
-               const double* __restrict__ lohi, int G, const KdeColumn* __restrict__ cols,
-               const float* __restrict__ s32, double* __restrict__ mode_out,
-               int64_t* __restrict__ index_out) {
-    extern __shared__ __align__(16) unsigned char kde_smem_raw[];
-    double* xs = reinterpret_cast<double*>(kde_smem_raw);      // [N] members, float64
+// The float64 decision for one column (see above): `row` = the column's fp32 scan, `xs` = its N members
+// as float64 in shared memory.  Called by every thread of a 256-thread CTA.
+__device__ __forceinline__ void kde_select_column(int64_t N, int64_t col, double lo, double hi, int G,
+                                                  const KdeColumn kc, const float* row,
+                                                  const double* __restrict__ xs, double* __restrict__ mode_out,
+                                                  int64_t* __restrict__ index_out) {
     __shared__ float redf[8];
     __shared__ double redv[8];
     __shared__ int redi[8];
@@ -457,14 +454,11 @@ k_kde_select64(const T* __restrict__ a, int64_t N, int64_t Q, int64_t col0,
     __shared__ int ncand;
     const int tid = threadIdx.x, nthr = blockDim.x, lane = tid & 31, warp = tid >> 5;
     const int nwarps = nthr >> 5;
-    const int64_t col = col0 + blockIdx.x;
-    const KdeColumn kc = cols[col];
-    const float* row = s32 + (int64_t)blockIdx.x * G;
     if (tid == 0) ncand = 0;
-    for (int64_t i = tid; i < N; i += nthr) xs[i] = (double)a[i * Q + col];
     // fp32 maximum of the column's scan
     float mx = 0.f;
-    for (int g = tid; g < G; g += nthr) mx = fmaxf(mx, row[g]);
+    // (__ldcg: in the fused kernel other CTAs of this launch wrote the scan -- read it through L2)
+    for (int g = tid; g < G; g += nthr) mx = fmaxf(mx, __ldcg(row + g));
 #pragma unroll
     for (int o = 16; o > 0; o >>= 1) mx = fmaxf(mx, __shfl_xor_sync(0xffffffffu, mx, o));
     if (lane == 0) redf[warp] = mx;
@@ -474,7 +468,7 @@ k_kde_select64(const T* __restrict__ a, int64_t N, int64_t Q, int64_t col0,
     const bool degenerate = !(kc.neg_inv_2h2 > -CUDART_INF) || !(kc.neg_inv_2h2 == kc.neg_inv_2h2);
     const float thr = mx * (1.0f - KDE_TOL);
     for (int g = tid; g < G; g += nthr) {
-        if (row[g] >= thr) {
+        if (__ldcg(row + g) >= thr) {
             const int k = atomicAdd(&ncand, 1);
             if (k < KDE_MAX_CAND) cand[k] = g;
         }
@@ -484,7 +478,6 @@ k_kde_select64(const T* __restrict__ a, int64_t N, int64_t Q, int64_t col0,
     // evaluating every grid point in float64
     const bool all = ncand > KDE_MAX_CAND || !(mx > 0.f);
     const int n_eval = all ? G : ncand;
-    const double lo = lohi[0], hi = lohi[1];
     const double step = (hi - lo) / (double)(G - 1);
     double best = -1.0;
     int besti = 0x7fffffff;
@@ -513,6 +506,134 @@ k_kde_select64(const T* __restrict__ a, int64_t N, int64_t Q, int64_t col0,
             if (mode_out) mode_out[col] = kde_grid_point(besti, G, lo, hi, step);
         }
     }
+}
+
+
+// grid = columns of this batch, 256 threads.
+template <typename T>
+__global__ void __launch_bounds__(256)
+k_kde_select64(const T* __restrict__ a, int64_t N, int64_t Q, int64_t col0,
+               const double* __restrict__ lohi, int G, const KdeColumn* __restrict__ cols,
+               const float* __restrict__ s32, double* __restrict__ mode_out,
+               int64_t* __restrict__ index_out) {
+    extern __shared__ __align__(16) unsigned char kde_smem_raw[];
+    double* xs = reinterpret_cast<double*>(kde_smem_raw);      // [N] members, float64
+    const int64_t col = col0 + blockIdx.x;
+    for (int64_t i = threadIdx.x; i < N; i += blockDim.x) xs[i] = (double)a[i * Q + col];
+    kde_select_column(N, col, lohi[0], lohi[1], G, cols[col], s32 + (int64_t)blockIdx.x * G, xs, mode_out, index_out);
+}
+
+// ------------------------------------------------------------------------------------------
+// Small ensembles (N*Q <= 64 K values, the chain's own (members, 29) output): the five dependent
+// launches above (two for the global range, column constants, scan, select) cost more in start-up
+// latency than in work, so ONE launch does it all.  grid = (Q, n_gchunks), 256 threads:
+//   1. every CTA takes the global min / max of the whole array itself (a few dozen loads per thread)
+//   2. its column's members -> shared memory (float64), mean / ddof-1 variance / bandwidth
+//   3. the fp32 scan of its chunk of grid points -> s32
+//   4. the last CTA of a column to finish (atomic ticket) runs the float64 selection
+template <typename T>
+__global__ void __launch_bounds__(256)
+k_kde_small(const T* __restrict__ a, int64_t N, int64_t Q, int compute_range, double* __restrict__ lohi,
+            int G, int gchunk, double scott_factor_sq, float* __restrict__ s32,
+            unsigned int* __restrict__ tickets, double* __restrict__ mode_out, int64_t* __restrict__ index_out) {
+    extern __shared__ __align__(16) unsigned char kde_smem_raw[];
+    double* xs = reinterpret_cast<double*>(kde_smem_raw);                       // [N] members, float64
+    float* xc = reinterpret_cast<float*>(kde_smem_raw + (size_t)N * sizeof(double));   // [N] centred, fp32
+    __shared__ double rlo[8], rhi[8], rsum[8];
+    __shared__ int rnan[8];
+    __shared__ int s_last;
+    const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
+    const int64_t col = blockIdx.x;
+    // ---- 1. grid range (np.min / np.max of the whole array; NaN propagates) ---------------------
+    double lo, hi;
+    if (compute_range) {
+        lo = CUDART_INF; hi = -CUDART_INF;
+        int has_nan = 0;
+        const int64_t n = N * Q;
+        for (int64_t i = tid; i < n; i += 256) {
+            const double v = (double)a[i];
+            has_nan |= (v != v);
+            lo = fmin(lo, v);
+            hi = fmax(hi, v);
+        }
+#pragma unroll
+        for (int o = 16; o > 0; o >>= 1) {
+            lo = fmin(lo, __shfl_xor_sync(0xffffffffu, lo, o));
+            hi = fmax(hi, __shfl_xor_sync(0xffffffffu, hi, o));
+            has_nan |= __shfl_xor_sync(0xffffffffu, has_nan, o);
+        }
+        if (lane == 0) { rlo[warp] = lo; rhi[warp] = hi; rnan[warp] = has_nan; }
+        __syncthreads();
+#pragma unroll
+        for (int w = 0; w < 8; ++w) { lo = fmin(lo, rlo[w]); hi = fmax(hi, rhi[w]); has_nan |= rnan[w]; }
+        if (has_nan) { lo = CUDART_NAN; hi = CUDART_NAN; }
+        if (col == 0 && blockIdx.y == 0 && tid == 0) { lohi[0] = lo; lohi[1] = hi; }
+    } else {
+        lo = lohi[0]; hi = lohi[1];
+    }
+    // ---- 2. column constants ------------------------------------------------------------------------
+    double sum = 0.0;
+    for (int64_t i = tid; i < N; i += 256) { const double v = (double)a[i * Q + col]; xs[i] = v; sum += v; }
+#pragma unroll
+    for (int o = 16; o > 0; o >>= 1) sum += __shfl_xor_sync(0xffffffffu, sum, o);
+    __syncthreads();
+    if (lane == 0) rsum[warp] = sum;
+    __syncthreads();
+    sum = 0.0;
+#pragma unroll
+    for (int w = 0; w < 8; ++w) sum += rsum[w];
+    const double mean = sum / (double)N;
+    double ss = 0.0;
+    for (int64_t i = tid; i < N; i += 256) { const double d = xs[i] - mean; ss += d * d; xc[i] = (float)d; }
+#pragma unroll
+    for (int o = 16; o > 0; o >>= 1) ss += __shfl_xor_sync(0xffffffffu, ss, o);
+    __syncthreads();
+    if (lane == 0) rsum[warp] = ss;
+    __syncthreads();
+    ss = 0.0;
+#pragma unroll
+    for (int w = 0; w < 8; ++w) ss += rsum[w];
+    KdeColumn kc;
+    kc.mean = mean;
+    kc.neg_inv_2h2 = -0.5 / ((ss / (double)(N - 1)) * scott_factor_sq);        // -inf when the column is constant
+    // ---- 3. fp32 scan of this CTA's grid points (same arithmetic as k_kde_scan32) ---------------------
+    const double step = (hi - lo) / (double)(G - 1);
+    const float c2 = (float)(kc.neg_inv_2h2 * 1.4426950408889634);
+    const int g_begin = blockIdx.y * gchunk;
+    const int g_end = min(G, g_begin + gchunk);
+    float* out = s32 + col * G;
+    for (int g0 = g_begin + tid; g0 < g_end; g0 += 512) {
+        const int g1 = g0 + 256;
+        const float ga = (float)(kde_grid_point(g0, G, lo, hi, step) - kc.mean);
+        const float gb = (float)(kde_grid_point(min(g1, G - 1), G, lo, hi, step) - kc.mean);
+        double sa = 0.0, sb = 0.0;
+        for (int64_t i0 = 0; i0 < N; i0 += 64) {
+            const int64_t i1 = (i0 + 64 < N) ? i0 + 64 : N;
+            float pa = 0.f, pb = 0.f;
+            for (int64_t i = i0; i < i1; ++i) {
+                const float xi = xc[i];
+                const float da = ga - xi, db = gb - xi;
+                pa += ex2_approx(da * da * c2);
+                pb += ex2_approx(db * db * c2);
+            }
+            sa += (double)pa;
+            sb += (double)pb;
+        }
+        out[g0] = (float)sa;
+        if (g1 < g_end) out[g1] = (float)sb;
+    }
+    // ---- 4. the last CTA of the column selects -----------------------------------------------------------
+    __threadfence();
+    __syncthreads();
+    if (tid == 0) {
+        const unsigned int t = atomicAdd(&tickets[col], 1u);
+        s_last = (t == gridDim.y - 1);
+        if (s_last) tickets[col] = 0u;            // self-cleaning for the next call
+    }
+    __syncthreads();
+    if (!s_last) return;
+    __threadfence();
+    kde_select_column(N, col, lo, hi, G, kc, out, xs, mode_out, index_out);
 }
 
 // ------------------------------------------------------------------------------------------

@@ -126,16 +126,19 @@ def ensemble_kde_mode(a, n_grid=5000, grid_range=None, device=None, return_index
     with torch.cuda.device(t.device):
         st = _lib.stream_ptr(t.device)
         if grid_range is None:
-            _lib.check(lib.ertdiff_minmax(_lib.ptr(t), _DT[t.dtype], t.numel(), _lib.ptr(lohi), st),
-                       "minmax")
-        elif isinstance(grid_range, torch.Tensor):       # (lo, hi) already on the device: no host round trip
-            lohi.copy_(grid_range.to(device=t.device, dtype=torch.float64).reshape(2))
+            if Q > 0:      # range from the data: one entry point (a single fused launch for small ensembles)
+                _lib.check(lib.ertdiff_ensemble_kde_mode_auto(_lib.ptr(t), _DT[t.dtype], N, Q, int(n_grid),
+                                                              _lib.ptr(lohi), _lib.ptr(mode), _lib.ptr(index), st),
+                           "ensemble_kde_mode")
         else:
-            lohi.copy_(torch.tensor([float(grid_range[0]), float(grid_range[1])], dtype=torch.float64))
-        if Q > 0:
-            _lib.check(lib.ertdiff_ensemble_kde_mode(_lib.ptr(t), _DT[t.dtype], N, Q, _lib.ptr(lohi),
-                                                     int(n_grid), _lib.ptr(mode), _lib.ptr(index), st),
-                       "ensemble_kde_mode")
+            if isinstance(grid_range, torch.Tensor):       # (lo, hi) already on the device: no host round trip
+                lohi.copy_(grid_range.to(device=t.device, dtype=torch.float64).reshape(2))
+            else:
+                lohi.copy_(torch.tensor([float(grid_range[0]), float(grid_range[1])], dtype=torch.float64))
+            if Q > 0:
+                _lib.check(lib.ertdiff_ensemble_kde_mode(_lib.ptr(t), _DT[t.dtype], N, Q, _lib.ptr(lohi),
+                                                         int(n_grid), _lib.ptr(mode), _lib.ptr(index), st),
+                           "ensemble_kde_mode")
     m = _finish(mode, trailing, was_numpy)
     return (m, _finish(index, trailing, was_numpy)) if return_index else m
 
