@@ -37,6 +37,9 @@ FLOP_TIME_ROW = 65536               # per step, shared by all members
 FLOP_AS_WRITTEN = 20864384          # per member per step, reference-equivalent work
 PERCENTILES = [2.5, 25.0, 50.0, 75.0, 97.5]
 KDE_GRID = 5000
+SHARD_STATS_ABOVE = 4096   # gathered members above which the statistics' columns are split over the ranks
+                           # (below it the second all-gather and the packing cost more than they save)
+MAX_STAT_MEMBERS = 25600   # one statistics call holds a column in shared memory (KDE: N*8 B <= 200 KB)
 
 
 def load_peaks():
@@ -182,8 +185,8 @@ def workload_config(args, members_per_gpu):
             "members_per_gpu": members_per_gpu, "T": args.T, "param_dim": P, "hidden_dim": H,
             "loop_mode": args.loop_mode, "rng": "device Philox4x32-10",
             "l2": "flushed between steps (256 MiB memset outside the per-step event pairs)",
-            "parallelism": f"members sharded over {args.gpus} GPU(s), one all-gather of (B/G,29) f32; statistics "
-                           "columns sharded over the ranks, one all-gather of the maps"}
+            "parallelism": f"members sharded over {args.gpus} GPU(s), one all-gather of (B/G,29) f32; statistics on the "
+                           f"gathered fields (columns split over the ranks above {SHARD_STATS_ABOVE} members)"}
 
 
 # ------------------------------------------------------------------------------------------
@@ -203,6 +206,9 @@ def run_ours(args):
         dist.init_process_group("nccl", device_id=dev)
     members, T = args.members, args.T                 # per GPU (weak scaling)
     total = members * world
+    if total > MAX_STAT_MEMBERS:
+        raise SystemExit(f"bench.py: {total} gathered members exceed the {MAX_STAT_MEMBERS} a single statistics "
+                         "call supports (a column is held in shared memory); lower --members")
     sd, cond_host = synthetic_inputs(members, args.distinct_conditions)
     model = eb.ConditionalDiffusionModel(P, H)
     model.load_state_dict(sd)
@@ -216,7 +222,7 @@ def run_ours(args):
     stream = torch.cuda.current_stream(dev)
 
     def stats(x):
-        if world > 1:                       # per-column statistics: columns split over the ranks
+        if world > 1 and total > SHARD_STATS_ABOVE:     # per-column statistics: columns split over the ranks
             return eb.parallel.sharded_statistics(x, PERCENTILES, KDE_GRID)
         out = eb.ensemble_moments(x)
         out["pct"] = eb.ensemble_percentile(x, PERCENTILES)
