@@ -75,7 +75,7 @@ def test_golden_maps(cuda_dev, golden):
 
 
 @pytest.mark.parametrize("dtype", [np.float32, np.float64])
-@pytest.mark.parametrize("N", [16, 50, 256])
+@pytest.mark.parametrize("N", [16, 50, 256, 1000, 3000])      # 3000 x 24 values: beyond the fused small-ensemble launch
 def test_kde_mode_index_is_scipy(cuda_dev, dtype, N):
     a = np.random.default_rng(N).lognormal(size=(N, 24)).astype(dtype)
     # the reference's maps are float64 (ECD.py:716); float32 input is defined as promoted first
@@ -111,3 +111,27 @@ def test_statistics_of_large_ensembles_properties(cuda_dev):
     assert torch.equal(q[1].float(), ((srt[4095].double() + (srt[4096] - srt[4095]).double() * 0.5)).float())
     perm = a[torch.randperm(8192, device=cuda_dev)]
     assert torch.equal(eb.ensemble_percentile(perm, [0, 50, 100]), q)   # order of members is irrelevant
+
+
+def test_kde_fused_and_staged_paths_agree(cuda_dev):
+    # the same data through the one-launch small-ensemble kernel (range from the data) and through the
+    # staged kernels (explicit range): same grid, same argmax
+    a = np.random.default_rng(12).normal(size=(400, 29)).astype(np.float32) * np.linspace(0.5, 30, 29, dtype=np.float32)
+    m1, i1 = eb.ensemble_kde_mode(a, 5000, return_index=True)
+    m2, i2 = eb.ensemble_kde_mode(a, 5000, grid_range=(float(a.min()), float(a.max())), return_index=True)
+    assert np.array_equal(i1, i2) and np.array_equal(m1, m2)
+    # repeated calls reuse the self-cleaning tickets
+    m3, i3 = eb.ensemble_kde_mode(a, 5000, return_index=True)
+    assert np.array_equal(i1, i3)
+
+
+def test_sharded_statistics_single_rank_equals_plain(cuda_dev):
+    x = torch.randn(700, 29, device=cuda_dev, generator=torch.Generator(cuda_dev).manual_seed(3)) * 5
+    qs = (2.5, 50.0, 97.5)
+    sh = eb.parallel.sharded_statistics(x, qs, 1000)
+    st = eb.ensemble_statistics(x, percentiles=(), n_grid=1000)
+    pct = eb.ensemble_percentile(x, list(qs))
+    for k in ("mean", "std", "var"):
+        assert torch.equal(sh[k].to(st[k].dtype), st[k])
+    assert torch.equal(sh["pct"], pct.double()) and torch.equal(sh["mode"], st["mode"])
+    assert torch.equal(sh["mode_index"], st["mode_index"])
