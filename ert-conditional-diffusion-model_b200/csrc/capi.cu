@@ -768,12 +768,12 @@ int ertdiff_ensemble_kde_mode(const void* d_a, int dtype, int64_t N, int64_t Q,
     }
     for (int64_t c0 = 0; c0 < Q; c0 += qb) {
         const int64_t nc = (Q - c0) < qb ? (Q - c0) : qb;
-        // split the grid so that nc * n_gchunks CTAs fill the machine, >= 128 grid points per CTA
-        int n_gchunks = 1;
-        while (nc * n_gchunks < 4 * kNumSMs && (G + 2 * n_gchunks - 1) / (2 * n_gchunks) >= 128 && n_gchunks < 64)
-            n_gchunks *= 2;
+        // CTAs per column: one 256-thread pass over the grid each while nc * n_gchunks stays within ~4
+        // CTAs per SM; with many columns (maps) one CTA walks the whole grid of its column
+        int n_gchunks = (G + 255) / 256;
+        while (n_gchunks > 1 && nc * n_gchunks > 4 * kNumSMs) n_gchunks = (n_gchunks + 1) / 2;
         const int gchunk = (G + n_gchunks - 1) / n_gchunks;
-        const int threads = gchunk >= 512 ? 256 : (gchunk >= 256 ? 128 : 64);
+        const int threads = 256;
         const dim3 grid((unsigned)nc, (unsigned)n_gchunks);
         if (f32in) {
             k_kde_scan32<float><<<grid, threads, (size_t)N * 4, st>>>((const float*)d_a, N, Q, c0, d_lohi, G, gchunk, cols, s32);
@@ -814,9 +814,13 @@ int ertdiff_ensemble_kde_mode_auto(const void* d_a, int dtype, int64_t N, int64_
     const int G = n_grid;
     void* ws = nullptr;
     if (int rc = workspace((size_t)Q * G * sizeof(float), &ws)) return rc;
-    int n_gchunks = 1;
-    while (Q * n_gchunks < 4 * kNumSMs && (G + 2 * n_gchunks - 1) / (2 * n_gchunks) >= 128 && n_gchunks < 64)
-        n_gchunks *= 2;
+    // CTAs per column: one 256-thread pass over the grid each (every thread scans one point) when that
+    // still fits in one wave of co-resident CTAs (a second, nearly empty wave would double the
+    // duration); otherwise fewer, longer chunks
+    int n_gchunks = (G + 255) / 256;
+    if (const char* e = std::getenv("ERTDIFF_KDE_GCHUNKS")) n_gchunks = std::atoi(e) > 0 ? std::atoi(e) : 1;
+    else
+        while (n_gchunks > 1 && Q * n_gchunks > 4 * kNumSMs) n_gchunks = (n_gchunks + 1) / 2;
     const int gchunk = (G + n_gchunks - 1) / n_gchunks;
     const double factor = std::pow((double)N, -1.0 / 5.0);
     const dim3 grid((unsigned)Q, (unsigned)n_gchunks);

@@ -399,6 +399,103 @@ __device__ __forceinline__ double kde_grid_point(int g, int G, double lo, double
     return (g == G - 1) ? hi : __dadd_rn(__dmul_rn((double)g, step), lo);
 }
 
+// The fp32 scan of one column, split over `nparts` CTAs (this one is `part`).  `xs` = the column's N
+// members centred at kc.mean (fp32, shared memory).
+//
+// Grid points further than reach = R*h from every member (R^2 = 2 ln(1e7 N)) have a KDE sum below 1e-7
+// and cannot hold the maximum whenever the maximum is known to be >= 1e-3 -- which it is if the grid is
+// not coarser than 7 bandwidths and at least one member lies inside it (some grid point is then within
+// step/2 of a member).  Those points are written as zero and only the "active" range
+// [x_min - reach, x_max + reach] is evaluated, split evenly over the parts: a column that occupies a
+// small part of the common grid (ECD.py:749-751 spans the GLOBAL min..max) costs proportionally less.
+// Inside the active range every member is summed, so the values equal the full scan's bit for bit.
+__device__ __forceinline__ void kde_scan_column(const float* __restrict__ xs, int64_t N, const KdeColumn kc,
+                                                double lo, double hi, int G, int part, int nparts,
+                                                float* __restrict__ out) {
+    __shared__ float s_mn[8], s_mx[8];
+    __shared__ int s_in[8];
+    __shared__ int s_range[2];
+    const int tid = threadIdx.x, nthr = blockDim.x, lane = tid & 31, warp = tid >> 5, nwarps = nthr >> 5;
+    const double step = (hi - lo) / (double)(G - 1);
+    // ---- the column's extent and whether a member lies inside the grid ------------------------------
+    float mn = CUDART_INF_F, mx = -CUDART_INF_F;
+    int inside = 0;
+    const float glo = (float)(lo - kc.mean), ghi = (float)(hi - kc.mean);
+    for (int64_t i = tid; i < N; i += nthr) {
+        const float v = xs[i];
+        mn = fminf(mn, v); mx = fmaxf(mx, v);
+        inside |= (v >= glo && v <= ghi);
+    }
+#pragma unroll
+    for (int o = 16; o > 0; o >>= 1) {
+        mn = fminf(mn, __shfl_xor_sync(0xffffffffu, mn, o));
+        mx = fmaxf(mx, __shfl_xor_sync(0xffffffffu, mx, o));
+        inside |= __shfl_xor_sync(0xffffffffu, inside, o);
+    }
+    if (lane == 0) { s_mn[warp] = mn; s_mx[warp] = mx; s_in[warp] = inside; }
+    __syncthreads();
+    if (tid == 0) {
+        for (int w = 1; w < nwarps; ++w) { mn = fminf(mn, s_mn[w]); mx = fmaxf(mx, s_mx[w]); inside |= s_in[w]; }
+        int ga = 0, gb = G - 1;
+        const double h = sqrt(-0.5 / kc.neg_inv_2h2);               // 0 for a constant column, NaN for NaN data
+        if (inside && h > 0.0 && step > 0.0 && step <= 7.0 * h) {
+            const double reach = h * sqrt(2.0 * log(1e7 * (double)N));
+            const double a = ((kc.mean + (double)mn - reach) - lo) / step;
+            const double b = ((kc.mean + (double)mx + reach) - lo) / step;
+            if (a > 1.0) ga = (int)fmin(a - 1.0, (double)(G - 1));  // one grid point of slack on both sides
+            if (b < (double)(G - 2)) gb = (int)fmax(b + 1.0, 0.0);
+            if (gb < ga) { ga = 0; gb = G - 1; }
+        }
+        s_range[0] = ga; s_range[1] = gb;
+    }
+    __syncthreads();
+    const int ga = s_range[0], gb = s_range[1];
+    // ---- zeros outside the active range (each part clears its static slice of the row) --------------
+    {
+        const int z0 = (int)((int64_t)G * part / nparts), z1 = (int)((int64_t)G * (part + 1) / nparts);
+        for (int g = z0 + tid; g < z1; g += nthr)
+            if (g < ga || g > gb) out[g] = 0.f;
+    }
+    // ---- this part's share of the active range ---------------------------------------------------------
+    const int n_act = gb - ga + 1;
+    const int chunk = (n_act + nparts - 1) / nparts;
+    const int g_begin = ga + part * chunk;
+    const int g_end = min(gb + 1, g_begin + chunk);
+    const float c2 = (float)(kc.neg_inv_2h2 * 1.4426950408889634);   // exponent in base 2
+    for (int g0 = g_begin + tid; g0 < g_end; g0 += 2 * nthr) {
+        const int g1 = g0 + nthr;
+        const float va = (float)(kde_grid_point(g0, G, lo, hi, step) - kc.mean);
+        double sa = 0.0, sb = 0.0;
+        if (g1 < g_end) {                          // two grid points per thread: one shared-memory read feeds both
+            const float vb = (float)(kde_grid_point(g1, G, lo, hi, step) - kc.mean);
+            for (int64_t i0 = 0; i0 < N; i0 += 64) {
+                const int64_t i1 = (i0 + 64 < N) ? i0 + 64 : N;
+                float pa = 0.f, pb = 0.f;
+                for (int64_t i = i0; i < i1; ++i) {
+                    const float xi = xs[i];
+                    const float da = va - xi, db = vb - xi;
+                    pa += ex2_approx(da * da * c2);
+                    pb += ex2_approx(db * db * c2);
+                }
+                sa += (double)pa;
+                sb += (double)pb;
+            }
+            out[g1] = (float)sb;
+        } else {                                   // the tail of a chunk: no wasted second evaluation
+            for (int64_t i0 = 0; i0 < N; i0 += 64) {
+                const int64_t i1 = (i0 + 64 < N) ? i0 + 64 : N;
+                float pa = 0.f;
+                for (int64_t i = i0; i < i1; ++i) {
+                    const float da = va - xs[i];
+                    pa += ex2_approx(da * da * c2);
+                }
+                sa += (double)pa;
+            }
+        }
+        out[g0] = (float)sa;
+    }
+}
+
 // grid = (columns of this batch, n_gchunks); CTA (c, gc) scans grid points
 // [gc*gchunk, (gc+1)*gchunk) of column col0 + c and writes s32[c*G + g].
 template <typename T>
@@ -413,32 +510,8 @@ k_kde_scan32(const T* __restrict__ a, int64_t N, int64_t Q, int64_t col0,
     const KdeColumn kc = cols[col];
     for (int64_t i = tid; i < N; i += nthr) xs[i] = (float)((double)a[i * Q + col] - kc.mean);
     __syncthreads();
-    const double lo = lohi[0], hi = lohi[1];
-    const double step = (hi - lo) / (double)(G - 1);
-    const float c2 = (float)(kc.neg_inv_2h2 * 1.4426950408889634);   // exponent in base 2
-    const int g_begin = blockIdx.y * gchunk;
-    const int g_end = min(G, g_begin + gchunk);
-    float* out = s32 + (int64_t)blockIdx.x * G;
-    for (int g0 = g_begin + tid; g0 < g_end; g0 += 2 * nthr) {
-        const int g1 = g0 + nthr;
-        const float ga = (float)(kde_grid_point(g0, G, lo, hi, step) - kc.mean);
-        const float gb = (float)(kde_grid_point(min(g1, G - 1), G, lo, hi, step) - kc.mean);
-        double sa = 0.0, sb = 0.0;
-        for (int64_t i0 = 0; i0 < N; i0 += 64) {
-            const int64_t i1 = (i0 + 64 < N) ? i0 + 64 : N;
-            float pa = 0.f, pb = 0.f;
-            for (int64_t i = i0; i < i1; ++i) {
-                const float xi = xs[i];
-                const float da = ga - xi, db = gb - xi;
-                pa += ex2_approx(da * da * c2);
-                pb += ex2_approx(db * db * c2);
-            }
-            sa += (double)pa;
-            sb += (double)pb;
-        }
-        out[g0] = (float)sa;
-        if (g1 < g_end) out[g1] = (float)sb;
-    }
+    (void)gchunk;
+    kde_scan_column(xs, N, kc, lohi[0], lohi[1], G, (int)blockIdx.y, (int)gridDim.y, s32 + (int64_t)blockIdx.x * G);
 }
 
 // The float64 decision for one column (see above): `row` = the column's fp32 scan, `xs` = its N members
@@ -596,32 +669,11 @@ k_kde_small(const T* __restrict__ a, int64_t N, int64_t Q, int compute_range, do
     KdeColumn kc;
     kc.mean = mean;
     kc.neg_inv_2h2 = -0.5 / ((ss / (double)(N - 1)) * scott_factor_sq);        // -inf when the column is constant
-    // ---- 3. fp32 scan of this CTA's grid points (same arithmetic as k_kde_scan32) ---------------------
-    const double step = (hi - lo) / (double)(G - 1);
-    const float c2 = (float)(kc.neg_inv_2h2 * 1.4426950408889634);
-    const int g_begin = blockIdx.y * gchunk;
-    const int g_end = min(G, g_begin + gchunk);
+    // ---- 3. fp32 scan of this CTA's share of the column's active grid range ------------------------------
+    (void)gchunk;
     float* out = s32 + col * G;
-    for (int g0 = g_begin + tid; g0 < g_end; g0 += 512) {
-        const int g1 = g0 + 256;
-        const float ga = (float)(kde_grid_point(g0, G, lo, hi, step) - kc.mean);
-        const float gb = (float)(kde_grid_point(min(g1, G - 1), G, lo, hi, step) - kc.mean);
-        double sa = 0.0, sb = 0.0;
-        for (int64_t i0 = 0; i0 < N; i0 += 64) {
-            const int64_t i1 = (i0 + 64 < N) ? i0 + 64 : N;
-            float pa = 0.f, pb = 0.f;
-            for (int64_t i = i0; i < i1; ++i) {
-                const float xi = xc[i];
-                const float da = ga - xi, db = gb - xi;
-                pa += ex2_approx(da * da * c2);
-                pb += ex2_approx(db * db * c2);
-            }
-            sa += (double)pa;
-            sb += (double)pb;
-        }
-        out[g0] = (float)sa;
-        if (g1 < g_end) out[g1] = (float)sb;
-    }
+    __syncthreads();                           // xc complete
+    kde_scan_column(xc, N, kc, lo, hi, G, (int)blockIdx.y, (int)gridDim.y, out);
     // ---- 4. the last CTA of the column selects -----------------------------------------------------------
     __threadfence();
     __syncthreads();

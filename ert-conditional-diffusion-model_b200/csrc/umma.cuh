@@ -51,6 +51,9 @@ __device__ __forceinline__ uint32_t smem_u32(const void* p) {
 }
 
 // ---- mbarrier -------------------------------------------------------------------------------
+#ifndef MBAR_SUSPEND_HINT_NS
+#define MBAR_SUSPEND_HINT_NS 20000u
+#endif
 __device__ __forceinline__ void mbar_init(uint32_t bar, uint32_t count) {
     asm volatile("mbarrier.init.shared::cta.b64 [%0], %1;" ::"r"(bar), "r"(count) : "memory");
 }
@@ -67,11 +70,13 @@ __device__ __forceinline__ void mbar_arrive(uint32_t bar) {
 __device__ __forceinline__ bool mbar_wait(uint32_t bar, uint32_t parity) {
     uint32_t ok = 0;
     for (uint32_t spin = 0; spin < (1u << 20); ++spin) {
+        // the suspend-time hint lets the hardware park the warp until the phase completes (or the hint
+        // expires) instead of returning early: far fewer polls competing for issue slots
         asm volatile(
             "{\n\t.reg .pred p;\n\t"
-            "mbarrier.try_wait.parity.shared::cta.b64 p, [%1], %2;\n\t"
+            "mbarrier.try_wait.parity.shared::cta.b64 p, [%1], %2, %3;\n\t"
             "selp.u32 %0, 1, 0, p;\n\t}"
-            : "=r"(ok) : "r"(bar), "r"(parity) : "memory");
+            : "=r"(ok) : "r"(bar), "r"(parity), "r"(MBAR_SUSPEND_HINT_NS) : "memory");
         if (ok) return true;
     }
     return false;
