@@ -721,6 +721,23 @@ int ertdiff_minmax(const void* d_a, int dtype, int64_t n, double* d_out2, void* 
     return 0;
 }
 
+// persistent, self-cleaning per-column tickets (last-CTA-done pattern of the KDE kernels)
+static int kde_tickets(unsigned int** out) {
+    static unsigned int* tickets[64] = {};
+    int dev = 0;
+    ERT_CUDA(cudaGetDevice(&dev));
+    ERT_REQUIRE(dev >= 0 && dev < 64, "kde: device index out of range");
+    if (!tickets[dev]) {
+        std::lock_guard<std::mutex> lock(g_ws_mutex);
+        if (!tickets[dev]) {
+            ERT_CUDA(cudaMalloc(&tickets[dev], 4096 * sizeof(unsigned int)));
+            ERT_CUDA(cudaMemset(tickets[dev], 0, 4096 * sizeof(unsigned int)));
+        }
+    }
+    *out = tickets[dev];
+    return 0;
+}
+
 int ertdiff_ensemble_kde_mode(const void* d_a, int dtype, int64_t N, int64_t Q,
                               const double* d_lohi, int32_t n_grid, double* d_mode,
                               int64_t* d_index, void* stream) {
@@ -739,9 +756,16 @@ int ertdiff_ensemble_kde_mode(const void* d_a, int dtype, int64_t N, int64_t Q,
     if (qb > 65535 * 16) qb = 65535 * 16;
     void* ws = nullptr;
     const size_t cols_bytes = ((size_t)Q * sizeof(KdeColumn) + 255) & ~(size_t)255;
-    if (int rc = workspace(cols_bytes + (size_t)qb * G * sizeof(float), &ws)) return rc;
+    // the float64 selection of a column is shared by several CTAs when there are few columns and many
+    // members (one CTA would re-evaluate ~100 candidates x N members alone)
+    const int sel_parts = (qb <= 4096 && N >= 1024) ? (qb * 8 <= 4 * kNumSMs ? 8 : (qb * 2 <= 4 * kNumSMs ? 2 : 1)) : 1;
+    const size_t part_bytes = (size_t)qb * sel_parts * 2 * sizeof(double);
+    if (int rc = workspace(cols_bytes + part_bytes + (size_t)qb * G * sizeof(float), &ws)) return rc;
+    unsigned int* tk = nullptr;
+    if (int rc = kde_tickets(&tk)) return rc;
     KdeColumn* cols = (KdeColumn*)ws;
-    float* s32 = (float*)((char*)ws + cols_bytes);
+    double* partials = (double*)((char*)ws + cols_bytes);
+    float* s32 = (float*)((char*)ws + cols_bytes + part_bytes);
     const bool f32in = dtype == ERTDIFF_F32;
     if (Q <= SQ_MAXQ && N >= 64) {
         static_assert(sizeof(KdeColumn) == 2 * sizeof(double), "KdeColumn is written as two doubles");
@@ -778,11 +802,11 @@ int ertdiff_ensemble_kde_mode(const void* d_a, int dtype, int64_t N, int64_t Q,
         if (f32in) {
             k_kde_scan32<float><<<grid, threads, (size_t)N * 4, st>>>((const float*)d_a, N, Q, c0, d_lohi, G, gchunk, cols, s32);
             ERT_LAUNCH_CHECK("k_kde_scan32");
-            k_kde_select64<float><<<(unsigned)nc, 256, (size_t)N * 8, st>>>((const float*)d_a, N, Q, c0, d_lohi, G, cols, s32, d_mode, d_index);
+            k_kde_select64<float><<<dim3((unsigned)nc, (unsigned)sel_parts), 256, (size_t)N * 8, st>>>((const float*)d_a, N, Q, c0, d_lohi, G, cols, s32, d_mode, d_index, partials, tk);
         } else {
             k_kde_scan32<double><<<grid, threads, (size_t)N * 4, st>>>((const double*)d_a, N, Q, c0, d_lohi, G, gchunk, cols, s32);
             ERT_LAUNCH_CHECK("k_kde_scan32");
-            k_kde_select64<double><<<(unsigned)nc, 256, (size_t)N * 8, st>>>((const double*)d_a, N, Q, c0, d_lohi, G, cols, s32, d_mode, d_index);
+            k_kde_select64<double><<<dim3((unsigned)nc, (unsigned)sel_parts), 256, (size_t)N * 8, st>>>((const double*)d_a, N, Q, c0, d_lohi, G, cols, s32, d_mode, d_index, partials, tk);
         }
         ERT_LAUNCH_CHECK("k_kde_select64");
     }
@@ -800,17 +824,8 @@ int ertdiff_ensemble_kde_mode_auto(const void* d_a, int dtype, int64_t N, int64_
         return ertdiff_ensemble_kde_mode(d_a, dtype, N, Q, d_lohi, n_grid, d_mode, d_index, stream);
     }
     // one fused launch (k_kde_small); tickets: a persistent, self-cleaning counter per column
-    static unsigned int* tickets[64] = {};
-    int dev = 0;
-    ERT_CUDA(cudaGetDevice(&dev));
-    ERT_REQUIRE(dev >= 0 && dev < 64, "ensemble_kde_mode_auto: device index out of range");
-    if (!tickets[dev]) {
-        std::lock_guard<std::mutex> lock(g_ws_mutex);
-        if (!tickets[dev]) {
-            ERT_CUDA(cudaMalloc(&tickets[dev], 4096 * sizeof(unsigned int)));
-            ERT_CUDA(cudaMemset(tickets[dev], 0, 4096 * sizeof(unsigned int)));
-        }
-    }
+    unsigned int* tk = nullptr;
+    if (int rc = kde_tickets(&tk)) return rc;
     const int G = n_grid;
     void* ws = nullptr;
     if (int rc = workspace((size_t)Q * G * sizeof(float), &ws)) return rc;
@@ -827,10 +842,10 @@ int ertdiff_ensemble_kde_mode_auto(const void* d_a, int dtype, int64_t N, int64_
     const size_t smem = (size_t)N * 12;
     if (dtype == ERTDIFF_F32)
         k_kde_small<float><<<grid, 256, smem, st>>>((const float*)d_a, N, Q, 1, d_lohi, G, gchunk, factor * factor,
-                                                    (float*)ws, tickets[dev], d_mode, d_index);
+                                                    (float*)ws, tk, d_mode, d_index);
     else
         k_kde_small<double><<<grid, 256, smem, st>>>((const double*)d_a, N, Q, 1, d_lohi, G, gchunk, factor * factor,
-                                                     (float*)ws, tickets[dev], d_mode, d_index);
+                                                     (float*)ws, tk, d_mode, d_index);
     ERT_LAUNCH_CHECK("k_kde_small");
     return 0;
 }

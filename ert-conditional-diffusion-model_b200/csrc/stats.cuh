@@ -516,10 +516,15 @@ k_kde_scan32(const T* __restrict__ a, int64_t N, int64_t Q, int64_t col0,
 
 // The float64 decision for one column (see above): `row` = the column's fp32 scan, `xs` = its N members
 // as float64 in shared memory.  Called by every thread of a 256-thread CTA.
+// With nparts > 1 several CTAs share a column: part p re-evaluates the candidates whose grid index is
+// congruent to p (the candidates of a mode are neighbours on the grid), and the last part to finish (atomic ticket, `slot` = the column's index in
+// the launch) combines the partial maxima (first index wins ties, as in the single-CTA form).
 __device__ __forceinline__ void kde_select_column(int64_t N, int64_t col, double lo, double hi, int G,
                                                   const KdeColumn kc, const float* row,
                                                   const double* __restrict__ xs, double* __restrict__ mode_out,
-                                                  int64_t* __restrict__ index_out) {
+                                                  int64_t* __restrict__ index_out, int part = 0, int nparts = 1,
+                                                  int64_t slot = 0, double* partials = nullptr,
+                                                  unsigned int* tickets = nullptr) {
     __shared__ float redf[8];
     __shared__ double redv[8];
     __shared__ int redi[8];
@@ -540,22 +545,28 @@ __device__ __forceinline__ void kde_select_column(int64_t N, int64_t col, double
     for (int w = 1; w < nwarps; ++w) mx = fmaxf(mx, redf[w]);
     const bool degenerate = !(kc.neg_inv_2h2 > -CUDART_INF) || !(kc.neg_inv_2h2 == kc.neg_inv_2h2);
     const float thr = mx * (1.0f - KDE_TOL);
+    __shared__ int ntotal;
+    if (tid == 0) ntotal = 0;
+    __syncthreads();
     for (int g = tid; g < G; g += nthr) {
         if (__ldcg(row + g) >= thr) {
-            const int k = atomicAdd(&ncand, 1);
-            if (k < KDE_MAX_CAND) cand[k] = g;
+            atomicAdd(&ntotal, 1);
+            if (g % nparts == part) {
+                const int k = atomicAdd(&ncand, 1);
+                if (k < KDE_MAX_CAND) cand[k] = g;
+            }
         }
     }
     __syncthreads();
     // a flat scan (more candidates than the list holds, or an all-zero scan) falls back to
-    // evaluating every grid point in float64
-    const bool all = ncand > KDE_MAX_CAND || !(mx > 0.f);
-    const int n_eval = all ? G : ncand;
+    // evaluating every grid point in float64 (the decision is the same in every part)
+    const bool all = ntotal > KDE_MAX_CAND || !(mx > 0.f);
+    const int n_eval = all ? (G - part + nparts - 1) / nparts : ncand;
     const double step = (hi - lo) / (double)(G - 1);
     double best = -1.0;
     int besti = 0x7fffffff;
     for (int k = warp; k < n_eval; k += nwarps) {
-        const int g = all ? k : cand[k];
+        const int g = all ? part + k * nparts : cand[k];
         const double gv = kde_grid_point(g, G, lo, hi, step);
         double acc = 0.0;
         for (int64_t i = lane; i < N; i += 32) {
@@ -571,6 +582,21 @@ __device__ __forceinline__ void kde_select_column(int64_t N, int64_t col, double
     if (tid == 0) {
         for (int w = 1; w < nwarps; ++w)
             if (redv[w] > best || (redv[w] == best && redi[w] < besti)) { best = redv[w]; besti = redi[w]; }
+        if (nparts > 1) {
+            double* mine = partials + (slot * nparts + part) * 2;
+            mine[0] = best; mine[1] = (double)besti;
+            __threadfence();
+            const unsigned int t = atomicAdd(&tickets[slot], 1u);
+            if (t != (unsigned int)(nparts - 1)) return;        // not the last part of this column
+            tickets[slot] = 0u;                                   // self-cleaning
+            __threadfence();
+            best = -1.0; besti = 0x7fffffff;
+            for (int p = 0; p < nparts; ++p) {
+                const double v = __ldcg(partials + (slot * nparts + p) * 2);
+                const int gi = (int)__ldcg(partials + (slot * nparts + p) * 2 + 1);
+                if (v > best || (v == best && gi < besti)) { best = v; besti = gi; }
+            }
+        }
         if (degenerate) {
             if (index_out) index_out[col] = -1;
             if (mode_out) mode_out[col] = CUDART_NAN;
@@ -582,18 +608,20 @@ __device__ __forceinline__ void kde_select_column(int64_t N, int64_t col, double
 }
 
 
-// grid = columns of this batch, 256 threads.
+// grid = (columns of this batch, parts), 256 threads.
 template <typename T>
 __global__ void __launch_bounds__(256)
 k_kde_select64(const T* __restrict__ a, int64_t N, int64_t Q, int64_t col0,
                const double* __restrict__ lohi, int G, const KdeColumn* __restrict__ cols,
                const float* __restrict__ s32, double* __restrict__ mode_out,
-               int64_t* __restrict__ index_out) {
+               int64_t* __restrict__ index_out, double* __restrict__ partials,
+               unsigned int* __restrict__ tickets) {
     extern __shared__ __align__(16) unsigned char kde_smem_raw[];
     double* xs = reinterpret_cast<double*>(kde_smem_raw);      // [N] members, float64
     const int64_t col = col0 + blockIdx.x;
     for (int64_t i = threadIdx.x; i < N; i += blockDim.x) xs[i] = (double)a[i * Q + col];
-    kde_select_column(N, col, lohi[0], lohi[1], G, cols[col], s32 + (int64_t)blockIdx.x * G, xs, mode_out, index_out);
+    kde_select_column(N, col, lohi[0], lohi[1], G, cols[col], s32 + (int64_t)blockIdx.x * G, xs, mode_out, index_out,
+                      (int)blockIdx.y, (int)gridDim.y, (int64_t)blockIdx.x, partials, tickets);
 }
 
 // ------------------------------------------------------------------------------------------
