@@ -818,7 +818,8 @@ int ertdiff_ensemble_kde_mode_auto(const void* d_a, int dtype, int64_t N, int64_
     ERT_REQUIRE(d_a && d_lohi && N > 1 && Q > 0 && n_grid > 1, "ensemble_kde_mode_auto: bad arguments");
     ERT_REQUIRE(dtype == ERTDIFF_F32 || dtype == ERTDIFF_F64, "ensemble_kde_mode_auto: bad dtype");
     cudaStream_t st = (cudaStream_t)stream;
-    const bool small = N * Q <= 65536 && (size_t)N * 12 <= 48 * 1024 && Q <= 4096;
+    // (from ~1000 members on, the staged kernels win: their float64 selection is shared by 8 CTAs per column)
+    const bool small = N * Q <= 65536 && N < 1024 && Q <= 4096;
     if (!small) {
         if (int rc = ertdiff_minmax(d_a, dtype, N * Q, d_lohi, stream)) return rc;
         return ertdiff_ensemble_kde_mode(d_a, dtype, N, Q, d_lohi, n_grid, d_mode, d_index, stream);

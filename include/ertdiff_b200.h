@@ -207,7 +207,7 @@ int ertdiff_ensemble_kde_mode(const void* d_a, int dtype, int64_t N, int64_t Q,
                               const double* d_lohi, int32_t n_grid, double* d_mode,
                               int64_t* d_index, void* stream);
 /* the same with the grid range taken from the data: d_lohi (2 float64, output) = global min / max of
- * the whole (N, Q) array (ECD.py:749-750).  Small ensembles (N*Q <= 65,536 values) run as ONE fused
+ * the whole (N, Q) array (ECD.py:749-750).  Small ensembles (N < 1024, N*Q <= 65,536 values) run as ONE fused
  * launch (range + column constants + scan + selection); larger ones as ertdiff_minmax followed by
  * ertdiff_ensemble_kde_mode. */
 int ertdiff_ensemble_kde_mode_auto(const void* d_a, int dtype, int64_t N, int64_t Q, int32_t n_grid,
