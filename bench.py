@@ -156,9 +156,13 @@ def run_reference(args):
     threads = os.cpu_count() or 1
     members, T = args.members, args.T
     sd, cond = synthetic_inputs(members, args.distinct_conditions)
-    sample_steps = args.ref_sample_steps
+    # each timed step = a bounded sample of the T-step chain; sized from a calibration run so that the
+    # whole --steps K run stays within ~2.5 minutes of CPU time (at most --ref-sample-steps per sample)
+    t_cal, _ = cpu_reference_sample(sd, cond, members, T, 2, threads)
+    per_step_s = max(t_cal / 2, 1e-4)
+    sample_steps = int(max(5, min(args.ref_sample_steps, 150.0 / (max(args.steps, 1) * per_step_s), T)))
     for _ in range(args.warmup):
-        cpu_reference_sample(sd, cond, members, T, max(1, sample_steps // 4), threads)
+        cpu_reference_sample(sd, cond, members, T, max(1, sample_steps // 8), threads)
     runs = [cpu_reference_sample(sd, cond, members, T, sample_steps, threads) for _ in range(args.steps)]
     secs = [r[0] for r in runs]
     stats_s = cpu_reference_stats(runs[-1][1])
@@ -359,8 +363,8 @@ def run_ours(args):
         # CPU baseline on a bounded sample (rank 0, N=1 only)
         if world == 1 and not args.no_cpu_baseline:
             threads = os.cpu_count() or 1
-            sample_steps = args.ref_sample_steps
-            cpu_reference_sample(sd, cond_host, members, T, 2, threads)            # warm-up
+            t_cal, _ = cpu_reference_sample(sd, cond_host, members, T, 2, threads)            # warm-up + calibration
+            sample_steps = int(max(5, min(args.ref_sample_steps, 12.0 / max(t_cal / 2, 1e-4), T)))   # ~10 s of CPU work
             secs, xs = cpu_reference_sample(sd, cond_host, members, T, sample_steps, threads)
             per_chain = secs * (T / sample_steps) + cpu_reference_stats(xs)
             line["cpu_baseline"] = {
@@ -385,7 +389,7 @@ def main():
     ap.add_argument("--distinct-conditions", action="store_true")
     ap.add_argument("--precision", default="fp32", choices=["fp32", "bf16"],
                     help="fp32 = CUDA-core FFMA chain (BASELINE config 2); bf16 = tcgen05 chain (configs 3/4)")
-    ap.add_argument("--ref-sample-steps", type=int, default=10,
+    ap.add_argument("--ref-sample-steps", type=int, default=250,
                     help="steps of the T-step chain the CPU arm actually runs per sample")
     ap.add_argument("--no-cpu-baseline", action="store_true")
     args = ap.parse_args()
