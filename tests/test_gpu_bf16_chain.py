@@ -128,3 +128,18 @@ def test_bf16_unsupported_shapes_fail_loudly(cuda_dev):
     b, a, ab = eb.get_diffusion_schedule(5)
     with pytest.raises(eb.ErtdiffError, match="hidden_dim = 128"):
         eb.run_chain(m, torch.rand(2, C, 50, device=cuda_dev), 5, b, a, ab, cuda_dev, seed=1, precision="bf16")
+
+
+def test_bf16_chain_small_param_dim(cuda_dev):
+    # param_dim < 29: the padded parameter columns carry zeros / never-stored values
+    torch.manual_seed(4)
+    m = eb.ConditionalDiffusionModel(5, 128).to(cuda_dev).eval()
+    T, B = 30, 150
+    cond = torch.rand(3, C, 200, generator=torch.Generator().manual_seed(1)).to(cuda_dev)
+    noise = torch.randn(T, B, 5, generator=torch.Generator().manual_seed(2)).to(cuda_dev)
+    b, a, ab = eb.get_diffusion_schedule(T)
+    x32 = eb.run_chain(m, cond, T, b, a, ab, cuda_dev, n_members=B, noise=noise)
+    x16 = eb.run_chain(m, cond, T, b, a, ab, cuda_dev, n_members=B, noise=noise, precision="bf16")
+    assert m.umma_status() == 0
+    scale = x32.abs().max().item()
+    assert torch.isfinite(x16).all() and (x16 - x32).abs().max().item() <= 5e-2 * scale
