@@ -122,7 +122,15 @@ static int run_encoder_umma(ertdiff_model* m, const float* d_cond, int64_t n_con
     ERT_REQUIRE(m->enc_w1_pk, "encode_condition: tensor-core encoder weights missing");
     const int64_t L1 = conv_out_len(L), L2 = conv_out_len(L1);
     ERT_REQUIRE(4 * (L2 + 128) + 16 < (int64_t)1 << 30, "encode_condition: L too large");
-    const int n_chunks = (int)((L2 + EU_TPC * 128 - 1) / (EU_TPC * 128));
+    // tiles per CTA: as few as it takes to give every CTA slot (two per SM) work, up to 10 (a whole
+    // condition of the reference grid) -- longer chunks amortise the per-CTA set-up (weights, TMEM,
+    // barriers): 4096 conditions 472 -> 400 us
+    const int64_t tiles = (L2 + 127) / 128;
+    int64_t want_chunks = (2 * kNumSMs) / n_cond;           // chunks per condition that fill the CTA slots
+    want_chunks = want_chunks < 1 ? 1 : (want_chunks > tiles ? tiles : want_chunks);
+    int tpc = (int)((tiles + want_chunks - 1) / want_chunks);
+    if (const char* e = std::getenv("ERTDIFF_ENC_TPC")) { const int v = std::atoi(e); if (v >= 1 && v <= 64) tpc = v; }
+    const int n_chunks = (int)((tiles + tpc - 1) / tpc);
     if (int rc = grow(m->enc_partial, m->enc_partial_n, (size_t)n_cond * n_chunks * kConv2Out)) return rc;
     static PerDeviceOnce once;
     bool& attr_set = *once.slot();
@@ -139,7 +147,7 @@ static int run_encoder_umma(ertdiff_model* m, const float* d_cond, int64_t n_con
         EncUmmaParams p{};
         p.base = (const float*)base; p.elem0 = elem0; p.member_stride = member_stride;
         p.total = (elem0 + (nc - 1) * member_stride + kInChannels * L + 3) & ~(int64_t)3; p.L = (int)L; p.L1 = (int)L1; p.L2 = (int)L2;
-        p.n_chunks = n_chunks;
+        p.n_chunks = n_chunks; p.tpc = tpc;
         p.w1_pk = reinterpret_cast<const uint4*>(m->enc_w1_pk); p.w2_pk = reinterpret_cast<const uint4*>(m->enc_w2_pk);
         p.b1 = m->raw[1]; p.b2 = m->raw[3]; p.conv1_w = m->conv1_w;
         p.partial = m->enc_partial + (size_t)c0 * n_chunks * kConv2Out; p.status = m->umma_status;

@@ -3,7 +3,9 @@
 // average pool fused into the TMEM epilogues.  Used by precision = bf16 (BASELINE configs 3/4);
 // the fp32 CUDA-core kernel of encoder.cuh serves the fp32 contract.
 //
-// One CTA = one condition x one chunk of up to EU_TPC tiles of 128 conv2 positions.  Per tile
+// One CTA = one condition x one chunk of `tpc` tiles of 128 conv2 positions (5 when there are few
+// conditions, so that the grid still fills the machine; a whole condition otherwise, which halves the
+// per-CTA set-up cost per tile).  Per tile
 // (p0 = first conv2 position):
 //   TMA     14 channel rows of the fp32 condition, window l = 4(p0-1) .. 4(p0+128)-1, into a
 //           double-buffered staging area: one bulk copy (cp.async.bulk, mbarrier complete_tx) per
@@ -50,7 +52,6 @@ namespace ertdiff {
 
 constexpr int EU_WORKERS = 256;                 // conversion + epilogue threads (8 warps)
 constexpr int EU_THREADS = EU_WORKERS + 32;     // + the TMA producer warp
-constexpr int EU_TPC = 5;                       // tiles per CTA (L2 = 1174 -> 2 chunks of 5 tiles)
 constexpr int EU_ROWS = 129;                    // rows per block: the tile's 128 + one neighbour
 constexpr int EU_BLK = EU_ROWS * 16;            // bytes per block
 constexpr int EU_COPY = 4 * EU_ROWS + 4;        // fp32 elements per bulk copy: the window + up to 3 leading elements
@@ -106,6 +107,7 @@ struct EncUmmaParams {
     int64_t member_stride;    // elements between conditions
     int L, L1, L2;
     int n_chunks;
+    int tpc;                  // tiles per CTA
     const uint4* w1_pk;
     const uint4* w2_pk;
     const float* b1;
@@ -174,9 +176,9 @@ k_encoder_umma(const EncUmmaParams a) {
     tc_fence_after();
     const uint32_t tmem = s.tmem_slot;
 
-    const int p_begin = chunk * EU_TPC * 128;
+    const int p_begin = chunk * a.tpc * 128;
     int n_tiles = (a.L2 - p_begin + 127) / 128;
-    if (n_tiles > EU_TPC) n_tiles = EU_TPC;
+    if (n_tiles > a.tpc) n_tiles = a.tpc;
     const int64_t cond_elem = a.elem0 + cond * a.member_stride;
     // A bulk copy needs a 16-byte aligned source, but a channel row of an odd-length condition starts
     // anywhere: each row is fetched from the aligned element below its window, and readers skip the
