@@ -51,7 +51,7 @@
 namespace ertdiff {
 
 constexpr int EU_WORKERS = 256;                 // conversion + epilogue threads (8 warps)
-constexpr int EU_THREADS = EU_WORKERS + 32;     // + the TMA producer warp
+constexpr int EU_THREADS = EU_WORKERS + 64;     // + the TMA producer warp + the MMA-issue warp
 constexpr int EU_ROWS = 129;                    // rows per block: the tile's 128 + one neighbour
 constexpr int EU_BLK = EU_ROWS * 16;            // bytes per block
 constexpr int EU_COPY = 4 * EU_ROWS + 4;        // fp32 elements per bulk copy: the window + up to 3 leading elements
@@ -69,7 +69,7 @@ struct EncUmmaSmem {
     alignas(16) float b1[kConv1Out];
     alignas(16) float b2[kConv2Out];
     unsigned long long desc[24];                // MMA operand descriptors (thread 0 builds and uses them)
-    unsigned long long bar_tma[2], bar_free[2], bar_mma;
+    unsigned long long bar_tma[2], bar_free[2], bar_mma, bar_mma2;
     uint32_t tmem_slot;
     int timeout;
 };
@@ -134,8 +134,9 @@ k_encoder_umma(const EncUmmaParams a) {
     uint32_t sPH = smem_u32(&s.ph[0][0][0]), sHE = smem_u32(&s.he[0][0]), sHO = smem_u32(&s.ho[0][0]);
     uint32_t sW1 = smem_u32(s.w1), sW2 = smem_u32(s.w2), sB1 = smem_u32(s.b1), sB2 = smem_u32(s.b2);
     uint32_t bar_tma = smem_u32(&s.bar_tma[0]), bar_free = smem_u32(&s.bar_free[0]), bar_mma = smem_u32(&s.bar_mma);
+    uint32_t bar_mma2 = smem_u32(&s.bar_mma2);
     asm volatile("" : "+r"(sStage), "+r"(sPH), "+r"(sHE), "+r"(sHO), "+r"(sW1), "+r"(sW2), "+r"(sB1), "+r"(sB2),
-                      "+r"(bar_tma), "+r"(bar_free), "+r"(bar_mma));
+                      "+r"(bar_tma), "+r"(bar_free), "+r"(bar_mma), "+r"(bar_mma2));
     constexpr uint32_t STAGE_BYTES = kInChannels * EU_STG_ROW * 4;
 
     // ---- one-time setup ------------------------------------------------------------------------
@@ -155,6 +156,7 @@ k_encoder_umma(const EncUmmaParams a) {
             mbar_init(bar_free + 8u * i, EU_WORKERS / 32);
         }
         mbar_init(bar_mma, 1);
+        mbar_init(bar_mma2, 1);
         fence_mbar_init();
         // MMA operand descriptors: all loop-invariant, built once by the issuing thread and parked in
         // shared memory (21 64-bit values would otherwise occupy registers in every thread)
@@ -212,8 +214,44 @@ k_encoder_umma(const EncUmmaParams a) {
             if (bytes) tma_bulk_load(dst, a.base + first, bytes, bar);
         }
         if (!ok) s.timeout = 1;
+    } else if (warp == EU_WORKERS / 32 + 1) {
+        // ===== MMA-issue warp: paced by the workers' arrive-only named barriers ===========================
+        // barrier 2 ("phase blocks of the next tile written") -> GEMM1, barrier 3 ("HE/HO written") -> GEMM2
+        constexpr uint32_t IDESC1 = idesc_bf16_f32(128, kConv1Out);
+        constexpr uint32_t IDESC2 = idesc_bf16_f32(128, kConv2Out);
+        auto gemm1 = [&]() {                     // even positions -> TMEM columns 0..31, odd -> 32..63
+            asm volatile("bar.sync 2, %0;" ::"n"(EU_WORKERS + 32) : "memory");
+            if (lane == 0) {
+                tc_fence_after();
+                mma_bf16_first(tmem, s.desc[3], s.desc[0], IDESC1);
+                mma_bf16_acc(tmem, s.desc[4], s.desc[1], IDESC1);
+                mma_bf16_acc(tmem, s.desc[5], s.desc[2], IDESC1);
+                mma_bf16_first(tmem + 32, s.desc[6], s.desc[0], IDESC1);
+                mma_bf16_acc(tmem + 32, s.desc[7], s.desc[1], IDESC1);
+                mma_bf16_acc(tmem + 32, s.desc[8], s.desc[2], IDESC1);
+                mma_commit(bar_mma);
+            }
+            __syncwarp();
+        };
+        if (n_tiles > 0) gemm1();
+        for (int tile = 0; tile < n_tiles; ++tile) {
+            asm volatile("bar.sync 3, %0;" ::"n"(EU_WORKERS + 32) : "memory");
+            if (lane == 0) {
+                tc_fence_after();
+                mma_bf16_first(tmem + 64, s.desc[9], s.desc[15], IDESC2);
+#pragma unroll
+                for (int ks = 1; ks < 6; ++ks) mma_bf16_acc(tmem + 64, s.desc[9 + ks], s.desc[15 + ks], IDESC2);
+                mma_commit(bar_mma2);
+            }
+            __syncwarp();
+            if (tile + 1 < n_tiles) gemm1();
+        }
     } else {
-        // ===== worker warps: conversion, MMA issue (thread 0), TMEM epilogues ============================
+        // ===== worker warps: conversion and TMEM epilogues, software-pipelined across tiles ==============
+        //   epilogue 1 (t) | convert (t+1) while GEMM2 (t) runs | epilogue 2 (t) while GEMM1 (t+1) runs
+        // Workers never wait for each other inside the loop: they wait on the MMA / TMA mbarriers and only
+        // ARRIVE on the named barriers that pace the MMA warp.  After a timeout every wait is skipped so that
+        // all arrivals still happen (nobody is left blocked); the chunk's result is poisoned.
         // every warp may touch the TMEM lane quarter (warp % 4): warps 0-3 and 4-7 split the columns
         const int row = (warp & 3) * 32 + lane;      // tile row = TMEM lane
         const int wh = warp >> 2;                    // 0: even conv1 phase / conv2 channels 0..31, 1: odd / 32..63
@@ -226,28 +264,21 @@ k_encoder_umma(const EncUmmaParams a) {
             const int cic = ci < kInChannels ? ci : 0;
             src_row[u] = 4u * (uint32_t)(cic * EU_STG_ROW + ((e0 + cic * Lm) & 3) + (tid & 127));
         }
-        constexpr uint32_t IDESC1 = idesc_bf16_f32(128, kConv1Out);
-        constexpr uint32_t IDESC2 = idesc_bf16_f32(128, kConv2Out);
+        volatile int* timeout_flag = &s.timeout;
+        auto wait_bar = [&](uint32_t bar, uint32_t parity) {
+            if (*timeout_flag) return;
+            if (!mbar_wait(bar, parity)) *timeout_flag = 1;
+        };
 
-        float2 acc[16];                              // pooled running sums: conv2 channels 32 wh .. 32 wh + 31 of this row
-#pragma unroll
-        for (int c = 0; c < 16; ++c) acc[c] = make_float2(0.f, 0.f);
-        uint4 carry[4];                              // thread (row 127, odd phase): O[127] = next tile's HO row 0
-#pragma unroll
-        for (int c = 0; c < 4; ++c) carry[c] = make_uint4(0u, 0u, 0u, 0u);
-        EU_T(const bool timed = a.timing && blockIdx.x == 0 && blockIdx.y == 0 && tid == 0; long long tt[8] = {0,0,0,0,0,0,0,0}, q0 = 0, q1 = 0;)
-#pragma unroll 1
-        for (int tile = 0; tile < n_tiles; ++tile) {
-            EU_T(if (timed) q0 = clock64();)
+        // staging (fp32, [ci][l]) -> bf16 phase blocks of one tile, then "phase blocks written" (barrier 2).
+        // lanes run along l: the eight 4-byte reads are conflict-free and the 16-byte stores of a quarter
+        // warp fall into distinct banks.  Only the first / last tiles of a row need masks.
+        auto convert_tile = [&](int tile) {
             const int p0 = p_begin + tile * 128;
             const int lbase = 4 * (p0 - 1);
             const int buf = tile & 1;
-            if (!mbar_wait(bar_tma + 8u * buf, (uint32_t)(tile >> 1) & 1u)) s.timeout = 1;
-            EU_T(if (timed) { q1 = clock64(); tt[0] += q1 - q0; q0 = q1; })
+            wait_bar(bar_tma + 8u * buf, (uint32_t)(tile >> 1) & 1u);
             const uint32_t stg = sStage + (uint32_t)buf * STAGE_BYTES;
-            // ---- staging (fp32, [ci][l]) -> bf16 phase blocks -------------------------------------
-            // lanes run along l: the eight 4-byte reads are conflict-free and the 16-byte stores of a
-            // quarter warp fall into distinct banks.  Only the first / last tiles of a row need masks.
             const bool edge = lbase < 0 || lbase + 4 * EU_ROWS > a.L;
             auto convert = [&](int ll) {
                 float v[8];
@@ -267,8 +298,7 @@ k_encoder_umma(const EncUmmaParams a) {
 #pragma unroll
             for (int n = 0; n < 4; ++n) convert((tid & 127) + 128 * n);      // 4 x 128 = 512 of the 516 positions
             if ((tid & 127) < 4 * EU_ROWS - 512) convert((tid & 127) + 512);
-            EU_T(if (timed) { q1 = clock64(); tt[1] += q1 - q0; q0 = q1; })
-            // ---- HO row 0 = h1[2 p0 - 1] for a chunk's first tile (later tiles: carried, see epilogue 2) --
+            // HO row 0 = h1[2 p0 - 1] for a chunk's first tile (later tiles: carried, see epilogue 2)
             if (tile == 0 && warp == 7) {            // lane = output channel; fp32 from the staged window
                 const int q = 2 * p0 - 1;
                 float h = 0.f;
@@ -291,22 +321,24 @@ k_encoder_umma(const EncUmmaParams a) {
             __syncwarp();
             if (lane == 0) mbar_arrive(bar_free + 8u * buf);        // this warp is done with the staging buffer
             fence_proxy_async();
-            tc_fence_before();
-            worker_barrier();                      // phase blocks complete, TMEM of the last tile read
-            if (s.timeout) break;                  // uniform: written before the barrier
-            if (tid == 0) {
-                tc_fence_after();
-                // even positions -> TMEM columns 0..31, odd -> 32..63
-                mma_bf16_first(tmem, s.desc[3], s.desc[0], IDESC1);
-                mma_bf16_acc(tmem, s.desc[4], s.desc[1], IDESC1);
-                mma_bf16_acc(tmem, s.desc[5], s.desc[2], IDESC1);
-                mma_bf16_first(tmem + 32, s.desc[6], s.desc[0], IDESC1);
-                mma_bf16_acc(tmem + 32, s.desc[7], s.desc[1], IDESC1);
-                mma_bf16_acc(tmem + 32, s.desc[8], s.desc[2], IDESC1);
-                mma_commit(bar_mma);
-            }
-            EU_T(if (timed) { q1 = clock64(); tt[2] += q1 - q0; q0 = q1; })
-            if (!mbar_wait(bar_mma, 0u)) s.timeout = 1;
+            tc_fence_before();                     // (this thread's TMEM reads of earlier tiles are complete)
+            asm volatile("bar.arrive 2, %0;" ::"n"(EU_WORKERS + 32) : "memory");
+        };
+
+        float2 acc[16];                              // pooled running sums: conv2 channels 32 wh .. 32 wh + 31 of this row
+#pragma unroll
+        for (int c = 0; c < 16; ++c) acc[c] = make_float2(0.f, 0.f);
+        uint4 carry[4];                              // thread (row 127, odd phase): O[127] = next tile's HO row 0
+#pragma unroll
+        for (int c = 0; c < 4; ++c) carry[c] = make_uint4(0u, 0u, 0u, 0u);
+        EU_T(const bool timed = a.timing && blockIdx.x == 0 && blockIdx.y == 0 && tid == 0; long long tt[8] = {0,0,0,0,0,0,0,0}, q0 = 0, q1 = 0;)
+        if (n_tiles > 0) convert_tile(0);
+#pragma unroll 1
+        for (int tile = 0; tile < n_tiles; ++tile) {
+            EU_T(if (timed) q0 = clock64();)
+            const int p0 = p_begin + tile * 128;
+            const uint32_t par = (uint32_t)tile & 1u;
+            wait_bar(bar_mma, par);                 // GEMM1 (tile) complete
             EU_T(if (timed) { q1 = clock64(); tt[3] += q1 - q0; q0 = q1; })
             tc_fence_after();
             // ---- epilogue 1: bias + ReLU -> bf16 HE (warps 0-3) / HO (warps 4-7) --------------------
@@ -331,23 +363,17 @@ k_encoder_umma(const EncUmmaParams a) {
                     if (tid == EU_WORKERS - 1) carry[c] = pk;
                 }
             }
-            EU_T(if (timed) { q1 = clock64(); tt[4] += q1 - q0; q0 = q1; })
             fence_proxy_async();
             tc_fence_before();
-            worker_barrier();
-            if (s.timeout) break;
-            if (tid == 0) {
-                tc_fence_after();
-                mma_bf16_first(tmem + 64, s.desc[9], s.desc[15], IDESC2);
-#pragma unroll
-                for (int ks = 1; ks < 6; ++ks) mma_bf16_acc(tmem + 64, s.desc[9 + ks], s.desc[15 + ks], IDESC2);
-                mma_commit(bar_mma);
-            }
-            EU_T(if (timed) { q1 = clock64(); tt[5] += q1 - q0; q0 = q1; })
-            if (!mbar_wait(bar_mma, 1u)) s.timeout = 1;
+            asm volatile("bar.arrive 3, %0;" ::"n"(EU_WORKERS + 32) : "memory");     // HE / HO written -> GEMM2 (tile)
+            EU_T(if (timed) { q1 = clock64(); tt[4] += q1 - q0; q0 = q1; })
+            // ---- next tile's phase blocks while GEMM2 runs (GEMM1 of this tile has completed: PH is free) ----
+            if (tile + 1 < n_tiles) convert_tile(tile + 1);
+            EU_T(if (timed) { q1 = clock64(); tt[1] += q1 - q0; q0 = q1; })
+            wait_bar(bar_mma2, par);                // GEMM2 (tile) complete
             EU_T(if (timed) { q1 = clock64(); tt[6] += q1 - q0; q0 = q1; })
             tc_fence_after();
-            // ---- epilogue 2: bias + ReLU + pooled running sums --------------------------------------
+            // ---- epilogue 2: bias + ReLU + pooled running sums (GEMM1 of the next tile is in flight) ----
             {
                 uint32_t dv[32];
                 tmem_ld32(tlane + 64 + 32 * wh, dv);
