@@ -264,6 +264,7 @@ k_encoder_umma(const EncUmmaParams a) {
             const int cic = ci < kInChannels ? ci : 0;
             src_row[u] = 4u * (uint32_t)(cic * EU_STG_ROW + ((e0 + cic * Lm) & 3) + (tid & 127));
         }
+        EU_T(const bool timed = a.timing && blockIdx.x == 0 && blockIdx.y == 0 && tid == 0; long long tt[8] = {0,0,0,0,0,0,0,0}, q0 = 0, q1 = 0;)
         volatile int* timeout_flag = &s.timeout;
         auto wait_bar = [&](uint32_t bar, uint32_t parity) {
             if (*timeout_flag) return;
@@ -277,7 +278,9 @@ k_encoder_umma(const EncUmmaParams a) {
             const int p0 = p_begin + tile * 128;
             const int lbase = 4 * (p0 - 1);
             const int buf = tile & 1;
+            EU_T(long long w0 = 0; if (timed) w0 = clock64();)
             wait_bar(bar_tma + 8u * buf, (uint32_t)(tile >> 1) & 1u);
+            EU_T(if (timed) tt[0] += clock64() - w0;)
             const uint32_t stg = sStage + (uint32_t)buf * STAGE_BYTES;
             const bool edge = lbase < 0 || lbase + 4 * EU_ROWS > a.L;
             auto convert = [&](int ll) {
@@ -331,7 +334,6 @@ k_encoder_umma(const EncUmmaParams a) {
         uint4 carry[4];                              // thread (row 127, odd phase): O[127] = next tile's HO row 0
 #pragma unroll
         for (int c = 0; c < 4; ++c) carry[c] = make_uint4(0u, 0u, 0u, 0u);
-        EU_T(const bool timed = a.timing && blockIdx.x == 0 && blockIdx.y == 0 && tid == 0; long long tt[8] = {0,0,0,0,0,0,0,0}, q0 = 0, q1 = 0;)
         if (n_tiles > 0) convert_tile(0);
 #pragma unroll 1
         for (int tile = 0; tile < n_tiles; ++tile) {

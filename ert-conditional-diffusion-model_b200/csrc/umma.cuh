@@ -72,11 +72,19 @@ __device__ __forceinline__ bool mbar_wait(uint32_t bar, uint32_t parity) {
     for (uint32_t spin = 0; spin < (1u << 20); ++spin) {
         // the suspend-time hint lets the hardware park the warp until the phase completes (or the hint
         // expires) instead of returning early: far fewer polls competing for issue slots
+#if MBAR_SUSPEND_HINT_NS > 0
         asm volatile(
             "{\n\t.reg .pred p;\n\t"
             "mbarrier.try_wait.parity.shared::cta.b64 p, [%1], %2, %3;\n\t"
             "selp.u32 %0, 1, 0, p;\n\t}"
             : "=r"(ok) : "r"(bar), "r"(parity), "r"(MBAR_SUSPEND_HINT_NS) : "memory");
+#else
+        asm volatile(
+            "{\n\t.reg .pred p;\n\t"
+            "mbarrier.try_wait.parity.shared::cta.b64 p, [%1], %2;\n\t"
+            "selp.u32 %0, 1, 0, p;\n\t}"
+            : "=r"(ok) : "r"(bar), "r"(parity) : "memory");
+#endif
         if (ok) return true;
     }
     return false;
