@@ -164,8 +164,8 @@ __global__ void __launch_bounds__(UC_THREADS, 1) k_chain_umma(const ChainParams 
     bool ok = true;
 
     if (warp == UC_EPI_WARPS + UC_RNG_WARPS) {
-        // ===== MMA-issue warp: one elected thread, everything it does is asynchronous ============
-        if (lane == 0) {
+        // ===== MMA-issue warp: the whole warp walks the loop (converged), one elected lane issues ==========
+        {
             constexpr uint32_t IDESC1 = idesc_bf16_f32(UC_M, UC_H);
             constexpr uint32_t IDESC2 = idesc_bf16_f32(UC_M, UC_N2);
             // all operand descriptors are loop-invariant: build them once, so that a step costs this
@@ -183,7 +183,7 @@ __global__ void __launch_bounds__(UC_THREADS, 1) k_chain_umma(const ChainParams 
             }
             const uint32_t tmemE = tmem + 128;
 #if UC_TIMING
-            const bool timed = ex.timing != nullptr && blockIdx.x == 0;
+            const bool timed = ex.timing != nullptr && blockIdx.x == 0 && lane == 0;
             long long tm[4] = {0, 0, 0, 0}, c0 = 0, c1 = 0;
 #endif
             for (int it = 0; it < n_steps && ok; ++it) {
@@ -192,23 +192,29 @@ __global__ void __launch_bounds__(UC_THREADS, 1) k_chain_umma(const ChainParams 
                 ok = mbar_wait(bar_x, ph);
                 UC_T(if (timed) { c1 = clock64(); tm[0] += c1 - c0; })
                 tc_fence_after();
-                mma_bf16_first(tmem, dA1[0], dB1[0], IDESC1);
+                if (elect_one()) {
+                    mma_bf16_first(tmem, dA1[0], dB1[0], IDESC1);
 #pragma unroll
-                for (int k = 1; k < UC_K1 / 16; ++k) mma_bf16_acc(tmem, dA1[k], dB1[k], IDESC1);
-                mma_commit(bar_d);
+                    for (int k = 1; k < UC_K1 / 16; ++k) mma_bf16_acc(tmem, dA1[k], dB1[k], IDESC1);
+                    mma_commit(bar_d);
+                }
+                __syncwarp();
                 UC_T(if (timed) { c0 = clock64(); tm[1] += c0 - c1; })
 #pragma unroll
                 for (int part = 0; part < UC_TPM; ++part) {      // each part's K columns as soon as they are written
                     ok = ok && mbar_wait(bar_h0 + 8u * part, ph);
                     tc_fence_after();
+                    if (elect_one()) {
 #pragma unroll
-                    for (int kk = 0; kk < 8 / UC_TPM; ++kk) {
-                        const int k = 8 / UC_TPM * part + kk;
-                        if (k == 0) mma_bf16_first(tmemE, dA2[0], dB2[0], IDESC2);
-                        else mma_bf16_acc(tmemE, dA2[k], dB2[k], IDESC2);
+                        for (int kk = 0; kk < 8 / UC_TPM; ++kk) {
+                            const int k = 8 / UC_TPM * part + kk;
+                            if (k == 0) mma_bf16_first(tmemE, dA2[0], dB2[0], IDESC2);
+                            else mma_bf16_acc(tmemE, dA2[k], dB2[k], IDESC2);
+                        }
+                        if (part == UC_TPM - 1) mma_commit(bar_e);
                     }
+                    __syncwarp();
                 }
-                mma_commit(bar_e);
                 UC_T(if (timed) { c1 = clock64(); tm[2] += c1 - c0; })
             }
             UC_T(if (timed) { ex.timing[8] = tm[0]; ex.timing[9] = tm[1]; ex.timing[10] = tm[2]; })

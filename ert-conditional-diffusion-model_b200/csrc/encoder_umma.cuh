@@ -219,16 +219,19 @@ k_encoder_umma(const EncUmmaParams a) {
         // barrier 2 ("phase blocks of the next tile written") -> GEMM1, barrier 3 ("HE/HO written") -> GEMM2
         constexpr uint32_t IDESC1 = idesc_bf16_f32(128, kConv1Out);
         constexpr uint32_t IDESC2 = idesc_bf16_f32(128, kConv2Out);
+        uint64_t d[21];                          // the loop-invariant operand descriptors, in registers
+#pragma unroll
+        for (int i = 0; i < 21; ++i) d[i] = s.desc[i];
         auto gemm1 = [&]() {                     // even positions -> TMEM columns 0..31, odd -> 32..63
             asm volatile("bar.sync 2, %0;" ::"n"(EU_WORKERS + 32) : "memory");
-            if (lane == 0) {
-                tc_fence_after();
-                mma_bf16_first(tmem, s.desc[3], s.desc[0], IDESC1);
-                mma_bf16_acc(tmem, s.desc[4], s.desc[1], IDESC1);
-                mma_bf16_acc(tmem, s.desc[5], s.desc[2], IDESC1);
-                mma_bf16_first(tmem + 32, s.desc[6], s.desc[0], IDESC1);
-                mma_bf16_acc(tmem + 32, s.desc[7], s.desc[1], IDESC1);
-                mma_bf16_acc(tmem + 32, s.desc[8], s.desc[2], IDESC1);
+            tc_fence_after();
+            if (elect_one()) {
+                mma_bf16_first(tmem, d[3], d[0], IDESC1);
+                mma_bf16_acc(tmem, d[4], d[1], IDESC1);
+                mma_bf16_acc(tmem, d[5], d[2], IDESC1);
+                mma_bf16_first(tmem + 32, d[6], d[0], IDESC1);
+                mma_bf16_acc(tmem + 32, d[7], d[1], IDESC1);
+                mma_bf16_acc(tmem + 32, d[8], d[2], IDESC1);
                 mma_commit(bar_mma);
             }
             __syncwarp();
@@ -236,11 +239,11 @@ k_encoder_umma(const EncUmmaParams a) {
         if (n_tiles > 0) gemm1();
         for (int tile = 0; tile < n_tiles; ++tile) {
             asm volatile("bar.sync 3, %0;" ::"n"(EU_WORKERS + 32) : "memory");
-            if (lane == 0) {
-                tc_fence_after();
-                mma_bf16_first(tmem + 64, s.desc[9], s.desc[15], IDESC2);
+            tc_fence_after();
+            if (elect_one()) {
+                mma_bf16_first(tmem + 64, d[9], d[15], IDESC2);
 #pragma unroll
-                for (int ks = 1; ks < 6; ++ks) mma_bf16_acc(tmem + 64, s.desc[9 + ks], s.desc[15 + ks], IDESC2);
+                for (int ks = 1; ks < 6; ++ks) mma_bf16_acc(tmem + 64, d[9 + ks], d[15 + ks], IDESC2);
                 mma_commit(bar_mma2);
             }
             __syncwarp();
