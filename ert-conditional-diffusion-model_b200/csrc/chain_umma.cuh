@@ -68,15 +68,22 @@ constexpr int UC_EPI_WARPS = 4 * UC_TPM;
 constexpr int UC_RNG_WARPS = UC_RNG_WARPS_N;   // 4 or 8
 constexpr int UC_THREADS = (UC_EPI_WARPS + UC_RNG_WARPS + 1) * 32;   // + the MMA-issue warp
 constexpr int UC_AUG = 29;      // first augmentation column (param_dim <= 29)
-constexpr int UC_NSLOT = 4;     // depth of the noise ring (steps)
+// Two builds of the kernel (template parameter CTAS): one CTA per SM (up to 128 registers per thread, a
+// 4-deep noise ring, all 64 accumulator columns of a thread in flight per tcgen05.wait::ld) and, for
+// ensembles of more than 148 tiles with a shared condition, two co-resident CTAs per SM (72 registers,
+// 2-deep ring, 32 columns per wait): each CTA is then ~17 % slower, but their MMA / mbarrier waits
+// overlap -- 37,888 members: 2.76 -> 2.29 ms.
+__host__ __device__ constexpr int uc_nslot(int ctas) { return ctas == 2 ? 2 : 4; }        // depth of the noise ring (steps)
+__host__ __device__ constexpr int uc_epi_chunk(int ctas) { return ctas == 2 ? 32 : 64; }
 
+template <int NSLOT>
 struct UmmaChainSmem {
     unsigned char x[UC_M * UC_K1 * 2];      // A of GEMM1
     unsigned char h[UC_M * UC_H * 2];       // A of GEMM2
     unsigned char w1[UC_H * UC_K1 * 2];     // B of GEMM1 (W0x augmented)
     unsigned char w2[UC_N2 * UC_H * 2];     // B of GEMM2 (W2 padded)
-    float zring[UC_NSLOT][UC_M][kPPad];     // noise ring; 16-byte chunk c of member m sits at chunk c ^ (m & 7)
-    unsigned long long bar_x, bar_d, bar_e, bar_h[UC_TPM], bar_full[UC_NSLOT], bar_empty[UC_NSLOT];
+    float zring[NSLOT][UC_M][kPPad];     // noise ring; 16-byte chunk c of member m sits at chunk c ^ (m & 7)
+    unsigned long long bar_x, bar_d, bar_e, bar_h[UC_TPM], bar_full[NSLOT], bar_empty[NSLOT];
     alignas(16) float b2[kPPad];
     uint32_t tmem_slot;
     int timeout;
@@ -107,11 +114,14 @@ struct UmmaChainExtra {
     long long* timing;      // optional (16 int64): phase cycle sums of CTA 0, see ertdiff_debug_umma_timing
 };
 
-template <bool REPLAY, bool TRACE, bool SHARED>
-__global__ void __launch_bounds__(UC_THREADS, 1) k_chain_umma(const ChainParams a, const UmmaChainExtra ex) {
+template <bool REPLAY, bool TRACE, bool SHARED, int CTAS>
+__global__ void __launch_bounds__(UC_THREADS, CTAS) k_chain_umma(const ChainParams a, const UmmaChainExtra ex) {
+    static_assert(CTAS == 1 || (CTAS == 2 && SHARED), "two CTAs per SM: shared condition only (TMEM: 2 x 256 columns)");
+    constexpr int UC_NSLOT = uc_nslot(CTAS);
+    constexpr int UC_EPI_CHUNK = uc_epi_chunk(CTAS);
     using namespace umma;
     extern __shared__ __align__(128) unsigned char uc_smem_raw[];
-    UmmaChainSmem& s = *reinterpret_cast<UmmaChainSmem*>(uc_smem_raw);
+    UmmaChainSmem<UC_NSLOT>& s = *reinterpret_cast<UmmaChainSmem<UC_NSLOT>*>(uc_smem_raw);
     const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
     const uint32_t sX_ = smem_u32(s.x), sH_ = smem_u32(s.h), sW1_ = smem_u32(s.w1), sW2_ = smem_u32(s.w2);
     const uint32_t sZ_ = smem_u32(&s.zring[0][0][0]);
@@ -384,17 +394,21 @@ __global__ void __launch_bounds__(UC_THREADS, 1) k_chain_umma(const ChainParams 
             tc_fence_after();
             // ---- epilogue 1: h = ReLU(D [+ c_b]) -> bf16 A operand of GEMM2 ----------------------
             if (SHARED) {
-                uint32_t dv[CW];             // all loads in flight, one wait
 #pragma unroll
-                for (int hh = 0; hh < CW / 16; ++hh) tmem_ld16(tD + 16 * hh, *reinterpret_cast<uint32_t(*)[16]>(&dv[16 * hh]));
-                tmem_ld_wait();
+                for (int half2 = 0; half2 < CW / UC_EPI_CHUNK; ++half2) {     // UC_EPI_CHUNK columns in flight per wait
+                    uint32_t dv[UC_EPI_CHUNK];
 #pragma unroll
-                for (int q = 0; q < CW / 8; ++q)
-                    sts_u4(hrow + (uint32_t)q * kLBO,
-                           pack_bf16_relu(__uint_as_float(dv[8 * q]), __uint_as_float(dv[8 * q + 1])),
-                           pack_bf16_relu(__uint_as_float(dv[8 * q + 2]), __uint_as_float(dv[8 * q + 3])),
-                           pack_bf16_relu(__uint_as_float(dv[8 * q + 4]), __uint_as_float(dv[8 * q + 5])),
-                           pack_bf16_relu(__uint_as_float(dv[8 * q + 6]), __uint_as_float(dv[8 * q + 7])));
+                    for (int hh = 0; hh < UC_EPI_CHUNK / 16; ++hh)
+                        tmem_ld16(tD + UC_EPI_CHUNK * half2 + 16 * hh, *reinterpret_cast<uint32_t(*)[16]>(&dv[16 * hh]));
+                    tmem_ld_wait();
+#pragma unroll
+                    for (int q = 0; q < UC_EPI_CHUNK / 8; ++q)
+                        sts_u4(hrow + (uint32_t)(half2 * (UC_EPI_CHUNK / 8) + q) * kLBO,
+                               pack_bf16_relu(__uint_as_float(dv[8 * q]), __uint_as_float(dv[8 * q + 1])),
+                               pack_bf16_relu(__uint_as_float(dv[8 * q + 2]), __uint_as_float(dv[8 * q + 3])),
+                               pack_bf16_relu(__uint_as_float(dv[8 * q + 4]), __uint_as_float(dv[8 * q + 5])),
+                               pack_bf16_relu(__uint_as_float(dv[8 * q + 6]), __uint_as_float(dv[8 * q + 7])));
+                }
             } else {
 #pragma unroll
                 for (int hh = 0; hh < CW / 16; ++hh) {       // 16 columns at a time: accumulator + c_b
