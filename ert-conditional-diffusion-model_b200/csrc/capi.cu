@@ -261,8 +261,8 @@ static int run_chain(ertdiff_model* m, const ertdiff_chain_args* a, const float*
         UmmaChainExtra ex{reinterpret_cast<const uint4*>(m->w1_pk), reinterpret_cast<const uint4*>(m->w2_pk), m->umma_status,
                           m->umma_timing_on ? m->umma_timing : nullptr};
         const unsigned grid = (unsigned)((q.B + UC_M - 1) / UC_M);
-        // more tiles than SMs and a shared condition: the build that keeps two CTAs resident per SM
-        const bool two = q.n_cond == 1 && grid > (unsigned)kNumSMs && !std::getenv("ERTDIFF_UMMA_ONE_CTA");
+        // more tiles than SMs: the build that keeps two CTAs resident per SM
+        const bool two = grid > (unsigned)kNumSMs && !std::getenv("ERTDIFF_UMMA_ONE_CTA");
         const size_t smem = two ? sizeof(UmmaChainSmem<uc_nslot(2)>) : sizeof(UmmaChainSmem<uc_nslot(1)>);
         const int variant = (q.noise != nullptr ? 4 : 0) | (q.eps_trace != nullptr ? 2 : 0) | (q.n_cond == 1 ? 1 : 0);
         using Kern = void (*)(const ChainParams, const UmmaChainExtra);
@@ -271,9 +271,11 @@ static int run_chain(ertdiff_model* m, const ertdiff_chain_args* a, const float*
             k_chain_umma<false, true, false, 1>,  k_chain_umma<false, true, true, 1>,
             k_chain_umma<true, false, false, 1>,  k_chain_umma<true, false, true, 1>,
             k_chain_umma<true, true, false, 1>,   k_chain_umma<true, true, true, 1>};
-        static const Kern kerns2[4] = {             // shared condition, two CTAs per SM: [replay][trace]
-            k_chain_umma<false, false, true, 2>, k_chain_umma<false, true, true, 2>,
-            k_chain_umma<true, false, true, 2>,  k_chain_umma<true, true, true, 2>};
+        static const Kern kerns2[8] = {             // two CTAs per SM
+            k_chain_umma<false, false, false, 2>, k_chain_umma<false, false, true, 2>,
+            k_chain_umma<false, true, false, 2>,  k_chain_umma<false, true, true, 2>,
+            k_chain_umma<true, false, false, 2>,  k_chain_umma<true, false, true, 2>,
+            k_chain_umma<true, true, false, 2>,   k_chain_umma<true, true, true, 2>};
         static PerDeviceOnce once;
         bool& attr_set = *once.slot();
         if (!attr_set) {
@@ -283,7 +285,7 @@ static int run_chain(ertdiff_model* m, const ertdiff_chain_args* a, const float*
                 ERT_CUDA(cudaFuncSetAttribute(k, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)sizeof(UmmaChainSmem<uc_nslot(2)>)));
             attr_set = true;
         }
-        if (two) kerns2[(q.noise != nullptr ? 2 : 0) | (q.eps_trace != nullptr ? 1 : 0)]<<<grid, UC_THREADS, smem, s2>>>(q, ex);
+        if (two) kerns2[variant]<<<grid, UC_THREADS, smem, s2>>>(q, ex);
         else kerns[variant]<<<grid, UC_THREADS, smem, s2>>>(q, ex);
         ERT_LAUNCH_CHECK("k_chain_umma");
         return 0;

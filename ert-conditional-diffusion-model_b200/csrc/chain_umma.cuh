@@ -70,7 +70,7 @@ constexpr int UC_THREADS = (UC_EPI_WARPS + UC_RNG_WARPS + 1) * 32;   // + the MM
 constexpr int UC_AUG = 29;      // first augmentation column (param_dim <= 29)
 // Two builds of the kernel (template parameter CTAS): one CTA per SM (up to 128 registers per thread, a
 // 4-deep noise ring, all 64 accumulator columns of a thread in flight per tcgen05.wait::ld) and, for
-// ensembles of more than 148 tiles with a shared condition, two co-resident CTAs per SM (72 registers,
+// ensembles of more than 148 tiles, two co-resident CTAs per SM (72 registers,
 // 2-deep ring, 32 columns per wait): each CTA is then ~17 % slower, but their MMA / mbarrier waits
 // overlap -- 37,888 members: 2.76 -> 2.29 ms.
 __host__ __device__ constexpr int uc_nslot(int ctas) { return ctas == 2 ? 2 : 4; }        // depth of the noise ring (steps)
@@ -116,7 +116,7 @@ struct UmmaChainExtra {
 
 template <bool REPLAY, bool TRACE, bool SHARED, int CTAS>
 __global__ void __launch_bounds__(UC_THREADS, CTAS) k_chain_umma(const ChainParams a, const UmmaChainExtra ex) {
-    static_assert(CTAS == 1 || (CTAS == 2 && SHARED), "two CTAs per SM: shared condition only (TMEM: 2 x 256 columns)");
+    static_assert(CTAS == 1 || CTAS == 2, "one or two CTAs per SM");
     constexpr int UC_NSLOT = uc_nslot(CTAS);
     constexpr int UC_EPI_CHUNK = uc_epi_chunk(CTAS);
     using namespace umma;
@@ -134,7 +134,12 @@ __global__ void __launch_bounds__(UC_THREADS, CTAS) k_chain_umma(const ChainPara
     // (S2R SR_CgaCtaId + LEA, a long-scoreboard read) inside the step loop
     asm volatile("" : "+r"(sX), "+r"(sH), "+r"(sW1), "+r"(sW2), "+r"(sZ), "+r"(bar_x), "+r"(bar_d), "+r"(bar_e),
                       "+r"(bar_h0), "+r"(bar_full0), "+r"(bar_empty0));
-    constexpr uint32_t TMEM_COLS = SHARED ? 256 : 512;
+    // TMEM columns: D 0..127; E 128..159; c_b (distinct conditions) 256..383.  Two CTAs per SM have 256
+    // columns each: with distinct conditions E then aliases D's first 32 columns (GEMM2 is issued only after
+    // every epilogue warp has consumed D) and c_b moves to 128..255
+    constexpr uint32_t TMEM_COLS = (SHARED || CTAS == 2) ? 256 : 512;
+    constexpr uint32_t E_COL = (!SHARED && CTAS == 2) ? 0 : 128;
+    constexpr uint32_t CB_COL = (CTAS == 2) ? 128 : 256;
     constexpr uint32_t SLOT_BYTES = UC_M * kPPad * 4;
 
     // ---- one-time setup ------------------------------------------------------------------------
@@ -191,7 +196,7 @@ __global__ void __launch_bounds__(UC_THREADS, CTAS) k_chain_umma(const ChainPara
                 dA2[k] = smem_desc(sH + 2 * k * kLBO, kLBO, sbo_bytes(UC_H));
                 dB2[k] = smem_desc(sW2 + 2 * k * kLBO, kLBO, sbo_bytes(UC_H));
             }
-            const uint32_t tmemE = tmem + 128;
+            const uint32_t tmemE = tmem + E_COL;
 #if UC_TIMING
             const bool timed = ex.timing != nullptr && blockIdx.x == 0 && lane == 0;
             long long tm[4] = {0, 0, 0, 0}, c0 = 0, c1 = 0;
@@ -285,8 +290,8 @@ __global__ void __launch_bounds__(UC_THREADS, CTAS) k_chain_umma(const ChainPara
         const int64_t mg = mvalid ? (m0 + row) : (a.B - 1);
         const uint32_t tlane = tmem + ((uint32_t)(quarter * 32) << 16);
         const uint32_t tD = tlane + CW * part;           // this thread's hidden columns of D
-        const uint32_t tE = tlane + 128 + PW * part;     // this thread's parameter columns of E
-        const uint32_t tCB = tlane + 256 + CW * part;    // c_b of this member (distinct conditions)
+        const uint32_t tE = tlane + E_COL + PW * part;   // this thread's parameter columns of E
+        const uint32_t tCB = tlane + CB_COL + CW * part; // c_b of this member (distinct conditions)
         const uint32_t bar_h = bar_h0 + 8u * part;
         const uint32_t zrow = sZ + (uint32_t)row * (kPPad * 4);
         const uint32_t zsw = (uint32_t)(row & 7);

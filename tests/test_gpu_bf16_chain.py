@@ -145,14 +145,18 @@ def test_bf16_chain_small_param_dim(cuda_dev):
     assert torch.isfinite(x16).all() and (x16 - x32).abs().max().item() <= 5e-2 * scale
 
 
-def test_bf16_two_ctas_per_sm_build_is_bit_identical(gpu_model, cuda_dev, monkeypatch):
+@pytest.mark.parametrize("distinct", [False, True])
+def test_bf16_two_ctas_per_sm_build_is_bit_identical(gpu_model, cuda_dev, monkeypatch, distinct):
     # more tiles than SMs with a shared condition selects the build that keeps two CTAs resident per SM;
     # it must reproduce the one-CTA build exactly (same arithmetic, different scheduling)
     B, T = 148 * 128 + 300, 9
-    cond = torch.rand(1, C, 120, generator=torch.Generator().manual_seed(8)).to(cuda_dev).expand(B, C, 120)
+    cond = torch.rand(7 if distinct else 1, C, 120, generator=torch.Generator().manual_seed(8)).to(cuda_dev)
+    if not distinct:
+        cond = cond.expand(B, C, 120)
     b, a, ab = eb.get_diffusion_schedule(T)
-    x2 = eb.run_chain(gpu_model, cond, T, b, a, ab, cuda_dev, seed=5, offset=0, precision="bf16")
+    kw = dict(seed=5, offset=0, precision="bf16", n_members=B - B % 7 if distinct else B)
+    x2 = eb.run_chain(gpu_model, cond, T, b, a, ab, cuda_dev, **kw)
     monkeypatch.setenv("ERTDIFF_UMMA_ONE_CTA", "1")
-    x1 = eb.run_chain(gpu_model, cond, T, b, a, ab, cuda_dev, seed=5, offset=0, precision="bf16")
+    x1 = eb.run_chain(gpu_model, cond, T, b, a, ab, cuda_dev, **kw)
     assert gpu_model.umma_status() == 0
     assert torch.equal(x1, x2)
