@@ -186,6 +186,19 @@ static int launch_chain_h(const ChainParams& p, int mpb, cudaStream_t st) {
     return 0;
 }
 
+// rows of the tensor-core chain's 128-row tile that carry members (ERTDIFF_UMMA_MPC overrides: 32, 64, 128)
+static int pick_umma_mpc(int64_t B) {
+    if (const char* e = std::getenv("ERTDIFF_UMMA_MPC")) {
+        const int v = std::atoi(e);
+        if (v == 32 || v == 64 || v == 128) return v;
+    }
+    // measured (T=1000, one CTA per SM): 1.08 / 1.21 / 1.38 us per step at 32 / 64 / 128 rows; two
+    // part-filled CTAs per SM are slower than one fuller one (2 x 32 rows: 1.53 us)
+    for (int mpc = 32; mpc < UC_M; mpc *= 2)
+        if ((B + mpc - 1) / mpc <= (int64_t)kNumSMs) return mpc;
+    return UC_M;
+}
+
 static int launch_chain(int H, const ChainParams& p, int mpb, cudaStream_t st) {
     switch (H) {
         case 32: return launch_chain_h<32>(p, mpb, st);
@@ -259,8 +272,11 @@ static int run_chain(ertdiff_model* m, const ertdiff_chain_args* a, const float*
     auto launch_any = [&](const ChainParams& q, cudaStream_t s2) -> int {
         if (!use_umma) return launch_chain(H, q, mpb, s2);
         UmmaChainExtra ex{reinterpret_cast<const uint4*>(m->w1_pk), reinterpret_cast<const uint4*>(m->w2_pk), m->umma_status,
-                          m->umma_timing_on ? m->umma_timing : nullptr};
-        const unsigned grid = (unsigned)((q.B + UC_M - 1) / UC_M);
+                          m->umma_timing_on ? m->umma_timing : nullptr, UC_M};
+        // members per CTA: the fewest rows per tile that still fit one wave of CTAs, so that a mid-size
+        // ensemble runs on all SMs (the step is latency-bound: a part-filled tile steps faster)
+        ex.mpc = pick_umma_mpc(q.B);
+        const unsigned grid = (unsigned)((q.B + ex.mpc - 1) / ex.mpc);
         // more tiles than SMs: the build that keeps two CTAs resident per SM
         const bool two = grid > (unsigned)kNumSMs && !std::getenv("ERTDIFF_UMMA_ONE_CTA");
         const size_t smem = two ? sizeof(UmmaChainSmem<uc_nslot(2)>) : sizeof(UmmaChainSmem<uc_nslot(1)>);

@@ -112,6 +112,8 @@ struct UmmaChainExtra {
     const uint4* w2_pk;     // 8 KB
     int* status;            // [0] = 1 when an mbarrier wait timed out
     long long* timing;      // optional (16 int64): phase cycle sums of CTA 0, see ertdiff_debug_umma_timing
+    int mpc;                // members per CTA: 32, 64 or 128 rows of the 128-row tile are in use, so that a
+                            // mid-size ensemble spreads over all SMs; the unused rows' warps only keep the barriers' counts
 };
 
 template <bool REPLAY, bool TRACE, bool SHARED, int CTAS>
@@ -170,7 +172,8 @@ __global__ void __launch_bounds__(UC_THREADS, CTAS) k_chain_umma(const ChainPara
     const uint32_t tmem = s.tmem_slot;
     const int n_steps = a.t_count;
     const int d_first = a.S - a.t_hi;
-    const int64_t m0 = (int64_t)blockIdx.x * UC_M;
+    const int mpc = ex.mpc;
+    const int64_t m0 = (int64_t)blockIdx.x * mpc;
     const int P = a.P;
     // ring items, in consumption order: [x_T when the launch starts a chain] then one per step with
     // t > 0 (steps run t = t_hi, t_hi-1, ...; the step with t == 0 adds no noise, ECD.py:115)
@@ -235,10 +238,10 @@ __global__ void __launch_bounds__(UC_THREADS, CTAS) k_chain_umma(const ChainPara
             UC_T(if (timed) { ex.timing[8] = tm[0]; ex.timing[9] = tm[1]; ex.timing[10] = tm[2]; })
         }
     } else if (warp < UC_RNG_WARPS) {
-        // ===== noise warps: thread (member m, half) produces the 16 draws of that member's
-        // parameters 16*half..16*half+15 for one ring item at a time ===============================
+        // ===== noise warps: thread (member m, unit u) produces the 8 draws of that member's
+        // parameters 8u..8u+7, units u0, u0+ustep, ... for one ring item at a time ===================
         const int r = tid;
-        const int m = r & (UC_M - 1), half = r >> 7;
+        const int m = r & (mpc - 1), u0 = r / mpc, ustep = UC_RNG_WARPS * 32 / mpc;
         const int64_t mg = (m0 + m) < a.B ? (m0 + m) : (a.B - 1);
         const int64_t gmember = a.member_offset + mg;
         const int n_items = first_item_step + n_noisy;
@@ -255,23 +258,31 @@ __global__ void __launch_bounds__(UC_THREADS, CTAS) k_chain_umma(const ChainPara
             ok = mbar_wait(bar_empty0 + 8u * slot, (use & 1u) ^ 1u);    // passes at once on the first lap
             UC_T(if (timed) { g1 = clock64(); tg[0] += g1 - g0; })
             const uint32_t draw = (item < first_item_step) ? 0u : (uint32_t)(d_first + item - first_item_step);
-#pragma unroll 1
-            for (int hf = half; hf < 2; hf += UC_RNG_WARPS / 4) {
-                float z[16];
+            // NU units of 8 draws per call: two (four Philox chains in flight) when a thread owns a whole member
+            auto produce = [&](auto nu_tag, int u) {
+                constexpr int NU = decltype(nu_tag)::value;
+                float z[8 * NU];
                 if (REPLAY) {
-                    const float* zr = a.noise + ((int64_t)(draw - 1) * a.noise_B + mg) * P + 16 * hf;
+                    const float* zr = a.noise + ((int64_t)(draw - 1) * a.noise_B + mg) * P + 8 * u;
 #pragma unroll
-                    for (int i = 0; i < 16; ++i) z[i] = (16 * hf + i < P) ? zr[i] : 0.f;
+                    for (int i = 0; i < 8 * NU; ++i) z[i] = (8 * u + i < P) ? zr[i] : 0.f;
                 } else {
-                    philox_normal8(a.keys, a.offset, gmember, draw, 4 * hf, &z[0]);
-                    philox_normal8(a.keys, a.offset, gmember, draw, 4 * hf + 2, &z[8]);
 #pragma unroll
-                    for (int i = 0; i < 16; ++i) z[i] = (16 * hf + i < P) ? z[i] : 0.f;
+                    for (int k = 0; k < NU; ++k) philox_normal8(a.keys, a.offset, gmember, draw, 2 * (u + k), &z[8 * k]);
+#pragma unroll
+                    for (int i = 0; i < 8 * NU; ++i) z[i] = (8 * u + i < P) ? z[i] : 0.f;
                 }
 #pragma unroll
-                for (int c = 0; c < 4; ++c)
-                    sts128(zrow + (uint32_t)slot * SLOT_BYTES + (uint32_t)(((4 * hf + c) ^ (m & 7)) * 16),
+                for (int c = 0; c < 2 * NU; ++c)
+                    sts128(zrow + (uint32_t)slot * SLOT_BYTES + (uint32_t)(((2 * u + c) ^ (m & 7)) * 16),
                            make_float4(z[4 * c], z[4 * c + 1], z[4 * c + 2], z[4 * c + 3]));
+            };
+            if (ustep == 1) {
+#pragma unroll 1
+                for (int u = 0; u < 4; u += 2) produce(std::integral_constant<int, 2>{}, u);
+            } else {
+#pragma unroll 1
+                for (int u = u0; u < 4; u += ustep) produce(std::integral_constant<int, 1>{}, u);
             }
             __syncwarp();
             if (lane == 0) mbar_arrive(bar_full0 + 8u * slot);
@@ -286,7 +297,7 @@ __global__ void __launch_bounds__(UC_THREADS, CTAS) k_chain_umma(const ChainPara
         const int quarter = warp & 3;            // TMEM lane quarter this warp may access (warp % 4)
         const int part = et >> 7;                // hidden columns CW*part..+CW-1, parameters PW*part..+PW-1
         const int row = quarter * 32 + lane;     // member of the tile = TMEM lane
-        const bool mvalid = (m0 + row) < a.B;
+        const bool mvalid = row < mpc && (m0 + row) < a.B;
         const int64_t mg = mvalid ? (m0 + row) : (a.B - 1);
         const uint32_t tlane = tmem + ((uint32_t)(quarter * 32) << 16);
         const uint32_t tD = tlane + CW * part;           // this thread's hidden columns of D
@@ -296,6 +307,55 @@ __global__ void __launch_bounds__(UC_THREADS, CTAS) k_chain_umma(const ChainPara
         const uint32_t zrow = sZ + (uint32_t)row * (kPPad * 4);
         const uint32_t zsw = (uint32_t)(row & 7);
 
+        // epilogue threads 0..127 own row j = et of W1aug: v = c_t[t][j] (+ c_b[j] of the shared condition),
+        // written as its 3-term bf16 split (v_hi | v_mid v_lo) against the three constant-one columns of Xaug
+        const float cb0 = (et < UC_H && SHARED) ? a.cond_bias[et] : 0.f;
+        const uint32_t w1aug = sW1 + elem_offset(et & (UC_H - 1), UC_AUG, UC_K1);
+        const float* ctcol = a.table + (et & (UC_H - 1));
+        auto refresh_w1aug = [&](float ct) {
+            const float v = ct + cb0;
+            const float v_hi = bf16_round(v);
+            const float r1 = v - v_hi;                    // exact
+            const float v_mid = bf16_round(r1);
+            const float v_lo = r1 - v_mid;                // exact; rounded to bf16 by the pack
+            const __nv_bfloat16 hb = __float2bfloat16_rn(v_hi);
+            asm volatile("st.shared.b16 [%0], %1;" ::"r"(w1aug), "h"(*reinterpret_cast<const unsigned short*>(&hb)) : "memory");
+            asm volatile("st.shared.b32 [%0], %1;" ::"r"(w1aug + 2u), "r"(pack_bf16(v_mid, v_lo)) : "memory");
+        };
+
+        if (quarter * 32 >= mpc) {
+            // rows of the tile beyond mpc carry no member: this warp keeps the barrier counts in step with
+            // the working warps (one arrival per barrier phase, after the event that orders it behind the
+            // previous phase) and, in part 0, still refreshes its rows of W1aug -- as soon as GEMM1 of the
+            // step has completed, off the working warps' critical path
+            if (et < UC_H) {
+                refresh_w1aug(__ldg(ctcol + (int64_t)a.t_hi * UC_H));
+                fence_proxy_async();
+            }
+            __syncwarp();
+            if (lane == 0) {
+                if (!a.x_in) mbar_arrive(bar_empty0);
+                mbar_arrive(bar_x);
+            }
+#pragma unroll 1
+            for (int it = 0; it < n_steps && ok; ++it) {
+                const uint32_t ph = (uint32_t)it & 1u;
+                float ct_next = 0.f;
+                if (et < UC_H && it + 1 < n_steps) ct_next = __ldg(ctcol + (int64_t)(a.t_hi - it - 1) * UC_H);
+                ok = mbar_wait(bar_d, ph);
+                if (et < UC_H && it + 1 < n_steps) {
+                    refresh_w1aug(ct_next);
+                    fence_proxy_async();
+                }
+                __syncwarp();
+                if (lane == 0) mbar_arrive(bar_h);
+                ok = ok && mbar_wait(bar_e, ph);
+                if (lane == 0) {
+                    if (a.t_hi - it > 0) mbar_arrive(bar_empty0 + 8u * ((it + first_item_step) % UC_NSLOT));
+                    if (it + 1 < n_steps) mbar_arrive(bar_x);
+                }
+            }
+        } else {
         if (!SHARED) {   // park c_b of this member's hidden columns in TMEM for the whole chain
             const float4* cbrow = reinterpret_cast<const float4*>(a.cond_bias + (mg % a.n_cond) * UC_H + CW * part);
 #pragma unroll 1
@@ -311,8 +371,6 @@ __global__ void __launch_bounds__(UC_THREADS, CTAS) k_chain_umma(const ChainPara
             }
             tmem_st_wait();
         }
-        // epilogue threads 0..127 own row j = et of W1aug: v = c_t[t][j] (+ c_b[j] of the shared condition)
-        const float cb0 = (et < UC_H && SHARED) ? a.cond_bias[et] : 0.f;
         uint32_t b2a = smem_u32(&s.b2[PW * part]);
         asm volatile("" : "+r"(b2a));
 
@@ -347,7 +405,6 @@ __global__ void __launch_bounds__(UC_THREADS, CTAS) k_chain_umma(const ChainPara
 
         const uint32_t xchunk = sX + (uint32_t)(row / 8) * sbo_bytes(UC_K1) + (uint32_t)(row % 8) * 16u + (uint32_t)(PW / 8 * part) * kLBO;
         const uint32_t hrow = sH + (uint32_t)(row / 8) * sbo_bytes(UC_H) + (uint32_t)(row % 8) * 16u + (uint32_t)(CW / 8 * part) * kLBO;
-        const uint32_t w1aug = sW1 + elem_offset(et & (UC_H - 1), UC_AUG, UC_K1);   // (v_hi | v_mid v_lo) of row j = et
 
         // operands of the next GEMM1: this thread's chunk(s) of Xaug; epilogue threads 0..127 also
         // refresh the augmentation columns of W1 with the 3-term bf16 split of v; one arrival per warp
@@ -359,22 +416,12 @@ __global__ void __launch_bounds__(UC_THREADS, CTAS) k_chain_umma(const ChainPara
                 const uint32_t w3 = last ? 0x3F803F80u : pack_bf16(x[4 * c + 3].x, x[4 * c + 3].y);
                 sts_u4(xchunk + (uint32_t)c * kLBO, pack_bf16(x[4 * c].x, x[4 * c].y), pack_bf16(x[4 * c + 1].x, x[4 * c + 1].y), w2, w3);
             }
-            if (et < UC_H) {
-                const float v = ct + cb0;
-                const float v_hi = bf16_round(v);
-                const float r1 = v - v_hi;                    // exact
-                const float v_mid = bf16_round(r1);
-                const float v_lo = r1 - v_mid;                // exact; rounded to bf16 by the pack
-                const __nv_bfloat16 hb = __float2bfloat16_rn(v_hi);
-                asm volatile("st.shared.b16 [%0], %1;" ::"r"(w1aug), "h"(*reinterpret_cast<const unsigned short*>(&hb)) : "memory");
-                asm volatile("st.shared.b32 [%0], %1;" ::"r"(w1aug + 2u), "r"(pack_bf16(v_mid, v_lo)) : "memory");
-            }
+            if (et < UC_H) refresh_w1aug(ct);
             fence_proxy_async();
             tc_fence_before();          // this thread's TMEM reads of the step are complete
             __syncwarp();
             if (lane == 0) mbar_arrive(bar_x);
         };
-        const float* ctcol = a.table + (et & (UC_H - 1));
         publish_gemm1_operands(et < UC_H ? __ldg(ctcol + (int64_t)a.t_hi * UC_H) : 0.f);
 
 #if UC_TIMING
@@ -497,12 +544,13 @@ __global__ void __launch_bounds__(UC_THREADS, CTAS) k_chain_umma(const ChainPara
                 if (PW * part + 2 * i + 1 < P) dst[2 * i + 1] = x[i].y;
             }
         }
+        }   // working epilogue warp
     }
     if (!ok) s.timeout = 1;
     tc_fence_before();
     __syncthreads();
     if (s.timeout != 0) {                   // an MMA never completed: poison the tile's output
-        for (int i = tid; i < UC_M * a.P; i += UC_THREADS)
+        for (int i = tid; i < mpc * a.P; i += UC_THREADS)
             if (m0 + i / a.P < a.B) a.x_out[m0 * a.P + i] = __int_as_float(0x7fc00000);
         if (tid == 0) ex.status[0] = 1;
     }

@@ -160,3 +160,27 @@ def test_bf16_two_ctas_per_sm_build_is_bit_identical(gpu_model, cuda_dev, monkey
     x1 = eb.run_chain(gpu_model, cond, T, b, a, ab, cuda_dev, **kw)
     assert gpu_model.umma_status() == 0
     assert torch.equal(x1, x2)
+
+
+@pytest.mark.parametrize("distinct", [False, True])
+@pytest.mark.parametrize("B", [37, 300, 5000])
+def test_bf16_members_per_cta_is_bit_identical(gpu_model, cuda_dev, monkeypatch, distinct, B):
+    # mid-size ensembles use 32 or 64 of the tile's 128 rows per CTA to reach every SM; the rows a
+    # member sits in must not change its result (device RNG streams are keyed by the global member)
+    T = 12
+    n = 5 if distinct else 1
+    cond = torch.rand(n, C, 96, generator=torch.Generator().manual_seed(11)).to(cuda_dev)
+    if not distinct:
+        cond = cond.expand(B, C, 96)
+    b, a, ab = eb.get_diffusion_schedule(T)
+    kw = dict(seed=9, offset=3, precision="bf16", n_members=B - B % n)
+    out = {}
+    for mpc in ("32", "64", "128"):
+        monkeypatch.setenv("ERTDIFF_UMMA_MPC", mpc)
+        out[mpc] = eb.run_chain(gpu_model, cond, T, b, a, ab, cuda_dev, **kw)
+        assert gpu_model.umma_status() == 0
+    monkeypatch.delenv("ERTDIFF_UMMA_MPC")
+    auto = eb.run_chain(gpu_model, cond, T, b, a, ab, cuda_dev, **kw)
+    assert torch.isfinite(auto).all()
+    for mpc in out:
+        assert torch.equal(out[mpc], auto), mpc
