@@ -2,6 +2,7 @@
 #include <cmath>
 #include <cstdlib>
 #include <cstring>
+#include <map>
 #include <mutex>
 #include <vector>
 
@@ -10,6 +11,7 @@
 #include "encoder.cuh"
 #include "denoiser.cuh"
 #include "stats.cuh"
+#include "misfit.cuh"
 #include "umma.cuh"
 #include "chain_umma.cuh"
 #include "encoder_umma.cuh"
@@ -908,6 +910,111 @@ int ertdiff_untransform_bounds(const float* d_u, int64_t B, int32_t P, float a, 
         d_u, B, P, a, b, d_scaler_min, d_scaler_scale, d_lim_lo, d_lim_hi, d_phys, d_valid, d_first_bad);
     ERT_LAUNCH_CHECK("k_untransform_bounds");
     return 0;
+}
+
+// ---- per-member misfit metrics (ECD.py:764-785, 927-930) ---------------------------------------
+// numpy's pairwise-summation tree for n elements, flattened once per (device, n) and kept on the device
+extern "C++" {
+struct PairwiseNodes {
+    std::vector<int2> leaves, nodes;      // nodes: children as (is_node ? -1 - k : leaf index) until fixed up
+    std::vector<int> height;
+    int build(int64_t start, int64_t n) {
+        if (n <= 128) {
+            leaves.push_back(make_int2((int)start, (int)n));
+            return (int)leaves.size() - 1;
+        }
+        int64_t n2 = n / 2;
+        n2 -= n2 % 8;
+        const int l = build(start, n2), r = build(start + n2, n - n2);
+        const int hl = l < 0 ? height[-1 - l] : 0, hr = r < 0 ? height[-1 - r] : 0;
+        nodes.push_back(make_int2(l, r));
+        height.push_back((hl > hr ? hl : hr) + 1);
+        return -(int)nodes.size();
+    }
+};
+
+static int pairwise_plan(int64_t n, PairwisePlan* out) {
+    static std::map<std::pair<int, int64_t>, PairwisePlan> cache;
+    int dev = 0;
+    ERT_CUDA(cudaGetDevice(&dev));
+    std::lock_guard<std::mutex> lock(g_ws_mutex);
+    auto it = cache.find({dev, n});
+    if (it != cache.end()) { *out = it->second; return 0; }
+    PairwiseNodes t;
+    t.build(0, n);
+    const int nl = (int)t.leaves.size(), nn = (int)t.nodes.size();
+    int n_levels = 0;
+    for (int h : t.height) n_levels = h > n_levels ? h : n_levels;
+    // order the internal nodes by height (children always sit on a lower level), remap the child indices
+    std::vector<int> order, pos(nn), level_off(n_levels + 1, 0);
+    for (int h = 1; h <= n_levels; ++h) {
+        level_off[h - 1] = (int)order.size();
+        for (int k = 0; k < nn; ++k)
+            if (t.height[k] == h) { pos[k] = (int)order.size(); order.push_back(k); }
+    }
+    level_off[n_levels] = nn;
+    std::vector<int2> nodes(nn);
+    for (int i = 0; i < nn; ++i) {
+        const int2 c = t.nodes[order[i]];
+        nodes[i] = make_int2(c.x < 0 ? nl + pos[-1 - c.x] : c.x, c.y < 0 ? nl + pos[-1 - c.y] : c.y);
+    }
+    int2 *d_leaves = nullptr, *d_nodes = nullptr;
+    int* d_off = nullptr;
+    ERT_CUDA(cudaMalloc(&d_leaves, sizeof(int2) * nl));
+    ERT_CUDA(cudaMalloc(&d_nodes, sizeof(int2) * (nn > 0 ? nn : 1)));
+    ERT_CUDA(cudaMalloc(&d_off, sizeof(int) * (n_levels + 1)));
+    ERT_CUDA(cudaMemcpy(d_leaves, t.leaves.data(), sizeof(int2) * nl, cudaMemcpyHostToDevice));
+    if (nn) ERT_CUDA(cudaMemcpy(d_nodes, nodes.data(), sizeof(int2) * nn, cudaMemcpyHostToDevice));
+    ERT_CUDA(cudaMemcpy(d_off, level_off.data(), sizeof(int) * (n_levels + 1), cudaMemcpyHostToDevice));
+    PairwisePlan pl{d_leaves, d_nodes, d_off, nl, nn, n_levels};
+    cache[{dev, n}] = pl;
+    *out = pl;
+    return 0;
+}
+
+template <typename T>
+static int launch_misfit(const void* d_sims, const void* d_obs, int64_t N, int64_t L, int64_t C, double A, double B,
+                         void* d_wsse, void* d_wsse_total, void* d_mse, cudaStream_t st) {
+    static PerDeviceOnce once;
+    bool& attr_set = *once.slot();
+    if (!attr_set) {
+        ERT_CUDA(cudaFuncSetAttribute(k_misfit_wsse<T>, cudaFuncAttributeMaxDynamicSharedMemorySize, 200 * 1024));
+        ERT_CUDA(cudaFuncSetAttribute(k_misfit_mse<T>, cudaFuncAttributeMaxDynamicSharedMemorySize, 200 * 1024));
+        attr_set = true;
+    }
+    if (d_wsse) {
+        PairwisePlan pl;
+        if (int rc = pairwise_plan(L, &pl)) return rc;
+        // rows per chunk: whole leaves (<= 128 rows each), sized so that several CTAs stay resident per SM
+        int rcap = (int)(L < 512 ? (L < 128 ? 128 : L) : 512);
+        while (rcap > 128 && (size_t)C * (rcap | 1) * sizeof(T) > 64 * 1024) rcap = rcap / 2 < 128 ? 128 : rcap / 2;
+        const size_t smem = ((size_t)C * (pl.n_leaves + pl.n_nodes) + C + (size_t)C * (rcap | 1)) * sizeof(T);
+        ERT_REQUIRE(smem <= 200 * 1024, "misfit_metrics: L x C too large for the on-chip summation tree");
+        k_misfit_wsse<T><<<(unsigned)N, kMisfitThreads, smem, st>>>((const T*)d_sims, (const T*)d_obs, (int)L, (int)C, (T)A, (T)B,
+                                                                    rcap, pl, (T*)d_wsse, (T*)d_wsse_total);
+        ERT_LAUNCH_CHECK("k_misfit_wsse");
+    }
+    if (d_mse) {
+        PairwisePlan pl;
+        if (int rc = pairwise_plan(L * C, &pl)) return rc;
+        const size_t smem = (size_t)(pl.n_leaves + pl.n_nodes) * sizeof(T);
+        ERT_REQUIRE(smem <= 200 * 1024, "misfit_metrics: map too large for the on-chip summation tree");
+        k_misfit_mse<T><<<(unsigned)N, kMisfitThreads, smem, st>>>((const T*)d_sims, (const T*)d_obs, L * C, pl, (T*)d_mse);
+        ERT_LAUNCH_CHECK("k_misfit_mse");
+    }
+    return 0;
+}
+}  // extern "C++"
+
+int ertdiff_misfit_metrics(const void* d_sims, const void* d_obs, int dtype, int64_t N, int64_t L, int64_t C,
+                           double A, double B, void* d_wsse, void* d_wsse_total, void* d_mse, void* stream) {
+    ERT_REQUIRE(d_sims && d_obs && N > 0 && L > 0 && C > 0, "misfit_metrics: bad arguments");
+    ERT_REQUIRE(C <= 128 && L * C < (int64_t(1) << 31), "misfit_metrics: need C <= 128 and L*C < 2^31");
+    ERT_REQUIRE((d_wsse == nullptr) == (d_wsse_total == nullptr), "misfit_metrics: give both WSSE outputs or neither");
+    ERT_REQUIRE(d_wsse || d_mse, "misfit_metrics: no output requested");
+    if (dtype == ERTDIFF_F32) return launch_misfit<float>(d_sims, d_obs, N, L, C, A, B, d_wsse, d_wsse_total, d_mse, (cudaStream_t)stream);
+    if (dtype == ERTDIFF_F64) return launch_misfit<double>(d_sims, d_obs, N, L, C, A, B, d_wsse, d_wsse_total, d_mse, (cudaStream_t)stream);
+    return fail(ERTDIFF_ERR_ARG, "misfit_metrics: bad dtype");
 }
 
 }  // extern "C"

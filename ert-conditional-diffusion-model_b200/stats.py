@@ -216,3 +216,44 @@ def uq_calibration(generated, true, n_prob=30, device=None):
     out.update(param_avg_proportion=pavg, param_accuracy=scores[:, 0], param_precision=scores[:, 1],
                param_goodness=scores[:, 2])
     return out
+
+
+def misfit_metrics(sim_data, observed, A=0.1, B=0.01, device=None):
+    """Per-member data misfit of the simulated maps ``sim_data (N, L, C)`` against the observed map
+    ``observed (L, C)`` (the conditional ERT sample), as the reference computes it inline:
+
+    * ``wsse (N, C)``: ``WSSE_metric(A, B, sim_data[i][:, es], observed[:, es])`` for every member and
+      survey (ECD.py:764-783), ``wsse_total (N)`` = ``wsse.sum(axis=1)`` and ``order`` = its argsort
+      (ECD.py:785-786);
+    * ``mse (N)``: ``mean_squared_error(observed.flatten(), sim_data[i].flatten())`` (ECD.py:927-930;
+      with a single map, e.g. the ensemble mean or mode, this is ECD.py:939-940).
+
+    Computed on the device in the arrays' dtype (float32 or float64) along numpy's pairwise-summation
+    tree: the values are bit-identical to numpy's.  numpy in -> numpy out, CUDA tensors in -> CUDA tensors."""
+    was_numpy = isinstance(sim_data, np.ndarray)
+    sims = torch.from_numpy(np.ascontiguousarray(sim_data)) if was_numpy else sim_data
+    obs = torch.from_numpy(np.ascontiguousarray(np.asarray(observed))) if not isinstance(observed, torch.Tensor) else observed
+    if sims.dim() == 2:
+        sims = sims[None]
+    if sims.dim() != 3 or tuple(obs.shape) != tuple(sims.shape[1:]):
+        raise ValueError("sim_data must be (N, L, C) and observed (L, C)")
+    if sims.dtype not in _DT:
+        sims = sims.to(torch.float64)
+    if sims.device.type != "cuda":
+        dev = torch.device(device) if device is not None else (
+            torch.device("cuda", torch.cuda.current_device()) if was_numpy else None)
+        if dev is None:
+            raise _lib.ErtdiffError("misfit metrics run on CUDA only: pass CUDA tensors, numpy arrays, or device=")
+        sims = sims.to(dev)
+    sims = sims.contiguous()
+    obs = obs.to(device=sims.device, dtype=sims.dtype).contiguous()
+    N, L, C = sims.shape
+    wsse = torch.empty(N, C, device=sims.device, dtype=sims.dtype)
+    total = torch.empty(N, device=sims.device, dtype=sims.dtype)
+    mse = torch.empty(N, device=sims.device, dtype=sims.dtype)
+    with torch.cuda.device(sims.device):
+        _lib.check(_lib.load().ertdiff_misfit_metrics(
+            _lib.ptr(sims), _lib.ptr(obs), _DT[sims.dtype], N, L, C, float(A), float(B), _lib.ptr(wsse),
+            _lib.ptr(total), _lib.ptr(mse), _lib.stream_ptr(sims.device)), "misfit_metrics")
+    out = {"wsse": wsse, "wsse_total": total, "order": torch.argsort(total, stable=True), "mse": mse}
+    return {k: v.cpu().numpy() for k, v in out.items()} if was_numpy else out

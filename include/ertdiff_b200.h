@@ -197,6 +197,16 @@ int ertdiff_ensemble_percentiles(const void* d_a, int dtype, int64_t N, int64_t 
 int ertdiff_interval_coverage(const double* d_low, const double* d_upp, const double* d_truth,
                               int32_t n_intervals, int64_t Q, int32_t P, int32_t* d_counts, void* stream);
 
+/* Per-member data misfit of N simulated maps d_sims (N, L, C) against the observed map d_obs (L, C),
+ * both `dtype` (F32 / F64), C fastest:
+ *   d_wsse (N, C)      np.average((pred-obs)**2 / (A*|obs|+B)**2) per survey column, ECD.py:764-783
+ *   d_wsse_total (N)   WSSE_sim.sum(axis=1), ECD.py:785
+ *   d_mse (N)          mean_squared_error(obs.flatten(), sim.flatten()), ECD.py:927-930, 939-940
+ * Outputs are `dtype`; each follows numpy's pairwise-summation tree and is bit-identical to numpy's.
+ * Either the two WSSE outputs or d_mse may be NULL.  C <= 128. */
+int ertdiff_misfit_metrics(const void* d_sims, const void* d_obs, int dtype, int64_t N, int64_t L, int64_t C,
+                           double A, double B, void* d_wsse, void* d_wsse_total, void* d_mse, void* stream);
+
 /* global min and max of n elements (the KDE grid's end points, ECD.py:749-750) -> d_out[2]
  * as float64. */
 int ertdiff_minmax(const void* d_a, int dtype, int64_t n, double* d_out2, void* stream);

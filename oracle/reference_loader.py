@@ -48,6 +48,7 @@ WANTED = (
     "accuracy_score",               # :1098-1100
     "preccision_score",             # :1102-1109
     "goodness_score",               # :1111-1115
+    "WSSE_metric",                  # :764-770
 )
 
 

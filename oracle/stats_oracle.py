@@ -213,3 +213,51 @@ def uq_calibration(generated, true, n_prob=30):
         pgood[j] = goodness_score(a_p, pavg[j], prob)
     out.update(param_avg_proportion=pavg, param_accuracy=pacc, param_precision=pprec, param_goodness=pgood)
     return out
+
+
+# ---- per-member misfit metrics (ECD.py:764-785, 927-940) -------------------------------------------
+def pairwise_sum(a: np.ndarray):
+    """numpy's add-reduction of a contiguous 1-D float array, restated (numpy 2.3
+    ``_core/src/umath/loops_utils.h.src``, ``@TYPE@_pairwise_sum``): n < 8 in order from 0; n <= 128
+    through 8 interleaved accumulators combined as ((r0+r1)+(r2+r3))+((r4+r5)+(r6+r7)) then the n % 8
+    tail in order; longer arrays split at n/2 rounded down to a multiple of 8.  Pure-Python loops: for
+    small cases only (tests check it against ``np.add.reduce`` itself)."""
+    T = a.dtype.type
+    n = len(a)
+    if n < 8:
+        r = T(0)
+        for v in a:
+            r = T(r + v)
+        return r
+    if n <= 128:
+        r = [a[k] for k in range(8)]
+        body = n - n % 8
+        for i in range(8, body, 8):
+            for k in range(8):
+                r[k] = T(r[k] + a[i + k])
+        res = T(T(T(r[0] + r[1]) + T(r[2] + r[3])) + T(T(r[4] + r[5]) + T(r[6] + r[7])))
+        for i in range(body, n):
+            res = T(res + a[i])
+        return res
+    n2 = n // 2
+    n2 -= n2 % 8
+    return T(pairwise_sum(a[:n2]) + pairwise_sum(a[n2:]))
+
+
+def wsse_metric(A, B, predictions, observations):               # ECD.py:764-770
+    sd = A * np.abs(observations) + B
+    wse = (predictions - observations) ** 2 / (sd) ** 2
+    return np.average(wse), wse
+
+
+def misfit_metrics(sim_data, observed, A=0.1, B=0.01):
+    """The reference's inline misfit loops: WSSE per (member, survey) and its per-member total and
+    ranking (ECD.py:773-786), MSE per member over the flattened maps (ECD.py:927-930 -- sklearn's
+    ``mean_squared_error`` is ``np.average((y_true - y_pred) ** 2)`` for 1-D inputs)."""
+    N, L, C = sim_data.shape
+    wsse = np.array([[wsse_metric(A, B, sim_data[i][:, es], observed[:, es])[0] for es in range(C)]
+                     for i in range(N)])
+    total = wsse.sum(axis=1)
+    yt = observed.flatten()
+    mse = np.array([np.average((yt - sim_data[i].flatten()) ** 2) for i in range(N)])
+    return {"wsse": wsse, "wsse_total": total, "order": np.argsort(total, kind="stable"), "mse": mse}
