@@ -1,6 +1,6 @@
 # Round-end evidence: launch lists (shares) and one `ncu --set full` capture per hot kernel.
 # Each command runs plain first (must exit 0), then under ncu; numbers printed under ncu are never bench values.
-# usage: gpu_profiles.sh launches|chain_fp32|chain_umma|encoder_umma   (one .ncu-rep per call: gpurun_out is capped at 64 MiB)
+# usage: gpu_profiles.sh launches|chain_fp32|chain_umma|chain_umma2|encoder_umma   (one .ncu-rep per call: gpurun_out is capped at 64 MiB)
 mkdir -p gpurun_out
 case "$1" in
 launches)
@@ -16,6 +16,10 @@ $C > gpurun_out/plain_c.log 2>&1 && ncu --set full --clock-control none --import
 chain_umma)
 D="python scripts/chain_sweep.py --members 18944 --precisions bf16 --T 200 --reps 1"
 $D > gpurun_out/plain_d.log 2>&1 && ncu --set full --clock-control none --import-source on -k regex:k_chain_umma -s 1 -c 1 -f -o gpurun_out/prof_chain_umma $D > gpurun_out/ncu_d.log 2>&1
+;;
+chain_umma2)
+F="python scripts/chain_sweep.py --members 37888 --precisions bf16 --T 200 --reps 1"
+$F > gpurun_out/plain_f.log 2>&1 && ncu --set full --clock-control none --import-source on -k regex:k_chain_umma -s 1 -c 1 -f -o gpurun_out/prof_chain_umma2 $F > gpurun_out/ncu_f.log 2>&1
 ;;
 encoder_umma)
 E="python scripts/encoder_bench.py --conds 1024 --reps 1"

@@ -37,6 +37,7 @@ jpath = os.path.join(out, f"{rnd}_ncu_kernels.json")
 summary = json.load(open(jpath)) if os.path.isfile(jpath) else {}      # captures arrive one per gpurun call
 for name, what in (("chain_fp32", "k_chain, 256 members, T=1000 (chain_sweep.py)"),
                    ("chain_umma", "k_chain_umma, 18,944 members, T=200 (chain_sweep.py)"),
+                   ("chain_umma2", "k_chain_umma, two CTAs per SM build, 37,888 members, T=200 (chain_sweep.py)"),
                    ("encoder_umma", "k_encoder_umma, 1024 conditions of 14x4693 (encoder_bench.py)")):
     rep = os.path.join(go, f"prof_{name}.ncu-rep")
     if not os.path.isfile(rep):
