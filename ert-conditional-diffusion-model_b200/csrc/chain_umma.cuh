@@ -3,7 +3,7 @@
 // as tcgen05.mma with accumulators in TMEM, everything between them stays on chip.
 //
 // One CTA = a tile of 128 members for all steps, 17 warps in three roles, no __syncthreads in the
-// step loop (mbarriers only):
+// step loop:
 //   * 8 epilogue warps.  TMEM lane r <-> member r of the tile; a warp may only touch the lane
 //     quarter (warp % 4), so warp w handles members 32*(w%4)..+31 and half = w/4 of the columns:
 //     TWO threads share one member, each owning 64 hidden columns (epilogue 1) and 16 of the 32
@@ -27,12 +27,18 @@
 //          issued per column half as soon as that half's 64 K-columns of H are written
 //   epi 2  eps = E + b2; bit-exact posterior update of the thread's 16 parameters (x stays in fp32
 //          registers for the whole chain) with the ring's noise, new Xaug chunks
-// Barriers (all mbarriers):
-//   bar_x     (8 warp arrivals)  Xaug / W1aug of the next step written    epilogue -> MMA warp
-//   bar_d     (tcgen05.commit)   D complete                               MMA warp -> epilogue
-//   bar_h[h]  (4 warp arrivals)  H columns of half h written              epilogue -> MMA warp
-//   bar_e     (tcgen05.commit)   E complete                               MMA warp -> epilogue
-//   bar_full[s] / bar_empty[s] (8 warp arrivals each)  noise ring slot s  noise <-> epilogue
+// Hand-offs.  The two that a tcgen05.commit signals are mbarriers; all others are hardware named
+// barriers (bar.arrive by the producing role, bar.sync by the consuming one), because a warp parked
+// on a named barrier costs no issue slots, while every mbarrier.try_wait sleeper was woken by every
+// arrival in the SM and polled again (ncu: a fifth of all issued instructions with mbarriers only):
+//   NB_X      Xaug / W1aug of the next step written    epilogue (arrive) -> MMA warp (sync)
+//   bar_d     (tcgen05.commit)   D complete            MMA warp -> epilogue (mbarrier wait)
+//   NB_H+h    H columns of half h written              epilogue (arrive) -> MMA warp (sync)
+//   bar_e     (tcgen05.commit)   E complete            MMA warp -> epilogue (mbarrier wait)
+//   NB_FULL+s / NB_EMPTY+s       noise ring slot s     noise warps <-> epilogue
+// A named barrier has no time-out, so a role never leaves its loop early: should an MMA never complete,
+// the epilogue warps stop waiting on the mbarriers but keep every named-barrier operation (the tile's
+// output is then poisoned and the status word set).
 // TMEM: D columns 0..127, E 128..159, c_b 256..383 (distinct conditions only).
 // Algorithmic work: 14,848 FLOP per member-step, as in the fp32 kernel (the K/N padding to
 // 32/32 is not counted).
@@ -83,7 +89,7 @@ struct UmmaChainSmem {
     unsigned char w1[UC_H * UC_K1 * 2];     // B of GEMM1 (W0x augmented)
     unsigned char w2[UC_N2 * UC_H * 2];     // B of GEMM2 (W2 padded)
     float zring[NSLOT][UC_M][kPPad];     // noise ring; 16-byte chunk c of member m sits at chunk c ^ (m & 7)
-    unsigned long long bar_x, bar_d, bar_e, bar_h[UC_TPM], bar_full[NSLOT], bar_empty[NSLOT];
+    unsigned long long bar_d, bar_e;
     alignas(16) float b2[kPPad];
     uint32_t tmem_slot;
     int timeout;
@@ -107,6 +113,12 @@ __global__ void k_pack_umma_weights(const float* __restrict__ w0xT /*(32,H)*/,
     }
 }
 
+// named-barrier ids of the chain kernel (0 is __syncthreads)
+constexpr uint32_t UC_NB_X = 1, UC_NB_H = 2, UC_NB_FULL = 4, UC_NB_EMPTY = 8;
+static_assert(UC_NB_H + UC_TPM <= UC_NB_FULL && UC_NB_EMPTY + 4 <= 16, "named barrier ids");
+__device__ __forceinline__ void nb_sync(uint32_t id, uint32_t n) { asm volatile("bar.sync %0, %1;" ::"r"(id), "r"(n) : "memory"); }
+__device__ __forceinline__ void nb_arrive(uint32_t id, uint32_t n) { asm volatile("bar.arrive %0, %1;" ::"r"(id), "r"(n) : "memory"); }
+
 struct UmmaChainExtra {
     const uint4* w1_pk;     // 8 KB
     const uint4* w2_pk;     // 8 KB
@@ -127,15 +139,11 @@ __global__ void __launch_bounds__(UC_THREADS, CTAS) k_chain_umma(const ChainPara
     const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
     const uint32_t sX_ = smem_u32(s.x), sH_ = smem_u32(s.h), sW1_ = smem_u32(s.w1), sW2_ = smem_u32(s.w2);
     const uint32_t sZ_ = smem_u32(&s.zring[0][0][0]);
-    const uint32_t bar_x_ = smem_u32(&s.bar_x), bar_d_ = smem_u32(&s.bar_d), bar_e_ = smem_u32(&s.bar_e);
-    const uint32_t bar_h0_ = smem_u32(&s.bar_h[0]);
-    const uint32_t bar_full0_ = smem_u32(&s.bar_full[0]), bar_empty0_ = smem_u32(&s.bar_empty[0]);
-    uint32_t sX = sX_, sH = sH_, sW1 = sW1_, sW2 = sW2_, sZ = sZ_, bar_x = bar_x_, bar_d = bar_d_, bar_e = bar_e_,
-             bar_h0 = bar_h0_, bar_full0 = bar_full0_, bar_empty0 = bar_empty0_;
+    const uint32_t bar_d_ = smem_u32(&s.bar_d), bar_e_ = smem_u32(&s.bar_e);
+    uint32_t sX = sX_, sH = sH_, sW1 = sW1_, sW2 = sW2_, sZ = sZ_, bar_d = bar_d_, bar_e = bar_e_;
     // opaque to the optimiser: otherwise every use re-derives the shared window base
     // (S2R SR_CgaCtaId + LEA, a long-scoreboard read) inside the step loop
-    asm volatile("" : "+r"(sX), "+r"(sH), "+r"(sW1), "+r"(sW2), "+r"(sZ), "+r"(bar_x), "+r"(bar_d), "+r"(bar_e),
-                      "+r"(bar_h0), "+r"(bar_full0), "+r"(bar_empty0));
+    asm volatile("" : "+r"(sX), "+r"(sH), "+r"(sW1), "+r"(sW2), "+r"(sZ), "+r"(bar_d), "+r"(bar_e));
     // TMEM columns: D 0..127; E 128..159; c_b (distinct conditions) 256..383.  Two CTAs per SM have 256
     // columns each: with distinct conditions E then aliases D's first 32 columns (GEMM2 is issued only after
     // every epilogue warp has consumed D) and c_b moves to 128..255
@@ -155,14 +163,8 @@ __global__ void __launch_bounds__(UC_THREADS, CTAS) k_chain_umma(const ChainPara
     }
     if (warp == 0) tmem_alloc(smem_u32(&s.tmem_slot), TMEM_COLS);
     if (tid == 0) {
-        mbar_init(bar_x, UC_EPI_WARPS);
         mbar_init(bar_d, 1);
         mbar_init(bar_e, 1);
-        for (int h = 0; h < UC_TPM; ++h) mbar_init(bar_h0 + 8u * h, 4);
-        for (int i = 0; i < UC_NSLOT; ++i) {
-            mbar_init(bar_full0 + 8u * i, UC_RNG_WARPS);
-            mbar_init(bar_empty0 + 8u * i, UC_EPI_WARPS);
-        }
         fence_mbar_init();
     }
     fence_proxy_async();          // the weight tiles were written through the generic proxy
@@ -172,190 +174,175 @@ __global__ void __launch_bounds__(UC_THREADS, CTAS) k_chain_umma(const ChainPara
     const uint32_t tmem = s.tmem_slot;
     const int n_steps = a.t_count;
     const int d_first = a.S - a.t_hi;
-    const int mpc = ex.mpc;
+    const int mpc = ex.mpc;                               // rows of the tile that carry members: 32, 64 or 128
     const int64_t m0 = (int64_t)blockIdx.x * mpc;
     const int P = a.P;
     // ring items, in consumption order: [x_T when the launch starts a chain] then one per step with
     // t > 0 (steps run t = t_hi, t_hi-1, ...; the step with t == 0 adds no noise, ECD.py:115)
     const int first_item_step = a.x_in ? 0 : 1;          // ring item of step `it` = it + first_item_step
     const int n_noisy = n_steps < a.t_hi ? n_steps : a.t_hi;
+    const int n_items = first_item_step + n_noisy;
+    // participants of the named barriers: the epilogue threads whose rows carry members, + the other role
+    const uint32_t n_epi = (uint32_t)(UC_TPM * mpc);
+    const uint32_t cnt_x = n_epi + 32u, cnt_h = (uint32_t)mpc + 32u, cnt_ring = n_epi + (uint32_t)mpc;   // + the noise warps of one item
     bool ok = true;
 
     if (warp == UC_EPI_WARPS + UC_RNG_WARPS) {
         // ===== MMA-issue warp: the whole warp walks the loop (converged), one elected lane issues ==========
-        {
-            constexpr uint32_t IDESC1 = idesc_bf16_f32(UC_M, UC_H);
-            constexpr uint32_t IDESC2 = idesc_bf16_f32(UC_M, UC_N2);
-            // all operand descriptors are loop-invariant: build them once, so that a step costs this
-            // (single, latency-bound) thread little more than the ten MMA issues themselves
-            uint64_t dA1[UC_K1 / 16], dB1[UC_K1 / 16], dA2[UC_H / 16], dB2[UC_H / 16];
+        constexpr uint32_t IDESC1 = idesc_bf16_f32(UC_M, UC_H);
+        constexpr uint32_t IDESC2 = idesc_bf16_f32(UC_M, UC_N2);
+        // all operand descriptors are loop-invariant: build them once, so that a step costs this
+        // (single, latency-bound) thread little more than the ten MMA issues themselves
+        uint64_t dA1[UC_K1 / 16], dB1[UC_K1 / 16], dA2[UC_H / 16], dB2[UC_H / 16];
 #pragma unroll
-            for (int k = 0; k < UC_K1 / 16; ++k) {
-                dA1[k] = smem_desc(sX + 2 * k * kLBO, kLBO, sbo_bytes(UC_K1));
-                dB1[k] = smem_desc(sW1 + 2 * k * kLBO, kLBO, sbo_bytes(UC_K1));
-            }
+        for (int k = 0; k < UC_K1 / 16; ++k) {
+            dA1[k] = smem_desc(sX + 2 * k * kLBO, kLBO, sbo_bytes(UC_K1));
+            dB1[k] = smem_desc(sW1 + 2 * k * kLBO, kLBO, sbo_bytes(UC_K1));
+        }
 #pragma unroll
-            for (int k = 0; k < UC_H / 16; ++k) {
-                dA2[k] = smem_desc(sH + 2 * k * kLBO, kLBO, sbo_bytes(UC_H));
-                dB2[k] = smem_desc(sW2 + 2 * k * kLBO, kLBO, sbo_bytes(UC_H));
-            }
-            const uint32_t tmemE = tmem + E_COL;
+        for (int k = 0; k < UC_H / 16; ++k) {
+            dA2[k] = smem_desc(sH + 2 * k * kLBO, kLBO, sbo_bytes(UC_H));
+            dB2[k] = smem_desc(sW2 + 2 * k * kLBO, kLBO, sbo_bytes(UC_H));
+        }
+        const uint32_t tmemE = tmem + E_COL;
 #if UC_TIMING
-            const bool timed = ex.timing != nullptr && blockIdx.x == 0 && lane == 0;
-            long long tm[4] = {0, 0, 0, 0}, c0 = 0, c1 = 0;
+        const bool timed = ex.timing != nullptr && blockIdx.x == 0 && lane == 0;
+        long long tm[4] = {0, 0, 0, 0}, c0 = 0, c1 = 0;
 #endif
-            for (int it = 0; it < n_steps && ok; ++it) {
-                const uint32_t ph = (uint32_t)it & 1u;
-                UC_T(if (timed) c0 = clock64();)
-                ok = mbar_wait(bar_x, ph);
-                UC_T(if (timed) { c1 = clock64(); tm[0] += c1 - c0; })
+#pragma unroll 1
+        for (int it = 0; it < n_steps; ++it) {
+            UC_T(if (timed) c0 = clock64();)
+            nb_sync(UC_NB_X, cnt_x);
+            UC_T(if (timed) { c1 = clock64(); tm[0] += c1 - c0; })
+            tc_fence_after();
+            if (elect_one()) {
+                mma_bf16_first(tmem, dA1[0], dB1[0], IDESC1);
+#pragma unroll
+                for (int k = 1; k < UC_K1 / 16; ++k) mma_bf16_acc(tmem, dA1[k], dB1[k], IDESC1);
+                mma_commit(bar_d);
+            }
+            __syncwarp();
+            UC_T(if (timed) { c0 = clock64(); tm[1] += c0 - c1; })
+#pragma unroll
+            for (int part = 0; part < UC_TPM; ++part) {      // each part's K columns as soon as they are written
+                nb_sync(UC_NB_H + part, cnt_h);
                 tc_fence_after();
                 if (elect_one()) {
-                    mma_bf16_first(tmem, dA1[0], dB1[0], IDESC1);
 #pragma unroll
-                    for (int k = 1; k < UC_K1 / 16; ++k) mma_bf16_acc(tmem, dA1[k], dB1[k], IDESC1);
-                    mma_commit(bar_d);
+                    for (int kk = 0; kk < 8 / UC_TPM; ++kk) {
+                        const int k = 8 / UC_TPM * part + kk;
+                        if (k == 0) mma_bf16_first(tmemE, dA2[0], dB2[0], IDESC2);
+                        else mma_bf16_acc(tmemE, dA2[k], dB2[k], IDESC2);
+                    }
+                    if (part == UC_TPM - 1) mma_commit(bar_e);
                 }
                 __syncwarp();
-                UC_T(if (timed) { c0 = clock64(); tm[1] += c0 - c1; })
-#pragma unroll
-                for (int part = 0; part < UC_TPM; ++part) {      // each part's K columns as soon as they are written
-                    ok = ok && mbar_wait(bar_h0 + 8u * part, ph);
-                    tc_fence_after();
-                    if (elect_one()) {
-#pragma unroll
-                        for (int kk = 0; kk < 8 / UC_TPM; ++kk) {
-                            const int k = 8 / UC_TPM * part + kk;
-                            if (k == 0) mma_bf16_first(tmemE, dA2[0], dB2[0], IDESC2);
-                            else mma_bf16_acc(tmemE, dA2[k], dB2[k], IDESC2);
-                        }
-                        if (part == UC_TPM - 1) mma_commit(bar_e);
-                    }
-                    __syncwarp();
-                }
-                UC_T(if (timed) { c1 = clock64(); tm[2] += c1 - c0; })
             }
-            UC_T(if (timed) { ex.timing[8] = tm[0]; ex.timing[9] = tm[1]; ex.timing[10] = tm[2]; })
+            UC_T(if (timed) { c1 = clock64(); tm[2] += c1 - c0; })
         }
+        UC_T(if (timed) { ex.timing[8] = tm[0]; ex.timing[9] = tm[1]; ex.timing[10] = tm[2]; })
     } else if (warp < UC_RNG_WARPS) {
-        // ===== noise warps: thread (member m, unit u) produces the 8 draws of that member's
-        // parameters 8u..8u+7, units u0, u0+ustep, ... for one ring item at a time ===================
-        const int r = tid;
-        const int m = r & (mpc - 1), u0 = r / mpc, ustep = UC_RNG_WARPS * 32 / mpc;
+        // ===== noise warps: a thread produces all 32 draws of one member for one ring item.  A tile with
+        // fewer than 128 members needs fewer than 4 warps per item, so the warps split into groups that work on
+        // different items at the same time: an item's latency (two dependent Philox + Box-Muller passes,
+        // ~2000 cycles for a lone warp per scheduler) would otherwise bound the step of a part-filled tile ======
+        const int G = mpc >> 5;                               // warps per item: 1, 2 or 4
+        // a slot must belong to one group (two groups parked on the same EMPTY barrier would mix their counts):
+        // at most UC_NSLOT groups; further warps stay idle
+        const int n_groups = (UC_RNG_WARPS / G < UC_NSLOT) ? UC_RNG_WARPS / G : UC_NSLOT;
+        const int grp = warp / G;
+        const int m = (warp % G) * 32 + lane;
         const int64_t mg = (m0 + m) < a.B ? (m0 + m) : (a.B - 1);
         const int64_t gmember = a.member_offset + mg;
-        const int n_items = first_item_step + n_noisy;
         const uint32_t zrow = sZ + (uint32_t)m * (kPPad * 4);
 #if UC_TIMING
-        const bool timed = ex.timing != nullptr && blockIdx.x == 0 && r == 0;
+        const bool timed = ex.timing != nullptr && blockIdx.x == 0 && tid == 0;
         long long tg[2] = {0, 0}, g0 = 0, g1 = 0;
 #endif
 #pragma unroll 1
-        for (int item = 0; item < n_items && ok; ++item) {
+        for (int item = grp < n_groups ? grp : n_items; item < n_items; item += n_groups) {
             const int slot = item % UC_NSLOT;
-            const uint32_t use = (uint32_t)(item / UC_NSLOT);
             UC_T(if (timed) g0 = clock64();)
-            ok = mbar_wait(bar_empty0 + 8u * slot, (use & 1u) ^ 1u);    // passes at once on the first lap
+            if (item >= UC_NSLOT) nb_sync(UC_NB_EMPTY + slot, cnt_ring);     // the slot's previous item was consumed
             UC_T(if (timed) { g1 = clock64(); tg[0] += g1 - g0; })
             const uint32_t draw = (item < first_item_step) ? 0u : (uint32_t)(d_first + item - first_item_step);
-            // NU units of 8 draws per call: two (four Philox chains in flight) when a thread owns a whole member
-            auto produce = [&](auto nu_tag, int u) {
-                constexpr int NU = decltype(nu_tag)::value;
-                float z[8 * NU];
+#pragma unroll 1
+            for (int u = 0; u < 4; u += 2) {                  // 16 draws per pass: four Philox chains in flight
+                float z[16];
                 if (REPLAY) {
                     const float* zr = a.noise + ((int64_t)(draw - 1) * a.noise_B + mg) * P + 8 * u;
 #pragma unroll
-                    for (int i = 0; i < 8 * NU; ++i) z[i] = (8 * u + i < P) ? zr[i] : 0.f;
+                    for (int i = 0; i < 16; ++i) z[i] = (8 * u + i < P) ? zr[i] : 0.f;
                 } else {
+                    philox_normal8(a.keys, a.offset, gmember, draw, 2 * u, &z[0]);
+                    philox_normal8(a.keys, a.offset, gmember, draw, 2 * u + 2, &z[8]);
 #pragma unroll
-                    for (int k = 0; k < NU; ++k) philox_normal8(a.keys, a.offset, gmember, draw, 2 * (u + k), &z[8 * k]);
-#pragma unroll
-                    for (int i = 0; i < 8 * NU; ++i) z[i] = (8 * u + i < P) ? z[i] : 0.f;
+                    for (int i = 0; i < 16; ++i) z[i] = (8 * u + i < P) ? z[i] : 0.f;
                 }
 #pragma unroll
-                for (int c = 0; c < 2 * NU; ++c)
+                for (int c = 0; c < 4; ++c)
                     sts128(zrow + (uint32_t)slot * SLOT_BYTES + (uint32_t)(((2 * u + c) ^ (m & 7)) * 16),
                            make_float4(z[4 * c], z[4 * c + 1], z[4 * c + 2], z[4 * c + 3]));
-            };
-            if (ustep == 1) {
-#pragma unroll 1
-                for (int u = 0; u < 4; u += 2) produce(std::integral_constant<int, 2>{}, u);
-            } else {
-#pragma unroll 1
-                for (int u = u0; u < 4; u += ustep) produce(std::integral_constant<int, 1>{}, u);
             }
-            __syncwarp();
-            if (lane == 0) mbar_arrive(bar_full0 + 8u * slot);
+            nb_arrive(UC_NB_FULL + slot, cnt_ring);
             UC_T(if (timed) tg[1] += clock64() - g1;)
         }
         UC_T(if (timed) { ex.timing[11] = tg[0]; ex.timing[12] = tg[1]; })
-    } else {
-        // ===== epilogue warps =========================================================================
+    } else if ((warp & 3) * 32 < mpc) {
+        // ===== epilogue warps (those whose TMEM lane quarter carries members) ==========================
         constexpr int CW = UC_H / UC_TPM;        // hidden columns per thread
         constexpr int PW = kPPad / UC_TPM;       // parameters per thread
         const int et = tid - UC_RNG_WARPS * 32;  // 0 .. 128*UC_TPM-1
         const int quarter = warp & 3;            // TMEM lane quarter this warp may access (warp % 4)
         const int part = et >> 7;                // hidden columns CW*part..+CW-1, parameters PW*part..+PW-1
         const int row = quarter * 32 + lane;     // member of the tile = TMEM lane
-        const bool mvalid = row < mpc && (m0 + row) < a.B;
+        const bool mvalid = (m0 + row) < a.B;
         const int64_t mg = mvalid ? (m0 + row) : (a.B - 1);
         const uint32_t tlane = tmem + ((uint32_t)(quarter * 32) << 16);
         const uint32_t tD = tlane + CW * part;           // this thread's hidden columns of D
         const uint32_t tE = tlane + E_COL + PW * part;   // this thread's parameter columns of E
         const uint32_t tCB = tlane + CB_COL + CW * part; // c_b of this member (distinct conditions)
-        const uint32_t bar_h = bar_h0 + 8u * part;
+        const uint32_t nb_h = UC_NB_H + (uint32_t)part;
         const uint32_t zrow = sZ + (uint32_t)row * (kPPad * 4);
         const uint32_t zsw = (uint32_t)(row & 7);
 
-        // epilogue threads 0..127 own row j = et of W1aug: v = c_t[t][j] (+ c_b[j] of the shared condition),
-        // written as its 3-term bf16 split (v_hi | v_mid v_lo) against the three constant-one columns of Xaug
-        const float cb0 = (et < UC_H && SHARED) ? a.cond_bias[et] : 0.f;
-        const uint32_t w1aug = sW1 + elem_offset(et & (UC_H - 1), UC_AUG, UC_K1);
-        const float* ctcol = a.table + (et & (UC_H - 1));
-        auto refresh_w1aug = [&](float ct) {
-            const float v = ct + cb0;
-            const float v_hi = bf16_round(v);
-            const float r1 = v - v_hi;                    // exact
-            const float v_mid = bf16_round(r1);
-            const float v_lo = r1 - v_mid;                // exact; rounded to bf16 by the pack
-            const __nv_bfloat16 hb = __float2bfloat16_rn(v_hi);
-            asm volatile("st.shared.b16 [%0], %1;" ::"r"(w1aug), "h"(*reinterpret_cast<const unsigned short*>(&hb)) : "memory");
-            asm volatile("st.shared.b32 [%0], %1;" ::"r"(w1aug + 2u), "r"(pack_bf16(v_mid, v_lo)) : "memory");
+        // The working epilogue threads share the augmentation columns of W1aug: v[j] = c_t[t][j] (+ c_b[j] of
+        // the shared condition) as its 3-term bf16 split (v_hi | v_mid v_lo) against the three constant-one
+        // columns of Xaug.  Working thread wt = part * mpc + row owns rows j = wt and wt + 2 mpc (< 128): one
+        // row per part-0 thread of a full tile, two rows per thread of a quarter-filled one.
+        const int wt = part * mpc + row, aug_stride = UC_TPM * mpc;
+        const bool aug_owner = wt < UC_H;
+        float cb0[2] = {0.f, 0.f};
+        if (aug_owner && SHARED) {
+#pragma unroll
+            for (int i = 0; i < 2; ++i)
+                if (wt + i * aug_stride < UC_H) cb0[i] = a.cond_bias[wt + i * aug_stride];
+        }
+        const uint32_t w1aug = sW1 + elem_offset(wt & (UC_H - 1), UC_AUG, UC_K1);
+        const uint32_t w1aug_pitch = (uint32_t)(aug_stride / 8) * sbo_bytes(UC_K1);      // aug_stride rows further down
+        const float* ctcol = a.table + wt;
+        auto load_ct = [&](int t, float (&ct)[2]) {
+#pragma unroll
+            for (int i = 0; i < 2; ++i)
+                if (wt + i * aug_stride < UC_H) ct[i] = __ldg(ctcol + (int64_t)t * UC_H + i * aug_stride);
+        };
+        auto refresh_w1aug = [&](const float (&ct)[2]) {
+#pragma unroll
+            for (int i = 0; i < 2; ++i) {
+                if (wt + i * aug_stride < UC_H) {
+                    const float v = ct[i] + cb0[i];
+                    const float v_hi = bf16_round(v);
+                    const float r1 = v - v_hi;                    // exact
+                    const float v_mid = bf16_round(r1);
+                    const float v_lo = r1 - v_mid;                // exact; rounded to bf16 by the pack
+                    const __nv_bfloat16 hb = __float2bfloat16_rn(v_hi);
+                    const uint32_t dst = w1aug + (uint32_t)i * w1aug_pitch;
+                    asm volatile("st.shared.b16 [%0], %1;" ::"r"(dst), "h"(*reinterpret_cast<const unsigned short*>(&hb)) : "memory");
+                    asm volatile("st.shared.b32 [%0], %1;" ::"r"(dst + 2u), "r"(pack_bf16(v_mid, v_lo)) : "memory");
+                }
+            }
         };
 
-        if (quarter * 32 >= mpc) {
-            // rows of the tile beyond mpc carry no member: this warp keeps the barrier counts in step with
-            // the working warps (one arrival per barrier phase, after the event that orders it behind the
-            // previous phase) and, in part 0, still refreshes its rows of W1aug -- as soon as GEMM1 of the
-            // step has completed, off the working warps' critical path
-            if (et < UC_H) {
-                refresh_w1aug(__ldg(ctcol + (int64_t)a.t_hi * UC_H));
-                fence_proxy_async();
-            }
-            __syncwarp();
-            if (lane == 0) {
-                if (!a.x_in) mbar_arrive(bar_empty0);
-                mbar_arrive(bar_x);
-            }
-#pragma unroll 1
-            for (int it = 0; it < n_steps && ok; ++it) {
-                const uint32_t ph = (uint32_t)it & 1u;
-                float ct_next = 0.f;
-                if (et < UC_H && it + 1 < n_steps) ct_next = __ldg(ctcol + (int64_t)(a.t_hi - it - 1) * UC_H);
-                ok = mbar_wait(bar_d, ph);
-                if (et < UC_H && it + 1 < n_steps) {
-                    refresh_w1aug(ct_next);
-                    fence_proxy_async();
-                }
-                __syncwarp();
-                if (lane == 0) mbar_arrive(bar_h);
-                ok = ok && mbar_wait(bar_e, ph);
-                if (lane == 0) {
-                    if (a.t_hi - it > 0) mbar_arrive(bar_empty0 + 8u * ((it + first_item_step) % UC_NSLOT));
-                    if (it + 1 < n_steps) mbar_arrive(bar_x);
-                }
-            }
-        } else {
         if (!SHARED) {   // park c_b of this member's hidden columns in TMEM for the whole chain
             const float4* cbrow = reinterpret_cast<const float4*>(a.cond_bias + (mg % a.n_cond) * UC_H + CW * part);
 #pragma unroll 1
@@ -377,12 +364,11 @@ __global__ void __launch_bounds__(UC_THREADS, CTAS) k_chain_umma(const ChainPara
         // one ring item: the thread's PW draws, 4 at a time
         auto ring_wait = [&](int item) -> uint32_t {
             const int slot = item % UC_NSLOT;
-            ok = ok && mbar_wait(bar_full0 + 8u * slot, (uint32_t)(item / UC_NSLOT) & 1u);
+            nb_sync(UC_NB_FULL + slot, cnt_ring);
             return zrow + (uint32_t)slot * SLOT_BYTES;
         };
-        auto ring_release = [&](int item) {
-            __syncwarp();
-            if (lane == 0) mbar_arrive(bar_empty0 + 8u * (item % UC_NSLOT));
+        auto ring_release = [&](int item) {       // only when the noise warps will wait for this slot again
+            if (item + UC_NSLOT < n_items) nb_arrive(UC_NB_EMPTY + item % UC_NSLOT, cnt_ring);
         };
 
         // ---- x_T -------------------------------------------------------------------------------
@@ -406,9 +392,8 @@ __global__ void __launch_bounds__(UC_THREADS, CTAS) k_chain_umma(const ChainPara
         const uint32_t xchunk = sX + (uint32_t)(row / 8) * sbo_bytes(UC_K1) + (uint32_t)(row % 8) * 16u + (uint32_t)(PW / 8 * part) * kLBO;
         const uint32_t hrow = sH + (uint32_t)(row / 8) * sbo_bytes(UC_H) + (uint32_t)(row % 8) * 16u + (uint32_t)(CW / 8 * part) * kLBO;
 
-        // operands of the next GEMM1: this thread's chunk(s) of Xaug; epilogue threads 0..127 also
-        // refresh the augmentation columns of W1 with the 3-term bf16 split of v; one arrival per warp
-        auto publish_gemm1_operands = [&](float ct) {
+        // operands of the next GEMM1: this thread's chunk(s) of Xaug (W1aug was refreshed earlier in the step)
+        auto publish_gemm1_operands = [&]() {
 #pragma unroll
             for (int c = 0; c < PW / 8; ++c) {
                 const bool last = (PW / 8 * part + c) == 3;   // parameters 24..28 + three constant-one columns (bf16 1.0 = 0x3F80)
@@ -416,32 +401,35 @@ __global__ void __launch_bounds__(UC_THREADS, CTAS) k_chain_umma(const ChainPara
                 const uint32_t w3 = last ? 0x3F803F80u : pack_bf16(x[4 * c + 3].x, x[4 * c + 3].y);
                 sts_u4(xchunk + (uint32_t)c * kLBO, pack_bf16(x[4 * c].x, x[4 * c].y), pack_bf16(x[4 * c + 1].x, x[4 * c + 1].y), w2, w3);
             }
-            if (et < UC_H) refresh_w1aug(ct);
             fence_proxy_async();
             tc_fence_before();          // this thread's TMEM reads of the step are complete
-            __syncwarp();
-            if (lane == 0) mbar_arrive(bar_x);
+            nb_arrive(UC_NB_X, cnt_x);
         };
-        publish_gemm1_operands(et < UC_H ? __ldg(ctcol + (int64_t)a.t_hi * UC_H) : 0.f);
+        {
+            float ct[2];
+            if (aug_owner) { load_ct(a.t_hi, ct); refresh_w1aug(ct); }
+            publish_gemm1_operands();
+        }
 
 #if UC_TIMING
         const bool timed = ex.timing != nullptr && blockIdx.x == 0 && et == 0;
         long long tw[6] = {0, 0, 0, 0, 0, 0}, k0 = 0, k1 = 0, tf[2] = {0, 0};
 #endif
 #pragma unroll 1
-        for (int it = 0; it < n_steps && ok; ++it) {
+        for (int it = 0; it < n_steps; ++it) {
             UC_T(if (timed) k0 = clock64();)
             const int t = a.t_hi - it;
             const uint32_t ph = (uint32_t)it & 1u;
-            // prefetches: the step scalars and (threads 0..127) the next step's c_t element
+            // prefetches: the step scalars and (part 0) the next step's c_t elements
             const float4 cf = __ldg(reinterpret_cast<const float4*>(a.coef) + t);
-            float ct_next = 0.f;
-            if (et < UC_H && it + 1 < n_steps) ct_next = __ldg(ctcol + (int64_t)(t - 1) * UC_H);
-            // this step's noise: the ring runs ahead, so this wait is normally already satisfied
+            float ct_next[2];
+            const bool more = it + 1 < n_steps;
+            if (aug_owner && more) load_ct(t - 1, ct_next);
+            // this step's noise: the ring runs ahead, so this rendezvous is normally already complete
             uint32_t zb = 0;
             if (t > 0) zb = ring_wait(it + first_item_step);
             UC_T(if (timed) { k1 = clock64(); tw[0] += k1 - k0; })
-            ok = ok && mbar_wait(bar_d, ph);
+            if (ok) ok = mbar_wait(bar_d, ph);
             UC_T(if (timed) { k0 = clock64(); tw[1] += k0 - k1; })
             tc_fence_after();
             // ---- epilogue 1: h = ReLU(D [+ c_b]) -> bf16 A operand of GEMM2 ----------------------
@@ -483,12 +471,14 @@ __global__ void __launch_bounds__(UC_THREADS, CTAS) k_chain_umma(const ChainPara
             fence_proxy_async();
             UC_T(if (timed) { const long long f1 = clock64(); tf[0] += f1 - f0; f0 = f1; })
             tc_fence_before();
-            __syncwarp();
-            if (lane == 0) mbar_arrive(bar_h);
+            nb_arrive(nb_h, cnt_h);
             UC_T(if (timed) tf[1] += clock64() - f0;)
+            // GEMM1 of this step has long read W1aug: write the next step's v while GEMM2 runs (made visible
+            // to the tensor core by the proxy fence of the publish below, before the next NB_X arrival)
+            if (aug_owner && more) refresh_w1aug(ct_next);
             UC_T(if (timed) { k1 = clock64(); tw[2] += k1 - k0; })
             UC_T(if (timed) { k0 = clock64(); tw[3] += k0 - k1; })
-            ok = ok && mbar_wait(bar_e, ph);
+            if (ok) ok = mbar_wait(bar_e, ph);
             UC_T(if (timed) { k1 = clock64(); tw[4] += k1 - k0; })
             tc_fence_after();
             // ---- epilogue 2: eps -> posterior update of this thread's parameters ----------------
@@ -523,7 +513,7 @@ __global__ void __launch_bounds__(UC_THREADS, CTAS) k_chain_umma(const ChainPara
                 }
             }
             if (t > 0) ring_release(it + first_item_step);
-            if (it + 1 < n_steps) publish_gemm1_operands(ct_next);
+            if (more) publish_gemm1_operands();
             UC_T(if (timed) tw[5] += clock64() - k1;)
         }
 #if UC_TIMING
@@ -544,8 +534,8 @@ __global__ void __launch_bounds__(UC_THREADS, CTAS) k_chain_umma(const ChainPara
                 if (PW * part + 2 * i + 1 < P) dst[2 * i + 1] = x[i].y;
             }
         }
-        }   // working epilogue warp
     }
+    // (epilogue warps whose rows carry no member have nothing to do)
     if (!ok) s.timeout = 1;
     tc_fence_before();
     __syncthreads();
