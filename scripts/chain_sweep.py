@@ -18,6 +18,7 @@ ap.add_argument("--precisions", default="fp32,bf16")
 ap.add_argument("--distinct", action="store_true")
 ap.add_argument("--reps", type=int, default=3)
 ap.add_argument("--timing", action="store_true")
+ap.add_argument("--flush", action="store_true", help="evict L2 (256 MiB memset) before every run, as bench.py does")
 ap.add_argument("--mpc", default="", help="bf16 only: comma list of members-per-CTA overrides (32,64,128) to sweep")
 a = ap.parse_args()
 dev = torch.device("cuda", 0)
@@ -38,6 +39,10 @@ for B in [int(v) for v in a.members.split(",")]:
             os.environ.pop("ERTDIFF_UMMA_MPC", None)
         ms = []
         for i in range(a.reps + 1):
+            if a.flush:
+                if "flush_buf" not in globals():
+                    flush_buf = torch.empty(256 << 20, dtype=torch.uint8, device=dev)
+                flush_buf.zero_()
             x = eb.run_chain(model, cond_b, a.T, *sched, dev, seed=7, offset=i, precision=prec,
                              n_members=B)
             ms.append(model.last_chain_ms())
