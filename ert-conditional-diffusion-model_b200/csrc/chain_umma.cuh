@@ -2,18 +2,20 @@
 // fp32 accumulation; BASELINE configs 3/4): the two projections of the hoisted denoiser step run
 // as tcgen05.mma with accumulators in TMEM, everything between them stays on chip.
 //
-// One CTA = a tile of 128 members for all steps, 17 warps in three roles, no __syncthreads in the
+// One CTA = a tile of up to 128 members for all steps, 13 warps in three roles, no __syncthreads in the
 // step loop:
 //   * 8 epilogue warps.  TMEM lane r <-> member r of the tile; a warp may only touch the lane
 //     quarter (warp % 4), so warp w handles members 32*(w%4)..+31 and half = w/4 of the columns:
 //     TWO threads share one member, each owning 64 hidden columns (epilogue 1) and 16 of the 32
-//     padded parameters (epilogue 2, x).
-//   * 8 noise warps.  They run ahead of the chain and fill a 4-deep shared-memory ring with the
-//     N(0,1) draws of the coming steps (Philox4x32-10 + Box-Muller, or the caller's replayed
-//     noise).  The generator is bound by the MUFU and integer-multiply pipes, the epilogues by
-//     conversion / packed-fp32 / shared-memory work: separate warps let the two overlap instead of
-//     alternating.
-//   * 1 MMA-issue warp (one elected thread).
+//     padded parameters (epilogue 2, x).  With a part-filled tile (32 or 64 members per CTA, so that a
+//     mid-size ensemble reaches every SM) the warps of the unused quarters retire at once.
+//   * 4 noise warps.  They run ahead of the chain and fill a shared-memory ring (4 deep; 2 in the
+//     two-CTAs-per-SM build) with the N(0,1) draws of the coming steps (Philox4x32-10 + Box-Muller, or
+//     the caller's replayed noise), one thread per member and item; with a part-filled tile the warps
+//     split into groups working on different items.  The generator is bound by the MUFU and
+//     integer-multiply pipes, the epilogues by conversion / packed-fp32 / shared-memory work: separate
+//     warps let the two overlap instead of alternating.
+//   * 1 MMA-issue warp (one elected thread); it also prefetches the coming rows of the c_t table into L2.
 //
 //   GEMM1  D[128 members x 128 hidden] = Xaug[128 x 32] * W1aug[128 x 32]^T           (2 MMAs, K=16)
 //          Xaug row     = [x_0..x_28, 1, 1, 1]   (bf16, rewritten by its two threads every step)
@@ -25,7 +27,7 @@
 //          conditions]) -> bf16 (cvt.rn.relu.bf16x2) into the K-major A operand of GEMM2
 //   GEMM2  E[128 members x 32] = Hbf16[128 x 128] * W2pad[32 x 128]^T                  (8 MMAs, K=16)
 //          issued per column half as soon as that half's 64 K-columns of H are written
-//   epi 2  eps = E + b2; bit-exact posterior update of the thread's 16 parameters (x stays in fp32
+//   epi 2  eps = E + b2; posterior update (packed fp32) of the thread's 16 parameters (x stays in fp32
 //          registers for the whole chain) with the ring's noise, new Xaug chunks
 // Hand-offs.  The two that a tcgen05.commit signals are mbarriers; all others are hardware named
 // barriers (bar.arrive by the producing role, bar.sync by the consuming one), because a warp parked
