@@ -79,6 +79,8 @@ SIGNATURES = {
                                             C.c_void_p, C.c_void_p]),
     "ertdiff_misfit_metrics": (C.c_int, [C.c_void_p, C.c_void_p, C.c_int, C.c_int64, C.c_int64, C.c_int64,
                                          C.c_double, C.c_double, C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p]),
+    "ertdiff_wasserstein_distance": (C.c_int, [C.c_void_p, C.c_void_p, C.c_int, C.c_int64, C.c_int64, C.c_int64,
+                                               C.c_void_p, C.c_void_p]),
     "ertdiff_debug_umma_gemm": (C.c_int, [C.c_void_p, C.c_void_p, C.c_int32, C.c_int32, C.c_void_p, C.c_void_p]),
     "ertdiff_untransform_bounds": (C.c_int, [C.c_void_p, C.c_int64, C.c_int32, C.c_float, C.c_float,
                                              C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p,

@@ -1017,5 +1017,40 @@ int ertdiff_misfit_metrics(const void* d_sims, const void* d_obs, int dtype, int
     return fail(ERTDIFF_ERR_ARG, "misfit_metrics: bad dtype");
 }
 
+extern "C++" {
+template <typename T>
+static int launch_sort_rows(const void* d_in, int64_t rows, int64_t stride, int n, int npad, double* d_out, cudaStream_t st) {
+    k_sort_rows_f64<T><<<(unsigned)rows, 1024, 0, st>>>((const T*)d_in, stride, n, npad, d_out);
+    ERT_LAUNCH_CHECK("k_sort_rows_f64");
+    return 0;
+}
+}  // extern "C++"
+
+int ertdiff_wasserstein_distance(const void* d_u, const void* d_v, int dtype, int64_t N, int64_t n, int64_t m,
+                                 double* d_out, void* stream) {
+    ERT_REQUIRE(d_u && d_v && d_out && N > 0 && n > 0 && m > 0, "wasserstein_distance: bad arguments");
+    ERT_REQUIRE(dtype == ERTDIFF_F32 || dtype == ERTDIFF_F64, "wasserstein_distance: bad dtype");
+    ERT_REQUIRE(n <= (1 << 24) && m <= (1 << 24), "wasserstein_distance: at most 2^24 values per sample");
+    cudaStream_t st = (cudaStream_t)stream;
+    int upad = 1, vpad = 1;
+    while (upad < n) upad <<= 1;
+    while (vpad < m) vpad <<= 1;
+    // scratch: sorted u rows, sorted v, the merged values and the u-counts of every pair
+    const size_t b_us = (size_t)N * upad * 8, b_vs = (size_t)vpad * 8, b_mg = (size_t)N * (n + m) * 8, b_cu = (size_t)N * (n + m) * 4;
+    char* ws = nullptr;
+    if (int rc = workspace(b_us + b_vs + b_mg + b_cu, (void**)&ws)) return rc;
+    double* us = (double*)ws;
+    double* vs = (double*)(ws + b_us);
+    double* mg = (double*)(ws + b_us + b_vs);
+    int* cu = (int*)(ws + b_us + b_vs + b_mg);
+    int rc = dtype == ERTDIFF_F32 ? launch_sort_rows<float>(d_u, N, n, (int)n, upad, us, st) : launch_sort_rows<double>(d_u, N, n, (int)n, upad, us, st);
+    if (rc) return rc;
+    rc = dtype == ERTDIFF_F32 ? launch_sort_rows<float>(d_v, 1, m, (int)m, vpad, vs, st) : launch_sort_rows<double>(d_v, 1, m, (int)m, vpad, vs, st);
+    if (rc) return rc;
+    k_wasserstein<<<(unsigned)N, 1024, 0, st>>>(us, (int)n, upad, vs, (int)m, mg, cu, d_out);
+    ERT_LAUNCH_CHECK("k_wasserstein");
+    return 0;
+}
+
 }  // extern "C"
 #pragma GCC visibility pop

@@ -196,4 +196,86 @@ __global__ void __launch_bounds__(kMisfitThreads) k_misfit_mse(const T* __restri
     if (threadIdx.x == 0) mse[blockIdx.x] = rn_div(val[pl.n_leaves + pl.n_nodes - 1], (T)n);
 }
 
+// ---- 1-D Wasserstein distance between a simulated map and the observed one -----------------------
+// ECD.py:860, 898-899: scipy.stats.wasserstein_distance(sim.flatten(), obs.flatten()), i.e. scipy's
+// _cdf_distance with p = 1 (scipy/stats/_stats_py.py): both samples as float64; all_values = the sorted
+// union; deltas = diff(all_values); u_cdf[k] = #{u <= all_values[k]} / n, v_cdf likewise;
+// result = vecdot(|u_cdf - v_cdf|, deltas).  The dot product runs through BLAS in scipy, so its
+// summation order is the host library's: parity is to a relative 1e-12, not bitwise.
+//
+// k_sort_rows_f64: one CTA per row, bitonic sort in global memory (the rows are L2-resident; padded to a
+// power of two with +inf).  k_wasserstein: one CTA per pair.  Ranks instead of a merge: u_i lands at
+// i + #{v < u_i}, v_j at j + #{u <= v_j} (ties: u first, as the stable sort of concat(u, v) leaves
+// them).  The count of u-elements up to position k equals scipy's searchsorted(..., 'right') wherever
+// all_values[k+1] > all_values[k]; inside a run of equal values delta is 0 and the term vanishes either way.
+template <typename T>
+__global__ void __launch_bounds__(1024) k_sort_rows_f64(const T* __restrict__ in, int64_t row_stride, int n, int npad,
+                                                        double* __restrict__ out /* (rows, npad) */) {
+    double* a = out + (int64_t)blockIdx.x * npad;
+    const T* src = in + (int64_t)blockIdx.x * row_stride;
+    for (int i = threadIdx.x; i < npad; i += blockDim.x) a[i] = i < n ? (double)src[i] : __longlong_as_double(0x7ff0000000000000LL);
+    __syncthreads();
+    for (int k = 2; k <= npad; k <<= 1) {
+        for (int j = k >> 1; j > 0; j >>= 1) {
+            for (int idx = threadIdx.x; idx < (npad >> 1); idx += blockDim.x) {
+                const int i = ((idx & ~(j - 1)) << 1) | (idx & (j - 1));     // element whose bit j is 0
+                const int p = i | j;
+                const double x = a[i], y = a[p];
+                const bool up = (i & k) == 0;
+                if ((x > y) == up) { a[i] = y; a[p] = x; }
+            }
+            __syncthreads();
+        }
+    }
+}
+
+__device__ __forceinline__ int lower_bound_f64(const double* a, int n, double v) {   // #{a < v}
+    int lo = 0, hi = n;
+    while (lo < hi) { const int mid = (lo + hi) >> 1; if (a[mid] < v) lo = mid + 1; else hi = mid; }
+    return lo;
+}
+__device__ __forceinline__ int upper_bound_f64(const double* a, int n, double v) {   // #{a <= v}
+    int lo = 0, hi = n;
+    while (lo < hi) { const int mid = (lo + hi) >> 1; if (a[mid] <= v) lo = mid + 1; else hi = mid; }
+    return lo;
+}
+
+__global__ void __launch_bounds__(1024) k_wasserstein(const double* __restrict__ u_sorted /* (N, upad) */, int n, int upad,
+                                                      const double* __restrict__ v_sorted, int m,
+                                                      double* __restrict__ merged /* (N, n+m) */,
+                                                      int* __restrict__ cnt_u /* (N, n+m) */, double* __restrict__ out) {
+    __shared__ double red[32];
+    const double* u = u_sorted + (int64_t)blockIdx.x * upad;
+    double* mg = merged + (int64_t)blockIdx.x * (n + m);
+    int* cu = cnt_u + (int64_t)blockIdx.x * (n + m);
+    for (int i = threadIdx.x; i < n; i += blockDim.x) {
+        const double x = u[i];
+        const int r = i + lower_bound_f64(v_sorted, m, x);
+        mg[r] = x; cu[r] = i + 1;
+    }
+    for (int j = threadIdx.x; j < m; j += blockDim.x) {
+        const double y = v_sorted[j];
+        const int c = upper_bound_f64(u, n, y);
+        mg[j + c] = y; cu[j + c] = c;
+    }
+    __syncthreads();
+    double acc = 0.0;
+    const double dn = (double)n, dm = (double)m;
+    for (int k = threadIdx.x; k < n + m - 1; k += blockDim.x) {
+        const int c = cu[k];
+        const double ucdf = __ddiv_rn((double)c, dn), vcdf = __ddiv_rn((double)(k + 1 - c), dm);
+        acc += fabs(ucdf - vcdf) * (mg[k + 1] - mg[k]);
+    }
+#pragma unroll
+    for (int o = 16; o > 0; o >>= 1) acc += __shfl_xor_sync(0xffffffffu, acc, o);
+    if ((threadIdx.x & 31) == 0) red[threadIdx.x >> 5] = acc;
+    __syncthreads();
+    if (threadIdx.x < 32) {
+        double t = threadIdx.x < (blockDim.x >> 5) ? red[threadIdx.x] : 0.0;
+#pragma unroll
+        for (int o = 16; o > 0; o >>= 1) t += __shfl_xor_sync(0xffffffffu, t, o);
+        if (threadIdx.x == 0) out[blockIdx.x] = t;
+    }
+}
+
 }  // namespace ertdiff

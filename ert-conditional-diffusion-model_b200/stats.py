@@ -257,3 +257,35 @@ def misfit_metrics(sim_data, observed, A=0.1, B=0.01, device=None):
             _lib.ptr(total), _lib.ptr(mse), _lib.stream_ptr(sims.device)), "misfit_metrics")
     out = {"wsse": wsse, "wsse_total": total, "order": torch.argsort(total, stable=True), "mse": mse}
     return {k: v.cpu().numpy() for k, v in out.items()} if was_numpy else out
+
+
+def wasserstein_distance(u_values, v_values, device=None):
+    """``scipy.stats.wasserstein_distance(u.flatten(), v.flatten())`` on the device, as the reference calls it
+    for a simulated / ensemble-mean / ensemble-mode map against the observed map (ECD.py:860, 898-899).
+    ``u_values`` may carry a leading member axis over ``v_values``' shape -- ``(N, L, C)`` against ``(L, C)``
+    -- and then yields the ``N`` distances in one call.  float64 arithmetic as in scipy; scipy's last step is
+    a BLAS dot product, so values agree to ~1e-12 relative, not bitwise.  numpy in -> float / numpy out."""
+    was_numpy = not isinstance(u_values, torch.Tensor)
+    u = torch.from_numpy(np.ascontiguousarray(np.asarray(u_values))) if was_numpy else u_values
+    v = v_values if isinstance(v_values, torch.Tensor) else torch.from_numpy(np.ascontiguousarray(np.asarray(v_values)))
+    batched = u.dim() == v.dim() + 1 and tuple(u.shape[1:]) == tuple(v.shape) and v.dim() >= 1
+    if u.numel() == 0 or v.numel() == 0:
+        raise ValueError("Distribution can't be empty.")          # scipy's message
+    if u.dtype not in _DT:
+        u = u.to(torch.float64)
+    if u.device.type != "cuda":
+        dev = torch.device(device) if device is not None else (
+            torch.device("cuda", torch.cuda.current_device()) if was_numpy else None)
+        if dev is None:
+            raise _lib.ErtdiffError("wasserstein_distance runs on CUDA only: pass CUDA tensors, numpy arrays, or device=")
+        u = u.to(dev)
+    u = u.reshape(u.size(0), -1).contiguous() if batched else u.reshape(1, -1).contiguous()
+    v = v.to(device=u.device, dtype=u.dtype).reshape(-1).contiguous()
+    out = torch.empty(u.size(0), device=u.device, dtype=torch.float64)
+    with torch.cuda.device(u.device):
+        _lib.check(_lib.load().ertdiff_wasserstein_distance(
+            _lib.ptr(u), _lib.ptr(v), _DT[u.dtype], u.size(0), u.size(1), v.numel(), _lib.ptr(out),
+            _lib.stream_ptr(u.device)), "wasserstein_distance")
+    if not batched:
+        return float(out.item()) if was_numpy else out[0]
+    return out.cpu().numpy() if was_numpy else out

@@ -207,6 +207,13 @@ int ertdiff_interval_coverage(const double* d_low, const double* d_upp, const do
 int ertdiff_misfit_metrics(const void* d_sims, const void* d_obs, int dtype, int64_t N, int64_t L, int64_t C,
                            double A, double B, void* d_wsse, void* d_wsse_total, void* d_mse, void* stream);
 
+/* scipy.stats.wasserstein_distance(u_row.flatten(), v.flatten()) for each of the N rows of d_u (N, n)
+ * against d_v (m), ECD.py:860, 898-899 (simulated / mean / mode map against the observed map).  Inputs
+ * `dtype`, arithmetic in float64 as scipy's; d_out (N) float64.  scipy's final dot product runs through
+ * BLAS, so parity is to a relative 1e-12, not bitwise. */
+int ertdiff_wasserstein_distance(const void* d_u, const void* d_v, int dtype, int64_t N, int64_t n, int64_t m,
+                                 double* d_out, void* stream);
+
 /* global min and max of n elements (the KDE grid's end points, ECD.py:749-750) -> d_out[2]
  * as float64. */
 int ertdiff_minmax(const void* d_a, int dtype, int64_t n, double* d_out2, void* stream);

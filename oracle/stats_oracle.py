@@ -261,3 +261,17 @@ def misfit_metrics(sim_data, observed, A=0.1, B=0.01):
     yt = observed.flatten()
     mse = np.array([np.average((yt - sim_data[i].flatten()) ** 2) for i in range(N)])
     return {"wsse": wsse, "wsse_total": total, "order": np.argsort(total, kind="stable"), "mse": mse}
+
+
+def wasserstein_distance(u_values, v_values):
+    """scipy 1.18 ``stats.wasserstein_distance`` = ``_cdf_distance(1, ...)`` (scipy/stats/_stats_py.py),
+    restated with numpy for unweighted samples; the reference calls it at ECD.py:860, 898-899."""
+    u = np.asarray(u_values, dtype=float)
+    v = np.asarray(v_values, dtype=float)
+    u_sorted, v_sorted = np.sort(u), np.sort(v)
+    all_values = np.concatenate((u, v))
+    all_values.sort(kind="mergesort")
+    deltas = np.diff(all_values)
+    u_cdf = u_sorted.searchsorted(all_values[:-1], "right") / u.size
+    v_cdf = v_sorted.searchsorted(all_values[:-1], "right") / v.size
+    return np.vecdot(np.abs(u_cdf - v_cdf), deltas)

@@ -95,3 +95,41 @@ def test_device_tensors_and_single_map(cuda_dev):
     assert one["mse"].shape == (1,) and one["mse"][0] == np.average((obs.flatten() - sims.mean(axis=0).flatten()) ** 2)
     with pytest.raises(ValueError):
         eb.misfit_metrics(sims, obs[:, :3], device=cuda_dev)
+
+
+# ---- Wasserstein distance (ECD.py:860, 898-899) -------------------------------------------------------
+def test_wasserstein_oracle_is_scipys():
+    from scipy.stats import wasserstein_distance
+    rng = np.random.default_rng(3)
+    for n, m in ((1, 1), (5, 3), (100, 100), (1000, 777), (65702, 65702)):
+        u, v = rng.normal(size=n), rng.normal(0.3, 1.2, size=m)
+        assert so.wasserstein_distance(u, v) == wasserstein_distance(u, v)
+    u = rng.integers(0, 5, size=200).astype(np.float32)               # heavy ties, float32 input
+    v = rng.integers(0, 5, size=150).astype(np.float32)
+    assert so.wasserstein_distance(u, v) == wasserstein_distance(u, v)
+
+
+@pytest.mark.gpu
+def test_wasserstein_device_matches_scipy(cuda_dev, golden):
+    import ertdiff_b200 as eb
+    from scipy.stats import wasserstein_distance
+    rng = np.random.default_rng(4)
+    for n, m, dt in ((1, 1, np.float64), (5, 3, np.float64), (100, 129, np.float32), (1000, 777, np.float64),
+                     (4096, 4096, np.float32)):
+        u, v = rng.normal(size=n).astype(dt), rng.normal(0.3, 1.2, size=m).astype(dt)
+        d = eb.wasserstein_distance(u, v, device=cuda_dev)
+        assert isinstance(d, float) and d == pytest.approx(wasserstein_distance(u, v), rel=1e-12, abs=1e-300)
+    u = rng.integers(0, 5, size=200).astype(np.float64)               # runs of equal values in and across samples
+    v = rng.integers(0, 5, size=150).astype(np.float64)
+    assert eb.wasserstein_distance(u, v, device=cuda_dev) == pytest.approx(wasserstein_distance(u, v), rel=1e-12)
+    assert eb.wasserstein_distance(u, u, device=cuda_dev) == 0.0
+    # the reference's use: every simulated map (and the ensemble mean) against the observed map, full grid
+    obs = rng.normal(size=(4693, 14)).astype(np.float32)
+    sims = obs[None] + rng.normal(scale=0.2, size=(6, 4693, 14)).astype(np.float32)
+    d = eb.wasserstein_distance(sims, obs, device=cuda_dev)
+    ref = np.array([wasserstein_distance(sims[i].flatten(), obs.flatten()) for i in range(6)])
+    assert d.shape == (6,) and np.allclose(d, ref, rtol=1e-12, atol=0)
+    dm = eb.wasserstein_distance(sims.mean(axis=0), obs, device=cuda_dev)
+    assert dm == pytest.approx(wasserstein_distance(sims.mean(axis=0).flatten(), obs.flatten()), rel=1e-12)
+    with pytest.raises(ValueError):
+        eb.wasserstein_distance(np.zeros(0), obs, device=cuda_dev)
