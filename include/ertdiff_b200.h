@@ -18,6 +18,10 @@
  *   - every function returns 0 on success or a negative ertdiff_status; the message of the
  *     last failure on the calling thread is ertdiff_last_error();
  *   - a model handle is bound to one device, is not thread-safe, distinct handles are;
+ *   - the handle-less statistics / metric functions (ensemble_*, minmax, misfit_metrics,
+ *     wasserstein_distance) share one scratch buffer per device that grows on demand: on one device
+ *     issue them from one host thread and on one stream at a time (work already enqueued is never
+ *     invalidated: a growing buffer synchronises the device before it is replaced);
  *   - there is no CPU fallback: without a CUDA device every compute call fails with
  *     ERTDIFF_ERR_CUDA.
  */
@@ -80,9 +84,11 @@ int ertdiff_model_last_chain_ms(ertdiff_model* m, float* h_ms);
  * (that tile's output was filled with NaN).  Synchronises the device. */
 int ertdiff_model_umma_status(ertdiff_model* m, int* h_status);
 /* development aid for the tensor-core chain: reads (if h_out16 != NULL) the 16 int64 cycle sums
- * CTA 0 recorded during the last chain launch -- worker thread 0: [0] noise half 1, [1] wait D,
- * [2] epilogue 1, [3] noise half 2, [4] wait E, [5] epilogue 2 + operand publish; MMA thread:
- * [8] wait X, [9] GEMM1 issue, [10] waits on H + GEMM2 issue; [15] steps -- then enables or
+ * CTA 0 recorded during the last chain launch -- epilogue thread 0: [0] loop top incl. the noise-ring
+ * rendezvous, [1] wait D, [2] epilogue 1, [4] wait E, [5] epilogue 2 + operand publish, [6]/[7] the proxy
+ * fence / arrive inside epilogue 1; MMA warp: [8] wait X, [9] GEMM1 issue, [10] waits on H + GEMM2
+ * issue; noise warp 0: [11] wait for a free slot, [12] generate (summed over ITS items); [15] steps --
+ * then enables or
  * disables the recording for the following launches.  Synchronises the device. */
 int ertdiff_debug_umma_timing(ertdiff_model* m, int enable, int64_t* h_out16);
 /* The 12 tensors in the reference's state_dict order:
