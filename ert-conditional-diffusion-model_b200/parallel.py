@@ -105,3 +105,28 @@ def sharded_statistics(x: torch.Tensor, percentiles=(25, 50, 75), n_grid: int = 
         full = local
     return {"mean": full[0], "std": full[1], "var": full[2], "pct": full[3:3 + nq], "mode": full[3 + nq],
             "mode_index": full[4 + nq].to(torch.int64)}
+
+
+def sharded_misfit(sim_local: torch.Tensor, observed: torch.Tensor, n_maps: int, A: float = 0.1, B: float = 0.01,
+                   group=None, misfit_fn=None):
+    """Per-map misfit metrics (ECD.py:764-786, 927-930) with the simulated MAPS split over the ranks: each
+    map's WSSE / MSE depends on that map alone, so rank r evaluates its ``member_slice(n_maps, r, world)``
+    maps ``sim_local (n_local, L, C)`` against the replicated ``observed (L, C)`` and one all-gather returns
+    every value to every rank in map order; the ranking (argsort of the totals) is then taken from the
+    gathered totals, so every result is identical to the unsharded ``stats.misfit_metrics`` for any number of
+    ranks.  ``misfit_fn(sim_local, observed) -> {"wsse","wsse_total","mse"}`` replaces the device kernels in
+    CPU tests."""
+    from . import stats as st
+    if misfit_fn is None:
+        def misfit_fn(s, o):
+            return st.misfit_metrics(s, o, A=A, B=B)
+    C = observed.shape[-1]
+    if sim_local.size(0):
+        r = misfit_fn(sim_local, observed)
+        packed = torch.cat([r["wsse"], r["wsse_total"][:, None], r["mse"][:, None]], dim=1)     # (n_local, C + 2)
+    else:
+        packed = torch.zeros(0, C + 2, device=sim_local.device, dtype=sim_local.dtype)
+    full = gather_members(packed, n_maps, 1, group)
+    total = full[:, C].contiguous()
+    return {"wsse": full[:, :C].contiguous(), "wsse_total": total, "order": torch.argsort(total, stable=True),
+            "mse": full[:, C + 1].contiguous()}

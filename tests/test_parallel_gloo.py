@@ -115,3 +115,37 @@ def test_two_rank_column_sharded_statistics(tmp_path, n_cols):
         assert np.array_equal(got["var"], full[2]) and np.array_equal(got["pct"], full[3:6])
         assert np.array_equal(got["mode"], full[6]) and np.array_equal(got["mode_index"], full[7].astype(np.int64))
     assert slices[0][0] == 0 and slices[0][1] == slices[1][0] and slices[1][1] == n_cols
+
+
+def _misfit_worker(rank, world, port, n_maps, out_dir):
+    import numpy as np
+    import torch
+    import torch.distributed as dist
+    from ertdiff_b200.parallel import member_slice, sharded_misfit
+    from oracle import stats_oracle as so
+    dist.init_process_group("gloo", init_method=f"tcp://127.0.0.1:{port}", rank=rank, world_size=world)
+    rng = np.random.default_rng(12)
+    obs = rng.normal(2.0, 1.0, size=(57, 5))
+    sims = obs[None] + rng.normal(scale=0.4, size=(n_maps, 57, 5))
+    a, b = member_slice(n_maps, rank, world)
+
+    def numpy_misfit(s, o):             # CPU stand-in for the device kernels: the oracle on this rank's maps
+        r = so.misfit_metrics(s.numpy(), o.numpy())
+        return {k: torch.from_numpy(np.ascontiguousarray(r[k])) for k in ("wsse", "wsse_total", "mse")}
+    out = sharded_misfit(torch.from_numpy(sims[a:b].copy()), torch.from_numpy(obs), n_maps, misfit_fn=numpy_misfit)
+    whole = so.misfit_metrics(sims, obs)
+    ok = all(np.array_equal(out[k].numpy(), whole[k]) for k in ("wsse", "wsse_total", "mse", "order"))
+    with open(f"{out_dir}/misfit_{rank}.txt", "w") as f:
+        f.write("ok" if ok else "mismatch")
+    dist.destroy_process_group()
+
+
+@pytest.mark.parametrize("n_maps", [1, 7, 10])
+def test_two_rank_map_sharded_misfit(tmp_path, n_maps):
+    # maps split unevenly (and, with one map, an empty slice on rank 1); gathered values and the ranking
+    # equal the unsharded oracle on every rank
+    import torch.multiprocessing as mp
+    port = _free_port()
+    mp.spawn(_misfit_worker, args=(2, port, n_maps, str(tmp_path)), nprocs=2, join=True)
+    for r in range(2):
+        assert open(tmp_path / f"misfit_{r}.txt").read() == "ok"
