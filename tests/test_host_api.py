@@ -76,9 +76,17 @@ def test_no_cpu_fallback():
     b, a, ab = eb.get_diffusion_schedule(10)
     with pytest.raises(eb.ErtdiffError, match="CUDA only"):
         eb.sample_model(m, torch.zeros(2, 14, 33), 10, b, a, ab, 29, "cpu")
+    # CPU tensors without a device= are refused outright; numpy inputs need a GPU to land on
+    with pytest.raises(eb.ErtdiffError, match="CUDA only"):
+        eb.misfit_metrics(torch.zeros(2, 5, 3), torch.zeros(5, 3))
+    with pytest.raises(eb.ErtdiffError, match="CUDA only"):
+        eb.wasserstein_distance(torch.zeros(7), torch.zeros(5))
     if not torch.cuda.is_available():
-        with pytest.raises(Exception):
-            eb.ensemble_mean(np.zeros((4, 3)))
+        for call in (lambda: eb.ensemble_mean(np.zeros((4, 3))),
+                     lambda: eb.misfit_metrics(np.zeros((2, 5, 3)), np.zeros((5, 3))),
+                     lambda: eb.wasserstein_distance(np.zeros(7), np.ones(5))):
+            with pytest.raises(Exception):
+                call()
 
 
 def test_product_never_imports_the_oracle():
