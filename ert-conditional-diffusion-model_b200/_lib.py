@@ -81,7 +81,12 @@ SIGNATURES = {
                                          C.c_double, C.c_double, C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p]),
     "ertdiff_wasserstein_distance": (C.c_int, [C.c_void_p, C.c_void_p, C.c_int, C.c_int64, C.c_int64, C.c_int64,
                                                C.c_void_p, C.c_void_p]),
+    "ertdiff_check_bounds": (C.c_int, [C.c_void_p, C.c_int, C.c_int64, C.c_int32, C.c_void_p, C.c_void_p, C.c_void_p,
+                                       C.c_void_p, C.c_void_p]),
+    "ertdiff_argsort_stable": (C.c_int, [C.c_void_p, C.c_int, C.c_int64, C.c_void_p, C.c_void_p]),
     "ertdiff_debug_umma_gemm": (C.c_int, [C.c_void_p, C.c_void_p, C.c_int32, C.c_int32, C.c_void_p, C.c_void_p]),
+    "ertdiff_debug_chain_floor": (C.c_int, [C.c_void_p, C.c_int]),
+    "ertdiff_debug_graph_stats": (C.c_int, [C.c_void_p, C.POINTER(C.c_int64)]),
     "ertdiff_untransform_bounds": (C.c_int, [C.c_void_p, C.c_int64, C.c_int32, C.c_float, C.c_float,
                                              C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p,
                                              C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p]),

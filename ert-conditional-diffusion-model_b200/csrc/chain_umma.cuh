@@ -64,10 +64,9 @@
 
 namespace ertdiff {
 
-constexpr int UC_M = 128;       // members per CTA
-constexpr int UC_H = 128;       // hidden_dim this kernel is built for
-constexpr int UC_K1 = 32;       // padded param_dim + 3 augmentation columns
-constexpr int UC_N2 = 32;       // padded param_dim
+// (UC_M = 128 members per CTA tile, UC_K1 = 32 = padded param_dim + 3 augmentation columns, UC_N2 = 32 = padded
+// param_dim: chain_params.cuh.)  The kernel is a template over hidden_dim H = 128 (the reference's default,
+// ECD.py:287) and 256 (the reference's one expressible widening, ECD.py:123; BASELINE config 5).
 #ifndef UC_TPM_N
 #define UC_TPM_N 2
 #endif
@@ -87,12 +86,12 @@ constexpr int UC_AUG = 29;      // first augmentation column (param_dim <= 29)
 __host__ __device__ constexpr int uc_nslot(int ctas) { return ctas == 2 ? 2 : 4; }        // depth of the noise ring (steps)
 __host__ __device__ constexpr int uc_epi_chunk(int ctas) { return ctas == 2 ? 32 : 64; }
 
-template <int NSLOT>
+template <int NSLOT, int H>
 struct UmmaChainSmem {
     unsigned char x[UC_M * UC_K1 * 2];      // A of GEMM1
-    unsigned char h[UC_M * UC_H * 2];       // A of GEMM2
-    unsigned char w1[UC_H * UC_K1 * 2];     // B of GEMM1 (W0x augmented)
-    unsigned char w2[UC_N2 * UC_H * 2];     // B of GEMM2 (W2 padded)
+    unsigned char h[UC_M * H * 2];          // A of GEMM2
+    unsigned char w1[H * UC_K1 * 2];        // B of GEMM1 (W0x augmented)
+    unsigned char w2[UC_N2 * H * 2];        // B of GEMM2 (W2 padded)
     float zring[NSLOT][UC_M][kPPad];     // noise ring; 16-byte chunk c of member m sits at chunk c ^ (m & 7)
     unsigned long long bar_d, bar_e;
     alignas(16) float b2[kPPad];
@@ -101,20 +100,20 @@ struct UmmaChainSmem {
 };
 
 // pack the bf16 B operands once per load_state_dict: byte layout = umma::elem_offset
-__global__ void k_pack_umma_weights(const float* __restrict__ w0xT /*(32,H)*/,
-                                    const float* __restrict__ w2p /*(32,H)*/, int P,
-                                    unsigned short* __restrict__ w1_pk, unsigned short* __restrict__ w2_pk) {
+static __global__ void k_pack_umma_weights(const float* __restrict__ w0xT /*(32,H)*/,
+                                           const float* __restrict__ w2p /*(32,H)*/, int P, int H,
+                                           unsigned short* __restrict__ w1_pk, unsigned short* __restrict__ w2_pk) {
     const int i = blockIdx.x * blockDim.x + threadIdx.x;
-    if (i < UC_H * UC_K1) {
+    if (i < H * UC_K1) {
         const int j = i / UC_K1, k = i % UC_K1;
-        const float v = (k < P) ? w0xT[k * UC_H + j] : 0.f;      // columns P..31 start as zero
+        const float v = (k < P) ? w0xT[k * H + j] : 0.f;      // columns P..31 start as zero
         const __nv_bfloat16 b = __float2bfloat16_rn(v);
         w1_pk[umma::elem_offset(j, k, UC_K1) / 2] = *reinterpret_cast<const unsigned short*>(&b);
     }
-    if (i < UC_N2 * UC_H) {
-        const int p = i / UC_H, k = i % UC_H;
-        const __nv_bfloat16 b = __float2bfloat16_rn(w2p[p * UC_H + k]);
-        w2_pk[umma::elem_offset(p, k, UC_H) / 2] = *reinterpret_cast<const unsigned short*>(&b);
+    if (i < UC_N2 * H) {
+        const int p = i / H, k = i % H;
+        const __nv_bfloat16 b = __float2bfloat16_rn(w2p[p * H + k]);
+        w2_pk[umma::elem_offset(p, k, H) / 2] = *reinterpret_cast<const unsigned short*>(&b);
     }
 }
 
@@ -124,23 +123,16 @@ static_assert(UC_NB_H + UC_TPM <= UC_NB_FULL && UC_NB_EMPTY + 4 <= 16, "named ba
 __device__ __forceinline__ void nb_sync(uint32_t id, uint32_t n) { asm volatile("bar.sync %0, %1;" ::"r"(id), "r"(n) : "memory"); }
 __device__ __forceinline__ void nb_arrive(uint32_t id, uint32_t n) { asm volatile("bar.arrive %0, %1;" ::"r"(id), "r"(n) : "memory"); }
 
-struct UmmaChainExtra {
-    const uint4* w1_pk;     // 8 KB
-    const uint4* w2_pk;     // 8 KB
-    int* status;            // [0] = 1 when an mbarrier wait timed out
-    long long* timing;      // optional (16 int64): phase cycle sums of CTA 0, see ertdiff_debug_umma_timing
-    int mpc;                // members per CTA: 32, 64 or 128 rows of the 128-row tile are in use, so that a
-                            // mid-size ensemble spreads over all SMs; the unused rows' warps only keep the barriers' counts
-};
-
-template <bool REPLAY, bool TRACE, bool SHARED, int CTAS>
+template <int H, bool REPLAY, bool TRACE, bool SHARED, int CTAS>
 __global__ void __launch_bounds__(UC_THREADS, CTAS) k_chain_umma(const ChainParams a, const UmmaChainExtra ex) {
     static_assert(CTAS == 1 || CTAS == 2, "one or two CTAs per SM");
+    static_assert(H == 128 || (H == 256 && CTAS == 1), "hidden_dim 128, or 256 with one CTA per SM");
+    constexpr int UC_H = H;
     constexpr int UC_NSLOT = uc_nslot(CTAS);
     constexpr int UC_EPI_CHUNK = uc_epi_chunk(CTAS);
     using namespace umma;
     extern __shared__ __align__(128) unsigned char uc_smem_raw[];
-    UmmaChainSmem<UC_NSLOT>& s = *reinterpret_cast<UmmaChainSmem<UC_NSLOT>*>(uc_smem_raw);
+    UmmaChainSmem<UC_NSLOT, H>& s = *reinterpret_cast<UmmaChainSmem<UC_NSLOT, H>*>(uc_smem_raw);
     const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
     const uint32_t sX_ = smem_u32(s.x), sH_ = smem_u32(s.h), sW1_ = smem_u32(s.w1), sW2_ = smem_u32(s.w2);
     const uint32_t sZ_ = smem_u32(&s.zring[0][0][0]);
@@ -149,12 +141,15 @@ __global__ void __launch_bounds__(UC_THREADS, CTAS) k_chain_umma(const ChainPara
     // opaque to the optimiser: otherwise every use re-derives the shared window base
     // (S2R SR_CgaCtaId + LEA, a long-scoreboard read) inside the step loop
     asm volatile("" : "+r"(sX), "+r"(sH), "+r"(sW1), "+r"(sW2), "+r"(sZ), "+r"(bar_d), "+r"(bar_e));
-    // TMEM columns: D 0..127; E 128..159; c_b (distinct conditions) 256..383.  Two CTAs per SM have 256
-    // columns each: with distinct conditions E then aliases D's first 32 columns (GEMM2 is issued only after
-    // every epilogue warp has consumed D) and c_b moves to 128..255
-    constexpr uint32_t TMEM_COLS = (SHARED || CTAS == 2) ? 256 : 512;
-    constexpr uint32_t E_COL = (!SHARED && CTAS == 2) ? 0 : 128;
-    constexpr uint32_t CB_COL = (CTAS == 2) ? 128 : 256;
+    // TMEM columns, H = 128: D 0..127; E 128..159; c_b (distinct conditions) 256..383.  Two CTAs per SM have 256
+    // columns each: with distinct conditions E then aliases D's first 32 columns (they belong to column part 0,
+    // and the part-0 GEMM2 issue waits for the part-0 threads' H_0 arrival, i.e. until they have consumed them)
+    // and c_b moves to 128..255.  H = 256: D 0..255; E 256..287 with a shared condition; with distinct
+    // conditions c_b takes 256..511 and E aliases D's first 32 columns in the same way.
+    constexpr bool E_ALIAS = !SHARED && (CTAS == 2 || H == 256);
+    constexpr uint32_t TMEM_COLS = (H == 256) ? 512 : ((SHARED || CTAS == 2) ? 256 : 512);
+    constexpr uint32_t E_COL = E_ALIAS ? 0 : (uint32_t)H;
+    constexpr uint32_t CB_COL = (H == 256) ? 256 : ((CTAS == 2) ? 128 : 256);
     constexpr uint32_t SLOT_BYTES = UC_M * kPPad * 4;
 
     // ---- one-time setup ------------------------------------------------------------------------
@@ -230,8 +225,8 @@ __global__ void __launch_bounds__(UC_THREADS, CTAS) k_chain_umma(const ChainPara
         // epilogue threads an L2 hit, not a DRAM round trip inside the step
         constexpr int PF_AHEAD = 8;
         auto prefetch_rows = [&](int t) {
-            if (t >= 0 && lane < 5) {
-                const void* ptr = lane < 4 ? (const void*)(a.table + (int64_t)t * UC_H + lane * 32)
+            if (t >= 0 && lane < UC_H / 32 + 1) {
+                const void* ptr = lane < UC_H / 32 ? (const void*)(a.table + (int64_t)t * UC_H + lane * 32)
                                            : (const void*)(reinterpret_cast<const float4*>(a.coef) + t);
                 asm volatile("prefetch.global.L2 [%0];" ::"l"(ptr));
             }
@@ -258,8 +253,8 @@ __global__ void __launch_bounds__(UC_THREADS, CTAS) k_chain_umma(const ChainPara
                 tc_fence_after();
                 if (elect_one()) {
 #pragma unroll
-                    for (int kk = 0; kk < 8 / UC_TPM; ++kk) {
-                        const int k = 8 / UC_TPM * part + kk;
+                    for (int kk = 0; kk < UC_H / 16 / UC_TPM; ++kk) {
+                        const int k = UC_H / 16 / UC_TPM * part + kk;
                         if (k == 0) mma_bf16_first(tmemE, dA2[0], dB2[0], IDESC2);
                         else mma_bf16_acc(tmemE, dA2[k], dB2[k], IDESC2);
                     }
@@ -341,23 +336,24 @@ __global__ void __launch_bounds__(UC_THREADS, CTAS) k_chain_umma(const ChainPara
         // row per part-0 thread of a full tile, two rows per thread of a quarter-filled one.
         const int wt = part * mpc + row, aug_stride = UC_TPM * mpc;
         const bool aug_owner = wt < UC_H;
-        float cb0[2] = {0.f, 0.f};
+        constexpr int NAUG = UC_H / 64;     // W1aug rows per working thread, at most (quarter-filled tile)
+        float cb0[NAUG] = {};
         if (aug_owner && SHARED) {
 #pragma unroll
-            for (int i = 0; i < 2; ++i)
+            for (int i = 0; i < NAUG; ++i)
                 if (wt + i * aug_stride < UC_H) cb0[i] = a.cond_bias[wt + i * aug_stride];
         }
         const uint32_t w1aug = sW1 + elem_offset(wt & (UC_H - 1), UC_AUG, UC_K1);
         const uint32_t w1aug_pitch = (uint32_t)(aug_stride / 8) * sbo_bytes(UC_K1);      // aug_stride rows further down
         const float* ctcol = a.table + wt;
-        auto load_ct = [&](int t, float (&ct)[2]) {
+        auto load_ct = [&](int t, float (&ct)[NAUG]) {
 #pragma unroll
-            for (int i = 0; i < 2; ++i)
+            for (int i = 0; i < NAUG; ++i)
                 if (wt + i * aug_stride < UC_H) ct[i] = __ldg(ctcol + (int64_t)t * UC_H + i * aug_stride);
         };
-        auto refresh_w1aug = [&](const float (&ct)[2]) {
+        auto refresh_w1aug = [&](const float (&ct)[NAUG]) {
 #pragma unroll
-            for (int i = 0; i < 2; ++i) {
+            for (int i = 0; i < NAUG; ++i) {
                 if (wt + i * aug_stride < UC_H) {
                     const float v = ct[i] + cb0[i];
                     const float v_hi = bf16_round(v);
@@ -437,9 +433,9 @@ __global__ void __launch_bounds__(UC_THREADS, CTAS) k_chain_umma(const ChainPara
         // c_t runs two steps ahead in registers: the row for step it+2 is requested at the top of step it and
         // written into W1aug in the middle of step it+1, so that even a DRAM-cold table row (each is read once)
         // has more than a full step to arrive
-        float ct_pending[2] = {0.f, 0.f};
+        float ct_pending[NAUG] = {};
         {
-            float ct[2];
+            float ct[NAUG];
             if (aug_owner) { load_ct(a.t_hi, ct); refresh_w1aug(ct); }
             if (aug_owner && n_steps > 1) load_ct(a.t_hi - 1, ct_pending);
             publish_gemm1_operands();
@@ -456,7 +452,7 @@ __global__ void __launch_bounds__(UC_THREADS, CTAS) k_chain_umma(const ChainPara
             const uint32_t ph = (uint32_t)it & 1u;
             // prefetches: the step scalars and the c_t elements of the step after next
             const float4 cf = __ldg(reinterpret_cast<const float4*>(a.coef) + t);
-            float ct_far[2] = {0.f, 0.f};
+            float ct_far[NAUG] = {};
             const bool more = it + 1 < n_steps;
             if (aug_owner && it + 2 < n_steps) load_ct(t - 2, ct_far);
             // this step's noise: the ring runs ahead, so this rendezvous is normally already complete
@@ -510,7 +506,8 @@ __global__ void __launch_bounds__(UC_THREADS, CTAS) k_chain_umma(const ChainPara
             // GEMM1 of this step has long read W1aug: write the next step's v while GEMM2 runs (made visible
             // to the tensor core by the proxy fence of the publish below, before the next NB_X arrival)
             if (aug_owner && more) refresh_w1aug(ct_pending);
-            ct_pending[0] = ct_far[0]; ct_pending[1] = ct_far[1];
+#pragma unroll
+            for (int i = 0; i < NAUG; ++i) ct_pending[i] = ct_far[i];
             UC_T(if (timed) { k1 = clock64(); tw[2] += k1 - k0; })
             UC_T(if (timed) { k0 = clock64(); tw[3] += k0 - k1; })
             if (ok) ok = mbar_wait(bar_e, ph);

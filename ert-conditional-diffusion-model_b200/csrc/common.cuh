@@ -52,6 +52,17 @@ inline int fail(int code, const std::string& msg) {
 // conv output length for kernel 3, stride 2, padding 1 (ECD.py:134,136)
 __host__ __device__ inline int64_t conv_out_len(int64_t L) { return (L + 2 - 3) / 2 + 1; }
 
+// cudaFuncSetAttribute is per device: every "set the dynamic shared memory limit once" site keeps one
+// flag per device (a process may drive several GPUs through several handles)
+struct PerDeviceOnce {
+    bool done[64] = {};
+    bool* slot() {
+        int dev = 0;
+        if (cudaGetDevice(&dev) != cudaSuccess || dev < 0 || dev >= 64) dev = 0;
+        return &done[dev];
+    }
+};
+
 struct DeviceGuard {
     int prev = -1;
     bool ok = true;

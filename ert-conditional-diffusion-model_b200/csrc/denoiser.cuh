@@ -11,6 +11,7 @@
 // members: one launch runs the whole chain (no grid-wide dependency exists between members).
 #pragma once
 #include "common.cuh"
+#include "chain_params.cuh"
 
 namespace ertdiff {
 
@@ -27,7 +28,7 @@ __device__ __forceinline__ float posterior_update_rn(float x, float eps, float z
     return xn;
 }
 
-__global__ void k_posterior_update(const float* __restrict__ x, const float* __restrict__ eps,
+static __global__ void k_posterior_update(const float* __restrict__ x, const float* __restrict__ eps,
                                    const float* __restrict__ z, float coef, float c1,
                                    float sigma, int64_t n, float* __restrict__ out) {
     // 4 elements per thread, 128-bit accesses when the pointers allow it
@@ -70,7 +71,7 @@ __device__ __forceinline__ void step_coefficients(const float* betas, const floa
     out4[3] = 0.f;
 }
 
-__global__ void k_step_coefficients(const float* betas, const float* alphas,
+static __global__ void k_step_coefficients(const float* betas, const float* alphas,
                                     const float* alpha_bar, int steps, double temperature,
                                     float* table4) {
     const int t = blockIdx.x * blockDim.x + threadIdx.x;
@@ -101,7 +102,7 @@ __device__ __forceinline__ void time_embed_row(float tf, const float* __restrict
     __syncthreads();
 }
 
-__global__ void k_time_table(const float* __restrict__ freq, const float* __restrict__ wtT,
+static __global__ void k_time_table(const float* __restrict__ freq, const float* __restrict__ wtT,
                              const float* __restrict__ bt, const float* __restrict__ w0tT,
                              int H, int t0, float* __restrict__ table) {
     __shared__ float emb[512];
@@ -124,7 +125,7 @@ __global__ void k_time_table(const float* __restrict__ freq, const float* __rest
 // Full forward for rows with their own t (ECD.py:155-164 as written; training passes random
 // t per row, ECD.py:312-315).  cond_bias already holds W0c @ c_emb + b0 for the row.
 // grid = B, block = H.
-__global__ void k_forward_rows(const float* __restrict__ x, const int64_t* __restrict__ t,
+static __global__ void k_forward_rows(const float* __restrict__ x, const int64_t* __restrict__ t,
                                const float* __restrict__ cond_bias, int64_t n_cond,
                                const float* __restrict__ freq, const float* __restrict__ wtT,
                                const float* __restrict__ bt, const float* __restrict__ w0tT,
@@ -173,21 +174,6 @@ __device__ __forceinline__ void mul_wide_u32(uint32_t a, uint32_t b, uint32_t& h
         : "=r"(lo), "=r"(hi) : "r"(a), "r"(b));
 }
 
-// The ten round keys of a stream depend only on the seed: the host expands them once and they
-// travel as kernel parameters, so every round reads its key straight from the constant bank.
-struct PhiloxKeys {
-    uint32_t k[20];
-};
-inline PhiloxKeys make_philox_keys(uint64_t seed) {
-    PhiloxKeys ks;
-    uint32_t k0 = (uint32_t)seed, k1 = (uint32_t)(seed >> 32);
-    for (int r = 0; r < 10; ++r) {
-        ks.k[2 * r] = k0; ks.k[2 * r + 1] = k1;
-        k0 += 0x9E3779B9u; k1 += 0xBB67AE85u;
-    }
-    return ks;
-}
-
 __device__ __forceinline__ uint4 philox4x32_10(uint4 c, const PhiloxKeys& ks) {
     const uint32_t M0 = 0xD2511F53u, M1 = 0xCD9E8D57u;
 #pragma unroll
@@ -202,13 +188,18 @@ __device__ __forceinline__ uint4 philox4x32_10(uint4 c, const PhiloxKeys& ks) {
 
 // Box-Muller on the special-function unit: lg2 / sqrt / sin / cos are single MUFU instructions
 // (abs. error ~1e-6 on a N(0,1) variate, far below what any statistic of the chain resolves).
-// The generator runs once per member, step and parameter, so its instruction count -- not its
-// last bit -- is what the chain kernels pay for.  Every kernel calls this one function, hence all
-// of them (and k_philox_fill, which the parity tests replay) produce bit-identical draws.
+// The generator runs once per member, step and parameter, so its instruction count -- and above all
+// its count of XU-pipe operations (MUFU and int->float conversions share that 16-lane pipe) -- is what
+// the chain kernels pay for.  The radius keeps all 32 random bits (one I2F; tails to 6.7 sigma, as
+// torch's CUDA generator); the angle takes 23 bits straight into the mantissa of a float in [1, 2)
+// with one logic op instead of a conversion: 5 XU operations per pair of normals instead of 6.
+// Every kernel calls this one function, hence all of them (and k_philox_fill, which the parity tests
+// replay) produce bit-identical draws.
 __device__ __forceinline__ void box_muller(uint32_t a, uint32_t b, float& n0, float& n1) {
     const float u1 = fmaf((float)a, 2.3283064365386963e-10f, 1.1641532182693481e-10f);  // (0,1]
-    // angle = 2*pi*u2 - pi in (-pi, pi]: the MUFU sin/cos need no further range reduction
-    const float ang = fmaf((float)b, 1.4629180792671596e-09f, -3.1415926528583304f);
+    // angle = 2*pi*(m - 1.5) in [-pi, pi), m = 1.mantissa(b): the MUFU sin/cos need no further range reduction
+    const float m = __uint_as_float((b & 0x007fffffu) | 0x3f800000u);
+    const float ang = fmaf(m, 6.2831853071795865f, -9.4247779607693797f);
     float lg, r, sn, cs;
     asm("lg2.approx.ftz.f32 %0, %1;" : "=f"(lg) : "f"(u1));            // u1 >= 2^-33: never denormal
     asm("sqrt.approx.ftz.f32 %0, %1;" : "=f"(r) : "f"(-1.3862943611198906f * lg));
@@ -241,7 +232,7 @@ __device__ __forceinline__ void philox_normal8(const PhiloxKeys& ks, uint64_t of
 
 // standalone generator with the chain's stream layout (tests compare the chain in device-RNG
 // mode against the oracle fed with these very draws): out[d][m][p], d = draw index.
-__global__ void k_philox_fill(const PhiloxKeys keys, uint64_t offset, int64_t member_offset, int64_t B,
+static __global__ void k_philox_fill(const PhiloxKeys keys, uint64_t offset, int64_t member_offset, int64_t B,
                               int P, int draws, float* __restrict__ out) {
     const int64_t idx = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;   // over (d, m, pquad)
     if (idx >= (int64_t)draws * B * 8) return;
@@ -256,31 +247,6 @@ __global__ void k_philox_fill(const PhiloxKeys keys, uint64_t offset, int64_t me
         if (p < P) out[((int64_t)d * B + m) * P + p] = z[u];
     }
 }
-
-// ------------------------------------------------------------------------------------------
-struct ChainParams {
-    int64_t B;             // members handled by this launch
-    int64_t n_cond;
-    int S;                 // chain length (num_steps); draw index of step t is S - t
-    int t_hi;              // first timestep of this launch (S-1 for the whole chain)
-    int t_count;           // steps in this launch
-    const float* w0xT;     // (32,H)
-    const float* w2p;      // (32,H)
-    const float* b2p;      // (32)
-    const float* table;    // (S,H)  c_t
-    const float* coef;     // (S,4)
-    const float* cond_bias;// (n_cond,H)
-    const float* x_in;     // (B rows, P) or nullptr -> Philox draw 0
-    int64_t x_in_stride;   // elements between rows of x_in
-    const float* noise;    // (S-1, noise_B, P) or nullptr -> Philox
-    int64_t noise_B;
-    PhiloxKeys keys;       // round keys of the device RNG stream (make_philox_keys(seed))
-    uint64_t offset;
-    int64_t member_offset;
-    float* x_out;          // (B,P)
-    float* eps_trace;      // (S,B,P) indexed by t, or nullptr
-    int P;
-};
 
 // ---- small PTX helpers for the chain kernel ----------------------------------------------------
 __device__ __forceinline__ void cp_async4(uint32_t smem_dst, const float* gsrc) {
@@ -325,28 +291,40 @@ __device__ __forceinline__ float2 ffma2(float2 a, float2 b, float2 c) {
 
 constexpr int CHAIN_NB = 4;     // steps per staging block (double-buffered, cp.async one block ahead)
 
-// One CTA = MPB members for all steps.  blockDim = H.
-//   layer 1: thread j owns hidden unit j (W0x row in registers, x broadcast from smem)
-//   layer 2: thread (p = tid / PARTS, part = tid % PARTS) owns a 32-wide slice of W2 row p;
-//            PARTS = H/32 partial sums are combined with xor-shuffles
+// minimum resident CTAs the register allocation must allow.  The one-member variant is the latency-critical
+// small-ensemble kernel: with the default cap ptxas interleaves each shared-memory load with its consumer and
+// exposes 8 load latencies per layer; a looser cap lets it issue all loads of a layer first (0.34 -> 0.28 us
+// per step for a lone CTA).  Two hidden units per thread hold twice the weights: no cap beyond the block size.
+__host__ __device__ constexpr int chain_min_blocks(int H, int MPB, int UPT) {
+    return UPT > 1 ? 1 : ((H <= 128 && MPB <= 2) ? 2 : 0);
+}
+
+// One CTA = MPB members for all steps.  blockDim = NT = H / UPT (UPT hidden units per thread).
+//   layer 1: thread j owns hidden units j, j + NT, ... (W0x rows in registers, x broadcast from smem)
+//   layer 2: thread (p = tid / PARTS, part = tid % PARTS), PARTS = NT / 32, owns a 32*UPT-wide slice of
+//            W2 row p; the PARTS partial sums are combined with xor-shuffles
 //   update : every lane of a p-group computes it; the part-0 lane ("owner") writes x back.
+// UPT = 2 halves the warps a member occupies (two warps at H = 128): a small ensemble that puts two members on
+// most SMs then runs one warp per scheduler, and layer 2 needs one shuffle level less.
 // Everything a step reads from global memory -- the c_t row, the three step scalars and (replay
 // mode) the injected noise row -- is staged one block of CHAIN_NB steps ahead into shared memory
-// with cp.async (one 16-byte copy per thread per block for the c_t rows), so the dependent chain
-// of a step never waits on L2/HBM latency.
-// Device RNG: every RP = min(H,128)/8 steps the first 8*RP threads run Philox once per member
+// with cp.async, so the dependent chain of a step never waits on L2/HBM latency.
+// Device RNG: every RP = min(NT,128)/8 steps the first 8*RP threads run Philox once per member
 // (thread -> (draw within the block, parameter quad)) and park the normals of the next RP draws
 // in shared memory, where the owner lanes pick them up.
-template <int H, int MPB, bool REPLAY, bool TRACE>
-// (MPB == 1 is the latency-critical small-ensemble variant: with the default cap of 128 registers ptxas
-// interleaves each shared-memory load with its consumer and exposes 8 load latencies per layer; a looser
-// cap lets it issue all loads of a layer first -- 0.34 -> 0.28 us per step for a lone CTA)
-__global__ void __launch_bounds__(H, (H <= 128 && MPB == 1) ? 2 : 0) k_chain(const ChainParams a) {
-    constexpr int PARTS = H / 32;
-    constexpr int RP = (H >= 128 ? 128 : H) / 8;   // draws per RNG refill
-    constexpr int HS_STRIDE = PARTS * 36;   // each 32-wide slice padded to 36: no bank conflicts
+// FLOOR: the same kernel with the two matrix-vector products removed (every load, store, barrier, shuffle,
+// the staging, the RNG and the posterior update stay): the latency floor of this structure, measured.
+template <int H, int MPB, int UPT, bool REPLAY, bool TRACE, bool FLOOR>
+__global__ void __launch_bounds__(H / UPT, chain_min_blocks(H, MPB, UPT)) k_chain(const ChainParams a) {
+    constexpr int NT = H / UPT;
+    constexpr int PARTS = NT / 32;
+    constexpr int SLICE = 32 * UPT;         // width of this thread's slice of a W2 row
+    constexpr int RP = (NT >= 128 ? 128 : NT) / 8;   // draws per RNG refill
+    constexpr int HS_STRIDE = (H / 32) * 36;   // each 32-wide slice padded to 36: no bank conflicts
     constexpr int CT_STRIDE = H + 4;        // c_t row + [coef, c1, sigma, 0]
     constexpr int ZB = REPLAY ? 1 : 0;
+    static_assert(NT >= 32 && NT % 32 == 0, "at least one warp, whole warps");
+    static_assert(UPT == 1 || UPT == 2, "one or two hidden units per thread");
     __shared__ __align__(16) float xs[MPB][kPPad];
     __shared__ __align__(16) float hs[MPB][HS_STRIDE];
     __shared__ __align__(16) float ctbuf[2][CHAIN_NB][CT_STRIDE];
@@ -359,13 +337,15 @@ __global__ void __launch_bounds__(H, (H <= 128 && MPB == 1) ? 2 : 0) k_chain(con
     const int P = a.P;
     const bool owner = (part == 0) && (p < P);
 
-    float2 w0x[kPPad / 2], w2r[16];
+    float2 w0x[UPT][kPPad / 2], w2r[SLICE / 2];
 #pragma unroll
-    for (int k = 0; k < kPPad / 2; ++k)
-        w0x[k] = make_float2(a.w0xT[(2 * k) * H + tid], a.w0xT[(2 * k + 1) * H + tid]);
+    for (int u = 0; u < UPT; ++u)
 #pragma unroll
-    for (int i = 0; i < 16; ++i)
-        w2r[i] = make_float2(a.w2p[p * H + part * 32 + 2 * i], a.w2p[p * H + part * 32 + 2 * i + 1]);
+        for (int k = 0; k < kPPad / 2; ++k)
+            w0x[u][k] = make_float2(a.w0xT[(2 * k) * H + tid + u * NT], a.w0xT[(2 * k + 1) * H + tid + u * NT]);
+#pragma unroll
+    for (int i = 0; i < SLICE / 2; ++i)
+        w2r[i] = make_float2(a.w2p[p * H + part * SLICE + 2 * i], a.w2p[p * H + part * SLICE + 2 * i + 1]);
     const float b2 = a.b2p[p];
 
     // 32-bit shared-window addresses, computed once
@@ -377,18 +357,19 @@ __global__ void __launch_bounds__(H, (H <= 128 && MPB == 1) ? 2 : 0) k_chain(con
     // make the bases opaque: otherwise the compiler re-derives them (S2UR SR_CgaCtaId + ULEA,
     // a long-latency special-register read) inside every step
     asm volatile("" : "+r"(xs_a), "+r"(hs_a), "+r"(ct_a), "+r"(zb_a), "+r"(zn_a));
-    const uint32_t hs_w = hs_a + 4u * ((tid >> 5) * 36 + (tid & 31));   // this thread's h slot (member 0)
-    const uint32_t hs_r = hs_a + 4u * (part * 36);                      // this thread's W2 slice of h
+    const uint32_t hs_w = hs_a + 4u * ((tid >> 5) * 36 + (tid & 31));   // this thread's first h slot (member 0)
+    const uint32_t hs_r = hs_a + 4u * (part * UPT * 36);                // this thread's W2 slice of h
     const uint32_t xs_w = xs_a + 4u * p;
 
-    float cb[MPB], x[MPB];
+    float cb[MPB][UPT], x[MPB];
     int64_t mg[MPB];      // clamped local member index
     bool mvalid[MPB];
 #pragma unroll
     for (int m = 0; m < MPB; ++m) {
         mvalid[m] = (m0 + m) < a.B;
         mg[m] = mvalid[m] ? (m0 + m) : (a.B - 1);
-        cb[m] = a.cond_bias[(mg[m] % a.n_cond) * H + tid];
+#pragma unroll
+        for (int u = 0; u < UPT; ++u) cb[m][u] = a.cond_bias[(mg[m] % a.n_cond) * H + tid + u * NT];
     }
 
     // ---- block staging ---------------------------------------------------------------------
@@ -398,8 +379,10 @@ __global__ void __launch_bounds__(H, (H <= 128 && MPB == 1) ? 2 : 0) k_chain(con
         if (b < nblocks) {
             const int buf = b & 1;
             const int it0 = b * CHAIN_NB;
-            {   // c_t rows: H/4 16-byte chunks per row, NB rows -> exactly one chunk per thread
-                const int r = tid / (H / 4), c4 = tid % (H / 4);
+            // c_t rows: H/4 16-byte chunks per row, NB rows -> UPT chunks per thread
+#pragma unroll
+            for (int c = tid; c < CHAIN_NB * (H / 4); c += NT) {
+                const int r = c / (H / 4), c4 = c % (H / 4);
                 if (it0 + r < a.t_count)
                     cp_async16(ct_a + 4u * ((buf * CHAIN_NB + r) * CT_STRIDE + 4 * c4),
                                a.table + (int64_t)(a.t_hi - it0 - r) * H + 4 * c4);
@@ -475,7 +458,9 @@ __global__ void __launch_bounds__(H, (H <= 128 && MPB == 1) ? 2 : 0) k_chain(con
             const int t = a.t_hi - it;
             const int d = d_first + it;          // draw index of this step's noise
             const uint32_t row_a = ct_a + 4u * ((buf * CHAIN_NB + r) * CT_STRIDE);
-            const float ct = lds32(row_a + 4u * tid);
+            float ct[UPT];
+#pragma unroll
+            for (int u = 0; u < UPT; ++u) ct[u] = lds32(row_a + 4u * (tid + u * NT));
             // next block of normals: written here, published by the barrier after layer 1, first
             // read after it (the previous block's last reader finished before the last barrier)
             if (!REPLAY && t > 0 && (d % RP) == 0 && it > 0) refill_rng(d);
@@ -485,13 +470,22 @@ __global__ void __launch_bounds__(H, (H <= 128 && MPB == 1) ? 2 : 0) k_chain(con
                 float4 xv[kPPad / 4];
 #pragma unroll
                 for (int k4 = 0; k4 < kPPad / 4; ++k4) xv[k4] = lds128(xs_a + 16u * (m * (kPPad / 4) + k4));
-                float2 A01 = make_float2(cb[m] + ct, 0.f), A23 = make_float2(0.f, 0.f);
 #pragma unroll
-                for (int k4 = 0; k4 < kPPad / 4; ++k4) {
-                    A01 = ffma2(w0x[2 * k4], make_float2(xv[k4].x, xv[k4].y), A01);
-                    A23 = ffma2(w0x[2 * k4 + 1], make_float2(xv[k4].z, xv[k4].w), A23);
+                for (int u = 0; u < UPT; ++u) {
+                    float hval;
+                    if (FLOOR) {
+                        hval = (cb[m][u] + ct[u]) + xv[kPPad / 4 - 1].w;
+                    } else {
+                        float2 A01 = make_float2(cb[m][u] + ct[u], 0.f), A23 = make_float2(0.f, 0.f);
+#pragma unroll
+                        for (int k4 = 0; k4 < kPPad / 4; ++k4) {
+                            A01 = ffma2(w0x[u][2 * k4], make_float2(xv[k4].x, xv[k4].y), A01);
+                            A23 = ffma2(w0x[u][2 * k4 + 1], make_float2(xv[k4].z, xv[k4].w), A23);
+                        }
+                        hval = (A01.x + A01.y) + (A23.x + A23.y);
+                    }
+                    sts32(hs_w + 4u * (m * HS_STRIDE + u * PARTS * 36), fmaxf(hval, 0.f));
                 }
-                sts32(hs_w + 4u * (m * HS_STRIDE), fmaxf((A01.x + A01.y) + (A23.x + A23.y), 0.f));
             }
             __syncthreads();          // hs complete (and, at block starts, staged rows are visible)
             // ---- layer 2 + posterior update --------------------------------------------------
@@ -499,9 +493,12 @@ __global__ void __launch_bounds__(H, (H <= 128 && MPB == 1) ? 2 : 0) k_chain(con
             float cf_coef, cf_c1, cf_sigma;
 #pragma unroll
             for (int m = 0; m < MPB; ++m) {
-                float4 hv[8];
+                float4 hv[SLICE / 4];
 #pragma unroll
-                for (int i4 = 0; i4 < 8; ++i4) hv[i4] = lds128(hs_r + 4u * (m * HS_STRIDE + 4 * i4));
+                for (int u = 0; u < UPT; ++u)
+#pragma unroll
+                    for (int i4 = 0; i4 < 8; ++i4)
+                        hv[8 * u + i4] = lds128(hs_r + 4u * (m * HS_STRIDE + u * 36 + 4 * i4));
                 float z = 0.f;
                 if (t > 0) {
                     if (REPLAY) { if (owner) z = lds32(zb_a + 4u * (((buf * CHAIN_NB + r) * MPB + m) * kPPad + p)); }
@@ -512,13 +509,31 @@ __global__ void __launch_bounds__(H, (H <= 128 && MPB == 1) ? 2 : 0) k_chain(con
                     cf_c1 = lds32(row_a + 4u * H + 4u);
                     cf_sigma = lds32(row_a + 4u * H + 8u);
                 }
-                float2 E01 = make_float2(0.f, 0.f), E23 = make_float2(0.f, 0.f);
+                float e;
+                if (FLOOR) {
+                    e = hv[SLICE / 4 - 1].w;
+                } else {
+                    float2 E01 = make_float2(0.f, 0.f), E23 = make_float2(0.f, 0.f);
+                    if (UPT == 1) {
 #pragma unroll
-                for (int i4 = 0; i4 < 8; ++i4) {
-                    E01 = ffma2(w2r[2 * i4], make_float2(hv[i4].x, hv[i4].y), E01);
-                    E23 = ffma2(w2r[2 * i4 + 1], make_float2(hv[i4].z, hv[i4].w), E23);
+                        for (int i4 = 0; i4 < 8; ++i4) {
+                            E01 = ffma2(w2r[2 * i4], make_float2(hv[i4].x, hv[i4].y), E01);
+                            E23 = ffma2(w2r[2 * i4 + 1], make_float2(hv[i4].z, hv[i4].w), E23);
+                        }
+                        e = (E01.x + E01.y) + (E23.x + E23.y);
+                    } else {
+                        // two 32-wide sub-slices: four independent accumulator chains of 8
+                        float2 F01 = make_float2(0.f, 0.f), F23 = make_float2(0.f, 0.f);
+#pragma unroll
+                        for (int i4 = 0; i4 < 8; ++i4) {
+                            E01 = ffma2(w2r[2 * i4], make_float2(hv[i4].x, hv[i4].y), E01);
+                            E23 = ffma2(w2r[2 * i4 + 1], make_float2(hv[i4].z, hv[i4].w), E23);
+                            F01 = ffma2(w2r[16 + 2 * i4], make_float2(hv[8 + i4].x, hv[8 + i4].y), F01);
+                            F23 = ffma2(w2r[16 + 2 * i4 + 1], make_float2(hv[8 + i4].z, hv[8 + i4].w), F23);
+                        }
+                        e = ((E01.x + E01.y) + (E23.x + E23.y)) + ((F01.x + F01.y) + (F23.x + F23.y));
+                    }
                 }
-                float e = (E01.x + E01.y) + (E23.x + E23.y);
 #pragma unroll
                 for (int o = 1; o < PARTS; o <<= 1) e += __shfl_xor_sync(0xffffffffu, e, o);
                 e += b2;

@@ -31,6 +31,7 @@ struct ertdiff_model {
     int* umma_status = nullptr;        // device flag: a tcgen05 chain tile timed out
     long long* umma_timing = nullptr;  // 16 int64: phase cycle sums of CTA 0 (debug aid)
     bool umma_timing_on = false;
+    bool floor_mode = false;           // debug: fp32 persistent chains launch the arithmetic-free floor build
 
     // scratch, grown on demand
     float* enc_partial = nullptr;  size_t enc_partial_n = 0;   // (n_cond, chunks, 64)
@@ -51,13 +52,21 @@ struct ertdiff_model {
         int64_t B = -1, n_cond = -1; int steps = -1; const void* noise = nullptr;
         const void* xT = nullptr; void* xout = nullptr; const void* cb = nullptr;
         uint64_t seed = 0, offset = 0; int64_t moff = 0, nstride = 0; void* trace = nullptr;
+        // everything else a captured node bakes in: which kernel (precision, members per CTA) and the
+        // handle's own buffers, which grow() may free and reallocate between two graph-mode calls
+        int precision = -1, mpb = -1, variant = -1;
+        const void* time_table = nullptr; const void* coef_table = nullptr;
+        const void* xbuf0 = nullptr; const void* xbuf1 = nullptr;
         bool operator==(const GraphKey& o) const {
             return B == o.B && n_cond == o.n_cond && steps == o.steps && noise == o.noise &&
                    xT == o.xT && xout == o.xout && cb == o.cb && seed == o.seed &&
                    offset == o.offset && moff == o.moff && nstride == o.nstride &&
-                   trace == o.trace;
+                   trace == o.trace && precision == o.precision && mpb == o.mpb &&
+                   variant == o.variant && time_table == o.time_table &&
+                   coef_table == o.coef_table && xbuf0 == o.xbuf0 && xbuf1 == o.xbuf1;
         }
     } graph_key;
+    int64_t graph_instantiations = 0, graph_updates = 0;   // bookkeeping (ertdiff_debug_graph_stats)
 };
 
 namespace ertdiff {
@@ -72,7 +81,7 @@ inline void raw_shapes(int P, int H, size_t n[12]) {
 }
 
 // One thread per packed element; tiny, runs once per load_state_dict.
-__global__ void k_pack_weights(const float* __restrict__ c1w, const float* __restrict__ c2w,
+static __global__ void k_pack_weights(const float* __restrict__ c1w, const float* __restrict__ c2w,
                                const float* __restrict__ w6, const float* __restrict__ wt,
                                const float* __restrict__ w0, const float* __restrict__ w2,
                                const float* __restrict__ b2, int P, int H,

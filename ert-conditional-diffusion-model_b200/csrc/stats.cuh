@@ -339,6 +339,169 @@ __global__ void k_percentiles(const T* __restrict__ a, int64_t N, int64_t Q, int
 }
 
 // ------------------------------------------------------------------------------------------
+// Percentiles of columns that do not fit one CTA's shared memory (any N): two kernels.
+//   k_sort_runs     the column is cut into runs of CH members; a CTA sorts one run of CT adjacent columns
+//                   in shared memory (same bitonic network) and writes it, as order-preserving unsigned
+//                   keys, to a column-major scratch array runs[col][N] (run r = [r*CH, min(N, (r+1)*CH)))
+//   k_select_runs   one warp per (column, query): the exact order statistic s[lo] is found by deciding the
+//                   key bit by bit -- "how many members are < try?" is a sum of lower bounds over the
+//                   sorted runs, each lane binary-searching its runs inside a window that shrinks with every
+//                   decided bit -- then s[hi] is either the same value (ties) or the smallest successor over
+//                   the runs, and numpy's `_lerp` finishes as in k_percentiles.  No full merge is needed:
+//                   a query costs O(R * (bits + log CH)) L2 reads.
+// Results are bit-identical to k_percentiles (and numpy) for any N.
+template <typename T> struct SortKey;
+template <> struct SortKey<float> {
+    using K = uint32_t;
+    static constexpr int BITS = 32;
+    static __device__ __forceinline__ K pad() { return 0xFFFFFFFFu; }
+    static __device__ __forceinline__ K of(float v) {
+        const uint32_t u = __float_as_uint(v);
+        return u ^ ((u >> 31) ? 0xFFFFFFFFu : 0x80000000u);
+    }
+    static __device__ __forceinline__ float back(K k) {
+        return __uint_as_float(k ^ ((k >> 31) ? 0x80000000u : 0xFFFFFFFFu));
+    }
+};
+template <> struct SortKey<double> {
+    using K = unsigned long long;
+    static constexpr int BITS = 64;
+    static __device__ __forceinline__ K pad() { return 0xFFFFFFFFFFFFFFFFull; }
+    static __device__ __forceinline__ K of(double v) {
+        const unsigned long long u = (unsigned long long)__double_as_longlong(v);
+        return u ^ ((u >> 63) ? 0xFFFFFFFFFFFFFFFFull : 0x8000000000000000ull);
+    }
+    static __device__ __forceinline__ double back(K k) {
+        return __longlong_as_double((long long)(k ^ ((k >> 63) ? 0x8000000000000000ull : 0xFFFFFFFFFFFFFFFFull)));
+    }
+};
+
+// grid = (runs, column groups of CT); columns [col0, col0 + ncols) of `a`; CH = run length (power of two)
+template <typename T>
+__global__ void __launch_bounds__(1024)
+k_sort_runs(const T* __restrict__ a, int64_t N, int64_t Q, int64_t col0, int ncols, int CH, int CT,
+            typename SortKey<T>::K* __restrict__ runs, int* __restrict__ nanflag /* [ncols] */) {
+    using K = typename SortKey<T>::K;
+    extern __shared__ __align__(16) unsigned char pct_smem_raw[];
+    K* sm = reinterpret_cast<K*>(pct_smem_raw);               // [CT][CH]
+    const int tid = threadIdx.x, nthr = blockDim.x;
+    const int64_t r0 = (int64_t)blockIdx.x * CH;              // first member of this run
+    const int cbase = blockIdx.y * CT;
+    const int total = CH * CT;
+    for (int idx = tid; idx < total; idx += nthr) {
+        const int c = idx % CT, i = idx / CT;
+        K k = SortKey<T>::pad();
+        if (r0 + i < N && cbase + c < ncols) {
+            T v = a[(r0 + i) * Q + col0 + cbase + c];
+            if (v != v) { nanflag[cbase + c] = 1; v = RN<T>::inf(); }
+            k = SortKey<T>::of(v);
+        }
+        sm[c * CH + i] = k;
+    }
+    __syncthreads();
+    const int pairs = total >> 1, half = CH >> 1;
+    for (int k = 2; k <= CH; k <<= 1) {
+        for (int j = k >> 1; j > 0; j >>= 1) {
+            for (int tp = tid; tp < pairs; tp += nthr) {
+                const int c = tp / half, r = tp % half;
+                const int i = ((r & ~(j - 1)) << 1) | (r & (j - 1));
+                const int ip = i | j;
+                K* colp = sm + c * CH;
+                const K x = colp[i], y = colp[ip];
+                const bool asc = (i & k) == 0;
+                if ((x > y) == asc) { colp[i] = y; colp[ip] = x; }
+            }
+            __syncthreads();
+        }
+    }
+    const int len = (int)((N - r0) < CH ? (N - r0) : CH);
+    for (int idx = tid; idx < len * CT; idx += nthr) {
+        const int c = idx / len, i = idx % len;
+        if (cbase + c < ncols) runs[(int64_t)(cbase + c) * N + r0 + i] = sm[c * CH + i];
+    }
+}
+
+// first index in [lo, hi) of the sorted run whose key is >= v (hi if none)
+template <typename K>
+__device__ __forceinline__ int run_lower_bound(const K* __restrict__ run, int lo, int hi, K v) {
+    while (lo < hi) {
+        const int mid = (lo + hi) >> 1;
+        if (__ldg(run + mid) < v) lo = mid + 1; else hi = mid;
+    }
+    return lo;
+}
+
+// grid.x covers (ncols * nq) warps, 4 warps per CTA; dynamic shared memory: 4 warps x 3 x R ints (the windows)
+template <typename T, typename G, typename O>
+__global__ void __launch_bounds__(128)
+k_select_runs(const typename SortKey<T>::K* __restrict__ runs, int64_t N, int64_t Q, int64_t col0, int ncols,
+              int CH, int R, const int* __restrict__ nanflag, const __grid_constant__ PctlQueryPack qs,
+              O* __restrict__ out) {
+    using K = typename SortKey<T>::K;
+    extern __shared__ int sel_win[];
+    const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+    const int64_t w = (int64_t)blockIdx.x * 4 + warp;
+    if (w >= (int64_t)ncols * qs.n) return;
+    const int c = (int)(w % ncols), kq = (int)(w / ncols);
+    const PctlQuery qq = qs.q[kq];
+    O* dst = out + (int64_t)kq * Q + col0 + c;
+    if (nanflag[c]) { if (lane == 0) *dst = RN<O>::nan(); return; }
+    const K* col = runs + (int64_t)c * N;
+    int* wa = sel_win + warp * 3 * R;       // window [wa[i], wb[i]] brackets lower_bound(run i, answer)
+    int* wb = wa + R;
+    int* wp = wb + R;                       // lower bound of the current trial key
+    for (int i = lane; i < R; i += 32) {
+        const int64_t r0 = (int64_t)i * CH;
+        wa[i] = 0; wb[i] = (int)((N - r0) < CH ? (N - r0) : CH);
+    }
+    __syncwarp();
+    const int64_t rank = qq.lo;
+    K ans = 0;
+    for (int bit = SortKey<T>::BITS - 1; bit >= 0; --bit) {
+        const K trial = ans | ((K)1 << bit);
+        int64_t below = 0;
+        for (int i = lane; i < R; i += 32) {
+            const int pos = run_lower_bound(col + (int64_t)i * CH, wa[i], wb[i], trial);
+            below += pos;
+            wp[i] = pos;                     // (entry i is only ever touched by this lane)
+        }
+#pragma unroll
+        for (int o = 16; o > 0; o >>= 1) below += __shfl_xor_sync(0xffffffffu, below, o);
+        const bool take = below <= rank;     // the rank-th member is >= trial
+        for (int i = lane; i < R; i += 32) {
+            if (take) wa[i] = wp[i]; else wb[i] = wp[i];
+        }
+        if (take) ans = trial;
+    }
+    const T A = SortKey<T>::back(ans);
+    T Bv = A;
+    if (qq.hi != qq.lo) {
+        // members <= ans: upper bound = lower bound of the next key
+        int64_t le = 0;
+        K succ = SortKey<T>::pad();
+        for (int i = lane; i < R; i += 32) {
+            const int64_t r0 = (int64_t)i * CH;
+            const int len = (int)((N - r0) < CH ? (N - r0) : CH);
+            const K* run = col + r0;
+            const int ub = (ans == SortKey<T>::pad()) ? len : run_lower_bound(run, wa[i], len, (K)(ans + 1));
+            le += ub;
+            if (ub < len) { const K nx = __ldg(run + ub); succ = nx < succ ? nx : succ; }
+        }
+#pragma unroll
+        for (int o = 16; o > 0; o >>= 1) {
+            le += __shfl_xor_sync(0xffffffffu, le, o);
+            const K other = __shfl_xor_sync(0xffffffffu, succ, o);
+            succ = other < succ ? other : succ;
+        }
+        if (le <= rank + 1) Bv = SortKey<T>::back(succ);     // no tie reaches rank + 1: the successor
+    }
+    if (lane == 0) {
+        if (sizeof(G) == 4) *dst = lerp_numpy<T, float, O>(A, Bv, qq.gamma_f);
+        else *dst = lerp_numpy<T, double, O>(A, Bv, qq.gamma_d);
+    }
+}
+
+// ------------------------------------------------------------------------------------------
 // Gaussian-KDE mode, ECD.py:751-762: per column, argmax over a common grid of
 //   pdf(g) = sum_i exp(-(g - x_i)^2 / (2 h^2)),   h^2 = var_ddof1 * N^(-2/5)   (Scott),
 // first maximum.  (The normalisation constant is common to a column's grid points and is
@@ -625,6 +788,215 @@ k_kde_select64(const T* __restrict__ a, int64_t N, int64_t Q, int64_t col0,
 }
 
 // ------------------------------------------------------------------------------------------
+// Columns longer than one CTA's shared memory (N > 25,600 members): the same two steps with the members
+// streamed through shared memory a tile at a time.  Per grid point the scan adds the same 64-term fp32 partial
+// sums in the same order as k_kde_scan32 would (tiles are multiples of 64 members), so the two forms agree bit
+// for bit; the float64 selection keeps one accumulator per candidate across the tiles.
+template <typename T>
+__global__ void __launch_bounds__(256)
+k_kde_scan32_tiled(const T* __restrict__ a, int64_t N, int64_t Q, int64_t col0,
+                   const double* __restrict__ lohi, int G, const KdeColumn* __restrict__ cols,
+                   float* __restrict__ s32, int tile /* members per tile, multiple of 64 */) {
+    extern __shared__ __align__(16) unsigned char kde_smem_raw[];
+    float* xs = reinterpret_cast<float*>(kde_smem_raw);        // [tile] centred members, fp32
+    __shared__ float s_mn[8], s_mx[8];
+    __shared__ int s_in[8];
+    __shared__ int s_range[2];
+    const int tid = threadIdx.x, nthr = blockDim.x, lane = tid & 31, warp = tid >> 5, nwarps = nthr >> 5;
+    const int64_t col = col0 + blockIdx.x;
+    const int part = blockIdx.y, nparts = gridDim.y;
+    const KdeColumn kc = cols[col];
+    const double lo = lohi[0], hi = lohi[1];
+    const double step = (hi - lo) / (double)(G - 1);
+    float* out = s32 + (int64_t)blockIdx.x * G;
+    // ---- the column's extent (one pass over the column, no staging) -------------------------------------
+    float mn = CUDART_INF_F, mx = -CUDART_INF_F;
+    int inside = 0;
+    const float glo = (float)(lo - kc.mean), ghi = (float)(hi - kc.mean);
+    for (int64_t i = tid; i < N; i += nthr) {
+        const float v = (float)((double)a[i * Q + col] - kc.mean);
+        mn = fminf(mn, v); mx = fmaxf(mx, v);
+        inside |= (v >= glo && v <= ghi);
+    }
+#pragma unroll
+    for (int o = 16; o > 0; o >>= 1) {
+        mn = fminf(mn, __shfl_xor_sync(0xffffffffu, mn, o));
+        mx = fmaxf(mx, __shfl_xor_sync(0xffffffffu, mx, o));
+        inside |= __shfl_xor_sync(0xffffffffu, inside, o);
+    }
+    if (lane == 0) { s_mn[warp] = mn; s_mx[warp] = mx; s_in[warp] = inside; }
+    __syncthreads();
+    if (tid == 0) {
+        for (int w = 1; w < nwarps; ++w) { mn = fminf(mn, s_mn[w]); mx = fmaxf(mx, s_mx[w]); inside |= s_in[w]; }
+        int ga = 0, gb = G - 1;
+        const double h = sqrt(-0.5 / kc.neg_inv_2h2);
+        if (inside && h > 0.0 && step > 0.0 && step <= 7.0 * h) {       // see kde_scan_column
+            const double reach = h * sqrt(2.0 * log(1e7 * (double)N));
+            const double aa = ((kc.mean + (double)mn - reach) - lo) / step;
+            const double bb = ((kc.mean + (double)mx + reach) - lo) / step;
+            if (aa > 1.0) ga = (int)fmin(aa - 1.0, (double)(G - 1));
+            if (bb < (double)(G - 2)) gb = (int)fmax(bb + 1.0, 0.0);
+            if (gb < ga) { ga = 0; gb = G - 1; }
+        }
+        s_range[0] = ga; s_range[1] = gb;
+    }
+    __syncthreads();
+    const int ga = s_range[0], gb = s_range[1];
+    {
+        const int z0 = (int)((int64_t)G * part / nparts), z1 = (int)((int64_t)G * (part + 1) / nparts);
+        for (int g = z0 + tid; g < z1; g += nthr)
+            if (g < ga || g > gb) out[g] = 0.f;
+    }
+    const int n_act = gb - ga + 1;
+    const int chunk = (n_act + nparts - 1) / nparts;
+    const int g_begin = ga + part * chunk;
+    const int g_end = min(gb + 1, g_begin + chunk);
+    const float c2 = (float)(kc.neg_inv_2h2 * 1.4426950408889634);
+    for (int gbase = g_begin; gbase < g_end; gbase += 2 * nthr) {       // uniform trip count: barriers inside
+        const int g0 = gbase + tid, g1 = g0 + nthr;
+        const bool has0 = g0 < g_end, has1 = g1 < g_end;
+        const float va = has0 ? (float)(kde_grid_point(g0, G, lo, hi, step) - kc.mean) : 0.f;
+        const float vb = has1 ? (float)(kde_grid_point(g1, G, lo, hi, step) - kc.mean) : 0.f;
+        double sa = 0.0, sb = 0.0;
+        for (int64_t t0 = 0; t0 < N; t0 += tile) {
+            const int n = (int)(N - t0 < tile ? N - t0 : tile);
+            __syncthreads();
+            for (int i = tid; i < n; i += nthr) xs[i] = (float)((double)a[(t0 + i) * Q + col] - kc.mean);
+            __syncthreads();
+            if (has1) {
+                for (int i0 = 0; i0 < n; i0 += 64) {
+                    const int i1 = (i0 + 64 < n) ? i0 + 64 : n;
+                    float pa = 0.f, pb = 0.f;
+                    for (int i = i0; i < i1; ++i) {
+                        const float xi = xs[i];
+                        const float da = va - xi, db = vb - xi;
+                        pa += ex2_approx(da * da * c2);
+                        pb += ex2_approx(db * db * c2);
+                    }
+                    sa += (double)pa;
+                    sb += (double)pb;
+                }
+            } else if (has0) {
+                for (int i0 = 0; i0 < n; i0 += 64) {
+                    const int i1 = (i0 + 64 < n) ? i0 + 64 : n;
+                    float pa = 0.f;
+                    for (int i = i0; i < i1; ++i) {
+                        const float da = va - xs[i];
+                        pa += ex2_approx(da * da * c2);
+                    }
+                    sa += (double)pa;
+                }
+            }
+        }
+        if (has1) out[g1] = (float)sb;
+        if (has0) out[g0] = (float)sa;
+    }
+}
+
+// grid = (columns of this batch, parts), 256 threads; dynamic shared memory: tile doubles + n_acc doubles
+template <typename T>
+__global__ void __launch_bounds__(256)
+k_kde_select64_tiled(const T* __restrict__ a, int64_t N, int64_t Q, int64_t col0,
+                     const double* __restrict__ lohi, int G, const KdeColumn* __restrict__ cols,
+                     const float* __restrict__ s32, double* __restrict__ mode_out,
+                     int64_t* __restrict__ index_out, double* __restrict__ partials,
+                     unsigned int* __restrict__ tickets, int tile /* multiple of 32 */, int n_acc) {
+    extern __shared__ __align__(16) unsigned char kde_smem_raw[];
+    double* xs = reinterpret_cast<double*>(kde_smem_raw);      // [tile] members, float64
+    double* accs = xs + tile;                                  // [n_acc] one running sum per candidate
+    __shared__ float redf[8];
+    __shared__ double redv[8];
+    __shared__ int redi[8];
+    __shared__ int cand[KDE_MAX_CAND];
+    __shared__ int ncand, ntotal;
+    const int tid = threadIdx.x, nthr = blockDim.x, lane = tid & 31, warp = tid >> 5, nwarps = nthr >> 5;
+    const int64_t col = col0 + blockIdx.x, slot = blockIdx.x;
+    const int part = blockIdx.y, nparts = gridDim.y;
+    const KdeColumn kc = cols[col];
+    const double lo = lohi[0], hi = lohi[1];
+    const float* row = s32 + (int64_t)blockIdx.x * G;
+    if (tid == 0) { ncand = 0; ntotal = 0; }
+    float mx = 0.f;
+    for (int g = tid; g < G; g += nthr) mx = fmaxf(mx, __ldcg(row + g));
+#pragma unroll
+    for (int o = 16; o > 0; o >>= 1) mx = fmaxf(mx, __shfl_xor_sync(0xffffffffu, mx, o));
+    if (lane == 0) redf[warp] = mx;
+    __syncthreads();
+    mx = redf[0];
+    for (int w = 1; w < nwarps; ++w) mx = fmaxf(mx, redf[w]);
+    const bool degenerate = !(kc.neg_inv_2h2 > -CUDART_INF) || !(kc.neg_inv_2h2 == kc.neg_inv_2h2);
+    const float thr = mx * (1.0f - KDE_TOL);
+    for (int g = tid; g < G; g += nthr) {
+        if (__ldcg(row + g) >= thr) {
+            atomicAdd(&ntotal, 1);
+            if (g % nparts == part) {
+                const int k = atomicAdd(&ncand, 1);
+                if (k < KDE_MAX_CAND) cand[k] = g;
+            }
+        }
+    }
+    __syncthreads();
+    const bool all = ntotal > KDE_MAX_CAND || !(mx > 0.f);
+    const int n_eval = all ? (G - part + nparts - 1) / nparts : ncand;      // <= n_acc by construction
+    const double step = (hi - lo) / (double)(G - 1);
+    for (int k = tid; k < n_eval && k < n_acc; k += nthr) accs[k] = 0.0;
+    for (int64_t t0 = 0; t0 < N; t0 += tile) {
+        const int n = (int)(N - t0 < tile ? N - t0 : tile);
+        __syncthreads();
+        for (int i = tid; i < n; i += nthr) xs[i] = (double)a[(t0 + i) * Q + col];
+        __syncthreads();
+        for (int k = warp; k < n_eval; k += nwarps) {           // candidate k belongs to warp k % nwarps throughout
+            const int g = all ? part + k * nparts : cand[k];
+            const double gv = kde_grid_point(g, G, lo, hi, step);
+            double acc = 0.0;
+            for (int i = lane; i < n; i += 32) {
+                const double d = gv - xs[i];
+                acc += exp(d * d * kc.neg_inv_2h2);
+            }
+#pragma unroll
+            for (int o = 16; o > 0; o >>= 1) acc += __shfl_xor_sync(0xffffffffu, acc, o);
+            if (lane == 0) accs[k] += acc;
+        }
+    }
+    __syncwarp();
+    double best = -1.0;
+    int besti = 0x7fffffff;
+    for (int k = warp; k < n_eval; k += nwarps) {
+        const int g = all ? part + k * nparts : cand[k];
+        const double acc = accs[k];
+        if (acc > best || (acc == best && g < besti)) { best = acc; besti = g; }
+    }
+    if (lane == 0) { redv[warp] = best; redi[warp] = besti; }
+    __syncthreads();
+    if (tid == 0) {
+        for (int w = 1; w < nwarps; ++w)
+            if (redv[w] > best || (redv[w] == best && redi[w] < besti)) { best = redv[w]; besti = redi[w]; }
+        if (nparts > 1) {
+            double* mine = partials + (slot * nparts + part) * 2;
+            mine[0] = best; mine[1] = (double)besti;
+            __threadfence();
+            const unsigned int t = atomicAdd(&tickets[slot], 1u);
+            if (t != (unsigned int)(nparts - 1)) return;
+            tickets[slot] = 0u;
+            __threadfence();
+            best = -1.0; besti = 0x7fffffff;
+            for (int p = 0; p < nparts; ++p) {
+                const double v = __ldcg(partials + (slot * nparts + p) * 2);
+                const int gi = (int)__ldcg(partials + (slot * nparts + p) * 2 + 1);
+                if (v > best || (v == best && gi < besti)) { best = v; besti = gi; }
+            }
+        }
+        if (degenerate) {
+            if (index_out) index_out[col] = -1;
+            if (mode_out) mode_out[col] = CUDART_NAN;
+        } else {
+            if (index_out) index_out[col] = besti;
+            if (mode_out) mode_out[col] = kde_grid_point(besti, G, lo, hi, step);
+        }
+    }
+}
+
+// ------------------------------------------------------------------------------------------
 // Small ensembles (N*Q <= 64 K values, the chain's own (members, 29) output): the five dependent
 // launches above (two for the global range, column constants, scan, select) cost more in start-up
 // latency than in work, so ONE launch does it all.  grid = (Q, n_gchunks), 256 threads:
@@ -717,6 +1089,37 @@ k_kde_small(const T* __restrict__ a, int64_t N, int64_t Q, int compute_range, do
 }
 
 // ------------------------------------------------------------------------------------------
+// Stable ascending argsort of a short vector (the misfit ranking of ECD.py:786, `np.argsort` of the
+// per-member totals; n = number of simulated maps, 50 in the reference): rank by counting,
+// rank(i) = #{j : v_j < v_i or (v_j == v_i and j < i)}, NaN last (numpy's order), order[rank(i)] = i.
+// O(n^2) compares on the whole machine beat any sort's launch count at these sizes.
+template <typename T>
+__global__ void __launch_bounds__(256)
+k_argsort_count(const T* __restrict__ v, int64_t n, int64_t* __restrict__ order) {
+    __shared__ T tile[1024];
+    const int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+    const T vi = i < n ? v[i] : (T)0;
+    const bool nan_i = vi != vi;
+    int64_t rank = 0;
+    for (int64_t j0 = 0; j0 < n; j0 += 1024) {
+        const int m = (int)(n - j0 < 1024 ? n - j0 : 1024);
+        __syncthreads();
+        for (int j = threadIdx.x; j < m; j += blockDim.x) tile[j] = v[j0 + j];
+        __syncthreads();
+        if (i < n) {
+            for (int j = 0; j < m; ++j) {
+                const T vj = tile[j];
+                const bool nan_j = vj != vj;
+                const bool less = nan_i ? !nan_j : (!nan_j && vj < vi);
+                const bool equal = nan_i ? nan_j : (vj == vi);
+                rank += (less || (equal && j0 + j < i)) ? 1 : 0;
+            }
+        }
+    }
+    if (i < n) order[rank] = i;
+}
+
+// ------------------------------------------------------------------------------------------
 // logits -> physical parameters -> bounds check (ECD.py:42-53, 402-406,
 // 183-218).  One warp per member; lane p handles parameter p.
 __global__ void k_untransform_bounds(const float* __restrict__ u, int64_t B, int P, float a,
@@ -739,6 +1142,28 @@ __global__ void k_untransform_bounds(const float* __restrict__ u, int64_t B, int
         }
         if (phys) phys[row * P + lane] = v;
         if (lim_lo) bad = ((double)v < lim_lo[lane]) || ((double)v > lim_hi[lane]);
+    }
+    const unsigned mask = __ballot_sync(0xffffffffu, bad);
+    if (lane == 0) {
+        if (valid) valid[row] = mask == 0;
+        if (first_bad) first_bad[row] = mask ? (__ffs(mask) - 1) : -1;
+    }
+}
+
+// check_param_bounds alone (ECD.py:183-218) on values of either dtype: a row is dropped when any parameter is
+// `< min or > max` (so a NaN never drops a row, as in the reference); first_bad = the parameter the reference's
+// loop reports before it breaks.  One warp per row.
+template <typename T>
+__global__ void k_check_bounds(const T* __restrict__ v, int64_t B, int P, const double* __restrict__ lim_lo,
+                               const double* __restrict__ lim_hi, uint8_t* __restrict__ valid,
+                               int32_t* __restrict__ first_bad) {
+    const int lane = threadIdx.x & 31;
+    const int64_t row = ((int64_t)blockIdx.x * blockDim.x + threadIdx.x) >> 5;
+    if (row >= B) return;
+    bool bad = false;
+    if (lane < P) {
+        const double x = (double)v[row * P + lane];
+        bad = (x < lim_lo[lane]) || (x > lim_hi[lane]);
     }
     const unsigned mask = __ballot_sync(0xffffffffu, bad);
     if (lane == 0) {

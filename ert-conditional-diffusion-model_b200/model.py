@@ -154,6 +154,17 @@ class ConditionalDiffusionModel(nn.Module):
         _lib.check(_lib.load().ertdiff_debug_umma_timing(self.handle(), int(bool(enable)), out), "umma_timing")
         return [int(v) for v in out]
 
+    def chain_floor(self, enable=True):
+        """Measurement aid (``ertdiff_debug_chain_floor``): fp32 persistent chains run the kernel with the
+        matrix-vector arithmetic removed -- the latency floor of its structure.  Outputs are meaningless."""
+        _lib.check(_lib.load().ertdiff_debug_chain_floor(self.handle(), int(bool(enable))), "chain_floor")
+
+    def graph_stats(self):
+        """(graphs instantiated, in-place graph updates) of ``loop_mode="graph"`` on this handle."""
+        out = (C.c_int64 * 2)()
+        _lib.check(_lib.load().ertdiff_debug_graph_stats(self.handle(), out), "graph_stats")
+        return int(out[0]), int(out[1])
+
     def last_chain_ms(self):
         ms = C.c_float()
         _lib.check(_lib.load().ertdiff_model_last_chain_ms(self.handle(), C.byref(ms)), "last_chain_ms")

@@ -128,5 +128,7 @@ def sharded_misfit(sim_local: torch.Tensor, observed: torch.Tensor, n_maps: int,
         packed = torch.zeros(0, C + 2, device=sim_local.device, dtype=sim_local.dtype)
     full = gather_members(packed, n_maps, 1, group)
     total = full[:, C].contiguous()
-    return {"wsse": full[:, :C].contiguous(), "wsse_total": total, "order": torch.argsort(total, stable=True),
+    # (CPU tensors only reach this point from the gloo tests' stand-in misfit_fn)
+    order = st.argsort_stable(total) if total.is_cuda else torch.argsort(total, stable=True)
+    return {"wsse": full[:, :C].contiguous(), "wsse_total": total, "order": order,
             "mse": full[:, C + 1].contiguous()}

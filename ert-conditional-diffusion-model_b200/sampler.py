@@ -80,7 +80,8 @@ def _schedule_on(device, *tensors):
 @torch.no_grad()
 def run_chain(model, condition, T, betas, alphas, alpha_bar, device, num_steps=None,
               temperature=1.0, *, n_members=None, noise=None, seed=None, offset=0,
-              member_offset=0, loop_mode="persistent", precision="fp32", return_eps=False):
+              member_offset=0, loop_mode="persistent", precision="fp32", return_eps=False,
+              check_status=True):
     """The engine behind ``sample_model`` / ``sample_ensemble``.
 
     condition: ``(n_cond, 14, L)``; member ``i`` of the ``n_members`` (default ``n_cond``)
@@ -88,6 +89,12 @@ def run_chain(model, condition, T, betas, alphas, alpha_bar, device, num_steps=N
     = ``x_T``, row k = k-th in-loop draw (the order ``torch.randn`` is called in ECD.py:107,116).
     Returns ``x_0 (n_members, P)`` on ``device`` (and the per-step predicted noise
     ``(num_steps, n_members, P)`` indexed by t when ``return_eps``).
+
+    ``precision="bf16"``: a tile of the tensor-core chain whose MMA never completes (a hardware or
+    driver fault; the waits are bounded) poisons its members with NaN and raises the handle's status
+    word.  With ``check_status`` (default) that word is read after the launch -- one 4-byte D2H copy,
+    which waits for the chain -- and ``ErtdiffError`` is raised; a caller that pipelines several
+    chains passes ``check_status=False`` and polls ``model.umma_status()`` itself.
     """
     if not isinstance(model, ConditionalDiffusionModel):
         raise TypeError("model must be an ertdiff_b200 ConditionalDiffusionModel")
@@ -160,12 +167,14 @@ def run_chain(model, condition, T, betas, alphas, alpha_bar, device, num_steps=N
                                             C.byref(args), _lib.stream_ptr(device)),
                    "sample_model")
     del keep
+    if check_status and precision == "bf16" and model.umma_status() != 0:
+        raise _lib.ErtdiffError("tensor-core chain: an MMA completion wait timed out; the affected members are NaN")
     return (x_out, eps) if return_eps else x_out
 
 
 def sample_model(model, condition, T, betas, alphas, alpha_bar, param_dim, device,
                  num_steps=None, temperature=1.0, *, noise=None, seed=None,
-                 loop_mode="persistent", precision="fp32"):
+                 loop_mode="persistent", precision="fp32", check_status=True):
     """Drop-in for the reference's ``sample_model`` (ECD.py:102-119): same positional
     signature, returns ``x_0 (B, param_dim)`` float32 on ``device``.
 
@@ -178,12 +187,12 @@ def sample_model(model, condition, T, betas, alphas, alpha_bar, param_dim, devic
         raise ValueError(f"param_dim={param_dim} but the model was built with {model.param_dim}")
     return run_chain(model, condition, T, betas, alphas, alpha_bar, device, num_steps,
                      temperature, noise=noise, seed=seed, loop_mode=loop_mode,
-                     precision=precision)
+                     precision=precision, check_status=check_status)
 
 
 def sample_ensemble(model, condition, T, betas, alphas, alpha_bar, param_dim, device,
                     n_realizations=50, num_steps=None, temperature=1.0, *, noise=None,
-                    seed=None, loop_mode="persistent", precision="fp32"):
+                    seed=None, loop_mode="persistent", precision="fp32", check_status=True):
     """The ensemble driver of ECD.py:394-412 / 1037-1079 as ONE batched chain.
 
     The reference loops ``for realization in range(50): sample_model(...)`` over the same
@@ -198,7 +207,7 @@ def sample_ensemble(model, condition, T, betas, alphas, alpha_bar, param_dim, de
     n_cond = condition.size(0)
     x = run_chain(model, condition, T, betas, alphas, alpha_bar, device, num_steps, temperature,
                   n_members=n_realizations * n_cond, noise=noise, seed=seed,
-                  loop_mode=loop_mode, precision=precision)
+                  loop_mode=loop_mode, precision=precision, check_status=check_status)
     return x.view(n_realizations, n_cond, model.param_dim)
 
 

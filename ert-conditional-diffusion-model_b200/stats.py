@@ -218,6 +218,20 @@ def uq_calibration(generated, true, n_prob=30, device=None):
     return out
 
 
+def argsort_stable(v):
+    """``np.argsort(v, kind="stable")`` of a 1-D CUDA tensor on the device (ECD.py:786 ranks the members by
+    their total WSSE); NaN sorts last, as in numpy."""
+    v = v.contiguous()
+    if v.dtype not in _DT:
+        v = v.to(torch.float64)
+    order = torch.empty(v.numel(), device=v.device, dtype=torch.int64)
+    if v.numel():
+        with torch.cuda.device(v.device):
+            _lib.check(_lib.load().ertdiff_argsort_stable(_lib.ptr(v), _DT[v.dtype], v.numel(), _lib.ptr(order),
+                                                          _lib.stream_ptr(v.device)), "argsort_stable")
+    return order
+
+
 def misfit_metrics(sim_data, observed, A=0.1, B=0.01, device=None):
     """Per-member data misfit of the simulated maps ``sim_data (N, L, C)`` against the observed map
     ``observed (L, C)`` (the conditional ERT sample), as the reference computes it inline:
@@ -255,7 +269,7 @@ def misfit_metrics(sim_data, observed, A=0.1, B=0.01, device=None):
         _lib.check(_lib.load().ertdiff_misfit_metrics(
             _lib.ptr(sims), _lib.ptr(obs), _DT[sims.dtype], N, L, C, float(A), float(B), _lib.ptr(wsse),
             _lib.ptr(total), _lib.ptr(mse), _lib.stream_ptr(sims.device)), "misfit_metrics")
-    out = {"wsse": wsse, "wsse_total": total, "order": torch.argsort(total, stable=True), "mse": mse}
+    out = {"wsse": wsse, "wsse_total": total, "order": argsort_stable(total), "mse": mse}
     return {k: v.cpu().numpy() for k, v in out.items()} if was_numpy else out
 
 

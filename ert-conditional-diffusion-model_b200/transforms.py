@@ -53,17 +53,38 @@ def inverse_transform(u, a, b):
     return untransform_and_check(u, a, b)[0]
 
 
-def check_param_bounds(param, limits):
-    """ECD.py:183-218 on the device: rows of ``param`` (B,P) with every parameter inside
-    ``limits`` (P,2); ``None`` when no row survives (as the reference returns)."""
-    t = param if isinstance(param, torch.Tensor) else torch.as_tensor(np.asarray(param))
+def check_param_bounds(param, limits, verbose=True):
+    """ECD.py:183-218 on the device: the rows of ``param`` (B,P) whose parameters all lie inside ``limits``
+    (P,2), in order; ``None`` when no row survives (as the reference returns).  Same semantics as the
+    reference's loop: a row is dropped when some parameter is ``< min or > max`` (compared in float64, as
+    numpy promotes; a NaN never drops a row), and with ``verbose`` the first offending parameter of every dropped
+    row is printed in the reference's format.  float32 and float64 inputs keep their dtype."""
     was_numpy = not isinstance(param, torch.Tensor)
-    t = t.to("cuda", torch.float32) if t.device.type != "cuda" else t.to(torch.float32)
+    t = torch.as_tensor(np.asarray(param)) if was_numpy else param
+    if t.dtype not in (torch.float32, torch.float64):
+        t = t.to(torch.float64)
+    if t.device.type != "cuda":
+        t = t.to(torch.device("cuda", torch.cuda.current_device()))
+    t = t.contiguous()
     lim = np.asarray(limits, dtype=np.float64)
-    # identity un-transform: sigmoid is skipped by checking the values as they are
     B, P = t.shape
+    if P > 32:
+        raise _lib.ErtdiffError("check_param_bounds: at most 32 parameters")
     dev = t.device
     lo, hi = _f64(dev, lim[:, 0]), _f64(dev, lim[:, 1])
-    ok = ((t.double() >= lo) & (t.double() <= hi)).all(dim=1)
-    kept = param[ok.cpu().numpy()] if was_numpy else param[ok]
+    valid = torch.empty(B, device=dev, dtype=torch.uint8)
+    first_bad = torch.empty(B, device=dev, dtype=torch.int32)
+    if B:
+        with torch.cuda.device(dev):
+            _lib.check(_lib.load().ertdiff_check_bounds(
+                _lib.ptr(t), _lib.F32 if t.dtype == torch.float32 else _lib.F64, B, P, _lib.ptr(lo), _lib.ptr(hi),
+                _lib.ptr(valid), _lib.ptr(first_bad), _lib.stream_ptr(dev)), "check_bounds")
+    ok = valid.bool().cpu().numpy()
+    if verbose and not ok.all():
+        fb = first_bad.cpu().numpy()
+        host = param if was_numpy else t.cpu().numpy()
+        for i in np.nonzero(~ok)[0]:
+            j = int(fb[i])
+            print(f"Sample {i} Parameter {j}: {host[i][j]:.4f} (out of bounds [{lim[j, 0]:.4f}, {lim[j, 1]:.4f}])")
+    kept = param[ok] if was_numpy else param[torch.from_numpy(ok).to(param.device)]
     return kept if kept.shape[0] else None

@@ -250,12 +250,34 @@ int ertdiff_untransform_bounds(const float* d_u, int64_t B, int32_t P, float a, 
                                const double* d_lim_lo, const double* d_lim_hi, float* d_phys,
                                uint8_t* d_valid, int32_t* d_first_bad, void* stream);
 
+/* check_param_bounds alone (ECD.py:183-218) for values (B, P) of dtype ERTDIFF_F32 / F64, P <= 32: d_valid[row] = 1
+ * unless some parameter is `< lim_lo or > lim_hi` (compared in float64, as numpy promotes; NaN never drops a row, as
+ * in the reference); d_first_bad[row] = the first offending parameter (the one the reference prints) or -1.
+ * Either output may be NULL. */
+int ertdiff_check_bounds(const void* d_v, int dtype, int64_t B, int32_t P, const double* d_lim_lo,
+                         const double* d_lim_hi, uint8_t* d_valid, int32_t* d_first_bad, void* stream);
+
+/* Stable ascending argsort of a device vector (n values, dtype ERTDIFF_F32 / F64), NaN last: the ranking
+ * `np.argsort(WSSE_sim_total)` of ECD.py:786.  d_order[k] = index of the k-th smallest value. */
+int ertdiff_argsort_stable(const void* d_v, int dtype, int64_t n, int64_t* d_order, void* stream);
+
 /* ---- self-test of the tcgen05 building blocks -------------------------------------------------
  * D (128,N) = A (128,K) @ B (N,K)^T on the tensor cores (bf16 operands, fp32 accumulate in TMEM),
- * one CTA; (N,K) in {(128,32), (32,128), (128,128), (64,96)}.  Row-major fp32 in and out.
+ * one CTA; (N,K) in {(128,32), (32,128), (128,128), (64,96), (256,32), (32,256)}.  Row-major fp32 in and out.
  * Synchronises the stream; fails with ERTDIFF_ERR_CUDA if the MMA never signals completion. */
 int ertdiff_debug_umma_gemm(const float* d_A, const float* d_B, int32_t N, int32_t K, float* d_D,
                             void* stream);
+
+/* ---- measurement aids -----------------------------------------------------------------------------
+ * Latency floor of the fp32 chain kernel (SURVEY.md §8 d): while enabled, fp32 persistent chains of
+ * this handle launch the SAME kernel with the two matrix-vector products removed -- every barrier,
+ * shared-memory hand-off, shuffle, staging copy, RNG refill and the posterior update stay -- so that
+ * its duration (ertdiff_model_last_chain_ms) is the cost of num_steps dependent steps of this
+ * structure.  The fields it writes are meaningless.  hidden_dim 128 / 256, device RNG, no trace. */
+int ertdiff_debug_chain_floor(ertdiff_model* m, int enable);
+/* Graph-mode bookkeeping: h_out2[0] = graphs instantiated, h_out2[1] = in-place updates of the
+ * instantiated graph (cudaGraphExecUpdate) since the handle was created. */
+int ertdiff_debug_graph_stats(ertdiff_model* m, int64_t* h_out2);
 
 #ifdef __cplusplus
 }

@@ -61,12 +61,20 @@ def test_checkpoint_roundtrip(tmp_path):
     path = tmp_path / "best_model.pt"
     eb.save_checkpoint(path, m, epoch=7, best_val_loss=0.25)
     m2 = eb.ConditionalDiffusionModel(29, 64)
-    ck = eb.load_best_model(path, m2, map_location="cpu")
-    assert set(ck) == {"epoch", "model_state_dict", "optimizer_state_dict", "best_val_loss",
-                       "train_history", "val_history", "param_dim"}
+    ck = eb.load_best_model(path, m2, map_location="cpu")        # weights_only=True by default
+    assert set(ck) == {"epoch", "model_state_dict", "best_val_loss", "train_history", "val_history", "param_dim"}
     assert all(torch.equal(a, b) for a, b in zip(m.state_dict().values(), m2.state_dict().values()))
     torch.save(m.state_dict(), tmp_path / "bare.pt")
     eb.load_best_model(tmp_path / "bare.pt", m2, map_location="cpu")
+    # with an optimizer the reference's 7-key dict is written and its loader pattern (ECD.py:369-377) works
+    opt = torch.optim.Adam(m.parameters(), lr=1e-4)
+    eb.save_checkpoint(path, m, epoch=3, best_val_loss=0.5, optimizer=opt, train_history=[1.0], val_history=[2.0])
+    opt2 = torch.optim.Adam(m2.parameters(), lr=1e-4)
+    ck = eb.load_best_model(path, m2, optimizer=opt2, map_location="cpu")
+    assert set(ck) == set(eb.checkpoint.CHECKPOINT_KEYS) and ck["epoch"] == 3
+    # a checkpoint written without optimizer state loads into a caller that passes an optimizer
+    eb.save_checkpoint(path, m)
+    eb.load_best_model(path, m2, optimizer=opt2, map_location="cpu")
 
 
 def test_no_cpu_fallback():
