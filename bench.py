@@ -2,17 +2,25 @@
 """Benchmark of the ensemble posterior-sampling path (BASELINE.json metric).
 
     python bench.py [--gpus N] [--steps K] [--warmup W] [--impl ours|reference] [--members M]
-                    [--T T] [--loop-mode persistent|graph] [--distinct-conditions]
+                    [--T T] [--loop-mode persistent|graph] [--precision fp32|bf16]
+                    [--distinct-conditions] [--no-extra-configs] [--no-cpu-baseline]
 
 One "step" = one pass of the hot path over one ensemble: condition encoder -> full DDPM reverse
-chain of T steps for every member -> (N>1: all-gather) -> ensemble mean/std/var, percentiles
-and KDE mode of the final fields.  Metric: posterior samples/sec (members completing the full
-chain per second, whole job).  Default workload = BASELINE.json configs[1]: 256 members per
-GPU, T = 1000, fp32, one synthetic condition of the reference's grid (14 x 4693) shared by all
-members, random-init weights, device-side RNG.
+chain of T steps for every member -> (N>1: all-gather of the fields) -> ensemble mean/std/var,
+5 percentiles and the KDE mode of the final fields (columns split over the ranks when N>1).
+Metric: posterior samples/sec (members completing the full chain per second, whole job).
 
-Prints ONE JSON line (rank 0).  `--impl reference` times the reference's CPU algorithm (the
-oracle port, as written: condition encoder re-run every step) on the host cores.
+The TOP-LEVEL line is BASELINE.json configs[1] (256 members per GPU, T = 1000, fp32, one synthetic
+condition of the reference's grid 14 x 4693 shared by all members, random-init weights, device RNG).
+The same JSON line carries `configs`: sub-records measured the same way (value, e2e, roofline, clocks) for
+the other BASELINE configurations -- config 3 (bf16 tensor-core chain, 1024 members; persistent loop and
+CUDA-graph loop), 8192 and 18,944 members in bf16, 256 members with 256 distinct conditions, config 5's
+reference-expressible widening (hidden 256, L = 9386, 4096 members over the job) and, for N > 1, config 4
+(1024 members per GPU, bf16) -- plus `bf16_vs_fp32`, the deviation of the tensor-core chain from the fp32
+chain on identical RNG streams at T = 1000.
+
+Prints ONE JSON line (rank 0).  `--impl reference` times the reference's CPU algorithm (the oracle port,
+as written: condition encoder re-run every step) on the host cores.
 """
 from __future__ import annotations
 
@@ -30,16 +38,17 @@ import torch
 ROOT = os.path.dirname(os.path.abspath(__file__))
 sys.path.insert(0, ROOT)
 
-P, H, C, L = 29, 128, 14, 4693
-FLOP_STEP_MEMBER = 14848            # 2*(29*128 + 128*29): x-block of mlp.0 + mlp.2 (SURVEY §8 d)
-FLOP_ENCODER = 20751232 + 32768     # per distinct condition, once per chain
-FLOP_TIME_ROW = 65536               # per step, shared by all members
-FLOP_AS_WRITTEN = 20864384          # per member per step, reference-equivalent work
+P, C = 29, 14
+L_REF, H_REF = 4693, 128
+FLOP_AS_WRITTEN = 20864384          # per member per step at (H=128, L=4693), reference-equivalent work
 PERCENTILES = [2.5, 25.0, 50.0, 75.0, 97.5]
 KDE_GRID = 5000
-SHARD_STATS_ABOVE = 4096   # gathered members above which the statistics' columns are split over the ranks
-                           # (below it the second all-gather and the packing cost more than they save)
-MAX_STAT_MEMBERS = 25600   # one statistics call holds a column in shared memory (KDE: N*8 B <= 200 KB)
+METRIC = "posterior_samples_per_sec_full_chain"
+
+
+def flop_step_member(H):
+    """2*(P*H + H*P): x-block of mlp.0 + mlp.2 (SURVEY.md §8 d: 14,848 at H = 128)."""
+    return 4 * P * H
 
 
 def load_peaks():
@@ -54,12 +63,13 @@ def load_peaks():
 
 
 def ncu_traffic(kernel):
-    """DRAM bytes of one launch of `kernel` from the committed `ncu --set full` summary (or None)."""
-    path = os.path.join(ROOT, "profiles", "r01_ncu_kernels.json")
-    try:
-        return json.load(open(path))[kernel]["traffic_bytes_per_launch"]
-    except Exception:
-        return None
+    """DRAM bytes of one launch of `kernel` from the committed `ncu --set full` summaries (or None)."""
+    for name in ("r02_ncu_kernels.json", "r01_ncu_kernels.json"):
+        try:
+            return json.load(open(os.path.join(ROOT, "profiles", name)))[kernel]["traffic_bytes_per_launch"]
+        except Exception:
+            continue
+    return None
 
 
 class ClockSampler:
@@ -69,13 +79,13 @@ class ClockSampler:
          "clocks_event_reasons.sw_power_cap")
 
     def __init__(self, index):
-        self.index, self.rows, self.proc = index, [], None
+        self.index, self.rows, self.proc, self.mark = index, [], None, 0
 
     def start(self):
         try:
             self.proc = subprocess.Popen(
                 ["nvidia-smi", f"--id={self.index}", f"--query-gpu={self.Q}",
-                 "--format=csv,noheader,nounits", "-lms", "100"],
+                 "--format=csv,noheader,nounits", "-lms", "50"],
                 stdout=subprocess.PIPE, stderr=subprocess.DEVNULL, text=True)
             self.thread = threading.Thread(target=self._read, daemon=True)
             self.thread.start()
@@ -86,18 +96,18 @@ class ClockSampler:
         for line in self.proc.stdout:
             self.rows.append([c.strip() for c in line.split(",")])
 
-    def stop(self):
+    def begin_window(self):
+        self.mark = len(self.rows)
+
+    def window(self):
+        """Summary of the samples since begin_window() (the whole run if the window caught none)."""
         if self.proc is None:
             return {"sm_mhz": None, "sm_max_mhz": None, "reasons": ["nvidia-smi unavailable"]}
-        time.sleep(0.15)
-        self.proc.terminate()
-        try:
-            self.proc.wait(timeout=2)
-        except Exception:
-            self.proc.kill()
+        time.sleep(0.06)
+        rows = self.rows[self.mark:] or self.rows[-3:]
         sm, smax, reasons = [], [], set()
         names = ["hw_slowdown", "hw_thermal_slowdown", "sw_thermal_slowdown", "sw_power_cap"]
-        for r in self.rows:
+        for r in rows:
             try:
                 sm.append(float(r[0])); smax.append(float(r[1]))
                 for n, v in zip(names, r[3:7]):
@@ -109,30 +119,72 @@ class ClockSampler:
                 "sm_max_mhz": float(max(smax)) if smax else None,
                 "samples": len(sm), "reasons": sorted(reasons)}
 
+    def stop(self):
+        if self.proc is None:
+            return
+        self.proc.terminate()
+        try:
+            self.proc.wait(timeout=2)
+        except Exception:
+            self.proc.kill()
+
 
 # ------------------------------------------------------------------------------------------
-def synthetic_inputs(members, distinct):
+class Spec:
+    """One benchmark workload."""
+
+    def __init__(self, name, members, precision="fp32", distinct=False, loop_mode="persistent", hidden=H_REF,
+                 L=L_REF, T=1000, baseline_config=None, note=None):
+        self.name, self.members, self.precision, self.distinct = name, members, precision, distinct
+        self.loop_mode, self.hidden, self.L, self.T = loop_mode, hidden, L, T
+        self.baseline_config, self.note = baseline_config, note
+
+    def config(self, world):
+        wl = (f"{self.baseline_config + ': ' if self.baseline_config else ''}{self.members} members/GPU, T={self.T} full DDPM "
+              f"chain, {self.precision}, hidden_dim {self.hidden}, grid 14x{self.L}, "
+              f"{'one condition per member' if self.distinct else 'one shared condition'}, {self.loop_mode} loop, "
+              "+ ensemble mean/std/var, 5 percentiles, KDE mode")
+        cfg = {"workload": wl, "members_per_gpu": self.members, "members_total": self.members * world, "T": self.T,
+               "param_dim": P, "hidden_dim": self.hidden, "grid": [C, self.L], "loop_mode": self.loop_mode,
+               "precision": self.precision, "rng": "device Philox4x32-10 + Box-Muller",
+               "l2": "flushed between steps (256 MiB memset outside the per-step event pairs)",
+               "cached_across_steps": "the (T,H) time-embedding table c_t depends only on the weights: computed by "
+                                      "k_time_table in the first (warm-up) call after load_state_dict and reused; the "
+                                      "(T,4) step-scalar table and the condition encoder run every step",
+               "parallelism": f"members sharded over {world} GPU(s), one all-gather of (B/G,29) f32"
+                              + ("; statistics columns split over the ranks (one packed all-gather of the results)"
+                                 if world > 1 else "")}
+        if self.note:
+            cfg["note"] = self.note
+        return cfg
+
+
+def synthetic_inputs(spec):
     """weights = the reference's default init under manual_seed(0) (the host
     mirror draws exactly what the reference's constructor draws), condition seed 1."""
     import ertdiff_b200 as eb
     torch.manual_seed(0)
-    sd = {k: v.detach().clone() for k, v in eb.ConditionalDiffusionModel(P, H).state_dict().items()}
+    sd = {k: v.detach().clone() for k, v in eb.ConditionalDiffusionModel(P, spec.hidden).state_dict().items()}
     g = torch.Generator().manual_seed(1)
-    n = members if distinct else 1
-    cond = torch.rand(n, C, L, generator=g)
+    n = spec.members if spec.distinct else 1
+    cond = torch.rand(n, C, spec.L, generator=g)
     return sd, cond
 
 
-def cpu_reference_sample(sd, cond1, members, T, steps_sample, threads):
-    """The reference algorithm as written (oracle port of ECD.py:102-119: the encoder runs
-    every step) for `steps_sample` of the T steps; returns seconds."""
+# ---- CPU arms (the oracle port; only these functions touch oracle/) -------------------------------------
+def cpu_reference_sample(sd, cond1, members, T, steps_sample, threads, hoisted=False):
+    """The reference algorithm as written (oracle port of ECD.py:102-119: the encoder runs every step) --
+    or, with `hoisted`, the same chain with the loop-invariant work hoisted (oracle.sample_chain_hoisted) --
+    for `steps_sample` of the T steps; returns (seconds, fields)."""
     from oracle import denoiser_oracle as do
     torch.set_num_threads(threads)
     betas, alphas, alpha_bar = do.diffusion_schedule(T)
+    L = cond1.size(2)
     cond = cond1.expand(members, C, L) if cond1.size(0) == 1 else cond1
     noise = torch.randn(steps_sample, members, P, generator=torch.Generator().manual_seed(2))
+    fn = do.sample_chain_hoisted if hoisted else do.sample_chain
     t0 = time.perf_counter()
-    x = do.sample_chain(sd, cond, T, betas, alphas, alpha_bar, P, noise, num_steps=steps_sample)
+    x = fn(sd, cond, T, betas, alphas, alpha_bar, P, noise, num_steps=steps_sample)
     return time.perf_counter() - t0, x
 
 
@@ -149,13 +201,37 @@ def cpu_reference_stats(x):
     return time.perf_counter() - t0
 
 
+def cpu_baselines(sd, cond_host, members, T, budget_s, max_sample_steps):
+    """`cpu_baseline` objects: the as-written reference (bounded sample of steps, scaled: its cost is linear in
+    the steps) and the hoisted chain (the whole T-step chain: it is ~500x cheaper), both + numpy/scipy statistics."""
+    threads = os.cpu_count() or 1
+    t_cal, _ = cpu_reference_sample(sd, cond_host, members, T, 2, threads)            # warm-up + calibration
+    sample_steps = int(max(5, min(max_sample_steps, budget_s / max(t_cal / 2, 1e-4), T)))
+    secs, xs = cpu_reference_sample(sd, cond_host, members, T, sample_steps, threads)
+    stats_s = cpu_reference_stats(xs)
+    per_chain = secs * (T / sample_steps) + stats_s
+    cpu_reference_sample(sd, cond_host, members, T, 20, threads, hoisted=True)        # warm-up
+    hsecs, hx = cpu_reference_sample(sd, cond_host, members, T, T, threads, hoisted=True)
+    hoisted_chain = hsecs + stats_s
+    base = {"value": members / per_chain, "unit": "samples/s", "cores": threads, "kind": "port",
+            "sample": f"{members} members x {sample_steps} of {T} steps of the as-written chain (ECD.py:102-119: the "
+                      f"condition encoder re-run every step) in {secs:.2f} s, scaled by {T}/{sample_steps}, + the "
+                      f"numpy/scipy statistics ({stats_s:.2f} s)",
+            "hoisted": {"value": members / hoisted_chain, "unit": "samples/s", "cores": threads, "kind": "port",
+                        "sample": f"{members} members x all {T} steps of the same chain with the loop-invariant work "
+                                  f"hoisted (encoder once, time embedding once per step; plain torch CPU) in {hsecs:.2f} s "
+                                  f"+ the same statistics: separates the algorithmic saving from the hardware speed-up"}}
+    return base
+
+
 def run_reference(args):
     rank = int(os.environ.get("RANK", "0"))
     if rank != 0:
         return
     threads = os.cpu_count() or 1
-    members, T = args.members, args.T
-    sd, cond = synthetic_inputs(members, args.distinct_conditions)
+    spec = main_spec(args)
+    members, T = spec.members, spec.T
+    sd, cond = synthetic_inputs(spec)
     # each timed step = a bounded sample of the T-step chain; sized from a calibration run so that the
     # whole --steps K run stays within ~2.5 minutes of CPU time (at most --ref-sample-steps per sample)
     t_cal, _ = cpu_reference_sample(sd, cond, members, T, 2, threads)
@@ -168,35 +244,279 @@ def run_reference(args):
     stats_s = cpu_reference_stats(runs[-1][1])
     per_chain = float(np.mean(secs)) * (T / sample_steps) + stats_s   # chain cost is linear in steps
     value = members / per_chain
+    cpu_reference_sample(sd, cond, members, T, 20, threads, hoisted=True)
+    hsecs, _ = cpu_reference_sample(sd, cond, members, T, T, threads, hoisted=True)
     line = {
-        "impl": "reference", "metric": "posterior_samples_per_sec_full_chain", "value": value,
+        "impl": "reference", "metric": METRIC, "value": value,
         "unit": "samples/s", "n_gpus": args.gpus, "steps": args.steps, "warmup": args.warmup,
-        "ms_per_step": per_chain * 1e3, "higher_is_better": True, "scaling": "weak",
+        # the time one timed step actually took (a bounded sample, see cpu_baseline.sample); the metric scales it
+        "ms_per_step": float(np.mean(secs)) * 1e3,
+        "ms_per_full_chain_extrapolated": per_chain * 1e3,
+        "higher_is_better": True, "scaling": "weak",
         "vs_baseline": None, "dtype": "f32", "data": "synthetic",
-        "config": workload_config(args, members),
+        "config": spec.config(args.gpus),
         "cpu_baseline": {"value": value, "unit": "samples/s", "cores": threads, "kind": "port",
-                         "sample": f"{members} members x {sample_steps} of {T} steps of the as-written "
-                                   f"chain (encoder re-run every step), scaled by {T}/{sample_steps}, + numpy/scipy statistics"},
+                         "sample": f"each timed step = {members} members x {sample_steps} of {T} steps of the as-written "
+                                   f"chain (encoder re-run every step); value = members / (mean step time x {T}/{sample_steps} "
+                                   f"+ numpy/scipy statistics {stats_s:.2f} s)",
+                         "hoisted": {"value": members / (hsecs + stats_s), "unit": "samples/s", "cores": threads, "kind": "port",
+                                     "sample": f"all {T} steps with the loop-invariant work hoisted, {hsecs:.2f} s + the same statistics"}},
         "e2e": {"value": value, "unit": "samples/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
     }
     print(json.dumps(line))
 
 
-def workload_config(args, members_per_gpu):
-    return {"workload": f"BASELINE configs[1]: {members_per_gpu} members/GPU, T={args.T} full DDPM chain, "
-                        f"{args.precision}, grid 14x{L}, {'distinct' if args.distinct_conditions else 'one shared'} "
-                        "condition, + ensemble mean/std/var, 5 percentiles, KDE mode",
-            "members_per_gpu": members_per_gpu, "T": args.T, "param_dim": P, "hidden_dim": H,
-            "loop_mode": args.loop_mode, "rng": "device Philox4x32-10",
-            "l2": "flushed between steps (256 MiB memset outside the per-step event pairs)",
-            "parallelism": f"members sharded over {args.gpus} GPU(s), one all-gather of (B/G,29) f32; statistics on the "
-                           f"gathered fields (columns split over the ranks above {SHARD_STATS_ABOVE} members)"}
-
-
 # ------------------------------------------------------------------------------------------
+class Runner:
+    """Measures one Spec on this process's GPU (and its peers): device-resident throughput, the dominant kernel's
+    duration, and the end-to-end number through the public API with host buffers."""
+
+    def __init__(self, world, rank, local, dev, sampler):
+        self.world, self.rank, self.local, self.dev, self.sampler = world, rank, local, dev, sampler
+        self.flush = torch.empty(256 << 20, dtype=torch.uint8, device=dev)
+        self.stream = torch.cuda.current_stream(dev)
+        self.peaks = load_peaks()
+
+    def barrier(self):
+        if self.world > 1:
+            import torch.distributed as dist
+            dist.barrier()
+        torch.cuda.synchronize(self.dev)
+
+    def timed(self, fn, steps):
+        import torch.distributed as dist
+        evs = [(torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)) for _ in range(steps)]
+        self.barrier()
+        wall0 = time.perf_counter()
+        for i, (e0, e1) in enumerate(evs):
+            self.flush.zero_()                  # L2 flush, outside the event pair
+            e0.record(self.stream)
+            fn(i)
+            e1.record(self.stream)
+        self.barrier()
+        wall = time.perf_counter() - wall0
+        ms = sum(e0.elapsed_time(e1) for e0, e1 in evs)
+        if self.world > 1:
+            t = torch.tensor([ms], device=self.dev, dtype=torch.float64)
+            dist.all_reduce(t, op=dist.ReduceOp.MAX)
+            ms = float(t.item())
+        return ms, wall
+
+    def measure(self, spec, steps, warmup, cpu_baseline_budget=0.0, ref_sample_steps=250, floor=True):
+        import ertdiff_b200 as eb
+        world, rank, dev = self.world, self.rank, self.dev
+        members, T, H, L = spec.members, spec.T, spec.hidden, spec.L
+        total = members * world
+        sd, cond_host = synthetic_inputs(spec)
+        model = eb.ConditionalDiffusionModel(P, H)
+        model.load_state_dict(sd)
+        model.to(dev).eval()
+        betas, alphas, alpha_bar = eb.get_diffusion_schedule(T)
+        sched_dev = [t.to(dev) for t in (betas, alphas, alpha_bar)]
+        cond_dev = cond_host.to(dev)
+        cond_dev_b = cond_dev if spec.distinct else cond_dev.expand(members, C, L)
+        cond_pinned = cond_host.pin_memory()
+        kw = dict(loop_mode=spec.loop_mode, precision=spec.precision)
+
+        def stats(x):
+            if world > 1:                       # per-column statistics: columns split over the ranks
+                return eb.parallel.sharded_statistics(x, PERCENTILES, KDE_GRID)
+            out = eb.ensemble_moments(x)
+            out["pct"] = eb.ensemble_percentile(x, PERCENTILES)
+            out["mode"] = eb.ensemble_kde_mode(x, KDE_GRID)
+            return out
+
+        def step_device(i):
+            """inputs resident in HBM"""
+            x = eb.run_chain(model, cond_dev_b, T, *sched_dev, dev, seed=1234, offset=4 * i,
+                             member_offset=rank * members, check_status=False, **kw)
+            if world > 1:
+                x = eb.parallel.gather_members(x, total)
+            return x, stats(x)
+
+        host_out = []
+
+        def step_e2e(i):
+            """public API with HOST buffers: H2D of the condition (+ schedule), D2H of fields + statistics"""
+            c = cond_pinned.to(dev, non_blocking=True)
+            c = c if spec.distinct else c.expand(members, C, L)
+            if world == 1:
+                x = eb.sample_model(model, c, T, betas, alphas, alpha_bar, P, dev, seed=1234 + i, check_status=False, **kw)
+            else:
+                x = eb.run_chain(model, c, T, betas, alphas, alpha_bar, dev, seed=1234, offset=4 * i,
+                                 member_offset=rank * members, check_status=False, **kw)
+                x = eb.parallel.gather_members(x, total)
+            st = stats(x)
+            # D2H read of the step's results: fields + every statistic, straight into pinned host buffers
+            # (no staging kernels), one stream synchronise at the end
+            srcs = (x, st["packed"]) if "packed" in st else (x, st["mean"], st["std"], st["var"], st["pct"], st["mode"])
+            if not host_out:
+                host_out.extend(torch.empty(v.shape, dtype=v.dtype).pin_memory() for v in srcs)
+            for dst, src in zip(host_out, srcs):
+                dst.copy_(src, non_blocking=True)
+            self.stream.synchronize()
+            return host_out
+
+        for i in range(warmup):
+            step_device(i)
+            step_e2e(i)
+        self.barrier()
+        if spec.precision == "bf16" and model.umma_status() != 0:
+            raise SystemExit("bench.py: a tensor-core chain tile timed out during warm-up")
+
+        if rank == 0 and self.sampler:
+            self.sampler.begin_window()
+        eb.launch_count(reset=True)
+        model.profile_chain(True)
+        ms_dev, _ = self.timed(step_device, steps)
+        launches = eb.launch_count()
+        chain_ms, floor_ms = [], []
+        if spec.loop_mode == "persistent":      # duration of the dominant kernel, CUDA events inside the library
+            for i in range(steps):
+                self.flush.zero_()
+                step_device(i)
+                chain_ms.append(model.last_chain_ms())
+            if floor and spec.precision == "fp32" and H in (128, 256):
+                # latency floor of the kernel's structure: the same kernel with the matrix-vector arithmetic removed
+                model.chain_floor(True)
+                for i in range(max(3, steps // 2) + 1):
+                    self.flush.zero_()
+                    eb.run_chain(model, cond_dev_b, T, *sched_dev, dev, seed=1234, offset=4 * i,
+                                 member_offset=rank * members, **kw)
+                    floor_ms.append(model.last_chain_ms())
+                model.chain_floor(False)
+                floor_ms = floor_ms[1:]
+        model.profile_chain(False)
+        ms_e2e, wall_e2e = self.timed(step_e2e, steps)
+        if spec.precision == "bf16" and model.umma_status() != 0:
+            raise SystemExit("bench.py: a tensor-core chain tile timed out")
+        clocks = self.sampler.window() if (rank == 0 and self.sampler) else None
+
+        value = total * steps / (ms_dev * 1e-3)
+        e2e_value = total * steps / (ms_e2e * 1e-3)
+        h2d = cond_host.numel() * 4      # the condition; the 3 x 4 KB schedule is content-cached on the device after step 1
+        d2h = 4 * total * P + 8 * (5 + len(PERCENTILES)) * P if world > 1 else \
+            4 * (total * P + 3 * P) + 8 * (len(PERCENTILES) * P + P)
+        rec = {
+            "name": spec.name, "metric": METRIC, "value": value, "unit": "samples/s",
+            "n_gpus": world, "steps": steps, "warmup": warmup,
+            "ms_per_step": ms_dev / steps, "dtype": "f32" if spec.precision == "fp32" else "bf16",
+            "config": spec.config(world),
+            "ms_per_denoiser_step": (float(np.mean(chain_ms)) / T) if chain_ms else ms_dev / steps / T,
+            "e2e": {"value": e2e_value, "unit": "samples/s", "h2d_bytes_per_step": int(h2d),
+                    "d2h_bytes_per_step": int(d2h), "ms_per_step": ms_e2e / steps,
+                    "wall_ms_per_step": wall_e2e * 1e3 / steps},
+            "gpu_launches": int(launches),
+            "clocks": clocks,
+        }
+        if spec.loop_mode == "graph":
+            inst, upd = model.graph_stats()
+            rec["graph"] = {"instantiations": inst, "in_place_updates": upd,
+                            "note": "the RNG offset changes every step: the captured step sequence is updated in place "
+                                    "(cudaGraphExecUpdate) inside the timed region, not re-instantiated"}
+        if chain_ms and rank == 0:
+            rec["roofline"] = self.roofline(spec, members, float(np.mean(chain_ms)), ms_dev / steps, clocks,
+                                            float(np.mean(floor_ms)) if floor_ms else None)
+        if cpu_baseline_budget > 0 and world == 1 and rank == 0:
+            rec["cpu_baseline"] = cpu_baselines(sd, cond_host, members, T, cpu_baseline_budget, ref_sample_steps)
+        del model
+        return rec
+
+    def roofline(self, spec, members, k_ms, step_ms, clocks, floor_ms):
+        T, H = spec.T, spec.hidden
+        flops = members * T * flop_step_member(H)
+        achieved = flops / (k_ms * 1e-3) / 1e12
+        peak = self.peaks["bf16_tflops_sustained"]
+        fp32 = spec.precision == "fp32"
+        sm_mhz = (clocks or {}).get("sm_mhz") or 1965.0
+        fp32_peak = 148 * 128 * 2 * sm_mhz * 1e6 / 1e12
+        r = {
+            "kernel": "k_chain (persistent reverse loop, fp32 FFMA2)" if fp32
+                      else "k_chain_umma (persistent reverse loop, tcgen05 bf16, TMEM accumulators)",
+            # T dependent steps per member with ~15 KFLOP each and no HBM traffic beyond the tables: neither the
+            # tensor pipe nor HBM bounds this kernel, the per-step latency of its hand-off chain does.  `achieved`,
+            # `peak` and `frac` are still the FLOP rate against the measured bf16 tensor peak, as the contract asks.
+            "bound": "latency",
+            "achieved": achieved, "peak": peak, "unit": "TFLOP/s", "frac": achieved / peak,
+            "traffic": ncu_traffic("chain_fp32" if fp32 else "chain_umma") if (H == H_REF) else None,
+            "peak_source": self.peaks["source"] + ", sustained bf16",
+            "kernel_ms": k_ms, "us_per_denoiser_step": k_ms / T * 1e3, "flop_per_launch": flops,
+            "share_of_step": k_ms / step_ms,
+            "fp32_ffma_peak_tflops": fp32_peak,
+            "fp32_ffma_frac": (achieved / fp32_peak) if fp32 else None,
+            "as_written_equivalent_tflops": (members * T * FLOP_AS_WRITTEN / (k_ms * 1e-3) / 1e12)
+                                            if (H == H_REF and spec.L == L_REF) else None,
+            "traffic_note": "dram__bytes_read+write of one launch from the committed ncu capture "
+                            "(profiles/r0*_ncu_kernels.json; its workload is stated there), null if absent",
+        }
+        if floor_ms is not None:
+            r["latency_floor_ms"] = floor_ms
+            r["frac_of_floor"] = floor_ms / k_ms
+            r["floor_note"] = ("measured in this run: the same kernel launch with the two matrix-vector products removed "
+                               "(every barrier, shared-memory hand-off, shuffle, staging copy, RNG refill and the posterior "
+                               "update kept); frac_of_floor = floor / kernel time, i.e. the share of the kernel's duration "
+                               "that its dependency structure alone costs")
+        else:
+            r["latency_floor_ms"] = None
+            r["floor_note"] = ("tensor-core kernel: per step and 128-member tile the tensor pipe needs ~0.13 us, the "
+                               "Philox/Box-Muller generator the XU and integer-multiply pipes; the bound is the dependent "
+                               "hand-off chain of a step (operands -> MMA -> epilogue -> MMA -> update) and issue slots")
+        return r
+
+
+def main_spec(args):
+    name = "config2" if (args.members == 256 and args.precision == "fp32" and not args.distinct_conditions) else "custom"
+    return Spec(name, args.members, args.precision, args.distinct_conditions, args.loop_mode, args.hidden, args.L, args.T,
+                baseline_config="BASELINE configs[1]" if name == "config2" else None)
+
+
+def extra_specs(world):
+    """The other BASELINE configurations, measured like the top-level one (fewer steps)."""
+    specs = [
+        Spec("config3_bf16_1024_persistent", 1024, "bf16", baseline_config="BASELINE configs[2]"),
+        Spec("config3_bf16_1024_graph", 1024, "bf16", loop_mode="graph", baseline_config="BASELINE configs[2] (CUDA-graph reverse loop)"),
+        Spec("bf16_8192", 8192, "bf16", note="BASELINE configs[3]'s whole ensemble on every GPU" if world == 1 else None),
+        Spec("bf16_18944", 18944, "bf16", note="one full 128-member tile per SM (148 x 128)"),
+        Spec("fp32_256_distinct_conditions", 256, "fp32", distinct=True, note="the encoder runs for 256 conditions every step"),
+        Spec("config5_h256_L9386_bf16", 4096 // world if world > 1 else 4096, "bf16", hidden=256, L=2 * L_REF,
+             baseline_config="BASELINE configs[4]",
+             note="the reference-expressible widening (hidden_dim 256, ECD.py:123; L = 9386, ECD.py:134-138); the U-Net / "
+                  "attention of the config's wording has no reference counterpart (Tier U)"),
+        Spec("config5_h256_L9386_fp32", 4096 // world if world > 1 else 4096, "fp32", hidden=256, L=2 * L_REF,
+             baseline_config="BASELINE configs[4]", note="same, fp32 CUDA-core chain"),
+    ]
+    if world > 1:
+        specs.insert(2, Spec("config4_bf16_1024_per_gpu", 1024, "bf16", baseline_config="BASELINE configs[3]",
+                             note=f"{1024 * world} members over {world} GPUs"))
+    return specs
+
+
+def bf16_vs_fp32(dev, members=1024, T=1000):
+    """Both chain kernels draw identical Philox streams: their difference at T = 1000 on the same seeds is the
+    precision cost of the tensor-core path (per member, relative to that member's largest component)."""
+    import ertdiff_b200 as eb
+    spec = Spec("dev", members)
+    sd, cond = synthetic_inputs(spec)
+    model = eb.ConditionalDiffusionModel(P, H_REF)
+    model.load_state_dict(sd)
+    model.to(dev).eval()
+    sched = [t.to(dev) for t in eb.get_diffusion_schedule(T)]
+    c = cond.to(dev).expand(members, C, L_REF)
+    x32 = eb.run_chain(model, c, T, *sched, dev, seed=99, offset=0)
+    x16 = eb.run_chain(model, c, T, *sched, dev, seed=99, offset=0, precision="bf16")
+    d = (x16 - x32).abs()
+    scale = x32.abs().max().item()
+    rel = d.max(dim=1).values / x32.abs().max(dim=1).values
+    m32, m16 = eb.ensemble_moments(x32), eb.ensemble_moments(x16)
+    return {"members": members, "T": T, "bf16_vs_fp32_max_abs": d.max().item(), "fp32_abs_max": scale,
+            "bf16_vs_fp32_rel_of_scale": d.max().item() / scale,
+            "per_member_rel_median": rel.median().item(), "per_member_rel_max": rel.max().item(),
+            "ensemble_mean_max_abs_diff": (m16["mean"] - m32["mean"]).abs().max().item(),
+            "ensemble_std_max_abs_diff": (m16["std"] - m32["std"]).abs().max().item()}
+
+
 def run_ours(args):
     import torch.distributed as dist
-    import ertdiff_b200 as eb
 
     world = int(os.environ.get("WORLD_SIZE", "1"))
     rank = int(os.environ.get("RANK", "0"))
@@ -208,169 +528,36 @@ def run_ours(args):
     if world > 1:
         os.environ.setdefault("MASTER_ADDR", "127.0.0.1")
         dist.init_process_group("nccl", device_id=dev)
-    members, T = args.members, args.T                 # per GPU (weak scaling)
-    total = members * world
-    if total > MAX_STAT_MEMBERS:
-        raise SystemExit(f"bench.py: {total} gathered members exceed the {MAX_STAT_MEMBERS} a single statistics "
-                         "call supports (a column is held in shared memory); lower --members")
-    sd, cond_host = synthetic_inputs(members, args.distinct_conditions)
-    model = eb.ConditionalDiffusionModel(P, H)
-    model.load_state_dict(sd)
-    model.to(dev).eval()
-    betas, alphas, alpha_bar = eb.get_diffusion_schedule(T)
-    sched_dev = [t.to(dev) for t in (betas, alphas, alpha_bar)]
-    cond_dev = cond_host.to(dev)
-    cond_dev_b = cond_dev if args.distinct_conditions else cond_dev.expand(members, C, L)
-    cond_pinned = cond_host.pin_memory()
-    flush = torch.empty(256 << 20, dtype=torch.uint8, device=dev)
-    stream = torch.cuda.current_stream(dev)
-
-    def stats(x):
-        if world > 1 and total > SHARD_STATS_ABOVE:     # per-column statistics: columns split over the ranks
-            return eb.parallel.sharded_statistics(x, PERCENTILES, KDE_GRID)
-        out = eb.ensemble_moments(x)
-        out["pct"] = eb.ensemble_percentile(x, PERCENTILES)
-        out["mode"] = eb.ensemble_kde_mode(x, KDE_GRID)
-        return out
-
-    def step_device(i):
-        """inputs resident in HBM"""
-        x = eb.run_chain(model, cond_dev_b, T, *sched_dev, dev, seed=1234, offset=4 * i,
-                         member_offset=rank * members, loop_mode=args.loop_mode, precision=args.precision)
-        if world > 1:
-            x = eb.parallel.gather_members(x, total)
-        return x, stats(x)
-
-    host_out = []
-
-    def step_e2e(i):
-        """public API with HOST buffers: H2D of the condition + schedule, D2H of fields + statistics"""
-        c = cond_pinned.to(dev, non_blocking=True)
-        c = c if args.distinct_conditions else c.expand(members, C, L)
-        x = eb.sample_model(model, c, T, betas, alphas, alpha_bar, P, dev, seed=1234 + i,
-                            loop_mode=args.loop_mode, precision=args.precision) if world == 1 else \
-            eb.run_chain(model, c, T, betas, alphas, alpha_bar, dev, seed=1234, offset=4 * i,
-                         member_offset=rank * members, loop_mode=args.loop_mode, precision=args.precision)
-        if world > 1:
-            x = eb.parallel.gather_members(x, total)
-        st = stats(x)
-        # D2H read of the step's results: fields + every statistic, straight into pinned host buffers
-        # (no staging kernels), one stream synchronise at the end
-        srcs = (x, st["mean"], st["std"], st["var"], st["pct"], st["mode"])
-        if not host_out:
-            host_out.extend(torch.empty(v.shape, dtype=v.dtype).pin_memory() for v in srcs)
-        for dst, src in zip(host_out, srcs):
-            dst.copy_(src, non_blocking=True)
-        stream.synchronize()
-        return host_out
-
-    def barrier():
-        if world > 1:
-            dist.barrier()
-        torch.cuda.synchronize(dev)
-
-    def timed(fn, steps):
-        evs = [(torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)) for _ in range(steps)]
-        barrier()
-        wall0 = time.perf_counter()
-        for i, (e0, e1) in enumerate(evs):
-            flush.zero_()                       # L2 flush, outside the event pair
-            e0.record(stream)
-            fn(i)
-            e1.record(stream)
-        barrier()
-        wall = time.perf_counter() - wall0
-        ms = sum(e0.elapsed_time(e1) for e0, e1 in evs)
-        if world > 1:
-            t = torch.tensor([ms], device=dev, dtype=torch.float64)
-            dist.all_reduce(t, op=dist.ReduceOp.MAX)
-            ms = float(t.item())
-        return ms, wall
-
-    for i in range(args.warmup):
-        step_device(i)
-        step_e2e(i)
-    barrier()
-
-    sampler = ClockSampler(local)
-    if rank == 0:
+    sampler = ClockSampler(local) if rank == 0 else None
+    if sampler:
         sampler.start()
-    eb.launch_count(reset=True)
-    model.profile_chain(True)
-    ms_dev, _ = timed(step_device, args.steps)
-    launches = eb.launch_count()
-    chain_ms = []
-    if args.loop_mode == "persistent":      # duration of the dominant kernel, CUDA events inside the library
-        for i in range(args.steps):
-            flush.zero_()
-            step_device(i)
-            chain_ms.append(model.last_chain_ms())
-    model.profile_chain(False)
-    ms_e2e, wall_e2e = timed(step_e2e, args.steps)
-    clocks = sampler.stop() if rank == 0 else None
-
-    # latency floor: the same persistent kernel structure cannot go below T dependent steps;
-    # report an empty-dependency yardstick: ms per step of the chain kernel itself
-    value = total * args.steps / (ms_dev * 1e-3)
-    e2e_value = total * args.steps / (ms_e2e * 1e-3)
-    n_cond = members if args.distinct_conditions else 1
-    h2d = cond_host.numel() * 4          # the condition; the 3 x 4 KB schedule is content-cached on the device after step 1
-    d2h = 4 * (total * P + 3 * P) + 8 * (len(PERCENTILES) * P + P)      # fields + moments fp32, percentiles + mode fp64
-
+    runner = Runner(world, rank, local, dev, sampler)
+    spec = main_spec(args)
+    main = runner.measure(spec, args.steps, args.warmup,
+                          cpu_baseline_budget=0.0 if args.no_cpu_baseline else 12.0, ref_sample_steps=args.ref_sample_steps)
+    subs, deviation = [], None
+    if not args.no_extra_configs:
+        for s in extra_specs(world):
+            subs.append(runner.measure(s, min(args.steps, 10), 3))
+        if rank == 0:
+            deviation = bf16_vs_fp32(dev)
+    if sampler:
+        sampler.stop()
     if rank == 0:
-        peaks = load_peaks()
         line = {
-            "metric": "posterior_samples_per_sec_full_chain", "value": value, "unit": "samples/s",
-            "n_gpus": world, "steps": args.steps, "warmup": args.warmup,
-            "ms_per_step": ms_dev / args.steps, "higher_is_better": True, "scaling": "weak",
-            "vs_baseline": None, "dtype": "f32" if args.precision == "fp32" else "bf16", "data": "synthetic",
-            "config": workload_config(args, members),
-            "ms_per_denoiser_step": (float(np.mean(chain_ms)) / T) if chain_ms else ms_dev / args.steps / T,
-            "e2e": {"value": e2e_value, "unit": "samples/s", "h2d_bytes_per_step": int(h2d),
-                    "d2h_bytes_per_step": int(d2h), "ms_per_step": ms_e2e / args.steps,
-                    "wall_ms_per_step": wall_e2e * 1e3 / args.steps},
-            "gpu_launches": int(launches),
-            "clocks": clocks,
+            "metric": METRIC, "value": main["value"], "unit": "samples/s", "n_gpus": world, "steps": args.steps,
+            "warmup": args.warmup, "ms_per_step": main["ms_per_step"], "higher_is_better": True, "scaling": "weak",
+            "vs_baseline": None, "dtype": main["dtype"], "data": "synthetic", "config": main["config"],
+            "ms_per_denoiser_step": main["ms_per_denoiser_step"], "e2e": main["e2e"],
+            "gpu_launches": main["gpu_launches"], "clocks": main["clocks"],
         }
-        if chain_ms:
-            k_ms = float(np.mean(chain_ms))
-            flops = members * T * FLOP_STEP_MEMBER
-            achieved = flops / (k_ms * 1e-3) / 1e12
-            peak = peaks["bf16_tflops_sustained"]
-            fp32_peak = 148 * 128 * 2 * (clocks["sm_mhz"] or 1965.0) * 1e6 / 1e12 if clocks else None
-            fp32 = args.precision == "fp32"
-            line["roofline"] = {
-                "kernel": "k_chain (persistent reverse loop, fp32 FFMA2)" if fp32
-                          else "k_chain_umma (persistent reverse loop, tcgen05 bf16, TMEM accumulators)",
-                "bound": "tensor",
-                "achieved": achieved, "peak": peak, "unit": "TFLOP/s", "frac": achieved / peak,
-                "traffic": ncu_traffic("chain_fp32" if fp32 else "chain_umma"),
-                "peak_source": peaks["source"] + ", sustained bf16",
-                "kernel_ms": k_ms, "flop_per_launch": flops,
-                "share_of_step": k_ms / (ms_dev / args.steps),
-                "note": ("structurally latency-bound: T dependent steps per member, 14,848 FLOP each, no HBM traffic "
-                         "beyond the tables (device RNG); fp32 CUDA-core kernel, so also quoted against the fp32 FFMA peak"
-                         if fp32 else
-                         "T dependent steps per member; per step and 128-member tile the tensor pipe needs ~0.13 us, the "
-                         "Philox/Box-Muller generator ~0.5 us of MUFU + integer-multiply pipe time (measured, "
-                         "scripts/microbench/rng_bench.cu): the kernel is bound by issue slots / those pipes, not by the MMAs"),
-                "fp32_ffma_peak_tflops": fp32_peak,
-                "fp32_ffma_frac": (achieved / fp32_peak) if (fp32_peak and fp32) else None,
-                "as_written_equivalent_tflops": members * T * FLOP_AS_WRITTEN / (k_ms * 1e-3) / 1e12,
-                "traffic_note": "dram__bytes_read+write of one launch from the committed ncu capture "
-                                "(profiles/r01_ncu_kernels.json; its workload is stated there), null if absent",
-            }
-        # CPU baseline on a bounded sample (rank 0, N=1 only)
-        if world == 1 and not args.no_cpu_baseline:
-            threads = os.cpu_count() or 1
-            t_cal, _ = cpu_reference_sample(sd, cond_host, members, T, 2, threads)            # warm-up + calibration
-            sample_steps = int(max(5, min(args.ref_sample_steps, 12.0 / max(t_cal / 2, 1e-4), T)))   # ~10 s of CPU work
-            secs, xs = cpu_reference_sample(sd, cond_host, members, T, sample_steps, threads)
-            per_chain = secs * (T / sample_steps) + cpu_reference_stats(xs)
-            line["cpu_baseline"] = {
-                "value": members / per_chain, "unit": "samples/s", "cores": threads, "kind": "port",
-                "sample": f"{members} members x {sample_steps} of {T} steps of the as-written chain "
-                          f"(encoder re-run every step) in {secs:.2f} s, scaled by {T}/{sample_steps}"}
+        for k in ("roofline", "cpu_baseline", "graph"):
+            if k in main:
+                line[k] = main[k]
+        if subs:
+            line["configs"] = subs
+        if deviation:
+            line["bf16_vs_fp32"] = deviation
         print(json.dumps(line))
     if world > 1:
         dist.barrier()
@@ -385,6 +572,8 @@ def main():
     ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
     ap.add_argument("--members", type=int, default=256, help="ensemble members per GPU")
     ap.add_argument("--T", type=int, default=1000)
+    ap.add_argument("--hidden", type=int, default=H_REF)
+    ap.add_argument("--L", type=int, default=L_REF)
     ap.add_argument("--loop-mode", default="persistent", choices=["persistent", "graph", "stream"])
     ap.add_argument("--distinct-conditions", action="store_true")
     ap.add_argument("--precision", default="fp32", choices=["fp32", "bf16"],
@@ -392,6 +581,7 @@ def main():
     ap.add_argument("--ref-sample-steps", type=int, default=250,
                     help="steps of the T-step chain the CPU arm actually runs per sample")
     ap.add_argument("--no-cpu-baseline", action="store_true")
+    ap.add_argument("--no-extra-configs", action="store_true", help="only the top-level workload, no `configs` sub-records")
     args = ap.parse_args()
     if args.warmup < 3 and args.impl == "ours":
         args.warmup = 3                      # timing rule: at least 3 warm-up steps

@@ -461,6 +461,23 @@ int ertdiff_untransform_bounds(const float* d_u, int64_t B, int32_t P, float a, 
     return 0;
 }
 
+int ertdiff_pack_rows_f64(const void* const* h_rows, const int32_t* h_dtypes, int32_t n_rows, int64_t ncols,
+                          int64_t ld, double* d_out, void* stream) {
+    ERT_REQUIRE(h_rows && h_dtypes && d_out && n_rows > 0 && n_rows <= kMaxPackRows && ncols >= 0 && ld >= n_rows,
+                "pack_rows_f64: bad arguments (at most 64 rows, ld >= n_rows)");
+    if (ncols == 0) return 0;
+    PackRows p{};
+    p.n = n_rows;
+    for (int r = 0; r < n_rows; ++r) {
+        ERT_REQUIRE(h_rows[r] && h_dtypes[r] >= 0 && h_dtypes[r] <= 2, "pack_rows_f64: NULL row or bad dtype");
+        p.src[r] = h_rows[r]; p.dtype[r] = h_dtypes[r];
+    }
+    const int64_t n = ncols * n_rows;
+    k_pack_rows<<<(unsigned)((n + 255) / 256), 256, 0, (cudaStream_t)stream>>>(p, ncols, ld, d_out);
+    ERT_LAUNCH_CHECK("k_pack_rows");
+    return 0;
+}
+
 int ertdiff_check_bounds(const void* d_v, int dtype, int64_t B, int32_t P, const double* d_lim_lo,
                          const double* d_lim_hi, uint8_t* d_valid, int32_t* d_first_bad, void* stream) {
     ERT_REQUIRE(d_v && d_lim_lo && d_lim_hi && B > 0 && P > 0 && P <= 32, "check_bounds: bad arguments");

@@ -1150,6 +1150,27 @@ __global__ void k_untransform_bounds(const float* __restrict__ u, int64_t B, int
     }
 }
 
+// Row vectors of mixed dtype (float32 / float64 / int64) -> one float64 block, out[c * ld + r] = row r, column c
+// (column-major: one contiguous record per column).  The column-sharded statistics pack everything a rank
+// computed for its columns with this single launch before the (one) result all-gather.
+constexpr int kMaxPackRows = 64;
+struct PackRows {
+    const void* src[kMaxPackRows];
+    int32_t dtype[kMaxPackRows];      // ERTDIFF_F32, ERTDIFF_F64, 2 = int64
+    int32_t n;
+};
+__global__ void k_pack_rows(const __grid_constant__ PackRows p, int64_t ncols, int64_t ld, double* __restrict__ out) {
+    const int64_t idx = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+    if (idx >= ncols * p.n) return;
+    const int r = (int)(idx / ncols);
+    const int64_t c = idx % ncols;
+    double v;
+    if (p.dtype[r] == ERTDIFF_F32) v = (double)static_cast<const float*>(p.src[r])[c];
+    else if (p.dtype[r] == ERTDIFF_F64) v = static_cast<const double*>(p.src[r])[c];
+    else v = (double)static_cast<const long long*>(p.src[r])[c];
+    out[c * ld + r] = v;
+}
+
 // check_param_bounds alone (ECD.py:183-218) on values of either dtype: a row is dropped when any parameter is
 // `< min or > max` (so a NaN never drops a row, as in the reference); first_bad = the parameter the reference's
 // loop reports before it breaks.  One warp per row.

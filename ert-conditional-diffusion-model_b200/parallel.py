@@ -70,6 +70,9 @@ def column_slice(n_columns: int, rank: int, world_size: int):
     return member_slice(n_columns, rank, world_size, 1)
 
 
+_UNPAD_INDEX = {}      # (Q, world, device) -> row indices that drop the padding of the gathered (world*q_max) records
+
+
 def sharded_statistics(x: torch.Tensor, percentiles=(25, 50, 75), n_grid: int = 5000, group=None,
                        stats_fn=None):
     """Ensemble statistics of the gathered fields ``x (N, Q)`` with the COLUMNS split over the ranks:
@@ -78,7 +81,11 @@ def sharded_statistics(x: torch.Tensor, percentiles=(25, 50, 75), n_grid: int = 
     every rank.  The KDE grid spans the global min/max of the whole array (ECD.py:749-751), which each
     rank takes from its own copy of ``x`` -- so the result is bit-identical to the unsharded call for
     any number of ranks.  Returns ``{"mean","std","var","pct" (len(percentiles), Q),"mode","mode_index"}``
-    (float64 except as noted by the unsharded functions; packed and gathered as float64).
+    as float64 views of one gathered block ``"packed" (Q, 5 + len(percentiles))`` (``mode_index`` int64).
+
+    Per rank: the statistics kernels on its columns, ONE packing launch (``ertdiff_pack_rows_f64``: every
+    result row -> one float64 record per column), ONE equal-sized all-gather of ``(q_max, rows)`` records, and
+    (only when ``Q`` does not divide evenly) one gather that drops the padding records.
     ``stats_fn(x_cols, lohi) -> (rows, q_local)`` float64 replaces the device kernels in CPU tests."""
     from . import stats as st
     world = dist.get_world_size(group) if dist.is_initialized() else 1
@@ -86,25 +93,45 @@ def sharded_statistics(x: torch.Tensor, percentiles=(25, 50, 75), n_grid: int = 
     N, Q = x.shape
     a, b = column_slice(Q, rank, world)
     nq = len(percentiles)
-    if stats_fn is None:
-        def stats_fn(cols, lohi):
-            m = st.ensemble_moments(cols)
-            pct = st.ensemble_percentile(cols, list(percentiles)).double()
-            mode, idx = st.ensemble_kde_mode(cols, n_grid, grid_range=lohi, return_index=True)
-            return torch.cat([m["mean"].double()[None], m["std"].double()[None], m["var"].double()[None],
-                              pct, mode[None], idx.double()[None]], dim=0)
-        lohi = st.global_minmax(x)
-    else:
-        lohi = None
     rows = 5 + nq
-    local = stats_fn(x[:, a:b].contiguous(), lohi) if b > a else torch.zeros(rows, 0, device=x.device, dtype=torch.float64)
+    q_max = -(-Q // world)
+    block = torch.zeros(q_max, rows, device=x.device, dtype=torch.float64) if (b - a) < q_max else \
+        torch.empty(q_max, rows, device=x.device, dtype=torch.float64)
+    if b > a:
+        cols = x[:, a:b].contiguous()
+        if stats_fn is None:
+            lohi = st.global_minmax(x)
+            m = st.ensemble_moments(cols)
+            pct = st.ensemble_percentile(cols, list(percentiles))
+            mode, idx = st.ensemble_kde_mode(cols, n_grid, grid_range=lohi, return_index=True)
+            st.pack_rows_f64([m["mean"], m["std"], m["var"]] + [pct[k] for k in range(nq)] + [mode, idx], block)
+        else:
+            block[:b - a].copy_(stats_fn(cols, None).t())
     if world > 1:
-        # columns on axis 0 so that gather_members' (uneven) row gather applies
-        full = gather_members(local.t().contiguous(), Q, 1, group).t().contiguous()
+        gathered = torch.empty(world * q_max, rows, device=x.device, dtype=torch.float64)
+        if x.is_cuda:
+            dist.all_gather_into_tensor(gathered, block, group=group)      # one NCCL all-gather
+        else:
+            parts = [torch.empty_like(block) for _ in range(world)]
+            dist.all_gather(parts, block, group=group)
+            gathered = torch.cat(parts, dim=0)
+        if Q % world:
+            key = (Q, world, str(x.device))
+            index = _UNPAD_INDEX.get(key)
+            if index is None:
+                keep = []
+                for r in range(world):
+                    ra, rb = column_slice(Q, r, world)
+                    keep.extend(range(r * q_max, r * q_max + (rb - ra)))
+                index = torch.tensor(keep, device=x.device, dtype=torch.int64)
+                _UNPAD_INDEX[key] = index
+            gathered = gathered.index_select(0, index)
+        full = gathered
     else:
-        full = local
-    return {"mean": full[0], "std": full[1], "var": full[2], "pct": full[3:3 + nq], "mode": full[3 + nq],
-            "mode_index": full[4 + nq].to(torch.int64)}
+        full = block[:Q]
+    return {"mean": full[:, 0], "std": full[:, 1], "var": full[:, 2], "pct": full[:, 3:3 + nq].t(),
+            "mode": full[:, 3 + nq], "mode_index": full[:, 4 + nq].to(torch.int64),
+            "packed": full}        # (Q, 5 + nq) float64: everything above in one contiguous block (one D2H copy)
 
 
 def sharded_misfit(sim_local: torch.Tensor, observed: torch.Tensor, n_maps: int, A: float = 0.1, B: float = 0.01,

@@ -218,6 +218,25 @@ def uq_calibration(generated, true, n_prob=30, device=None):
     return out
 
 
+def pack_rows_f64(rows, out):
+    """``out[c, r] = float64(rows[r][c])``: pack 1-D CUDA row vectors (float32 / float64 / int64, equal length)
+    into the first ``len(rows[0])`` records of the float64 block ``out (>= ncols, len(rows))`` with ONE launch
+    (``ertdiff_pack_rows_f64``) instead of a cat and a conversion per row."""
+    codes = {torch.float32: _lib.F32, torch.float64: _lib.F64, torch.int64: 2}
+    rows = [r.contiguous() for r in rows]
+    n, ncols = len(rows), rows[0].numel()
+    if out.dtype != torch.float64 or out.dim() != 2 or out.size(1) != n or out.size(0) < ncols or not out.is_contiguous():
+        raise ValueError("out must be a contiguous float64 (>= ncols, n_rows) block")
+    if any(r.numel() != ncols or r.dtype not in codes for r in rows):
+        raise ValueError("rows must be float32/float64/int64 vectors of equal length")
+    ptrs = (C.c_void_p * n)(*[r.data_ptr() for r in rows])
+    dts = (C.c_int32 * n)(*[codes[r.dtype] for r in rows])
+    with torch.cuda.device(out.device):
+        _lib.check(_lib.load().ertdiff_pack_rows_f64(ptrs, dts, n, ncols, n, _lib.ptr(out), _lib.stream_ptr(out.device)),
+                   "pack_rows_f64")
+    return out
+
+
 def argsort_stable(v):
     """``np.argsort(v, kind="stable")`` of a 1-D CUDA tensor on the device (ECD.py:786 ranks the members by
     their total WSSE); NaN sorts last, as in numpy."""

@@ -250,6 +250,12 @@ int ertdiff_untransform_bounds(const float* d_u, int64_t B, int32_t P, float a, 
                                const double* d_lim_lo, const double* d_lim_hi, float* d_phys,
                                uint8_t* d_valid, int32_t* d_first_bad, void* stream);
 
+/* Pack n_rows (<= 64) device row vectors of ncols values each -- dtype per row: ERTDIFF_F32, ERTDIFF_F64 or 2 =
+ * int64 -- into one float64 block d_out[c * ld + r] (one contiguous record of ld >= n_rows doubles per column).
+ * h_rows / h_dtypes are HOST arrays.  Used by the column-sharded statistics: one launch, then one all-gather. */
+int ertdiff_pack_rows_f64(const void* const* h_rows, const int32_t* h_dtypes, int32_t n_rows, int64_t ncols,
+                          int64_t ld, double* d_out, void* stream);
+
 /* check_param_bounds alone (ECD.py:183-218) for values (B, P) of dtype ERTDIFF_F32 / F64, P <= 32: d_valid[row] = 1
  * unless some parameter is `< lim_lo or > lim_hi` (compared in float64, as numpy promotes; NaN never drops a row, as
  * in the reference); d_first_bad[row] = the first offending parameter (the one the reference prints) or -1.

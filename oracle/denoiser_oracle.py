@@ -143,6 +143,41 @@ def sample_chain(sd, condition, T, betas, alphas, alpha_bar, param_dim, noise,
     return (x, trace) if trace_eps_at else x
 
 
+@torch.no_grad()
+def sample_chain_hoisted(sd, condition, T, betas, alphas, alpha_bar, param_dim, noise,
+                         num_steps=None, temperature=1.0):
+    """The same chain with the loop-invariant work hoisted out of the step loop -- the algebra the CUDA
+    path uses, in plain torch on the CPU: the condition encoder runs once per DISTINCT condition
+    (a stride-0 ``expand`` is encoded once), the time embedding once per step for all members, and a step is
+    ``eps = W2 @ relu(W0x @ x + c_t + c_b) + b2``.  Not bit-identical to ``sample_chain`` (different summation
+    split; ``tests/test_oracle_pinning.py`` bounds the difference): it exists as the CPU baseline that separates
+    the algorithmic saving from the hardware speed-up in ``bench.py``."""
+    if num_steps is None:
+        num_steps = T
+    P = param_dim
+    H = sd["time_embed.0.weight"].shape[1]
+    W0 = sd["mlp.0.weight"]
+    W0x, W0t, W0c = W0[:, :P].contiguous(), W0[:, P:P + H].contiguous(), W0[:, P + H:].contiguous()
+    shared = condition.size(0) > 1 and condition.stride(0) == 0
+    cemb = encode_condition(sd, condition[:1] if shared else condition)
+    cb = F.linear(cemb, W0c, sd["mlp.0.bias"])                     # (n_cond, H); broadcasts when shared
+    ts = torch.arange(num_steps)
+    temb = F.relu(F.linear(timestep_embedding(ts, H), sd["time_embed.0.weight"], sd["time_embed.0.bias"]))
+    ct = F.linear(temb, W0t)                                       # (num_steps, H)
+    x = noise[0].clone()
+    draw = 1
+    for t_ in reversed(range(num_steps)):
+        h = F.relu(F.linear(x, W0x) + ct[t_] + cb)
+        eps = F.linear(h, sd["mlp.2.weight"], sd["mlp.2.bias"])
+        coef, c1, sigma = step_coefficients(betas, alphas, alpha_bar, t_, temperature)
+        z = None
+        if t_ > 0:
+            z = noise[draw]
+            draw += 1
+        x = posterior_update(x, eps, z, coef, c1, sigma)
+    return x
+
+
 def logistic_unconstrain_inverse(u, a, b):
     """ECD.py:42-53 (tensor branch): ``a + (b-a)*sigmoid(u)``."""
     return a + (b - a) * torch.sigmoid(u)

@@ -85,9 +85,91 @@ def make_misfit(ref):
     np.savez(os.path.join(OUT, "misfit.npz"), **misfit)
 
 
+def load_parameter_limits():
+    """``ParameterLimits().plims`` (Generate_ERT_utils.py:8-59), class loaded by AST like the rest."""
+    import ast
+    from oracle.reference_loader import REFERENCE_ROOT
+    path = os.path.join(REFERENCE_ROOT, "Generate_ERT_utils.py")
+    tree = ast.parse(open(path).read(), filename=path)
+    picked = [n for n in tree.body if isinstance(n, ast.ClassDef) and n.name == "ParameterLimits"]
+    ns = {"np": np}
+    exec(compile(ast.Module(body=picked, type_ignores=[]), path, "exec"), ns)
+    return ns["ParameterLimits"]().plims
+
+
+def make_round2(ref):
+    """Round-2 fixtures (each in its own file; the round-1 files stay byte-identical in git):
+    the BASELINE config-2 chain at full size, a 64-member T=1000 chain (the bf16 path's reference anchor),
+    a hidden_dim=256 / L=9386 chain (config 5's reference-expressible widening) and the f1 epilogue
+    (the reference's own inverse_transform + check_param_bounds around sklearn's MinMaxScaler)."""
+    import contextlib
+    import io
+    import re
+    import time
+    from sklearn.preprocessing import MinMaxScaler
+    model = ref_model(ref)
+    torch.manual_seed(1)
+    cond1 = torch.rand(1, C, L)
+    # ---- config 2: 256 members, T = 1000, one shared condition; noise regenerated from its seed ----------
+    out = {}
+    for name, B in (("cfg2_B256_T1000", 256), ("B64_T1000", 64)):
+        torch.manual_seed(2)
+        nz = torch.randn(1000, B, P)
+        t0 = time.time()
+        x, _ = run_chain(model, cond1.expand(B, C, L), 1000, nz)
+        print(name, "reference chain", round(time.time() - t0, 1), "s", flush=True)
+        out[name] = x.numpy()
+        out[name + "_noise_head"] = nz[:2].numpy()
+    np.savez(os.path.join(OUT, "chain_cfg2.npz"), **out)
+    # ---- hidden_dim = 256, L = 9386 ("2x grid"), 8 members, T = 200 ---------------------------------------
+    m256 = ref_model(ref, hidden=256, seed=5)
+    prev = np.load(os.path.join(OUT, "model_h256_case.npz"))
+    assert all(np.array_equal(prev["sd." + k], v.detach().numpy()) for k, v in m256.state_dict().items())
+    g = torch.Generator().manual_seed(11)
+    cond = torch.rand(2, C, 2 * L, generator=g)                  # two distinct conditions, 4 realisations each
+    nz = torch.randn(200, 8, P, generator=g)
+    refn = load_reference(noise=nz)
+    b, a, ab = refn.get_diffusion_schedule(200)
+    with torch.no_grad():
+        x = refn.sample_model(m256, cond.repeat(4, 1, 1), 200, b, a, ab, P, "cpu")
+    np.savez(os.path.join(OUT, "chain_h256.npz"), x0=x.numpy(), cond_seed=np.int64(11), noise_head=nz[:2].numpy(),
+             cond_head=cond[:, :2, :8].numpy())
+    # ---- f1: logits -> sigmoid -> MinMaxScaler.inverse_transform -> check_param_bounds (ECD.py:402-406) ----
+    plims = load_parameter_limits()
+    rng = np.random.default_rng(12)
+    width = plims[:, 1] - plims[:, 0]
+    sim_param = plims[:, 0] - 0.03 * width + rng.uniform(size=(500, P)) * 1.06 * width    # training range a little wider
+    scaler = MinMaxScaler(feature_range=(0.0, 1.0)).fit(sim_param)
+    u = torch.from_numpy(rng.normal(scale=2.5, size=(400, P)).astype(np.float32))
+    gen = ref.inverse_transform(u, 0.0, 1.0)                     # torch branch, float32
+    gen_np = scaler.inverse_transform(gen.cpu().numpy())
+    buf = io.StringIO()
+    with contextlib.redirect_stdout(buf):
+        kept = ref.check_param_bounds(gen_np, plims)
+    first_bad = -np.ones(u.shape[0], dtype=np.int32)
+    for m in re.finditer(r"Sample (\d+) Parameter (\d+):", buf.getvalue()):
+        first_bad[int(m.group(1))] = int(m.group(2))
+    valid = first_bad < 0
+    assert kept is not None and np.array_equal(kept, gen_np[valid]) and 0 < valid.sum() < valid.size
+    # the float64 form (numpy branch of inverse_transform), bounds only
+    gen64 = scaler.inverse_transform(ref.inverse_transform(u.numpy().astype(np.float64), 0.0, 1.0))
+    buf = io.StringIO()
+    with contextlib.redirect_stdout(buf):
+        kept64 = ref.check_param_bounds(gen64, plims)
+    first_bad64 = -np.ones(u.shape[0], dtype=np.int32)
+    for m in re.finditer(r"Sample (\d+) Parameter (\d+):", buf.getvalue()):
+        first_bad64[int(m.group(1))] = int(m.group(2))
+    np.savez(os.path.join(OUT, "transforms_f1.npz"), u=u.numpy(), sigmoid=gen.numpy(), phys=gen_np, valid=valid,
+             first_bad=first_bad, scaler_min=scaler.min_, scaler_scale=scaler.scale_, limits=plims,
+             phys64=gen64, first_bad64=first_bad64)
+    print({f: os.path.getsize(os.path.join(OUT, f)) for f in ("chain_cfg2.npz", "chain_h256.npz", "transforms_f1.npz")})
+
+
 def main():
     if sys.argv[1:] == ["misfit"]:          # only this fixture (the others stay byte-identical in git)
         return make_misfit(load_reference())
+    if sys.argv[1:] == ["round2"]:
+        return make_round2(load_reference())
     os.makedirs(OUT, exist_ok=True)
     ref = load_reference()
     model = ref_model(ref)

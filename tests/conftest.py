@@ -42,3 +42,24 @@ def gpu_model(cuda_dev, ref_state_dict):
     m = eb.ConditionalDiffusionModel(29, 128)
     m.load_state_dict(ref_state_dict)
     return m.to(cuda_dev).eval()
+
+
+def parity_error(got, want, rtol, atol):
+    """max over elements of |got - want| / (atol + rtol*|want|): <= 1 means every element is within
+    ``atol + rtol*|want|`` (the numpy.allclose criterion, element by element)."""
+    got, want = np.asarray(got, dtype=np.float64), np.asarray(want, dtype=np.float64)
+    assert got.shape == want.shape, (got.shape, want.shape)
+    if got.size == 0:
+        return 0.0
+    return float((np.abs(got - want) / (atol + rtol * np.abs(want))).max())
+
+
+def assert_close(got, want, rtol, atol, what=""):
+    """Element-wise ``|got - want| <= atol + rtol*|want|``; the message carries the measured errors."""
+    got, want = np.asarray(got, dtype=np.float64), np.asarray(want, dtype=np.float64)
+    ratio = parity_error(got, want, rtol, atol)
+    if not ratio <= 1.0:
+        d = np.abs(got - want)
+        raise AssertionError(f"{what}: worst element at {ratio:.3g}x its tolerance (rtol={rtol:g}, atol={atol:g}); "
+                             f"max|d|={d.max():.3e}, max|want|={np.abs(want).max():.3e}, "
+                             f"max|d|/|want|={float((d / np.maximum(np.abs(want), 1e-30)).max()):.3e}")

@@ -135,3 +135,112 @@ def test_sharded_statistics_single_rank_equals_plain(cuda_dev):
         assert torch.equal(sh[k].to(st[k].dtype), st[k])
     assert torch.equal(sh["pct"], pct.double()) and torch.equal(sh["mode"], st["mode"])
     assert torch.equal(sh["mode_index"], st["mode_index"])
+
+
+# ---- ensembles beyond one CTA's shared memory (round 2: no size cap) -------------------------------
+@pytest.fixture
+def env_override(monkeypatch):
+    def set_(name, value):
+        monkeypatch.setenv(name, str(value))
+    return set_
+
+
+@pytest.mark.parametrize("dtype", [np.float32, np.float64])
+@pytest.mark.parametrize("N,Q", [(40000, 29), (160000, 29), (33000, 3), (70001, 64)])
+def test_percentiles_any_size_bit_exact(cuda_dev, dtype, N, Q):
+    rng = np.random.default_rng(N + Q)
+    a = rng.normal(size=(N, Q)).astype(dtype)
+    a[:, 0] = np.round(a[:, 0] * 4) / 4                  # heavy ties
+    if Q > 2:
+        a[rng.integers(0, N, 5), 2] = np.inf
+    for q in (50, [2.5, 25.0, 50.0, 75.0, 97.5], [0, 100, 33.3], np.float64(12.5)):
+        ref = np.percentile(a, q, axis=0)
+        got = eb.ensemble_percentile(a, q)
+        assert same(got, ref), (q, np.abs(got - ref).max())
+    a[N // 2, 1] = np.nan                                # a NaN column is NaN, its neighbours untouched
+    assert same(eb.ensemble_percentile(a, [10, 50]), np.percentile(a, [10, 50], axis=0))
+    m = eb.ensemble_moments(a[:, :2])
+    assert same(m["mean"][:1], np.mean(a[:, :1], axis=0)) and same(m["std"][:1], np.std(a[:, :1], axis=0))
+
+
+@pytest.mark.parametrize("dtype", [np.float32, np.float64])
+@pytest.mark.parametrize("run_len", [2, 16, 256])
+@pytest.mark.parametrize("N,Q", [(1, 3), (2, 2), (5, 29), (17, 1), (255, 7), (1000, 33), (4097, 5)])
+def test_percentiles_run_path_small_runs(cuda_dev, env_override, dtype, run_len, N, Q):
+    # the sorted-runs / multi-run selection path forced onto small columns: ragged last runs, one-member runs,
+    # more runs than lanes (4097 / 16 = 257 runs), ties, infinities, every query form
+    env_override("ERTDIFF_PCTL_RUN_LEN", run_len)
+    if N / run_len > 4096:
+        pytest.skip("more runs than the selection kernel's window table holds")
+    rng = np.random.default_rng(N * 31 + Q + run_len)
+    a = rng.integers(-3, 4, size=(N, Q)).astype(dtype) if (N + Q) % 2 else rng.normal(size=(N, Q)).astype(dtype)
+    if N > 4:
+        a[1, 0], a[3, 0] = -np.inf, np.inf
+        a[2, Q - 1] = -0.0
+    for q in QS:
+        ref = np.percentile(a, q, axis=0)
+        got = eb.ensemble_percentile(a, q)
+        assert same(got, ref), (q, ref.dtype, got.dtype)
+
+
+@pytest.mark.parametrize("dtype", [np.float32, np.float64])
+@pytest.mark.parametrize("N", [30000, 70000])
+def test_kde_mode_any_size_index_is_scipy(cuda_dev, dtype, N):
+    a = np.random.default_rng(N).lognormal(size=(N, 6)).astype(dtype)
+    a64 = a.astype(np.float64)
+    grid = so.kde_grid(a64, 2000)
+    mode, idx = eb.ensemble_kde_mode(a, 2000, return_index=True)
+    _, idx_sp, pdfs = so.kde_mode_scipy(a64, grid)
+    for j in np.nonzero(idx != idx_sp)[0]:
+        p = pdfs[:, j]
+        assert abs(p[idx[j]] - p[idx_sp[j]]) <= 1e-13 * p[idx_sp[j]], (j, idx[j], idx_sp[j])
+    assert (idx != idx_sp).sum() <= 1
+    assert np.array_equal(mode, grid[idx])
+
+
+@pytest.mark.parametrize("tile", [64, 448, 4096])
+def test_kde_tiled_path_equals_resident_path(cuda_dev, env_override, tile):
+    # members streamed through shared memory in tiles vs the whole column resident: same argmax, and the fp32
+    # scan is the same sum in the same order (tiles are multiples of its 64-member blocks)
+    rng = np.random.default_rng(tile)
+    a = (rng.normal(size=(3000, 29)) * np.linspace(0.5, 30, 29)).astype(np.float32)
+    a[:, 5] = 2.0                                        # constant column: no KDE (NaN, -1)
+    lohi = (float(a.min()), float(a.max()))
+    m1, i1 = eb.ensemble_kde_mode(a, 5000, grid_range=lohi, return_index=True)
+    env_override("ERTDIFF_KDE_TILE", tile)
+    m2, i2 = eb.ensemble_kde_mode(a, 5000, grid_range=lohi, return_index=True)
+    assert np.array_equal(i1, i2) and np.array_equal(m1, m2, equal_nan=True)
+    assert i2[5] == -1 and np.isnan(m2[5])
+    b = rng.lognormal(size=(2500, 300))                  # many columns: one CTA walks its column's whole grid
+    env_override("ERTDIFF_KDE_TILE", 0)
+    r1 = eb.ensemble_kde_mode(b, 1000, grid_range=(b.min(), b.max()), return_index=True)[1]
+    env_override("ERTDIFF_KDE_TILE", tile)
+    r2 = eb.ensemble_kde_mode(b, 1000, grid_range=(b.min(), b.max()), return_index=True)[1]
+    assert np.array_equal(r1, r2)
+
+
+def test_statistics_full_size_151k_members(cuda_dev):
+    # 8 GPUs x 18,944 members (one full wave of 128-member tiles each): the gathered ensemble
+    N = 8 * 18944
+    a = torch.randn(N, 29, device=cuda_dev, generator=torch.Generator(cuda_dev).manual_seed(1)) * 3 + 1
+    q = eb.ensemble_percentile(a, [0.0, 50.0, 100.0])
+    assert torch.equal(q[0].float(), a.min(dim=0).values) and torch.equal(q[2].float(), a.max(dim=0).values)
+    srt = a.sort(dim=0).values
+    d = (srt[N // 2] - srt[N // 2 - 1]).double()         # numpy: subtract in the array's dtype, then promote
+    assert torch.equal(q[1], srt[N // 2].double() - d * 0.5)      # gamma = 0.5 exactly: the `b - d*(1-gamma)` branch
+    mode, idx = eb.ensemble_kde_mode(a, 5000, return_index=True)
+    assert ((mode - 1.0).abs() < 0.5).all()              # N(1, 3): the KDE mode sits near the mean
+    m = eb.ensemble_moments(a)
+    assert ((m["mean"] - 1.0).abs() < 0.05).all() and ((m["std"] - 3.0).abs() < 0.05).all()
+
+
+def test_argsort_stable_is_numpy(cuda_dev):
+    rng = np.random.default_rng(5)
+    for n in (1, 2, 50, 1025, 5000):
+        v = np.round(rng.normal(size=n), 1)              # ties
+        if n > 10:
+            v[7] = np.nan
+            v[3] = -np.inf
+        for dt in (np.float32, np.float64):
+            got = eb.stats.argsort_stable(torch.from_numpy(v.astype(dt)).to(cuda_dev)).cpu().numpy()
+            assert np.array_equal(got, np.argsort(v.astype(dt), kind="stable")), (n, dt)

@@ -71,3 +71,37 @@ def test_restatement_equals_reference_live():
     xo = do.sample_chain(sd, c, 40, b, a, ab, P, noise, num_steps=30, temperature=1.3)
     assert torch.equal(xr, xo)
     assert ref2.torch_proxy.draws == 30
+
+
+def test_f1_restatement_equals_the_reference_fixture(golden):
+    # the oracle-side restatement of the f1 epilogue (what the GPU test's tolerances are stated against) reproduces
+    # the reference-made fixture bit for bit: torch sigmoid, sklearn's `X -= min_; X /= scale_`, the bounds loop
+    import torch
+    g = golden("transforms_f1.npz")
+    s = do.logistic_unconstrain_inverse(torch.from_numpy(g["u"]), 0.0, 1.0).numpy()
+    assert np.array_equal(s, g["sigmoid"])
+    x = s.copy()
+    x -= g["scaler_min"]
+    x /= g["scaler_scale"]
+    assert x.dtype == np.float32 and np.array_equal(x, g["phys"])
+    lim = g["limits"]
+    first = np.array([next((j for j in range(x.shape[1]) if x[i, j] < lim[j, 0] or x[i, j] > lim[j, 1]), -1)
+                      for i in range(x.shape[0])], dtype=np.int32)
+    assert np.array_equal(first, g["first_bad"]) and np.array_equal(first < 0, g["valid"])
+
+
+def test_hoisted_chain_stays_within_reorder_noise_of_the_as_written_chain(ref_state_dict, golden):
+    # the hoisted CPU chain (bench.py's second CPU baseline) against the as-written oracle and the reference golden
+    c = golden("chain_cfg1.npz")
+    cond = torch.from_numpy(c["condition"]).expand(16, C, L)
+    noise = torch.from_numpy(c["noise"])
+    b, a, ab = do.diffusion_schedule(50)
+    x = do.sample_chain_hoisted(ref_state_dict, cond, 50, b, a, ab, P, noise)
+    assert np.abs(x.numpy() - c["x0"]).max() <= 2e-5 + 1e-4 * np.abs(c["x0"]).max()
+    g = torch.Generator().manual_seed(3)
+    cond = torch.rand(3, C, 200, generator=g)
+    nz = torch.randn(12, 6, P, generator=g)
+    b, a, ab = do.diffusion_schedule(40)
+    x1 = do.sample_chain(ref_state_dict, cond.repeat(2, 1, 1), 40, b, a, ab, P, nz, num_steps=12, temperature=0.8)
+    x2 = do.sample_chain_hoisted(ref_state_dict, cond.repeat(2, 1, 1), 40, b, a, ab, P, nz, num_steps=12, temperature=0.8)
+    assert (x1 - x2).abs().max().item() <= 2e-5
