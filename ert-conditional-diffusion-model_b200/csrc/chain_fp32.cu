@@ -5,30 +5,30 @@
 
 namespace ertdiff {
 
-// hidden units per thread for ensembles of at most two members per SM (1 or 2; chosen from the sweep in
-// profiles/r02_chain_fp32_variants.md)
-constexpr int kDefaultSmallUpt = 1;
-
 static int env_int(const char* name) {
     const char* e = std::getenv(name);
     return e ? std::atoi(e) : 0;
 }
 
-// members per CTA: spread small ensembles over all SMs (the chain is latency-bound), pack
-// large ones so that weight registers are amortised over more members.
-// hidden units per thread: 2 for ensembles that fit the machine two members per SM at most -- each member
-// then occupies half the warps (one warp per scheduler with two members on an SM).
+// Tiling of the fp32 chain, from the sweep in profiles/r02_chain_fp32_variants.md (one B200, T = 1000):
+//   hidden units per thread: 2 wherever that build exists (hidden_dim 128 / 256).  A member then occupies half
+//     the warps (two at hidden 128), layer 2 needs one shuffle level less and a step's barriers synchronise two
+//     warps instead of four: 256 members 0.356 -> 0.268 us per step, 1024 members 1.23 -> 0.70.
+//   members per CTA: the fewest for which the ensemble is ONE wave of co-resident CTAs (a CTA runs its members one
+//     after the other inside a step, so a second member costs almost a second step: 0.26 -> 0.46 us); the
+//     two-units build holds 4 (hidden 128) or 2 (hidden 256) CTAs per SM in registers.
 void chain_fp32_tiling(int64_t B, int H, int* mpb_out, int* upt_out) {
-    int upt = 1;
-    if (const int v = env_int("ERTDIFF_CHAIN_UPT")) {
-        if ((v == 1 || v == 2) && (v == 1 || H == 128 || H == 256)) upt = v;
-    } else if ((H == 128 || H == 256) && B <= 2 * kNumSMs) {
-        upt = kDefaultSmallUpt;
-    }
+    const bool two_ok = (H == 128 || H == 256);
+    int upt = two_ok ? 2 : 1;
+    if (const int v = env_int("ERTDIFF_CHAIN_UPT"))
+        if (v == 1 || (v == 2 && two_ok)) upt = v;
     int mpb;
     const int v = env_int("ERTDIFF_CHAIN_MPB");
     if (v == 1 || v == 2 || v == 4 || v == 8) {
         mpb = v;
+    } else if (upt == 2) {
+        const int64_t slots = (int64_t)kNumSMs * (H == 128 ? 4 : 2);
+        mpb = B <= slots ? 1 : (B <= 2 * slots ? 2 : 4);
     } else {
         const int64_t ctas_per_sm = (H <= 128) ? 4 : (H <= 256 ? 2 : 1);
         const int64_t slots = kNumSMs * ctas_per_sm;

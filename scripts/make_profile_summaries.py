@@ -17,7 +17,9 @@ out = os.path.join(ROOT, "profiles")
 go = os.path.join(ROOT, "gpurun_out")
 
 for cfg, title in (("fp32_b256", "bench.py default: 256 members, T=1000, fp32, shared condition"),
-                   ("bf16_b8192", "bench.py --precision bf16 --members 8192")):
+                   ("bf16_b8192", "bench.py --precision bf16 --members 8192"),
+                   ("bf16_b18944", "bench.py --precision bf16 --members 18944"),
+                   ("stats_maps1024", "scripts/stats_bench.py --maps 1024 --fields '' (maps (1024, 4693, 14) float64)")):
     src = os.path.join(go, f"launches_{cfg}.csv")
     if os.path.isfile(src):
         md = subprocess.run([sys.executable, os.path.join(ROOT, "scripts", "launch_summary.py"), src,
@@ -35,7 +37,14 @@ KEYS = ["gpu__time_duration.sum", "dram__bytes_read.sum", "dram__bytes_write.sum
 SCALE = {"byte": 1, "Kbyte": 1e3, "Mbyte": 1e6, "Gbyte": 1e9, "ns": 1e-3, "us": 1, "ms": 1e3}
 jpath = os.path.join(out, f"{rnd}_ncu_kernels.json")
 summary = json.load(open(jpath)) if os.path.isfile(jpath) else {}      # captures arrive one per gpurun call
-for name, what in (("chain_fp32", "k_chain, 256 members, T=1000 (chain_sweep.py)"),
+for name, what in (("chain_fp32", "k_chain (two hidden units per thread), 256 members, T=1000 (chain_sweep.py)"),
+                   ("moments", "k_moments<double>, maps (1024, 4693, 14) float64 (stats_bench.py)"),
+                   ("percentiles", "k_percentiles<double>, maps (1024, 4693, 14) float64 (stats_bench.py)"),
+                   ("kde_scan", "k_kde_scan32<double>, maps (1024, 4693, 14) float64 (stats_bench.py)"),
+                   ("kde_select", "k_kde_select64<double>, maps (1024, 4693, 14) float64 (stats_bench.py)"),
+                   ("posterior_update", "k_posterior_update, 2^26 elements (stats_bench.py)"),
+                   ("sort_runs", "k_sort_runs<float>, fields (151552, 29) float32 (stats_bench.py)"),
+                   ("select_runs", "k_select_runs<float>, fields (151552, 29) float32 (stats_bench.py)"),
                    ("chain_umma", "k_chain_umma, 18,944 members, T=200 (chain_sweep.py)"),
                    ("chain_umma2", "k_chain_umma, two CTAs per SM build, 37,888 members, T=200 (chain_sweep.py)"),
                    ("encoder_umma", "k_encoder_umma, 1024 conditions of 14x4693 (encoder_bench.py)")):

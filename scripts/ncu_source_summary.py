@@ -1,13 +1,14 @@
 #!/usr/bin/env python
 """Summarise `ncu --page source --csv` output (SASS view): instructions executed and stall samples
 per opcode, the dominant stall reasons, and the hottest instructions.
-usage: ncu_source_summary.py file.csv [top_n]"""
+usage: ncu_source_summary.py file.csv [top_n hottest instructions] [top_n opcodes, default all]"""
 import collections
 import csv
 import sys
 
 rows = list(csv.reader(open(sys.argv[1])))
 top = int(sys.argv[2]) if len(sys.argv) > 2 else 25
+top_ops = int(sys.argv[3]) if len(sys.argv) > 3 else 10 ** 6
 hdr = next(r for r in rows if r and r[0] == "Address")
 data = [dict(zip(hdr, r)) for r in rows[rows.index(hdr) + 1:] if len(r) == len(hdr)]
 def num(d, k):
@@ -25,7 +26,7 @@ for d in data:
     byop[op][0] += num(d, "Instructions Executed")
     byop[op][1] += num(d, "# Samples")
 print("\nper opcode: inst share | sample share")
-for op, (i, s) in sorted(byop.items(), key=lambda kv: -kv[1][0])[:top]:
+for op, (i, s) in sorted(byop.items(), key=lambda kv: -kv[1][0])[:top_ops]:
     print(f"  {op:12s} {100 * i / tot_inst:6.2f}%  {100 * s / max(tot_samp, 1):6.2f}%")
 stalls = [h for h in hdr if h.startswith("stall_") and "Not Issued" not in h]
 print("\nstall reasons (all samples):")

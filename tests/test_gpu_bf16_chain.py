@@ -87,8 +87,9 @@ def test_bf16_chain_matches_its_emulation(gpu_model, ref_state_dict, cuda_dev, B
 
 
 def test_bf16_chain_vs_fp32_oracle_tolerance(gpu_model, ref_state_dict, cuda_dev, golden):
-    # BASELINE config 1 inputs.  bf16 operands carry 8 mantissa bits: predicted noise is off by up to
-    # ~1e-2 of its scale per step, and the final fields by a few percent of theirs after 50 steps.
+    # BASELINE config 1 inputs.  bf16 operands carry 8 mantissa bits: measured against the reference's golden,
+    # predicted noise is off by up to 3.0e-3 of its scale inside the chain and the final fields by 1.8e-4 of theirs
+    # after 50 steps; the bounds are ten times that.
     c = golden("chain_cfg1.npz")
     cond = torch.from_numpy(c["condition"]).to(cuda_dev).expand(16, C, 4693)
     noise = torch.from_numpy(c["noise"]).to(cuda_dev)
@@ -96,9 +97,9 @@ def test_bf16_chain_vs_fp32_oracle_tolerance(gpu_model, ref_state_dict, cuda_dev
     x, eps = eb.run_chain(gpu_model, cond, 50, b, a, ab, cuda_dev, noise=noise, precision="bf16", return_eps=True)
     e49 = eps[49].cpu().numpy()
     assert np.abs(e49 - c["eps_t49"]).max() <= 2e-2 * np.abs(c["eps_t49"]).max()
-    assert np.abs(x.cpu().numpy() - c["x0"]).max() <= 5e-2 * np.abs(c["x0"]).max()
-    x32 = eb.run_chain(gpu_model, cond, 50, b, a, ab, cuda_dev, noise=noise)
-    assert np.abs(x32.cpu().numpy() - c["x0"]).max() <= 1e-4 + 1e-3 * np.abs(c["x0"]).max()
+    for t in (25, 0):
+        assert np.abs(eps[t].cpu().numpy() - c[f"eps_t{t}"]).max() <= 3e-2 * np.abs(c[f"eps_t{t}"]).max(), t
+    assert np.abs(x.cpu().numpy() - c["x0"]).max() <= 2e-3 * np.abs(c["x0"]).max()
 
 
 def test_bf16_chain_rng_modes_and_loop_modes(gpu_model, cuda_dev):
@@ -142,7 +143,7 @@ def test_bf16_chain_small_param_dim(cuda_dev):
     x16 = eb.run_chain(m, cond, T, b, a, ab, cuda_dev, n_members=B, noise=noise, precision="bf16")
     assert m.umma_status() == 0
     scale = x32.abs().max().item()
-    assert torch.isfinite(x16).all() and (x16 - x32).abs().max().item() <= 5e-2 * scale
+    assert torch.isfinite(x16).all() and (x16 - x32).abs().max().item() <= 5e-3 * scale
 
 
 @pytest.mark.parametrize("distinct", [False, True])
@@ -253,8 +254,8 @@ def test_bf16_hidden256_rng_and_golden(model256, golden, cuda_dev):
 # is carried -- and scaled -- to the end: the deviation is a fraction of the field's own scale that grows with the
 # chain length.  Measured on a B200 (scripts/measure_parity.py, profiles/r02_parity_measured.md) and bounded here at
 # about ten times the measurement, per member, relative to that member's largest component.
-BF16_T200_OF_SCALE = 5e-2
-BF16_T1000_OF_SCALE = 1e-1
+BF16_T200_OF_SCALE = 5e-3      # measured 4.9e-4 (hidden 256, T = 200, against the reference's output)
+BF16_T1000_OF_SCALE = 3e-2     # measured per member: median 1.5e-3, max 3.2e-3 (1024 members; 2.6e-3 against the reference golden)
 
 
 def test_bf16_T1000_against_the_reference_golden(gpu_model, golden, cuda_dev):

@@ -19,9 +19,10 @@ from conftest import assert_close
 
 pytestmark = pytest.mark.gpu
 P, C, L = 29, 14, 4693
-EPS_RTOL, EPS_ATOL = 1e-5, 2e-6          # one forward
-X50_RTOL, X50_ATOL = 1e-4, 2e-5          # fields after <= 120 steps
-X1000_RTOL, X1000_ATOL = 1e-4, 2e-3      # fields after 500-1000 steps (|x| up to ~1.5e3)
+# measured on a B200 (worst case over the golden cases)           -> tolerance (about 10x)
+EPS_RTOL, EPS_ATOL = 1e-5, 5e-7          # one forward: max|d| 1.8e-7 on values <= 0.58; 4.4e-8 beyond 1e-5*|want|
+X50_RTOL, X50_ATOL = 1e-5, 5e-6          # fields after <= 200 steps: max|d| 9.5e-7 on |x| <= 12, none beyond 1e-5*|want|
+X1000_RTOL, X1000_ATOL = 1e-5, 1.5e-3    # fields after 1000 steps (|x| up to 1.5e3): max|d| 8.5e-4, 1.4e-4 beyond 1e-5*|want|
 
 
 def test_forward_golden_cases(gpu_model, golden, cuda_dev):
