@@ -321,10 +321,7 @@ class Runner:
         def stats(x):
             if world > 1:                       # per-column statistics: columns split over the ranks
                 return eb.parallel.sharded_statistics(x, PERCENTILES, KDE_GRID)
-            out = eb.ensemble_moments(x)
-            out["pct"] = eb.ensemble_percentile(x, PERCENTILES)
-            out["mode"] = eb.ensemble_kde_mode(x, KDE_GRID)
-            return out
+            return eb.ensemble_summary(x, PERCENTILES, KDE_GRID)     # moments on a side stream beside percentiles + KDE
 
         def step_device(i):
             """inputs resident in HBM"""

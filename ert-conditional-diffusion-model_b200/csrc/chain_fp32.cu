@@ -14,9 +14,9 @@ static int env_int(const char* name) {
 //   hidden units per thread: 2 wherever that build exists (hidden_dim 128 / 256).  A member then occupies half
 //     the warps (two at hidden 128), layer 2 needs one shuffle level less and a step's barriers synchronise two
 //     warps instead of four: 256 members 0.356 -> 0.268 us per step, 1024 members 1.23 -> 0.70.
-//   members per CTA: the fewest for which the ensemble is ONE wave of co-resident CTAs (a CTA runs its members one
-//     after the other inside a step, so a second member costs almost a second step: 0.26 -> 0.46 us); the
-//     two-units build holds 4 (hidden 128) or 2 (hidden 256) CTAs per SM in registers.
+//   members per CTA: one while the ensemble is at most ~1.5 waves of co-resident CTAs (a CTA runs its members one
+//     after the other inside a step, so a second member costs almost a second step: 0.26 -> 0.46 us), two beyond;
+//     the two-units build holds 4 (hidden 128) or 2 (hidden 256) CTAs per SM in registers.
 void chain_fp32_tiling(int64_t B, int H, int* mpb_out, int* upt_out) {
     const bool two_ok = (H == 128 || H == 256);
     int upt = two_ok ? 2 : 1;
@@ -27,8 +27,10 @@ void chain_fp32_tiling(int64_t B, int H, int* mpb_out, int* upt_out) {
     if (v == 1 || v == 2 || v == 4 || v == 8) {
         mpb = v;
     } else if (upt == 2) {
+        // (measured: one member per CTA wins up to ~1.5 waves -- 700 members: 0.63 vs 0.68 us -- two members per CTA
+        // beyond -- 1184: 0.70 vs 0.76, 8192: 4.74 vs 5.14; four never do)
         const int64_t slots = (int64_t)kNumSMs * (H == 128 ? 4 : 2);
-        mpb = B <= slots ? 1 : (B <= 2 * slots ? 2 : 4);
+        mpb = 2 * B <= 3 * slots ? 1 : 2;
     } else {
         const int64_t ctas_per_sm = (H <= 128) ? 4 : (H <= 256 ? 2 : 1);
         const int64_t slots = kNumSMs * ctas_per_sm;

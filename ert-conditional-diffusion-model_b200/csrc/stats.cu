@@ -144,6 +144,50 @@ static int percentiles_by_runs_t(const void* d_a, int64_t N, int64_t Q, const st
     return 0;
 }
 
+template <typename T, typename G, typename O, int E>
+static int percentiles_by_warps_e(const void* d_a, int64_t N, int64_t Q, const std::vector<PctlQuery>& qs, void* d_out,
+                                  cudaStream_t st) {
+    // columns per warp: as many as keep the tile within ~96 KB, fewer when that would leave SMs without a CTA
+    int CPW = 4;
+    while (CPW > 1 && ((size_t)N * (8 * CPW + 1) * sizeof(T) > 96 * 1024 || (Q + 8 * CPW - 1) / (8 * CPW) < 2 * kNumSMs)) CPW >>= 1;
+    const size_t smem = (size_t)N * (8 * CPW + 1) * sizeof(T);
+    static PerDeviceOnce once;
+    bool& attr_set = *once.slot();
+    if (!attr_set) {
+        ERT_CUDA(cudaFuncSetAttribute(k_percentiles_warp<T, G, O, E>, cudaFuncAttributeMaxDynamicSharedMemorySize, 100 * 1024));
+        attr_set = true;
+    }
+    const unsigned grid = (unsigned)((Q + 8 * CPW - 1) / (8 * CPW));
+    const int nq = (int)qs.size();
+    for (int k0 = 0; k0 < nq; k0 += kMaxPctlQueries) {
+        PctlQueryPack pack{};
+        pack.n = (nq - k0) < kMaxPctlQueries ? (nq - k0) : kMaxPctlQueries;
+        for (int k = 0; k < pack.n; ++k) pack.q[k] = qs[k0 + k];
+        k_percentiles_warp<T, G, O, E><<<grid, 256, smem, st>>>((const T*)d_a, N, Q, CPW, pack, (O*)d_out + (size_t)k0 * Q);
+        ERT_LAUNCH_CHECK("k_percentiles_warp");
+    }
+    return 0;
+}
+
+template <typename T, typename G, typename O>
+static int percentiles_by_warps_t(const void* d_a, int64_t N, int64_t Q, const std::vector<PctlQuery>& qs, void* d_out,
+                                  cudaStream_t st) {
+    if (N <= 32) return percentiles_by_warps_e<T, G, O, 1>(d_a, N, Q, qs, d_out, st);
+    if (N <= 64) return percentiles_by_warps_e<T, G, O, 2>(d_a, N, Q, qs, d_out, st);
+    if (N <= 128) return percentiles_by_warps_e<T, G, O, 4>(d_a, N, Q, qs, d_out, st);
+    if (N <= 256) return percentiles_by_warps_e<T, G, O, 8>(d_a, N, Q, qs, d_out, st);
+    if (N <= 512) return percentiles_by_warps_e<T, G, O, 16>(d_a, N, Q, qs, d_out, st);
+    return percentiles_by_warps_e<T, G, O, 32>(d_a, N, Q, qs, d_out, st);
+}
+
+static int percentiles_by_warps(const void* d_a, int dtype, int64_t N, int64_t Q, const std::vector<PctlQuery>& qs,
+                                int index_dtype, void* d_out, cudaStream_t st) {
+    if (dtype == ERTDIFF_F32 && index_dtype == ERTDIFF_F32)
+        return percentiles_by_warps_t<float, float, float>(d_a, N, Q, qs, d_out, st);
+    if (dtype == ERTDIFF_F32) return percentiles_by_warps_t<float, double, double>(d_a, N, Q, qs, d_out, st);
+    return percentiles_by_warps_t<double, double, double>(d_a, N, Q, qs, d_out, st);
+}
+
 static int percentiles_by_runs(const void* d_a, int dtype, int64_t N, int64_t Q, const std::vector<PctlQuery>& qs,
                                int index_dtype, void* d_out, int CH, cudaStream_t st) {
     if (dtype == ERTDIFF_F32 && index_dtype == ERTDIFF_F32)
@@ -228,8 +272,17 @@ int ertdiff_ensemble_percentiles(const void* d_a, int dtype, int64_t N, int64_t 
         const int v = std::atoi(e);
         if (v >= 2 && v <= 8192 && (v & (v - 1)) == 0) run_len = v;
     }
-    if ((size_t)NP64 * esz + 64 > budget && run_len == 0) run_len = 8192;
+    if (run_len == 0) {
+        // too long for one CTA's shared memory -> runs.  Few columns (the chain's own (members, 29) output) also go
+        // through runs as soon as a column exceeds 2048 members: a single CTA per column would leave the machine to
+        // Q CTAs sorting 8K..32K elements each (18,944 x 29: 506 -> ~150 us), while short runs spread the sort over
+        // R x Q CTAs and the selection costs a warp per (column, query)
+        if ((size_t)NP64 * esz + 64 > budget) run_len = Q <= 1024 ? 2048 : 8192;
+        else if (N > 2048 && Q <= 1024) run_len = 2048;
+    }
     if (run_len) return percentiles_by_runs(d_a, dtype, N, Q, qs, index_dtype, d_out, run_len, st);
+    if (N <= 1024 && !std::getenv("ERTDIFF_PCTL_NO_WARP"))     // short columns: one warp sorts a column in registers
+        return percentiles_by_warps(d_a, dtype, N, Q, qs, index_dtype, d_out, st);
     const int NP = (int)NP64;
     int CT = 32;
     while (CT > 1 && ((size_t)CT * NP * esz + CT * sizeof(int) > budget / 2 || (int64_t)CT > Q)) CT >>= 1;

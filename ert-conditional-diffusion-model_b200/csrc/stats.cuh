@@ -241,11 +241,19 @@ __global__ void k_minmax_partial(const T* __restrict__ a, int64_t n, double* __r
 }
 __global__ void k_minmax_final(const double* __restrict__ part, int nblocks,
                                double* __restrict__ out2) {
-    if (threadIdx.x == 0 && blockIdx.x == 0) {
-        double lo = CUDART_INF, hi = -CUDART_INF, nn = 0.0;
-        for (int b = 0; b < nblocks; ++b) {
-            lo = fmin(lo, part[3 * b]); hi = fmax(hi, part[3 * b + 1]); nn += part[3 * b + 2];
-        }
+    // one warp: lanes stride over the per-block partials, then a shuffle tree (min / max / any-NaN commute)
+    const int lane = threadIdx.x;
+    double lo = CUDART_INF, hi = -CUDART_INF, nn = 0.0;
+    for (int b = lane; b < nblocks; b += 32) {
+        lo = fmin(lo, part[3 * b]); hi = fmax(hi, part[3 * b + 1]); nn += part[3 * b + 2];
+    }
+#pragma unroll
+    for (int o = 16; o > 0; o >>= 1) {
+        lo = fmin(lo, __shfl_xor_sync(0xffffffffu, lo, o));
+        hi = fmax(hi, __shfl_xor_sync(0xffffffffu, hi, o));
+        nn += __shfl_xor_sync(0xffffffffu, nn, o);
+    }
+    if (lane == 0) {
         out2[0] = nn > 0 ? CUDART_NAN : lo;
         out2[1] = nn > 0 ? CUDART_NAN : hi;
     }
@@ -335,6 +343,96 @@ __global__ void k_percentiles(const T* __restrict__ a, int64_t N, int64_t Q, int
             r = lerp_numpy<T, double, O>(colp[qq.lo], colp[qq.hi], qq.gamma_d);
         }
         out[(int64_t)k * Q + c0 + c] = r;
+    }
+}
+
+// ------------------------------------------------------------------------------------------
+// Percentiles of short columns (N <= 1024, e.g. the reference's 50 realisations of a 4693 x 14 map,
+// ECD.py:870-872): one WARP sorts one column in registers.  The CTA (8 warps) first loads a tile of
+// CT = 8 * CPW adjacent columns coalesced (CT * sizeof(T) contiguous bytes per member) into shared memory; each
+// warp then takes CPW columns in turn: lane l holds elements l, l+32, ..., l+32(E-1) (padding = +inf), the bitonic
+// network runs on registers -- compare-exchanges between registers for strides >= 32, xor-shuffles below -- with
+// no block-wide barrier, and lane k interpolates query k (numpy `_lerp`), fetching its two order statistics with
+// indexed shuffles.  Same results as k_percentiles, bit for bit.
+template <typename T>
+__device__ __forceinline__ void cmpx(T& a, T& b, bool asc) {      // ascending: a <= b afterwards
+    const T x = a, y = b;
+    if ((x > y) == asc) { a = y; b = x; }
+}
+
+template <typename T, typename G, typename O, int E>
+__global__ void __launch_bounds__(256)
+k_percentiles_warp(const T* __restrict__ a, int64_t N, int64_t Q, int CPW,
+                   const __grid_constant__ PctlQueryPack qs, O* __restrict__ out) {
+    extern __shared__ __align__(16) unsigned char pct_smem_raw[];
+    T* tile = reinterpret_cast<T*>(pct_smem_raw);                 // [N][CT + 1]
+    const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
+    const int CT = 8 * CPW, LD = CT + 1;
+    const int64_t c0 = (int64_t)blockIdx.x * CT;
+    const int n = (int)N;
+    for (int idx = tid; idx < n * CT; idx += 256) {
+        const int c = idx % CT, i = idx / CT;
+        tile[i * LD + c] = (c0 + c < Q) ? a[(int64_t)i * Q + c0 + c] : (T)0;
+    }
+    __syncthreads();
+    constexpr int LOG = (E == 1 ? 0 : E == 2 ? 1 : E == 4 ? 2 : E == 8 ? 3 : E == 16 ? 4 : 5) + 5;   // log2(32 E)
+    for (int cw = 0; cw < CPW; ++cw) {
+        const int c = warp * CPW + cw;
+        if (c0 + c >= Q) break;                                   // (warp-uniform)
+        T v[E];
+        bool has_nan = false;
+#pragma unroll
+        for (int r = 0; r < E; ++r) {
+            const int i = lane + 32 * r;
+            T x = i < n ? tile[i * LD + c] : RN<T>::inf();
+            if (x != x) { has_nan = true; x = RN<T>::inf(); }
+            v[r] = x;
+        }
+        has_nan = __any_sync(0xffffffffu, has_nan);
+#pragma unroll
+        for (int lk = 1; lk <= LOG; ++lk) {
+            const int k = 1 << lk;
+#pragma unroll
+            for (int lj = lk - 1; lj >= 0; --lj) {
+                const int j = 1 << lj;
+                if (j >= 32) {                                    // partner element lives in another register of this lane
+                    const int rj = j >> 5;
+#pragma unroll
+                    for (int r = 0; r < E; ++r)
+                        if ((r & rj) == 0) cmpx(v[r], v[r | rj], (((lane + 32 * r) & k) == 0));
+                } else {                                          // partner element lives in lane ^ j, same register
+                    const bool lower = (lane & j) == 0;
+#pragma unroll
+                    for (int r = 0; r < E; ++r) {
+                        const T other = __shfl_xor_sync(0xffffffffu, v[r], j);
+                        const bool asc = ((lane + 32 * r) & k) == 0;
+                        // the lower element of an ascending pair keeps the smaller value (ties: either copy)
+                        const bool take_other = lower == asc ? (v[r] > other) : (other > v[r]);
+                        if (take_other) v[r] = other;
+                    }
+                }
+            }
+        }
+        // element e of the sorted column sits in lane e % 32, register e / 32; lane k serves query k
+        for (int q0 = 0; q0 < qs.n; q0 += 32) {
+            const int k = q0 + lane;
+            const PctlQuery qq = qs.q[k < qs.n ? k : 0];
+            T A = v[0], Bv = v[0];
+#pragma unroll
+            for (int r = 0; r < E; ++r) {
+                const T fa = __shfl_sync(0xffffffffu, v[r], qq.lo & 31);
+                const T fb = __shfl_sync(0xffffffffu, v[r], qq.hi & 31);
+                if ((qq.lo >> 5) == r) A = fa;
+                if ((qq.hi >> 5) == r) Bv = fb;
+            }
+            if (k < qs.n) {
+                O res;
+                if (has_nan) res = RN<O>::nan();
+                else if (sizeof(G) == 4) res = lerp_numpy<T, float, O>(A, Bv, qq.gamma_f);
+                else res = lerp_numpy<T, double, O>(A, Bv, qq.gamma_d);
+                out[(int64_t)k * Q + c0 + c] = res;
+            }
+        }
     }
 }
 
@@ -562,13 +660,24 @@ __device__ __forceinline__ double kde_grid_point(int g, int G, double lo, double
     return (g == G - 1) ? hi : __dadd_rn(__dmul_rn((double)g, step), lo);
 }
 
+// How far from the column's members the fp32 scan has to look (in data units).
+//  * Always: a term ex2.approx.ftz(d^2 * c2) is EXACTLY +0 once d^2/(2h^2) * log2(e) > 126, i.e. |d| > 13.22 h, so a
+//    grid point further than 14 h from every member has a scan value of exactly zero -- skipping it changes
+//    nothing, whatever the grid spacing.  This is what keeps a column much narrower than the common grid's step
+//    (ECD.py:749-751 spans the GLOBAL min..max) from costing a full 5000-point scan.
+//  * If the grid is not coarser than 7 bandwidths and a member lies inside it, the maximum is >= 1e-3 (some
+//    grid point is within step/2 of a member) while points further than R h, R^2 = 2 ln(1e7 N), sum to < 1e-7:
+//    they cannot hold the maximum and are written as zero.
+__device__ __forceinline__ double kde_scan_reach(double h, double step, int64_t N, bool member_inside_grid) {
+    double reach = 14.0 * h;
+    if (member_inside_grid && step <= 7.0 * h) reach = fmin(reach, h * sqrt(2.0 * log(1e7 * (double)N)));
+    return reach;
+}
+
 // The fp32 scan of one column, split over `nparts` CTAs (this one is `part`).  `xs` = the column's N
 // members centred at kc.mean (fp32, shared memory).
 //
-// Grid points further than reach = R*h from every member (R^2 = 2 ln(1e7 N)) have a KDE sum below 1e-7
-// and cannot hold the maximum whenever the maximum is known to be >= 1e-3 -- which it is if the grid is
-// not coarser than 7 bandwidths and at least one member lies inside it (some grid point is then within
-// step/2 of a member).  Those points are written as zero and only the "active" range
+// Grid points further than `kde_scan_reach` from every member are written as zero and only the "active" range
 // [x_min - reach, x_max + reach] is evaluated, split evenly over the parts: a column that occupies a
 // small part of the common grid (ECD.py:749-751 spans the GLOBAL min..max) costs proportionally less.
 // Inside the active range every member is summed, so the values equal the full scan's bit for bit.
@@ -601,8 +710,8 @@ __device__ __forceinline__ void kde_scan_column(const float* __restrict__ xs, in
         for (int w = 1; w < nwarps; ++w) { mn = fminf(mn, s_mn[w]); mx = fmaxf(mx, s_mx[w]); inside |= s_in[w]; }
         int ga = 0, gb = G - 1;
         const double h = sqrt(-0.5 / kc.neg_inv_2h2);               // 0 for a constant column, NaN for NaN data
-        if (inside && h > 0.0 && step > 0.0 && step <= 7.0 * h) {
-            const double reach = h * sqrt(2.0 * log(1e7 * (double)N));
+        if (h > 0.0 && step > 0.0) {
+            const double reach = kde_scan_reach(h, step, N, inside != 0);
             const double a = ((kc.mean + (double)mn - reach) - lo) / step;
             const double b = ((kc.mean + (double)mx + reach) - lo) / step;
             if (a > 1.0) ga = (int)fmin(a - 1.0, (double)(G - 1));  // one grid point of slack on both sides
@@ -677,6 +786,36 @@ k_kde_scan32(const T* __restrict__ a, int64_t N, int64_t Q, int64_t col0,
     kde_scan_column(xs, N, kc, lohi[0], lohi[1], G, (int)blockIdx.y, (int)gridDim.y, s32 + (int64_t)blockIdx.x * G);
 }
 
+// All-grid fallback of the float64 decision: exp(-d^2/(2h^2)) is exactly 0 in float64 once d^2/(2h^2) > 745.2
+// (d > 38.6 h), so a grid point further than 40 h from every member has a KDE sum of exactly zero and only the
+// grid range [g_lo, g_hi] around the column's extent [xmin, xmax] needs evaluating.  If nothing in it is positive
+// every grid point is zero and the first maximum is index 0 (what an argmax over the full grid returns).
+__device__ __forceinline__ void kde_nonzero_range(double xmin, double xmax, const KdeColumn kc, double lo, double step,
+                                                  int G, int& g_lo, int& g_hi) {
+    g_lo = 0; g_hi = G - 1;
+    const double h = sqrt(-0.5 / kc.neg_inv_2h2);
+    if (h > 0.0 && step > 0.0 && xmin <= xmax) {
+        const double a = ((xmin - 40.0 * h) - lo) / step, b = ((xmax + 40.0 * h) - lo) / step;
+        if (a > 1.0) g_lo = (int)fmin(a - 1.0, (double)(G - 1));
+        if (b < (double)(G - 2)) g_hi = (int)fmax(b + 1.0, 0.0);
+    }
+}
+
+// min / max of a value over a 256-thread CTA (all threads call; result in every thread)
+__device__ __forceinline__ void block_minmax(double& mn, double& mx, double* red16 /* shared, 16 doubles */) {
+#pragma unroll
+    for (int o = 16; o > 0; o >>= 1) {
+        mn = fmin(mn, __shfl_xor_sync(0xffffffffu, mn, o));
+        mx = fmax(mx, __shfl_xor_sync(0xffffffffu, mx, o));
+    }
+    const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5, nwarps = blockDim.x >> 5;
+    __syncthreads();
+    if (lane == 0) { red16[warp] = mn; red16[8 + warp] = mx; }
+    __syncthreads();
+    mn = red16[0]; mx = red16[8];
+    for (int w = 1; w < nwarps; ++w) { mn = fmin(mn, red16[w]); mx = fmax(mx, red16[8 + w]); }
+}
+
 // The float64 decision for one column (see above): `row` = the column's fp32 scan, `xs` = its N members
 // as float64 in shared memory.  Called by every thread of a 256-thread CTA.
 // With nparts > 1 several CTAs share a column: part p re-evaluates the candidates whose grid index is
@@ -724,12 +863,22 @@ __device__ __forceinline__ void kde_select_column(int64_t N, int64_t col, double
     // a flat scan (more candidates than the list holds, or an all-zero scan) falls back to
     // evaluating every grid point in float64 (the decision is the same in every part)
     const bool all = ntotal > KDE_MAX_CAND || !(mx > 0.f);
-    const int n_eval = all ? (G - part + nparts - 1) / nparts : ncand;
     const double step = (hi - lo) / (double)(G - 1);
+    int g_first = part, n_eval = ncand;
+    if (all) {                                   // (uniform over the CTA)
+        __shared__ double red16[16];
+        double xmn = CUDART_INF, xmx = -CUDART_INF;
+        for (int64_t i = tid; i < N; i += nthr) { xmn = fmin(xmn, xs[i]); xmx = fmax(xmx, xs[i]); }
+        block_minmax(xmn, xmx, red16);
+        int g_lo, g_hi;
+        kde_nonzero_range(xmn, xmx, kc, lo, step, G, g_lo, g_hi);
+        g_first = g_lo + ((part - g_lo) % nparts + nparts) % nparts;      // first g >= g_lo with g % nparts == part
+        n_eval = (degenerate || g_first > g_hi) ? 0 : (g_hi - g_first) / nparts + 1;
+    }
     double best = -1.0;
     int besti = 0x7fffffff;
     for (int k = warp; k < n_eval; k += nwarps) {
-        const int g = all ? part + k * nparts : cand[k];
+        const int g = all ? g_first + k * nparts : cand[k];
         const double gv = kde_grid_point(g, G, lo, hi, step);
         double acc = 0.0;
         for (int64_t i = lane; i < N; i += 32) {
@@ -760,6 +909,7 @@ __device__ __forceinline__ void kde_select_column(int64_t N, int64_t col, double
                 if (v > best || (v == best && gi < besti)) { best = v; besti = gi; }
             }
         }
+        if (!(best > 0.0)) besti = 0;            // every grid point is zero: the first one is the maximum
         if (degenerate) {
             if (index_out) index_out[col] = -1;
             if (mode_out) mode_out[col] = CUDART_NAN;
@@ -830,8 +980,8 @@ k_kde_scan32_tiled(const T* __restrict__ a, int64_t N, int64_t Q, int64_t col0,
         for (int w = 1; w < nwarps; ++w) { mn = fminf(mn, s_mn[w]); mx = fmaxf(mx, s_mx[w]); inside |= s_in[w]; }
         int ga = 0, gb = G - 1;
         const double h = sqrt(-0.5 / kc.neg_inv_2h2);
-        if (inside && h > 0.0 && step > 0.0 && step <= 7.0 * h) {       // see kde_scan_column
-            const double reach = h * sqrt(2.0 * log(1e7 * (double)N));
+        if (h > 0.0 && step > 0.0) {                                    // see kde_scan_column
+            const double reach = kde_scan_reach(h, step, N, inside != 0);
             const double aa = ((kc.mean + (double)mn - reach) - lo) / step;
             const double bb = ((kc.mean + (double)mx + reach) - lo) / step;
             if (aa > 1.0) ga = (int)fmin(aa - 1.0, (double)(G - 1));
@@ -937,8 +1087,18 @@ k_kde_select64_tiled(const T* __restrict__ a, int64_t N, int64_t Q, int64_t col0
     }
     __syncthreads();
     const bool all = ntotal > KDE_MAX_CAND || !(mx > 0.f);
-    const int n_eval = all ? (G - part + nparts - 1) / nparts : ncand;      // <= n_acc by construction
     const double step = (hi - lo) / (double)(G - 1);
+    int g_first = part, n_eval = ncand;                                       // <= n_acc by construction
+    if (all) {                                   // (uniform over the CTA) one extra pass over the column for its extent
+        __shared__ double red16[16];
+        double xmn = CUDART_INF, xmx = -CUDART_INF;
+        for (int64_t i = tid; i < N; i += nthr) { const double v = (double)a[i * Q + col]; xmn = fmin(xmn, v); xmx = fmax(xmx, v); }
+        block_minmax(xmn, xmx, red16);
+        int g_lo, g_hi;
+        kde_nonzero_range(xmn, xmx, kc, lo, step, G, g_lo, g_hi);
+        g_first = g_lo + ((part - g_lo) % nparts + nparts) % nparts;
+        n_eval = (degenerate || g_first > g_hi) ? 0 : (g_hi - g_first) / nparts + 1;
+    }
     for (int k = tid; k < n_eval && k < n_acc; k += nthr) accs[k] = 0.0;
     for (int64_t t0 = 0; t0 < N; t0 += tile) {
         const int n = (int)(N - t0 < tile ? N - t0 : tile);
@@ -946,7 +1106,7 @@ k_kde_select64_tiled(const T* __restrict__ a, int64_t N, int64_t Q, int64_t col0
         for (int i = tid; i < n; i += nthr) xs[i] = (double)a[(t0 + i) * Q + col];
         __syncthreads();
         for (int k = warp; k < n_eval; k += nwarps) {           // candidate k belongs to warp k % nwarps throughout
-            const int g = all ? part + k * nparts : cand[k];
+            const int g = all ? g_first + k * nparts : cand[k];
             const double gv = kde_grid_point(g, G, lo, hi, step);
             double acc = 0.0;
             for (int i = lane; i < n; i += 32) {
@@ -962,7 +1122,7 @@ k_kde_select64_tiled(const T* __restrict__ a, int64_t N, int64_t Q, int64_t col0
     double best = -1.0;
     int besti = 0x7fffffff;
     for (int k = warp; k < n_eval; k += nwarps) {
-        const int g = all ? part + k * nparts : cand[k];
+        const int g = all ? g_first + k * nparts : cand[k];
         const double acc = accs[k];
         if (acc > best || (acc == best && g < besti)) { best = acc; besti = g; }
     }
@@ -986,6 +1146,7 @@ k_kde_select64_tiled(const T* __restrict__ a, int64_t N, int64_t Q, int64_t col0
                 if (v > best || (v == best && gi < besti)) { best = v; besti = gi; }
             }
         }
+        if (!(best > 0.0)) besti = 0;            // every grid point is zero: the first one is the maximum
         if (degenerate) {
             if (index_out) index_out[col] = -1;
             if (mode_out) mode_out[col] = CUDART_NAN;

@@ -101,10 +101,9 @@ def sharded_statistics(x: torch.Tensor, percentiles=(25, 50, 75), n_grid: int = 
         cols = x[:, a:b].contiguous()
         if stats_fn is None:
             lohi = st.global_minmax(x)
-            m = st.ensemble_moments(cols)
-            pct = st.ensemble_percentile(cols, list(percentiles))
-            mode, idx = st.ensemble_kde_mode(cols, n_grid, grid_range=lohi, return_index=True)
-            st.pack_rows_f64([m["mean"], m["std"], m["var"]] + [pct[k] for k in range(nq)] + [mode, idx], block)
+            m = st.ensemble_summary(cols, percentiles, n_grid, grid_range=lohi)
+            st.pack_rows_f64([m["mean"], m["std"], m["var"]] + [m["pct"][k] for k in range(nq)] +
+                             [m["mode"], m["mode_index"]], block)
         else:
             block[:b - a].copy_(stats_fn(cols, None).t())
     if world > 1:

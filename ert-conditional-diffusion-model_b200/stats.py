@@ -154,6 +154,32 @@ def global_minmax(a, device=None):
     return lohi
 
 
+_SIDE_STREAMS = {}
+
+
+def ensemble_summary(x, percentiles=(25, 50, 75), n_grid=5000, grid_range=None):
+    """Moments, percentiles and KDE mode of a CUDA tensor ``x (N, Q)`` as one step: the three are independent
+    per-column reductions, so the moments (a dependent add chain per column, numpy's order) run on a side stream
+    while the percentile and KDE kernels run on the current one; the streams are joined before returning.
+    Returns ``{"mean","std","var","pct" (len(percentiles), Q),"mode","mode_index"}``."""
+    if not (isinstance(x, torch.Tensor) and x.is_cuda and x.dim() == 2):
+        raise _lib.ErtdiffError("ensemble_summary takes a 2-D CUDA tensor")
+    x = x.contiguous()
+    main = torch.cuda.current_stream(x.device)
+    side = _SIDE_STREAMS.get(x.device)
+    if side is None:
+        side = _SIDE_STREAMS[x.device] = torch.cuda.Stream(x.device)
+    side.wait_stream(main)
+    with torch.cuda.stream(side):
+        out = ensemble_moments(x)
+    out["pct"] = ensemble_percentile(x, list(percentiles))
+    out["mode"], out["mode_index"] = ensemble_kde_mode(x, n_grid, grid_range=grid_range, return_index=True)
+    main.wait_stream(side)
+    for v in (out["mean"], out["std"], out["var"]):
+        v.record_stream(main)
+    return out
+
+
 def ensemble_statistics(a, percentiles=(25, 50, 75), mode=True, n_grid=5000, device=None):
     """Everything ECD.py:747-762 + 867-872 computes for an ensemble of maps, in one call:
     ``{"mean","std","var","percentiles":{q: map},"mode","mode_index"}``."""

@@ -30,8 +30,11 @@ QS = [25, 50, 75, 0, 100, 2.5, 97.5, 33.3, np.float64(50.5), [2.5, 97.5],
 
 
 @pytest.mark.parametrize("dtype", [np.float32, np.float64])
-@pytest.mark.parametrize("N,Q", [(2, 3), (5, 29), (16, 29), (50, 1000), (255, 64), (256, 29), (1000, 33), (1024, 29), (4096, 7), (8192, 29)])
+@pytest.mark.parametrize("N,Q", [(2, 3), (5, 29), (16, 29), (33, 9), (50, 1000), (64, 300), (65, 17), (255, 64), (256, 29), (513, 70),
+                                 (1000, 33), (1024, 29), (1025, 40), (1500, 40), (2048, 33), (3000, 1500), (4096, 7), (8192, 29)])
 def test_percentiles_bit_exact(cuda_dev, dtype, N, Q):
+    # N <= 1024: one warp per column in registers; 1024 < N <= 2048 (or many columns): one CTA per column group in
+    # shared memory; longer columns of few-column arrays: sorted runs + exact multi-run selection
     a = np.random.default_rng(N + Q).normal(size=(N, Q)).astype(dtype)
     for q in QS:
         ref = np.percentile(a, q, axis=0)
@@ -244,3 +247,33 @@ def test_argsort_stable_is_numpy(cuda_dev):
         for dt in (np.float32, np.float64):
             got = eb.stats.argsort_stable(torch.from_numpy(v.astype(dt)).to(cuda_dev)).cpu().numpy()
             assert np.array_equal(got, np.argsort(v.astype(dt), kind="stable")), (n, dt)
+
+
+@pytest.mark.parametrize("N,Q", [(50, 1000), (256, 29), (1000, 33)])
+def test_percentiles_shared_memory_kernel_on_short_columns(cuda_dev, env_override, N, Q):
+    # the CTA-per-column-group kernel (the path of 1024 < N <= 2048) forced onto short columns
+    env_override("ERTDIFF_PCTL_NO_WARP", 1)
+    a = np.random.default_rng(N + Q + 5).normal(size=(N, Q)).astype(np.float32)
+    a[0, 0] = np.nan
+    for q in QS:
+        assert same(eb.ensemble_percentile(a, q), np.percentile(a, q, axis=0)), q
+
+
+@pytest.mark.parametrize("N", [3000, 30000])
+def test_kde_columns_much_narrower_than_the_grid_step(cuda_dev, N):
+    # the grid spans the GLOBAL min..max (ECD.py:749-751): a column whose spread is far below the grid step has a
+    # KDE that is exactly zero on almost every grid point -- in float32 for the scan (beyond 13.2 bandwidths) and in
+    # float64 (beyond 38.6); the kernels skip those points and must still return scipy's argmax, index 0 when
+    # every grid point is zero
+    rng = np.random.default_rng(N)
+    sig = np.array([1e-3, 1e-2, 0.1, 0.5, 3.0, 40.0, 1000.0, 2e-4])
+    off = np.array([0.0, 17.3, -250.0, 1200.0, -3.0, 90.0, 0.0, -3999.0])
+    a = rng.normal(size=(N, sig.size)) * sig + off
+    grid = so.kde_grid(a, 5000)
+    mode, idx = eb.ensemble_kde_mode(a, 5000, return_index=True)
+    _, idx_sp, pdfs = so.kde_mode_scipy(a, grid)
+    for j in np.nonzero(idx != idx_sp)[0]:
+        p = pdfs[:, j]
+        assert abs(p[idx[j]] - p[idx_sp[j]]) <= 1e-13 * p[idx_sp[j]], (j, idx[j], idx_sp[j], p[idx[j]], p[idx_sp[j]])
+    assert (idx != idx_sp).sum() <= 1
+    assert (pdfs.max(axis=0) == 0).any() and (pdfs.max(axis=0) > 0).any()      # both kinds of column are present
