@@ -281,7 +281,11 @@ int ertdiff_ensemble_percentiles(const void* d_a, int dtype, int64_t N, int64_t 
         else if (N > 2048 && Q <= 1024) run_len = 2048;
     }
     if (run_len) return percentiles_by_runs(d_a, dtype, N, Q, qs, index_dtype, d_out, run_len, st);
-    if (N <= 1024 && !std::getenv("ERTDIFF_PCTL_NO_WARP"))     // short columns: one warp sorts a column in registers
+    // short columns of many-column arrays (the reference's 50 realisations of a 65,702-pixel map): one warp sorts a
+    // column in registers.  (Measured: beyond 256 members the shuffle count makes it slower than the shared-memory
+    // kernel -- 1024 x 65,702 f64: 4.2 vs 3.5 ms -- and with few columns it leaves the machine to Q/8 CTAs.)
+    const bool warp_ok = std::getenv("ERTDIFF_PCTL_WARP") ? N <= 1024 : (N <= 256 && Q >= 16 * kNumSMs);
+    if (warp_ok && !std::getenv("ERTDIFF_PCTL_NO_WARP"))
         return percentiles_by_warps(d_a, dtype, N, Q, qs, index_dtype, d_out, st);
     const int NP = (int)NP64;
     int CT = 32;

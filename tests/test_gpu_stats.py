@@ -32,9 +32,16 @@ QS = [25, 50, 75, 0, 100, 2.5, 97.5, 33.3, np.float64(50.5), [2.5, 97.5],
 @pytest.mark.parametrize("dtype", [np.float32, np.float64])
 @pytest.mark.parametrize("N,Q", [(2, 3), (5, 29), (16, 29), (33, 9), (50, 1000), (64, 300), (65, 17), (255, 64), (256, 29), (513, 70),
                                  (1000, 33), (1024, 29), (1025, 40), (1500, 40), (2048, 33), (3000, 1500), (4096, 7), (8192, 29)])
-def test_percentiles_bit_exact(cuda_dev, dtype, N, Q):
-    # N <= 1024: one warp per column in registers; 1024 < N <= 2048 (or many columns): one CTA per column group in
-    # shared memory; longer columns of few-column arrays: sorted runs + exact multi-run selection
+def test_percentiles_bit_exact(cuda_dev, dtype, N, Q, monkeypatch):
+    # three kernels, all bit-identical to numpy: one CTA per column group sorting in shared memory; one warp per column
+    # sorting in registers (short columns of many-column arrays -- forced here for every N <= 1024 as well); longer
+    # columns of few-column arrays: sorted runs + exact multi-run selection
+    if N <= 1024:
+        a = np.random.default_rng(N + Q).normal(size=(N, Q)).astype(dtype)
+        monkeypatch.setenv("ERTDIFF_PCTL_WARP", "1")
+        for q in QS:
+            assert same(eb.ensemble_percentile(a, q), np.percentile(a, q, axis=0)), ("warp kernel", q)
+        monkeypatch.delenv("ERTDIFF_PCTL_WARP")
     a = np.random.default_rng(N + Q).normal(size=(N, Q)).astype(dtype)
     for q in QS:
         ref = np.percentile(a, q, axis=0)
@@ -162,8 +169,9 @@ def test_percentiles_any_size_bit_exact(cuda_dev, dtype, N, Q):
         assert same(got, ref), (q, np.abs(got - ref).max())
     a[N // 2, 1] = np.nan                                # a NaN column is NaN, its neighbours untouched
     assert same(eb.ensemble_percentile(a, [10, 50]), np.percentile(a, [10, 50], axis=0))
-    m = eb.ensemble_moments(a[:, [0, 2]])                # (numpy sums a 1-column array pairwise: keep 2 columns)
-    assert same(m["mean"], np.mean(a[:, [0, 2]], axis=0)) and same(m["std"], np.std(a[:, [0, 2]], axis=0))
+    b = np.ascontiguousarray(a[:, [0, 2]])               # C order: numpy then adds row after row, as the kernel does
+    m = eb.ensemble_moments(b)                           # (a 1-column or Fortran-ordered array is summed pairwise instead)
+    assert same(m["mean"], np.mean(b, axis=0)) and same(m["std"], np.std(b, axis=0))
 
 
 @pytest.mark.parametrize("dtype", [np.float32, np.float64])
@@ -249,14 +257,16 @@ def test_argsort_stable_is_numpy(cuda_dev):
             assert np.array_equal(got, np.argsort(v.astype(dt), kind="stable")), (n, dt)
 
 
-@pytest.mark.parametrize("N,Q", [(50, 1000), (256, 29), (1000, 33)])
-def test_percentiles_shared_memory_kernel_on_short_columns(cuda_dev, env_override, N, Q):
-    # the CTA-per-column-group kernel (the path of 1024 < N <= 2048) forced onto short columns
+@pytest.mark.parametrize("N,Q", [(50, 4693 * 14), (200, 3000), (256, 2400)])
+def test_percentiles_many_short_columns(cuda_dev, env_override, N, Q):
+    # the reference's own shape (50 realisations of a 4693 x 14 map, ECD.py:870-872) takes the warp-per-column kernel;
+    # the shared-memory kernel forced onto the same data must agree with it and with numpy, NaN pixels included
+    a = np.random.default_rng(N + Q + 5).lognormal(size=(N, Q))
+    a[N // 2, 7] = np.nan
+    ref = np.percentile(a, [25, 50, 75], axis=0)
+    assert same(eb.ensemble_percentile(a, [25, 50, 75]), ref)
     env_override("ERTDIFF_PCTL_NO_WARP", 1)
-    a = np.random.default_rng(N + Q + 5).normal(size=(N, Q)).astype(np.float32)
-    a[0, 0] = np.nan
-    for q in QS:
-        assert same(eb.ensemble_percentile(a, q), np.percentile(a, q, axis=0)), q
+    assert same(eb.ensemble_percentile(a, [25, 50, 75]), ref)
 
 
 @pytest.mark.parametrize("N", [3000, 30000])
