@@ -321,7 +321,7 @@ class Runner:
         def stats(x):
             if world > 1:                       # per-column statistics: columns split over the ranks
                 return eb.parallel.sharded_statistics(x, PERCENTILES, KDE_GRID)
-            return eb.ensemble_summary(x, PERCENTILES, KDE_GRID)     # moments on a side stream beside percentiles + KDE
+            return eb.ensemble_summary(x, PERCENTILES, KDE_GRID)     # one library call, packed float64 records
 
         def step_device(i):
             """inputs resident in HBM"""
@@ -397,8 +397,7 @@ class Runner:
         value = total * steps / (ms_dev * 1e-3)
         e2e_value = total * steps / (ms_e2e * 1e-3)
         h2d = cond_host.numel() * 4      # the condition; the 3 x 4 KB schedule is content-cached on the device after step 1
-        d2h = 4 * total * P + 8 * (5 + len(PERCENTILES)) * P if world > 1 else \
-            4 * (total * P + 3 * P) + 8 * (len(PERCENTILES) * P + P)
+        d2h = 4 * total * P + 8 * (5 + len(PERCENTILES)) * P      # the fields (f32) + the packed statistics records (f64)
         rec = {
             "name": spec.name, "metric": METRIC, "value": value, "unit": "samples/s",
             "n_gpus": world, "steps": steps, "warmup": warmup,

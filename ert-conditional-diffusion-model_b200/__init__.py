@@ -16,7 +16,7 @@ from .sampler import (get_diffusion_schedule, get_timestep_embedding, sample_mod
                       sample_ensemble, run_chain, step_coefficients, posterior_update,
                       philox_normal, debug_umma_gemm)
 from .stats import (ensemble_moments, ensemble_mean, ensemble_std, ensemble_var,
-                    ensemble_percentile, ensemble_kde_mode, ensemble_statistics, ensemble_summary, uq_calibration, misfit_metrics,
+                    ensemble_percentile, ensemble_kde_mode, ensemble_statistics, ensemble_summary, ensemble_summary_packed, uq_calibration, misfit_metrics,
                     wasserstein_distance)
 from .transforms import untransform_and_check, inverse_transform, check_param_bounds
 from .checkpoint import load_best_model, save_checkpoint

@@ -81,6 +81,9 @@ SIGNATURES = {
                                          C.c_double, C.c_double, C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p]),
     "ertdiff_wasserstein_distance": (C.c_int, [C.c_void_p, C.c_void_p, C.c_int, C.c_int64, C.c_int64, C.c_int64,
                                                C.c_void_p, C.c_void_p]),
+    "ertdiff_ensemble_summary": (C.c_int, [C.c_void_p, C.c_int, C.c_int64, C.c_int64, C.c_int64, C.c_int64,
+                                           C.POINTER(C.c_double), C.c_int32, C.c_int32, C.c_void_p, C.c_void_p, C.c_int64,
+                                           C.c_void_p]),
     "ertdiff_pack_rows_f64": (C.c_int, [C.POINTER(C.c_void_p), C.POINTER(C.c_int32), C.c_int32, C.c_int64, C.c_int64,
                                         C.c_void_p, C.c_void_p]),
     "ertdiff_check_bounds": (C.c_int, [C.c_void_p, C.c_int, C.c_int64, C.c_int32, C.c_void_p, C.c_void_p, C.c_void_p,

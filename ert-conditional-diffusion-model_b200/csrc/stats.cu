@@ -535,6 +535,75 @@ int ertdiff_pack_rows_f64(const void* const* h_rows, const int32_t* h_dtypes, in
     return 0;
 }
 
+// Everything the path reports about an ensemble, for a window of columns, in ONE call (the column-sharded multi-GPU
+// statistics issue this once per step: no per-statistic host round trips, no allocations).
+int ertdiff_ensemble_summary(const void* d_a, int dtype, int64_t N, int64_t Q, int64_t col0, int64_t ncols,
+                             const double* h_q, int32_t nq, int32_t n_grid, double* d_lohi_out, double* d_out, int64_t ld,
+                             void* stream) {
+    ERT_REQUIRE(d_a && d_out && N > 1 && Q > 0 && col0 >= 0 && ncols > 0 && col0 + ncols <= Q, "ensemble_summary: bad arguments");
+    ERT_REQUIRE(dtype == ERTDIFF_F32 || dtype == ERTDIFF_F64, "ensemble_summary: bad dtype");
+    ERT_REQUIRE(nq >= 0 && 5 + nq <= kMaxPackRows && ld >= 5 + nq && (nq == 0 || h_q) && n_grid > 1, "ensemble_summary: bad query / ld");
+    cudaStream_t st = (cudaStream_t)stream;
+    const size_t esz = dtype == ERTDIFF_F32 ? 4 : 8;
+    auto up = [](size_t b) { return (b + 255) & ~(size_t)255; };
+    // private scratch (the statistics entry points called below use the shared workspace themselves)
+    static void* scratch[64] = {};
+    static size_t scratch_bytes[64] = {};
+    int dev = 0;
+    ERT_CUDA(cudaGetDevice(&dev));
+    ERT_REQUIRE(dev >= 0 && dev < 64, "ensemble_summary: device index out of range");
+    WorkspaceLease lease(st);           // serialises concurrent callers on this device (the nested calls re-enter it)
+    const bool whole = ncols == Q;
+    const size_t b_a = whole ? 0 : up((size_t)N * ncols * esz), b_m = up((size_t)ncols * esz), b_p = up((size_t)(nq ? nq : 1) * ncols * 8),
+                 b_v = up((size_t)ncols * 8);
+    const size_t need = b_a + 3 * b_m + b_p + 2 * b_v + 256;
+    if (scratch_bytes[dev] < need) {
+        if (scratch[dev]) { ERT_CUDA(cudaDeviceSynchronize()); cudaFree(scratch[dev]); scratch[dev] = nullptr; scratch_bytes[dev] = 0; }
+        ERT_CUDA(cudaMalloc(&scratch[dev], need));
+        scratch_bytes[dev] = need;
+    }
+    char* base = (char*)scratch[dev];
+    void* cols = whole ? const_cast<void*>(d_a) : (void*)base;
+    char* p_mean = base + b_a; char* p_std = p_mean + b_m; char* p_var = p_std + b_m; char* p_pct = p_var + b_m;
+    double* p_mode = (double*)(p_pct + b_p);
+    int64_t* p_idx = (int64_t*)((char*)p_mode + b_v);
+    double* p_lohi = (double*)((char*)p_idx + b_v);
+    if (!whole) {
+        const int64_t n = N * ncols;
+        if (dtype == ERTDIFF_F32) k_slice_columns<float><<<(unsigned)((n + 255) / 256), 256, 0, st>>>((const float*)d_a, N, Q, col0, ncols, (float*)cols);
+        else k_slice_columns<double><<<(unsigned)((n + 255) / 256), 256, 0, st>>>((const double*)d_a, N, Q, col0, ncols, (double*)cols);
+        ERT_LAUNCH_CHECK("k_slice_columns");
+    }
+    // the KDE grid spans the min / max of the WHOLE array (ECD.py:749-751), not of this window
+    if (int rc = ertdiff_minmax(d_a, dtype, N * Q, p_lohi, stream)) return rc;
+    if (d_lohi_out) ERT_CUDA(cudaMemcpyAsync(d_lohi_out, p_lohi, 2 * sizeof(double), cudaMemcpyDeviceToDevice, st));
+    // the moments are a dependent add chain per column (numpy's order; 170 us at 18,944 members): they run on a side
+    // stream beside the percentile and KDE kernels and are joined before the packing launch
+    static cudaStream_t side[64] = {};
+    static cudaEvent_t ev_fork[64] = {}, ev_join[64] = {};
+    if (!side[dev]) {
+        ERT_CUDA(cudaStreamCreateWithFlags(&side[dev], cudaStreamNonBlocking));
+        ERT_CUDA(cudaEventCreateWithFlags(&ev_fork[dev], cudaEventDisableTiming));
+        ERT_CUDA(cudaEventCreateWithFlags(&ev_join[dev], cudaEventDisableTiming));
+    }
+    ERT_CUDA(cudaEventRecord(ev_fork[dev], st));
+    ERT_CUDA(cudaStreamWaitEvent(side[dev], ev_fork[dev], 0));
+    if (int rc = ertdiff_ensemble_moments(cols, dtype, N, ncols, p_mean, p_std, p_var, side[dev])) return rc;
+    ERT_CUDA(cudaEventRecord(ev_join[dev], side[dev]));
+    if (nq)
+        if (int rc = ertdiff_ensemble_percentiles(cols, dtype, N, ncols, h_q, nq, ERTDIFF_F64, p_pct, stream)) return rc;
+    if (int rc = ertdiff_ensemble_kde_mode(cols, dtype, N, ncols, p_lohi, n_grid, p_mode, p_idx, stream)) return rc;
+    ERT_CUDA(cudaStreamWaitEvent(st, ev_join[dev], 0));
+    const void* rows[kMaxPackRows];
+    int32_t dts[kMaxPackRows];
+    rows[0] = p_mean; rows[1] = p_std; rows[2] = p_var;
+    dts[0] = dts[1] = dts[2] = dtype;
+    for (int k = 0; k < nq; ++k) { rows[3 + k] = p_pct + (size_t)k * ncols * 8; dts[3 + k] = ERTDIFF_F64; }
+    rows[3 + nq] = p_mode; dts[3 + nq] = ERTDIFF_F64;
+    rows[4 + nq] = p_idx; dts[4 + nq] = 2;
+    return ertdiff_pack_rows_f64(rows, dts, 5 + nq, ncols, ld, d_out, stream);
+}
+
 int ertdiff_check_bounds(const void* d_v, int dtype, int64_t B, int32_t P, const double* d_lim_lo,
                          const double* d_lim_hi, uint8_t* d_valid, int32_t* d_first_bad, void* stream) {
     ERT_REQUIRE(d_v && d_lim_lo && d_lim_hi && B > 0 && P > 0 && P <= 32, "check_bounds: bad arguments");

@@ -1332,6 +1332,15 @@ __global__ void k_pack_rows(const __grid_constant__ PackRows p, int64_t ncols, i
     out[c * ld + r] = v;
 }
 
+// columns [col0, col0 + ncols) of a row-major (N, Q) array -> a contiguous (N, ncols) copy
+template <typename T>
+__global__ void k_slice_columns(const T* __restrict__ a, int64_t N, int64_t Q, int64_t col0, int64_t ncols, T* __restrict__ out) {
+    const int64_t idx = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+    if (idx >= N * ncols) return;
+    const int64_t i = idx / ncols, c = idx % ncols;
+    out[idx] = a[i * Q + col0 + c];
+}
+
 // check_param_bounds alone (ECD.py:183-218) on values of either dtype: a row is dropped when any parameter is
 // `< min or > max` (so a NaN never drops a row, as in the reference); first_bad = the parameter the reference's
 // loop reports before it breaks.  One warp per row.

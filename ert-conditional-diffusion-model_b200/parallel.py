@@ -81,11 +81,11 @@ def sharded_statistics(x: torch.Tensor, percentiles=(25, 50, 75), n_grid: int = 
     every rank.  The KDE grid spans the global min/max of the whole array (ECD.py:749-751), which each
     rank takes from its own copy of ``x`` -- so the result is bit-identical to the unsharded call for
     any number of ranks.  Returns ``{"mean","std","var","pct" (len(percentiles), Q),"mode","mode_index"}``
-    as float64 views of one gathered block ``"packed" (Q, 5 + len(percentiles))`` (``mode_index`` int64).
+    as float64 views of one gathered block ``"packed" (Q, 5 + len(percentiles))`` (``mode_index``: integral values).
 
-    Per rank: the statistics kernels on its columns, ONE packing launch (``ertdiff_pack_rows_f64``: every
-    result row -> one float64 record per column), ONE equal-sized all-gather of ``(q_max, rows)`` records, and
-    (only when ``Q`` does not divide evenly) one gather that drops the padding records.
+    Per rank and step: ONE library call (``ertdiff_ensemble_summary``: the statistics kernels on its column window,
+    packed as one float64 record per column), ONE equal-sized all-gather of ``(q_max, rows)`` records, and (only
+    when ``Q`` does not divide evenly) one gather that drops the padding records.
     ``stats_fn(x_cols, lohi) -> (rows, q_local)`` float64 replaces the device kernels in CPU tests."""
     from . import stats as st
     world = dist.get_world_size(group) if dist.is_initialized() else 1
@@ -98,14 +98,10 @@ def sharded_statistics(x: torch.Tensor, percentiles=(25, 50, 75), n_grid: int = 
     block = torch.zeros(q_max, rows, device=x.device, dtype=torch.float64) if (b - a) < q_max else \
         torch.empty(q_max, rows, device=x.device, dtype=torch.float64)
     if b > a:
-        cols = x[:, a:b].contiguous()
         if stats_fn is None:
-            lohi = st.global_minmax(x)
-            m = st.ensemble_summary(cols, percentiles, n_grid, grid_range=lohi)
-            st.pack_rows_f64([m["mean"], m["std"], m["var"]] + [m["pct"][k] for k in range(nq)] +
-                             [m["mode"], m["mode_index"]], block)
+            st.ensemble_summary_packed(x, percentiles, n_grid, col0=a, ncols=b - a, out=block)
         else:
-            block[:b - a].copy_(stats_fn(cols, None).t())
+            block[:b - a].copy_(stats_fn(x[:, a:b].contiguous(), None).t())
     if world > 1:
         gathered = torch.empty(world * q_max, rows, device=x.device, dtype=torch.float64)
         if x.is_cuda:
@@ -128,9 +124,7 @@ def sharded_statistics(x: torch.Tensor, percentiles=(25, 50, 75), n_grid: int = 
         full = gathered
     else:
         full = block[:Q]
-    return {"mean": full[:, 0], "std": full[:, 1], "var": full[:, 2], "pct": full[:, 3:3 + nq].t(),
-            "mode": full[:, 3 + nq], "mode_index": full[:, 4 + nq].to(torch.int64),
-            "packed": full}        # (Q, 5 + nq) float64: everything above in one contiguous block (one D2H copy)
+    return st.summary_views(full, nq)
 
 
 def sharded_misfit(sim_local: torch.Tensor, observed: torch.Tensor, n_maps: int, A: float = 0.1, B: float = 0.01,

@@ -154,30 +154,43 @@ def global_minmax(a, device=None):
     return lohi
 
 
-_SIDE_STREAMS = {}
-
-
-def ensemble_summary(x, percentiles=(25, 50, 75), n_grid=5000, grid_range=None):
-    """Moments, percentiles and KDE mode of a CUDA tensor ``x (N, Q)`` as one step: the three are independent
-    per-column reductions, so the moments (a dependent add chain per column, numpy's order) run on a side stream
-    while the percentile and KDE kernels run on the current one; the streams are joined before returning.
-    Returns ``{"mean","std","var","pct" (len(percentiles), Q),"mode","mode_index"}``."""
-    if not (isinstance(x, torch.Tensor) and x.is_cuda and x.dim() == 2):
-        raise _lib.ErtdiffError("ensemble_summary takes a 2-D CUDA tensor")
+def ensemble_summary_packed(x, percentiles=(25, 50, 75), n_grid=5000, col0=0, ncols=None, out=None, lohi_out=None):
+    """One library call (``ertdiff_ensemble_summary``) for everything the path reports about the ensemble
+    ``x (N, Q)`` (CUDA, float32 / float64) for the column window ``[col0, col0 + ncols)``: returns the float64 block
+    ``(ncols, 5 + len(percentiles))`` with one record per column -- ``[mean, std, var, percentiles..., mode,
+    mode grid index]`` (the moments are the array-dtype results widened; the index is integral).  The KDE grid spans
+    the min / max of the WHOLE array (ECD.py:749-751).  ``out``: a preallocated contiguous float64 block with at
+    least ``ncols`` rows to write into."""
+    if not (isinstance(x, torch.Tensor) and x.is_cuda and x.dim() == 2 and x.dtype in _DT):
+        raise _lib.ErtdiffError("ensemble_summary_packed takes a 2-D float32 / float64 CUDA tensor")
     x = x.contiguous()
-    main = torch.cuda.current_stream(x.device)
-    side = _SIDE_STREAMS.get(x.device)
-    if side is None:
-        side = _SIDE_STREAMS[x.device] = torch.cuda.Stream(x.device)
-    side.wait_stream(main)
-    with torch.cuda.stream(side):
-        out = ensemble_moments(x)
-    out["pct"] = ensemble_percentile(x, list(percentiles))
-    out["mode"], out["mode_index"] = ensemble_kde_mode(x, n_grid, grid_range=grid_range, return_index=True)
-    main.wait_stream(side)
-    for v in (out["mean"], out["std"], out["var"]):
-        v.record_stream(main)
+    N, Q = x.shape
+    ncols = Q - col0 if ncols is None else ncols
+    nq = len(percentiles)
+    rows = 5 + nq
+    if out is None:
+        out = torch.empty(ncols, rows, device=x.device, dtype=torch.float64)
+    elif out.dtype != torch.float64 or out.dim() != 2 or out.size(1) != rows or out.size(0) < ncols or not out.is_contiguous():
+        raise ValueError("out must be a contiguous float64 (>= ncols, 5 + len(percentiles)) block")
+    qarr = (C.c_double * max(nq, 1))(*[float(q) for q in percentiles])
+    with torch.cuda.device(x.device):
+        _lib.check(_lib.load().ertdiff_ensemble_summary(
+            _lib.ptr(x), _DT[x.dtype], N, Q, int(col0), int(ncols), qarr, nq, int(n_grid), _lib.ptr(lohi_out),
+            _lib.ptr(out), rows, _lib.stream_ptr(x.device)), "ensemble_summary")
     return out
+
+
+def summary_views(block, nq):
+    """Named views of a packed summary block ``(Q, 5 + nq)``: ``mean, std, var, pct (nq, Q), mode, mode_index``
+    (``mode_index`` as the integral float64 values of the block; ``.long()`` them where an index tensor is needed)."""
+    return {"mean": block[:, 0], "std": block[:, 1], "var": block[:, 2], "pct": block[:, 3:3 + nq].t(),
+            "mode": block[:, 3 + nq], "mode_index": block[:, 4 + nq], "packed": block}
+
+
+def ensemble_summary(x, percentiles=(25, 50, 75), n_grid=5000):
+    """Moments, percentiles and KDE mode of a CUDA tensor ``x (N, Q)`` as one step and one library call; returns
+    float64 views of the packed block (see ``ensemble_summary_packed`` / ``summary_views``)."""
+    return summary_views(ensemble_summary_packed(x, percentiles, n_grid), len(percentiles))
 
 
 def ensemble_statistics(a, percentiles=(25, 50, 75), mode=True, n_grid=5000, device=None):

@@ -250,6 +250,16 @@ int ertdiff_untransform_bounds(const float* d_u, int64_t B, int32_t P, float a, 
                                const double* d_lim_lo, const double* d_lim_hi, float* d_phys,
                                uint8_t* d_valid, int32_t* d_first_bad, void* stream);
 
+/* Everything the path reports about an ensemble (ECD.py:747-762, 867-872), for columns [col0, col0 + ncols) of the
+ * row-major (N, Q) array d_a, in one call: mean / std / var, the nq percentiles h_q (float64 index arithmetic), and the
+ * KDE mode on the common grid of n_grid points spanning the min / max of the WHOLE array -- packed as float64 records
+ * d_out[c * ld + r], r = 0 mean, 1 std, 2 var, 3..2+nq percentiles, 3+nq mode, 4+nq mode grid index (integral), one record
+ * of ld >= 5 + nq doubles per column.  d_lohi_out (optional, 2 doubles) receives the grid range.  Same kernels and bits as
+ * the separate entry points; this is what each rank of the column-sharded statistics calls once per step. */
+int ertdiff_ensemble_summary(const void* d_a, int dtype, int64_t N, int64_t Q, int64_t col0, int64_t ncols,
+                             const double* h_q, int32_t nq, int32_t n_grid, double* d_lohi_out, double* d_out, int64_t ld,
+                             void* stream);
+
 /* Pack n_rows (<= 64) device row vectors of ncols values each -- dtype per row: ERTDIFF_F32, ERTDIFF_F64 or 2 =
  * int64 -- into one float64 block d_out[c * ld + r] (one contiguous record of ld >= n_rows doubles per column).
  * h_rows / h_dtypes are HOST arrays.  Used by the column-sharded statistics: one launch, then one all-gather. */

@@ -144,7 +144,7 @@ def test_sharded_statistics_single_rank_equals_plain(cuda_dev):
     for k in ("mean", "std", "var"):
         assert torch.equal(sh[k].to(st[k].dtype), st[k])
     assert torch.equal(sh["pct"], pct.double()) and torch.equal(sh["mode"], st["mode"])
-    assert torch.equal(sh["mode_index"], st["mode_index"])
+    assert torch.equal(sh["mode_index"].long(), st["mode_index"])
 
 
 # ---- ensembles beyond one CTA's shared memory (round 2: no size cap) -------------------------------
@@ -287,3 +287,23 @@ def test_kde_columns_much_narrower_than_the_grid_step(cuda_dev, N):
         assert abs(p[idx[j]] - p[idx_sp[j]]) <= 1e-13 * p[idx_sp[j]], (j, idx[j], idx_sp[j], p[idx[j]], p[idx_sp[j]])
     assert (idx != idx_sp).sum() <= 1
     assert (pdfs.max(axis=0) == 0).any() and (pdfs.max(axis=0) > 0).any()      # both kinds of column are present
+
+
+@pytest.mark.parametrize("dtype", [torch.float32, torch.float64])
+@pytest.mark.parametrize("N,Q,col0,ncols", [(300, 29, 0, 29), (300, 29, 8, 4), (5000, 29, 25, 4), (2000, 64, 3, 17)])
+def test_fused_summary_equals_the_separate_calls(cuda_dev, dtype, N, Q, col0, ncols):
+    # ertdiff_ensemble_summary (one call, packed records, a column window of the array) against the separate
+    # entry points on the sliced columns with the whole array's grid range: identical bits
+    x = (torch.randn(N, Q, device=cuda_dev, generator=torch.Generator(cuda_dev).manual_seed(N + Q)) * 7 + 1).to(dtype)
+    qs = [2.5, 50.0, 97.5]
+    lohi = torch.empty(2, device=cuda_dev, dtype=torch.float64)
+    block = eb.ensemble_summary_packed(x, qs, 777, col0=col0, ncols=ncols, lohi_out=lohi)
+    cols = x[:, col0:col0 + ncols].contiguous()
+    m = eb.ensemble_moments(cols)
+    pct = eb.ensemble_percentile(cols, qs)
+    assert torch.equal(lohi, eb.stats.global_minmax(x))
+    mode, idx = eb.ensemble_kde_mode(cols, 777, grid_range=lohi, return_index=True)
+    v = eb.stats.summary_views(block, 3)
+    for k in ("mean", "std", "var"):
+        assert torch.equal(v[k], m[k].double()), k
+    assert torch.equal(v["pct"], pct) and torch.equal(v["mode"], mode) and torch.equal(v["mode_index"].long(), idx)
