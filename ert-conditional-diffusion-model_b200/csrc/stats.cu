@@ -196,6 +196,26 @@ static int percentiles_by_runs(const void* d_a, int dtype, int64_t N, int64_t Q,
     return percentiles_by_runs_t<double, double, double>(d_a, N, Q, qs, d_out, CH, st);
 }
 
+// Run length of the sorted-runs percentile path for an (N, Q) array, or 0 when a shared-memory kernel serves it
+// (those need no scratch, so the fused summary can run them beside the KDE kernels).
+static int percentile_run_length(int dtype, int64_t N, int64_t Q) {
+    // (ERTDIFF_PCTL_RUN_LEN: forces the run path with that run length, for tests)
+    if (const char* e = std::getenv("ERTDIFF_PCTL_RUN_LEN")) {
+        const int v = std::atoi(e);
+        if (v >= 2 && v <= 8192 && (v & (v - 1)) == 0) return v;
+    }
+    const size_t esz = dtype == ERTDIFF_F32 ? 4 : 8;
+    int64_t NP64 = 1;
+    while (NP64 < N) NP64 <<= 1;
+    // too long for one CTA's shared memory -> runs.  Few columns (the chain's own (members, 29) output) also go
+    // through runs as soon as a column exceeds 2048 members: a single CTA per column would leave the machine to
+    // Q CTAs sorting 8K..32K elements each (18,944 x 29: 506 -> 92 us), while short runs spread the sort over
+    // R x Q CTAs and the selection costs a warp per (column, query)
+    if ((size_t)NP64 * esz + 64 > 200 * 1024) return Q <= 1024 ? 2048 : 8192;
+    if (N > 2048 && Q <= 1024) return 2048;
+    return 0;
+}
+
 }  // namespace ertdiff
 
 using namespace ertdiff;
@@ -265,21 +285,7 @@ int ertdiff_ensemble_percentiles(const void* d_a, int dtype, int64_t N, int64_t 
     const size_t budget = 200 * 1024;
     int64_t NP64 = 1;
     while (NP64 < N) NP64 <<= 1;
-    // columns longer than one CTA's shared memory (or ERTDIFF_PCTL_RUN_LEN set, for tests): sorted runs + exact
-    // multi-run selection
-    int run_len = 0;
-    if (const char* e = std::getenv("ERTDIFF_PCTL_RUN_LEN")) {
-        const int v = std::atoi(e);
-        if (v >= 2 && v <= 8192 && (v & (v - 1)) == 0) run_len = v;
-    }
-    if (run_len == 0) {
-        // too long for one CTA's shared memory -> runs.  Few columns (the chain's own (members, 29) output) also go
-        // through runs as soon as a column exceeds 2048 members: a single CTA per column would leave the machine to
-        // Q CTAs sorting 8K..32K elements each (18,944 x 29: 506 -> ~150 us), while short runs spread the sort over
-        // R x Q CTAs and the selection costs a warp per (column, query)
-        if ((size_t)NP64 * esz + 64 > budget) run_len = Q <= 1024 ? 2048 : 8192;
-        else if (N > 2048 && Q <= 1024) run_len = 2048;
-    }
+    const int run_len = percentile_run_length(dtype, N, Q);
     if (run_len) return percentiles_by_runs(d_a, dtype, N, Q, qs, index_dtype, d_out, run_len, st);
     // short columns of many-column arrays (the reference's 50 realisations of a 65,702-pixel map): one warp sorts a
     // column in registers.  (Measured: beyond 256 members the shuffle count makes it slower than the shared-memory
@@ -485,10 +491,34 @@ int ertdiff_ensemble_kde_mode_auto(const void* d_a, int dtype, int64_t N, int64_
     const dim3 grid((unsigned)Q, (unsigned)n_gchunks);
     const size_t smem = (size_t)N * 12;
     if (dtype == ERTDIFF_F32)
-        k_kde_small<float><<<grid, 256, smem, st>>>((const float*)d_a, N, Q, 1, d_lohi, G, gchunk, factor * factor,
+        k_kde_small<float><<<grid, 256, smem, st>>>((const float*)d_a, N, Q, 0, 1, d_lohi, G, gchunk, factor * factor,
                                                     (float*)ws, tk, d_mode, d_index);
     else
-        k_kde_small<double><<<grid, 256, smem, st>>>((const double*)d_a, N, Q, 1, d_lohi, G, gchunk, factor * factor,
+        k_kde_small<double><<<grid, 256, smem, st>>>((const double*)d_a, N, Q, 0, 1, d_lohi, G, gchunk, factor * factor,
+                                                     (float*)ws, tk, d_mode, d_index);
+    ERT_LAUNCH_CHECK("k_kde_small");
+    return 0;
+}
+
+// the fused small-ensemble KDE launch on a column window of the array (grid range from the WHOLE array)
+static int kde_small_window(const void* d_a, int dtype, int64_t N, int64_t Q, int64_t col0, int64_t ncols, int G,
+                            double* d_lohi, double* d_mode, int64_t* d_index, cudaStream_t st) {
+    WorkspaceLease lease(st);
+    unsigned int* tk = nullptr;
+    if (int rc = lease.tickets(&tk)) return rc;
+    void* ws = nullptr;
+    if (int rc = lease.get((size_t)ncols * G * sizeof(float), &ws)) return rc;
+    int n_gchunks = (G + 255) / 256;
+    while (n_gchunks > 1 && ncols * n_gchunks > 4 * kNumSMs) n_gchunks = (n_gchunks + 1) / 2;
+    const int gchunk = (G + n_gchunks - 1) / n_gchunks;
+    const double factor = std::pow((double)N, -1.0 / 5.0);
+    const dim3 grid((unsigned)ncols, (unsigned)n_gchunks);
+    const size_t smem = (size_t)N * 12;
+    if (dtype == ERTDIFF_F32)
+        k_kde_small<float><<<grid, 256, smem, st>>>((const float*)d_a, N, Q, col0, 1, d_lohi, G, gchunk, factor * factor,
+                                                    (float*)ws, tk, d_mode, d_index);
+    else
+        k_kde_small<double><<<grid, 256, smem, st>>>((const double*)d_a, N, Q, col0, 1, d_lohi, G, gchunk, factor * factor,
                                                      (float*)ws, tk, d_mode, d_index);
     ERT_LAUNCH_CHECK("k_kde_small");
     return 0;
@@ -574,26 +604,47 @@ int ertdiff_ensemble_summary(const void* d_a, int dtype, int64_t N, int64_t Q, i
         else k_slice_columns<double><<<(unsigned)((n + 255) / 256), 256, 0, st>>>((const double*)d_a, N, Q, col0, ncols, (double*)cols);
         ERT_LAUNCH_CHECK("k_slice_columns");
     }
-    // the KDE grid spans the min / max of the WHOLE array (ECD.py:749-751), not of this window
-    if (int rc = ertdiff_minmax(d_a, dtype, N * Q, p_lohi, stream)) return rc;
-    if (d_lohi_out) ERT_CUDA(cudaMemcpyAsync(d_lohi_out, p_lohi, 2 * sizeof(double), cudaMemcpyDeviceToDevice, st));
+    // the KDE grid spans the min / max of the WHOLE array (ECD.py:749-751), not of this window.  Small ensembles: the
+    // one-launch KDE kernel takes the range itself (every CTA scans the whole array: N*Q <= 64 K values)
+    const bool kde_small = N * Q <= 65536 && N < 1024 && ncols <= ertdiff::WorkspaceLease::kTicketSlots;
+    if (!kde_small)
+        if (int rc = ertdiff_minmax(d_a, dtype, N * Q, p_lohi, stream)) return rc;
     // the moments are a dependent add chain per column (numpy's order; 170 us at 18,944 members): they run on a side
     // stream beside the percentile and KDE kernels and are joined before the packing launch
-    static cudaStream_t side[64] = {};
-    static cudaEvent_t ev_fork[64] = {}, ev_join[64] = {};
-    if (!side[dev]) {
-        ERT_CUDA(cudaStreamCreateWithFlags(&side[dev], cudaStreamNonBlocking));
+    // the three statistics are independent per-column reductions.  The moments are a dependent add chain per column
+    // (numpy's order; 170 us at 18,944 members): they run on a side stream beside the percentile and KDE kernels.  The
+    // percentiles join them on a second side stream whenever they go through a kernel that needs no scratch (the
+    // run path shares the per-device scratch with the KDE kernels, so it stays on the caller's stream).  Both are
+    // joined before the packing launch.
+    static cudaStream_t side[64][2] = {};
+    static cudaEvent_t ev_fork[64] = {}, ev_join[64][2] = {};
+    if (!side[dev][0]) {
+        for (int k = 0; k < 2; ++k) {
+            ERT_CUDA(cudaStreamCreateWithFlags(&side[dev][k], cudaStreamNonBlocking));
+            ERT_CUDA(cudaEventCreateWithFlags(&ev_join[dev][k], cudaEventDisableTiming));
+        }
         ERT_CUDA(cudaEventCreateWithFlags(&ev_fork[dev], cudaEventDisableTiming));
-        ERT_CUDA(cudaEventCreateWithFlags(&ev_join[dev], cudaEventDisableTiming));
     }
     ERT_CUDA(cudaEventRecord(ev_fork[dev], st));
-    ERT_CUDA(cudaStreamWaitEvent(side[dev], ev_fork[dev], 0));
-    if (int rc = ertdiff_ensemble_moments(cols, dtype, N, ncols, p_mean, p_std, p_var, side[dev])) return rc;
-    ERT_CUDA(cudaEventRecord(ev_join[dev], side[dev]));
-    if (nq)
+    ERT_CUDA(cudaStreamWaitEvent(side[dev][0], ev_fork[dev], 0));
+    if (int rc = ertdiff_ensemble_moments(cols, dtype, N, ncols, p_mean, p_std, p_var, side[dev][0])) return rc;
+    ERT_CUDA(cudaEventRecord(ev_join[dev][0], side[dev][0]));
+    const bool pct_beside = nq > 0 && percentile_run_length(dtype, N, ncols) == 0;
+    if (pct_beside) {
+        ERT_CUDA(cudaStreamWaitEvent(side[dev][1], ev_fork[dev], 0));
+        if (int rc = ertdiff_ensemble_percentiles(cols, dtype, N, ncols, h_q, nq, ERTDIFF_F64, p_pct, side[dev][1])) return rc;
+        ERT_CUDA(cudaEventRecord(ev_join[dev][1], side[dev][1]));
+    } else if (nq) {
         if (int rc = ertdiff_ensemble_percentiles(cols, dtype, N, ncols, h_q, nq, ERTDIFF_F64, p_pct, stream)) return rc;
-    if (int rc = ertdiff_ensemble_kde_mode(cols, dtype, N, ncols, p_lohi, n_grid, p_mode, p_idx, stream)) return rc;
-    ERT_CUDA(cudaStreamWaitEvent(st, ev_join[dev], 0));
+    }
+    if (kde_small) {
+        if (int rc = kde_small_window(d_a, dtype, N, Q, col0, ncols, n_grid, p_lohi, p_mode, p_idx, st)) return rc;
+    } else {
+        if (int rc = ertdiff_ensemble_kde_mode(cols, dtype, N, ncols, p_lohi, n_grid, p_mode, p_idx, stream)) return rc;
+    }
+    if (d_lohi_out) ERT_CUDA(cudaMemcpyAsync(d_lohi_out, p_lohi, 2 * sizeof(double), cudaMemcpyDeviceToDevice, st));
+    ERT_CUDA(cudaStreamWaitEvent(st, ev_join[dev][0], 0));
+    if (pct_beside) ERT_CUDA(cudaStreamWaitEvent(st, ev_join[dev][1], 0));
     const void* rows[kMaxPackRows];
     int32_t dts[kMaxPackRows];
     rows[0] = p_mean; rows[1] = p_std; rows[2] = p_var;

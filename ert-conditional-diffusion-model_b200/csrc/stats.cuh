@@ -1161,13 +1161,14 @@ k_kde_select64_tiled(const T* __restrict__ a, int64_t N, int64_t Q, int64_t col0
 // Small ensembles (N*Q <= 64 K values, the chain's own (members, 29) output): the five dependent
 // launches above (two for the global range, column constants, scan, select) cost more in start-up
 // latency than in work, so ONE launch does it all.  grid = (Q, n_gchunks), 256 threads:
-//   1. every CTA takes the global min / max of the whole array itself (a few dozen loads per thread)
+//   1. every CTA takes the global min / max of the whole (N, Q) array itself (a few dozen loads per thread); the
+//      columns of the launch are the window [col0, col0 + gridDim.x), outputs are indexed within the window
 //   2. its column's members -> shared memory (float64), mean / ddof-1 variance / bandwidth
 //   3. the fp32 scan of its chunk of grid points -> s32
 //   4. the last CTA of a column to finish (atomic ticket) runs the float64 selection
 template <typename T>
 __global__ void __launch_bounds__(256)
-k_kde_small(const T* __restrict__ a, int64_t N, int64_t Q, int compute_range, double* __restrict__ lohi,
+k_kde_small(const T* __restrict__ a, int64_t N, int64_t Q, int64_t col0, int compute_range, double* __restrict__ lohi,
             int G, int gchunk, double scott_factor_sq, float* __restrict__ s32,
             unsigned int* __restrict__ tickets, double* __restrict__ mode_out, int64_t* __restrict__ index_out) {
     extern __shared__ __align__(16) unsigned char kde_smem_raw[];
@@ -1177,7 +1178,7 @@ k_kde_small(const T* __restrict__ a, int64_t N, int64_t Q, int compute_range, do
     __shared__ int rnan[8];
     __shared__ int s_last;
     const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
-    const int64_t col = blockIdx.x;
+    const int64_t col = blockIdx.x;            // index in this launch's column window [col0, col0 + gridDim.x) of the array
     // ---- 1. grid range (np.min / np.max of the whole array; NaN propagates) ---------------------
     double lo, hi;
     if (compute_range) {
@@ -1207,7 +1208,7 @@ k_kde_small(const T* __restrict__ a, int64_t N, int64_t Q, int compute_range, do
     }
     // ---- 2. column constants ------------------------------------------------------------------------
     double sum = 0.0;
-    for (int64_t i = tid; i < N; i += 256) { const double v = (double)a[i * Q + col]; xs[i] = v; sum += v; }
+    for (int64_t i = tid; i < N; i += 256) { const double v = (double)a[i * Q + col0 + col]; xs[i] = v; sum += v; }
 #pragma unroll
     for (int o = 16; o > 0; o >>= 1) sum += __shfl_xor_sync(0xffffffffu, sum, o);
     __syncthreads();
