@@ -188,6 +188,38 @@ static int percentiles_by_warps(const void* d_a, int dtype, int64_t N, int64_t Q
     return percentiles_by_warps_t<double, double, double>(d_a, N, Q, qs, d_out, st);
 }
 
+// exact selection by radix in shared memory (k_percentiles_select): medium-length columns, many columns, few quantiles
+template <typename T, typename G, typename O>
+static int percentiles_by_select_t(const void* d_a, int64_t N, int64_t Q, const std::vector<PctlQuery>& qs, void* d_out,
+                                   cudaStream_t st) {
+    using K = typename SortKey<T>::K;
+    int CT = (int)((64 * 1024) / ((size_t)N * sizeof(K)));
+    if (CT > 16) CT = 16;
+    if (CT < 1) CT = 1;
+    while (CT > 1 && (Q + CT - 1) / CT < 4 * kNumSMs) CT >>= 1;
+    const size_t smem = ((size_t)CT * N + 2 * PS_CAP) * sizeof(K) + (257 + CT) * sizeof(int);
+    static PerDeviceOnce once;
+    bool& attr_set = *once.slot();
+    if (!attr_set) {
+        ERT_CUDA(cudaFuncSetAttribute(k_percentiles_select<T, G, O>, cudaFuncAttributeMaxDynamicSharedMemorySize, 200 * 1024));
+        attr_set = true;
+    }
+    PctlQueryPack pack{};
+    pack.n = (int)qs.size();
+    for (int k = 0; k < pack.n; ++k) pack.q[k] = qs[k];
+    k_percentiles_select<T, G, O><<<(unsigned)((Q + CT - 1) / CT), 256, smem, st>>>((const T*)d_a, N, Q, CT, pack, (O*)d_out);
+    ERT_LAUNCH_CHECK("k_percentiles_select");
+    return 0;
+}
+
+static int percentiles_by_select(const void* d_a, int dtype, int64_t N, int64_t Q, const std::vector<PctlQuery>& qs,
+                                 int index_dtype, void* d_out, cudaStream_t st) {
+    if (dtype == ERTDIFF_F32 && index_dtype == ERTDIFF_F32)
+        return percentiles_by_select_t<float, float, float>(d_a, N, Q, qs, d_out, st);
+    if (dtype == ERTDIFF_F32) return percentiles_by_select_t<float, double, double>(d_a, N, Q, qs, d_out, st);
+    return percentiles_by_select_t<double, double, double>(d_a, N, Q, qs, d_out, st);
+}
+
 static int percentiles_by_runs(const void* d_a, int dtype, int64_t N, int64_t Q, const std::vector<PctlQuery>& qs,
                                int index_dtype, void* d_out, int CH, cudaStream_t st) {
     if (dtype == ERTDIFF_F32 && index_dtype == ERTDIFF_F32)
@@ -285,6 +317,11 @@ int ertdiff_ensemble_percentiles(const void* d_a, int dtype, int64_t N, int64_t 
     const size_t budget = 200 * 1024;
     int64_t NP64 = 1;
     while (NP64 < N) NP64 <<= 1;
+    // many medium-length columns, few quantiles (maps of 1024 .. 16K members, 25/50/75): exact radix selection, no sort
+    const bool select_forced = std::getenv("ERTDIFF_PCTL_SELECT") != nullptr;
+    if (!std::getenv("ERTDIFF_PCTL_RUN_LEN") && !std::getenv("ERTDIFF_PCTL_NO_SELECT") && nq <= 4 && N < (int64_t(1) << 30) &&
+        (size_t)N * esz <= 128 * 1024 && (select_forced || (N > 256 && Q > 1024)))
+        return percentiles_by_select(d_a, dtype, N, Q, qs, index_dtype, d_out, st);
     const int run_len = percentile_run_length(dtype, N, Q);
     if (run_len) return percentiles_by_runs(d_a, dtype, N, Q, qs, index_dtype, d_out, run_len, st);
     // short columns of many-column arrays (the reference's 50 realisations of a 65,702-pixel map): one warp sorts a
@@ -423,36 +460,41 @@ int ertdiff_ensemble_kde_mode(const void* d_a, int dtype, int64_t N, int64_t Q,
         // CTAs per SM; with many columns (maps) one CTA walks the whole grid of its column
         int n_gchunks = (G + 255) / 256;
         while (n_gchunks > 1 && nc * n_gchunks > 4 * kNumSMs) n_gchunks = (n_gchunks + 1) / 2;
-        const int gchunk = (G + n_gchunks - 1) / n_gchunks;
+        // few columns of a long ensemble (a rank's share of the chain's (members, 29) output: 4 columns x 20 chunks
+        // = 80 CTAs, each thread summing every member for its two grid points) leave most of the machine idle: let
+        // ms lanes share a grid point and split the members, with ms times as many CTAs per column
+        int ms = 1;
+        while (ms < 32 && nc * n_gchunks * 2 <= 4 * kNumSMs && N / (2 * ms) >= 512) { ms *= 2; n_gchunks *= 2; }
         const int threads = 256;
         const dim3 grid((unsigned)nc, (unsigned)n_gchunks);
         const dim3 sgrid((unsigned)nc, (unsigned)sel_parts);
         if (tiled) {
-            // scan: 48 K fp32 members per tile; selection: what is left of 200 KB after one float64 accumulator per
-            // candidate (or per grid point of this part, should the scan be flat)
-            const int stile = tile_override ? tile_override : 48 * 1024;
+            // scan: 48 K fp32 members per tile (16 K when lanes share grid points: more CTAs per SM); selection: what
+            // is left of 200 KB after one float64 accumulator per candidate (or per grid point of this part, should
+            // the scan be flat)
+            const int stile = tile_override ? tile_override : (ms > 1 ? 16 * 1024 : 48 * 1024);
             const int n_acc = std::max(KDE_MAX_CAND, (G + sel_parts - 1) / sel_parts);
             ERT_REQUIRE((size_t)n_acc * 8 + 64 * 8 <= 200 * 1024, "ensemble_kde_mode: n_grid too large");
             int dtile = (int)((200 * 1024 - (size_t)n_acc * 8) / 8) / 32 * 32;
             if (tile_override && tile_override < dtile) dtile = tile_override;
             const size_t dsmem = ((size_t)dtile + n_acc) * 8;
             if (f32in) {
-                k_kde_scan32_tiled<float><<<grid, threads, (size_t)stile * 4, st>>>((const float*)d_a, N, Q, c0, d_lohi, G, cols, s32, stile);
+                k_kde_scan32_tiled<float><<<grid, threads, (size_t)stile * 4, st>>>((const float*)d_a, N, Q, c0, d_lohi, G, cols, s32, stile, ms);
                 ERT_LAUNCH_CHECK("k_kde_scan32_tiled");
                 k_kde_select64_tiled<float><<<sgrid, 256, dsmem, st>>>((const float*)d_a, N, Q, c0, d_lohi, G, cols, s32, d_mode, d_index, partials, tk, dtile, n_acc);
             } else {
-                k_kde_scan32_tiled<double><<<grid, threads, (size_t)stile * 4, st>>>((const double*)d_a, N, Q, c0, d_lohi, G, cols, s32, stile);
+                k_kde_scan32_tiled<double><<<grid, threads, (size_t)stile * 4, st>>>((const double*)d_a, N, Q, c0, d_lohi, G, cols, s32, stile, ms);
                 ERT_LAUNCH_CHECK("k_kde_scan32_tiled");
                 k_kde_select64_tiled<double><<<sgrid, 256, dsmem, st>>>((const double*)d_a, N, Q, c0, d_lohi, G, cols, s32, d_mode, d_index, partials, tk, dtile, n_acc);
             }
             ERT_LAUNCH_CHECK("k_kde_select64_tiled");
         } else if (f32in) {
-            k_kde_scan32<float><<<grid, threads, (size_t)N * 4, st>>>((const float*)d_a, N, Q, c0, d_lohi, G, gchunk, cols, s32);
+            k_kde_scan32<float><<<grid, threads, (size_t)N * 4, st>>>((const float*)d_a, N, Q, c0, d_lohi, G, ms, cols, s32);
             ERT_LAUNCH_CHECK("k_kde_scan32");
             k_kde_select64<float><<<sgrid, 256, (size_t)N * 8, st>>>((const float*)d_a, N, Q, c0, d_lohi, G, cols, s32, d_mode, d_index, partials, tk);
             ERT_LAUNCH_CHECK("k_kde_select64");
         } else {
-            k_kde_scan32<double><<<grid, threads, (size_t)N * 4, st>>>((const double*)d_a, N, Q, c0, d_lohi, G, gchunk, cols, s32);
+            k_kde_scan32<double><<<grid, threads, (size_t)N * 4, st>>>((const double*)d_a, N, Q, c0, d_lohi, G, ms, cols, s32);
             ERT_LAUNCH_CHECK("k_kde_scan32");
             k_kde_select64<double><<<sgrid, 256, (size_t)N * 8, st>>>((const double*)d_a, N, Q, c0, d_lohi, G, cols, s32, d_mode, d_index, partials, tk);
             ERT_LAUNCH_CHECK("k_kde_select64");

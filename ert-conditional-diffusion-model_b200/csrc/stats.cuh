@@ -436,18 +436,7 @@ k_percentiles_warp(const T* __restrict__ a, int64_t N, int64_t Q, int CPW,
     }
 }
 
-// ------------------------------------------------------------------------------------------
-// Percentiles of columns that do not fit one CTA's shared memory (any N): two kernels.
-//   k_sort_runs     the column is cut into runs of CH members; a CTA sorts one run of CT adjacent columns
-//                   in shared memory (same bitonic network) and writes it, as order-preserving unsigned
-//                   keys, to a column-major scratch array runs[col][N] (run r = [r*CH, min(N, (r+1)*CH)))
-//   k_select_runs   one warp per (column, query): the exact order statistic s[lo] is found by deciding the
-//                   key bit by bit -- "how many members are < try?" is a sum of lower bounds over the
-//                   sorted runs, each lane binary-searching its runs inside a window that shrinks with every
-//                   decided bit -- then s[hi] is either the same value (ties) or the smallest successor over
-//                   the runs, and numpy's `_lerp` finishes as in k_percentiles.  No full merge is needed:
-//                   a query costs O(R * (bits + log CH)) L2 reads.
-// Results are bit-identical to k_percentiles (and numpy) for any N.
+// order-preserving unsigned keys of floating-point values (radix selection, sorted runs)
 template <typename T> struct SortKey;
 template <> struct SortKey<float> {
     using K = uint32_t;
@@ -474,6 +463,199 @@ template <> struct SortKey<double> {
     }
 };
 
+// ------------------------------------------------------------------------------------------
+// Percentiles of medium-length columns of many-column arrays with a few quantiles (an ensemble of 1024 .. 8192
+// simulated maps, 25/50/75: SURVEY.md §8 d) WITHOUT sorting: exact selection by radix.  A CTA loads CT adjacent
+// columns (coalesced) into shared memory as order-preserving unsigned keys and treats them one at a time:
+//   * one 256-bin histogram of the first byte below the bits all keys share (block-wide min / max) -- shared by all
+//     the column's ranks;
+//   * per rank: the bucket holding it is compacted into a small buffer (or, when it is too large for the buffer,
+//     narrowed in place by one more histogram round over the column with a prefix test) and the procedure repeats on
+//     the next byte until at most 256 candidates are left, where every thread ranks one candidate by counting.
+// Work per column ~ N (histogram) + ranks * N (one compaction pass each) + small rounds, against N log^2 N / 2
+// compare-exchanges for the bitonic sort: 8192 members x 65,702 pixels, float64: 43 ms -> a few ms.
+// The selected order statistics are the same keys a sort would deliver, so the results are bit-identical.
+constexpr int PS_CAP = 2048;        // candidates a compaction buffer holds
+
+template <typename K>
+struct SelectSmem {
+    int hist[256];
+    int wsum[8];
+    int bucket, before, count, counter;
+    K result, kmin[8], kmax[8];
+};
+
+// exact k-th smallest (0-based) of keys[0..n): every thread of the 256-thread CTA calls; returns the key in all.
+// State: bits [shift, BITS) of the answer are decided and held in `prefix`; a key is a candidate when it agrees with
+// the prefix on those bits.  `cur` holds exactly the candidates (physical) or a superset that is prefix-tested.
+template <typename K, int BITS>
+__device__ K block_select(const K* __restrict__ keys, int n, int k, int shift0, const int* __restrict__ cum0 /* [257] */,
+                          K* bufA, K* bufB, SelectSmem<K>& sm) {
+    const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
+    // round 0 comes from the column's shared histogram of byte [shift0, shift0 + 8): thread t tests bucket t
+    if (cum0[tid] <= k && k < cum0[tid + 1]) { sm.bucket = tid; sm.before = cum0[tid]; sm.count = cum0[tid + 1] - cum0[tid]; }
+    __syncthreads();
+    int kk = k - sm.before, c = sm.count, shift = shift0;
+    const K high = (shift0 + 8 >= BITS) ? (K)0 : (K)((keys[0] >> (shift0 + 8)) << (shift0 + 8));   // the bits all keys share
+    K prefix = high | ((K)sm.bucket << shift0);
+    const K* cur = keys;
+    int n_cur = n;
+    bool physical = false;
+    __syncthreads();
+    for (;;) {
+        if (!physical && c <= PS_CAP) {         // the bucket fits a buffer: compact it
+            K* dst = (cur == bufA) ? bufB : bufA;
+            if (tid == 0) sm.counter = 0;
+            __syncthreads();
+            for (int i = tid; i < n_cur; i += 256) {
+                const K key = cur[i];
+                if (((key ^ prefix) >> shift) == 0) dst[atomicAdd(&sm.counter, 1)] = key;
+            }
+            __syncthreads();
+            cur = dst; n_cur = c; physical = true;
+        }
+        if (physical && n_cur <= 256) break;
+        if (shift == 0) return prefix;          // every bit decided: all candidates equal the prefix
+        const int above = shift;                // candidates agree with the prefix on bits [above, BITS)
+        shift -= 8;
+        // ---- histogram of the next byte among the candidates ----------------------------------------------
+        sm.hist[tid] = 0;
+        __syncthreads();
+        for (int i = tid; i < n_cur; i += 256) {
+            const K key = cur[i];
+            if (physical || ((key ^ prefix) >> above) == 0) atomicAdd(&sm.hist[(int)((key >> shift) & 255)], 1);
+        }
+        __syncthreads();
+        const int v = sm.hist[tid];             // inclusive scan of the 256 bins: thread t owns bin t
+        int incl = v;
+#pragma unroll
+        for (int o = 1; o < 32; o <<= 1) {
+            const int up = __shfl_up_sync(0xffffffffu, incl, o);
+            if (lane >= o) incl += up;
+        }
+        if (lane == 31) sm.wsum[warp] = incl;
+        __syncthreads();
+        int off = 0;
+        for (int w = 0; w < warp; ++w) off += sm.wsum[w];
+        incl += off;
+        if (incl - v <= kk && kk < incl) { sm.bucket = tid; sm.before = incl - v; sm.count = v; }
+        __syncthreads();
+        prefix |= (K)sm.bucket << shift;
+        kk -= sm.before; c = sm.count;
+        physical = false;                       // the next round's candidates are a subset of cur
+        __syncthreads();
+    }
+    // ---- at most 256 candidates: thread t ranks candidate t by counting ------------------------------------
+    if (tid < n_cur) {
+        const K mine = cur[tid];
+        int less = 0;
+        for (int j = 0; j < n_cur; ++j) {
+            const K o = cur[j];
+            less += (o < mine || (o == mine && j < tid)) ? 1 : 0;
+        }
+        if (less == kk) sm.result = mine;
+    }
+    __syncthreads();
+    const K r = sm.result;
+    __syncthreads();
+    return r;
+}
+
+// grid = column groups of CT; 256 threads; dynamic shared memory: CT*N keys + 2 buffers of PS_CAP keys + 257 ints
+template <typename T, typename G, typename O>
+__global__ void __launch_bounds__(256)
+k_percentiles_select(const T* __restrict__ a, int64_t N, int64_t Q, int CT,
+                     const __grid_constant__ PctlQueryPack qs, O* __restrict__ out) {
+    using K = typename SortKey<T>::K;
+    constexpr int BITS = SortKey<T>::BITS;
+    extern __shared__ __align__(16) unsigned char pct_smem_raw[];
+    const int n = (int)N;
+    K* keys = reinterpret_cast<K*>(pct_smem_raw);                 // [CT][N]
+    K* bufA = keys + (size_t)CT * n;
+    K* bufB = bufA + PS_CAP;
+    int* cum0 = reinterpret_cast<int*>(bufB + PS_CAP);            // [257]
+    int* nanflag = cum0 + 257;                                    // [CT]
+    __shared__ SelectSmem<K> sm;
+    const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
+    const int64_t c0 = (int64_t)blockIdx.x * CT;
+    for (int c = tid; c < CT; c += 256) nanflag[c] = 0;
+    __syncthreads();
+    for (int idx = tid; idx < n * CT; idx += 256) {
+        const int c = idx % CT, i = idx / CT;
+        T v = (c0 + c < Q) ? a[(int64_t)i * Q + c0 + c] : (T)0;
+        if (v != v) { nanflag[c] = 1; v = RN<T>::inf(); }
+        keys[(size_t)c * n + i] = SortKey<T>::of(v);
+    }
+    __syncthreads();
+    for (int c = 0; c < CT; ++c) {
+        if (c0 + c >= Q) break;
+        const K* col = keys + (size_t)c * n;
+        if (nanflag[c]) {
+            for (int k = tid; k < qs.n; k += 256) out[(int64_t)k * Q + c0 + c] = RN<O>::nan();
+            continue;
+        }
+        // ---- bits shared by all keys, and the histogram of the first byte below them ------------------------
+        K kmn = ~(K)0, kmx = 0;
+        for (int i = tid; i < n; i += 256) { const K key = col[i]; kmn = key < kmn ? key : kmn; kmx = key > kmx ? key : kmx; }
+#pragma unroll
+        for (int o = 16; o > 0; o >>= 1) {
+            const K a1 = __shfl_xor_sync(0xffffffffu, kmn, o), a2 = __shfl_xor_sync(0xffffffffu, kmx, o);
+            kmn = a1 < kmn ? a1 : kmn; kmx = a2 > kmx ? a2 : kmx;
+        }
+        if (lane == 0) { sm.kmin[warp] = kmn; sm.kmax[warp] = kmx; }
+        sm.hist[tid] = 0;
+        __syncthreads();
+        for (int w = 0; w < 8; ++w) { kmn = sm.kmin[w] < kmn ? sm.kmin[w] : kmn; kmx = sm.kmax[w] > kmx ? sm.kmax[w] : kmx; }
+        const K diff = kmn ^ kmx;
+        int top = 0;                                              // highest differing bit (0 when all keys are equal)
+        if (diff) top = BITS - 1 - (BITS == 64 ? __clzll((long long)diff) : __clz((int)diff));
+        const int shift0 = (top / 8) * 8;
+        for (int i = tid; i < n; i += 256) atomicAdd(&sm.hist[(int)((col[i] >> shift0) & 255)], 1);
+        __syncthreads();
+        {   // exclusive prefix of the 256 bins -> cum0[0..256]
+            const int v = sm.hist[tid];
+            int incl = v;
+#pragma unroll
+            for (int o = 1; o < 32; o <<= 1) {
+                const int up = __shfl_up_sync(0xffffffffu, incl, o);
+                if (lane >= o) incl += up;
+            }
+            if (lane == 31) sm.wsum[warp] = incl;
+            __syncthreads();
+            int off = 0;
+            for (int w = 0; w < warp; ++w) off += sm.wsum[w];
+            cum0[tid + 1] = incl + off;
+            if (tid == 0) cum0[0] = 0;
+        }
+        __syncthreads();
+        for (int k = 0; k < qs.n; ++k) {
+            const PctlQuery qq = qs.q[k];
+            const K ka = block_select<K, BITS>(col, n, qq.lo, shift0, cum0, bufA, bufB, sm);
+            const K kb = qq.hi == qq.lo ? ka : block_select<K, BITS>(col, n, qq.hi, shift0, cum0, bufA, bufB, sm);
+            if (tid == 0) {
+                const T A = SortKey<T>::back(ka), Bv = SortKey<T>::back(kb);
+                O r;
+                if (sizeof(G) == 4) r = lerp_numpy<T, float, O>(A, Bv, qq.gamma_f);
+                else r = lerp_numpy<T, double, O>(A, Bv, qq.gamma_d);
+                out[(int64_t)k * Q + c0 + c] = r;
+            }
+        }
+        __syncthreads();
+    }
+}
+
+// ------------------------------------------------------------------------------------------
+// Percentiles of columns that do not fit one CTA's shared memory (any N): two kernels.
+//   k_sort_runs     the column is cut into runs of CH members; a CTA sorts one run of CT adjacent columns
+//                   in shared memory (same bitonic network) and writes it, as order-preserving unsigned
+//                   keys, to a column-major scratch array runs[col][N] (run r = [r*CH, min(N, (r+1)*CH)))
+//   k_select_runs   one warp per (column, query): the exact order statistic s[lo] is found by deciding the
+//                   key bit by bit -- "how many members are < try?" is a sum of lower bounds over the
+//                   sorted runs, each lane binary-searching its runs inside a window that shrinks with every
+//                   decided bit -- then s[hi] is either the same value (ties) or the smallest successor over
+//                   the runs, and numpy's `_lerp` finishes as in k_percentiles.  No full merge is needed:
+//                   a query costs O(R * (bits + log CH)) L2 reads.
+// Results are bit-identical to k_percentiles (and numpy) for any N.
 // grid = (runs, column groups of CT); columns [col0, col0 + ncols) of `a`; CH = run length (power of two)
 template <typename T>
 __global__ void __launch_bounds__(1024)
@@ -683,7 +865,7 @@ __device__ __forceinline__ double kde_scan_reach(double h, double step, int64_t 
 // Inside the active range every member is summed, so the values equal the full scan's bit for bit.
 __device__ __forceinline__ void kde_scan_column(const float* __restrict__ xs, int64_t N, const KdeColumn kc,
                                                 double lo, double hi, int G, int part, int nparts,
-                                                float* __restrict__ out) {
+                                                float* __restrict__ out, int ms = 1) {
     __shared__ float s_mn[8], s_mx[8];
     __shared__ int s_in[8];
     __shared__ int s_range[2];
@@ -734,13 +916,18 @@ __device__ __forceinline__ void kde_scan_column(const float* __restrict__ xs, in
     const int g_begin = ga + part * chunk;
     const int g_end = min(gb + 1, g_begin + chunk);
     const float c2 = (float)(kc.neg_inv_2h2 * 1.4426950408889634);   // exponent in base 2
-    for (int g0 = g_begin + tid; g0 < g_end; g0 += 2 * nthr) {
-        const int g1 = g0 + nthr;
-        const float va = (float)(kde_grid_point(g0, G, lo, hi, step) - kc.mean);
+    // `ms` adjacent lanes share a grid point and split the members between them in blocks of 64 (lane `sub` takes
+    // blocks sub, sub + ms, ...); their partial sums meet in a fixed xor-shuffle tree.  ms = 1 is one thread per grid
+    // point; few columns of a long ensemble (a rank's share of the chain's output) use ms > 1 to fill the machine.
+    const int sub = tid & (ms - 1), slot = tid / ms, slots = nthr / ms;
+    for (int gbase = g_begin; gbase < g_end; gbase += 2 * slots) {        // (uniform trip count: shuffles inside)
+        const int g0 = gbase + slot, g1 = g0 + slots;
+        const bool has0 = g0 < g_end, has1 = g1 < g_end;
+        const float va = has0 ? (float)(kde_grid_point(g0, G, lo, hi, step) - kc.mean) : 0.f;
         double sa = 0.0, sb = 0.0;
-        if (g1 < g_end) {                          // two grid points per thread: one shared-memory read feeds both
+        if (has1) {                                // two grid points per thread: one shared-memory read feeds both
             const float vb = (float)(kde_grid_point(g1, G, lo, hi, step) - kc.mean);
-            for (int64_t i0 = 0; i0 < N; i0 += 64) {
+            for (int64_t i0 = 64 * sub; i0 < N; i0 += 64 * ms) {
                 const int64_t i1 = (i0 + 64 < N) ? i0 + 64 : N;
                 float pa = 0.f, pb = 0.f;
                 for (int64_t i = i0; i < i1; ++i) {
@@ -752,9 +939,8 @@ __device__ __forceinline__ void kde_scan_column(const float* __restrict__ xs, in
                 sa += (double)pa;
                 sb += (double)pb;
             }
-            out[g1] = (float)sb;
-        } else {                                   // the tail of a chunk: no wasted second evaluation
-            for (int64_t i0 = 0; i0 < N; i0 += 64) {
+        } else if (has0) {                         // the tail of a chunk: no wasted second evaluation
+            for (int64_t i0 = 64 * sub; i0 < N; i0 += 64 * ms) {
                 const int64_t i1 = (i0 + 64 < N) ? i0 + 64 : N;
                 float pa = 0.f;
                 for (int64_t i = i0; i < i1; ++i) {
@@ -764,7 +950,14 @@ __device__ __forceinline__ void kde_scan_column(const float* __restrict__ xs, in
                 sa += (double)pa;
             }
         }
-        out[g0] = (float)sa;
+        for (int o = ms >> 1; o > 0; o >>= 1) {
+            sa += __shfl_xor_sync(0xffffffffu, sa, o);
+            sb += __shfl_xor_sync(0xffffffffu, sb, o);
+        }
+        if (sub == 0) {
+            if (has1) out[g1] = (float)sb;
+            if (has0) out[g0] = (float)sa;
+        }
     }
 }
 
@@ -773,7 +966,7 @@ __device__ __forceinline__ void kde_scan_column(const float* __restrict__ xs, in
 template <typename T>
 __global__ void __launch_bounds__(256)
 k_kde_scan32(const T* __restrict__ a, int64_t N, int64_t Q, int64_t col0,
-             const double* __restrict__ lohi, int G, int gchunk,
+             const double* __restrict__ lohi, int G, int ms /* lanes per grid point, a power of two <= 32 */,
              const KdeColumn* __restrict__ cols, float* __restrict__ s32) {
     extern __shared__ __align__(16) unsigned char kde_smem_raw[];
     float* xs = reinterpret_cast<float*>(kde_smem_raw);        // [N] centred members, fp32
@@ -782,8 +975,7 @@ k_kde_scan32(const T* __restrict__ a, int64_t N, int64_t Q, int64_t col0,
     const KdeColumn kc = cols[col];
     for (int64_t i = tid; i < N; i += nthr) xs[i] = (float)((double)a[i * Q + col] - kc.mean);
     __syncthreads();
-    (void)gchunk;
-    kde_scan_column(xs, N, kc, lohi[0], lohi[1], G, (int)blockIdx.y, (int)gridDim.y, s32 + (int64_t)blockIdx.x * G);
+    kde_scan_column(xs, N, kc, lohi[0], lohi[1], G, (int)blockIdx.y, (int)gridDim.y, s32 + (int64_t)blockIdx.x * G, ms);
 }
 
 // All-grid fallback of the float64 decision: exp(-d^2/(2h^2)) is exactly 0 in float64 once d^2/(2h^2) > 745.2
@@ -946,7 +1138,7 @@ template <typename T>
 __global__ void __launch_bounds__(256)
 k_kde_scan32_tiled(const T* __restrict__ a, int64_t N, int64_t Q, int64_t col0,
                    const double* __restrict__ lohi, int G, const KdeColumn* __restrict__ cols,
-                   float* __restrict__ s32, int tile /* members per tile, multiple of 64 */) {
+                   float* __restrict__ s32, int tile /* members per tile, multiple of 64 */, int ms /* lanes per grid point */) {
     extern __shared__ __align__(16) unsigned char kde_smem_raw[];
     float* xs = reinterpret_cast<float*>(kde_smem_raw);        // [tile] centred members, fp32
     __shared__ float s_mn[8], s_mx[8];
@@ -1002,8 +1194,9 @@ k_kde_scan32_tiled(const T* __restrict__ a, int64_t N, int64_t Q, int64_t col0,
     const int g_begin = ga + part * chunk;
     const int g_end = min(gb + 1, g_begin + chunk);
     const float c2 = (float)(kc.neg_inv_2h2 * 1.4426950408889634);
-    for (int gbase = g_begin; gbase < g_end; gbase += 2 * nthr) {       // uniform trip count: barriers inside
-        const int g0 = gbase + tid, g1 = g0 + nthr;
+    const int sub = tid & (ms - 1), slot = tid / ms, slots = nthr / ms;     // see kde_scan_column
+    for (int gbase = g_begin; gbase < g_end; gbase += 2 * slots) {          // uniform trip count: barriers inside
+        const int g0 = gbase + slot, g1 = g0 + slots;
         const bool has0 = g0 < g_end, has1 = g1 < g_end;
         const float va = has0 ? (float)(kde_grid_point(g0, G, lo, hi, step) - kc.mean) : 0.f;
         const float vb = has1 ? (float)(kde_grid_point(g1, G, lo, hi, step) - kc.mean) : 0.f;
@@ -1014,7 +1207,7 @@ k_kde_scan32_tiled(const T* __restrict__ a, int64_t N, int64_t Q, int64_t col0,
             for (int i = tid; i < n; i += nthr) xs[i] = (float)((double)a[(t0 + i) * Q + col] - kc.mean);
             __syncthreads();
             if (has1) {
-                for (int i0 = 0; i0 < n; i0 += 64) {
+                for (int i0 = 64 * sub; i0 < n; i0 += 64 * ms) {
                     const int i1 = (i0 + 64 < n) ? i0 + 64 : n;
                     float pa = 0.f, pb = 0.f;
                     for (int i = i0; i < i1; ++i) {
@@ -1027,7 +1220,7 @@ k_kde_scan32_tiled(const T* __restrict__ a, int64_t N, int64_t Q, int64_t col0,
                     sb += (double)pb;
                 }
             } else if (has0) {
-                for (int i0 = 0; i0 < n; i0 += 64) {
+                for (int i0 = 64 * sub; i0 < n; i0 += 64 * ms) {
                     const int i1 = (i0 + 64 < n) ? i0 + 64 : n;
                     float pa = 0.f;
                     for (int i = i0; i < i1; ++i) {
@@ -1038,8 +1231,14 @@ k_kde_scan32_tiled(const T* __restrict__ a, int64_t N, int64_t Q, int64_t col0,
                 }
             }
         }
-        if (has1) out[g1] = (float)sb;
-        if (has0) out[g0] = (float)sa;
+        for (int o = ms >> 1; o > 0; o >>= 1) {
+            sa += __shfl_xor_sync(0xffffffffu, sa, o);
+            sb += __shfl_xor_sync(0xffffffffu, sb, o);
+        }
+        if (sub == 0) {
+            if (has1) out[g1] = (float)sb;
+            if (has0) out[g0] = (float)sa;
+        }
     }
 }
 

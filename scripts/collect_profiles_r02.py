@@ -1,0 +1,45 @@
+#!/usr/bin/env python
+"""Copy the round-2 measurement logs brought back in gpurun_out/ into tracked summaries under profiles/
+(gpurun_out/ is scratch).  Re-run after every GPU pass; files whose source log is absent are left untouched."""
+import os
+
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+go, out = os.path.join(ROOT, "gpurun_out"), os.path.join(ROOT, "profiles")
+
+
+def emit(dst, title, sources, fence=True):
+    parts = []
+    for src, caption in sources:
+        p = os.path.join(go, src)
+        if not os.path.isfile(p):
+            continue
+        txt = open(p).read().rstrip()
+        parts.append((f"## {caption}\n\n" if caption else "") + (f"```\n{txt}\n```" if fence else txt))
+    if parts:
+        open(os.path.join(out, dst), "w").write(f"# {title}\n\n" + "\n\n".join(parts) + "\n")
+        print("wrote", dst)
+
+
+emit("r02_parity_measured.md",
+     "r02 measured parity errors, CUDA path vs the reference-made goldens (scripts/measure_parity.py, one B200)",
+     [("parity.log", "per case: max |got - want|, the golden's scale, and the smallest atol that makes the element-wise "
+                     "`|d| <= atol + rtol*|want|` hold at rtol = 1e-5 / 1e-4 / 1e-3 / 1e-2 (tests/ use ~10x these)")])
+emit("r02_chain_fp32_variants.md",
+     "r02 fp32 chain kernel: members per CTA (mpb) x hidden units per thread (upt), full kernel and arithmetic-free floor "
+     "(scripts/chain_fp32_variants.py; us per denoiser step = kernel duration / T, T = 1000, best of 4, L2 flushed)",
+     [("variants_h128.log", "hidden_dim 128, small ensembles"), ("variants_h128_b.log", "hidden_dim 128, larger ensembles"),
+      ("variants_h256.log", "hidden_dim 256, L = 9386")])
+emit("r02_chain_bf16_sweep.md", "r02 tensor-core chain (k_chain_umma), scripts/chain_sweep.py, T = 1000",
+     [("sweep_bf16.log", None)])
+emit("r02_stats_bench.md",
+     "r02 statistics kernels on the reference's map-shaped workload and on the chain's own output (scripts/stats_bench.py; "
+     "CUDA-event time of the whole library call, best of 3, L2 flushed; calls of a few microseconds are dominated by "
+     "launch overhead -- the ncu durations in r02_ncu_kernels.json are the kernel-only figures)",
+     [("stats_bench.log", None)])
+for n in (2, 4, 8):
+    emit(f"r02_multigpu_step_n{n}.md",
+         f"r02 one bench step on {n} GPUs: per-kernel device time on rank 0 (scripts/multi_gpu_breakdown.py, torch.profiler / CUPTI; "
+         "NCCL kernels included -- their duration contains the wait for the slowest rank)",
+         [(f"breakdown_fp32_256_n{n}.md", None), (f"breakdown_bf16_1024_n{n}.md", None)], fence=False)
+    emit(f"r02_multigpu_check_n{n}.md", f"r02 multi-GPU parity on {n} GPUs (scripts/multi_gpu_check.py): gathered fields and "
+         "column-sharded statistics against a single-GPU run of the whole ensemble", [(f"multi_gpu_check_{n}.log", None)])

@@ -23,7 +23,9 @@ ap.add_argument("--members", type=int, default=256)
 ap.add_argument("--precision", default="fp32")
 ap.add_argument("--steps", type=int, default=10)
 ap.add_argument("--T", type=int, default=1000)
+ap.add_argument("--shard", default="auto", choices=["auto", "yes", "no"])
 a = ap.parse_args()
+SHARD = {"auto": None, "yes": True, "no": False}[a.shard]
 rank, world, local = int(os.environ["RANK"]), int(os.environ["WORLD_SIZE"]), int(os.environ["LOCAL_RANK"])
 torch.cuda.set_device(local)
 dev = torch.device("cuda", local)
@@ -43,7 +45,7 @@ def step(i):
     x = eb.run_chain(model, cond_b, a.T, *sched, dev, seed=1234, offset=4 * i, member_offset=rank * a.members,
                      precision=a.precision, check_status=False)
     x = eb.parallel.gather_members(x, total)
-    return eb.parallel.sharded_statistics(x, bench.PERCENTILES, bench.KDE_GRID)
+    return eb.parallel.ensemble_statistics_distributed(x, bench.PERCENTILES, bench.KDE_GRID, shard=SHARD)
 
 
 for i in range(3):

@@ -307,3 +307,42 @@ def test_fused_summary_equals_the_separate_calls(cuda_dev, dtype, N, Q, col0, nc
     for k in ("mean", "std", "var"):
         assert torch.equal(v[k], m[k].double()), k
     assert torch.equal(v["pct"], pct) and torch.equal(v["mode"], mode) and torch.equal(v["mode_index"].long(), idx)
+
+
+@pytest.mark.parametrize("N,Q", [(5000, 3), (2048, 4), (30000, 2), (60000, 1)])
+def test_kde_few_columns_split_the_members_between_lanes(cuda_dev, N, Q):
+    # a rank's share of the chain's output is a handful of columns of a long ensemble: the scan then lets several
+    # lanes share a grid point and split the members (resident and tiled kernels); same argmax as scipy
+    a = np.random.default_rng(N + Q).normal(size=(N, Q)) * np.linspace(1.0, 50.0, Q) + 3.0
+    grid = so.kde_grid(a, 3000)
+    mode, idx = eb.ensemble_kde_mode(a, 3000, return_index=True)
+    _, idx_sp, pdfs = so.kde_mode_scipy(a, grid)
+    for j in np.nonzero(idx != idx_sp)[0]:
+        p = pdfs[:, j]
+        assert abs(p[idx[j]] - p[idx_sp[j]]) <= 1e-13 * p[idx_sp[j]], (j, idx[j], idx_sp[j])
+    assert (idx != idx_sp).sum() <= 1 and np.array_equal(mode, grid[idx])
+
+
+@pytest.mark.parametrize("dtype", [np.float32, np.float64])
+@pytest.mark.parametrize("N,Q", [(2, 3), (5, 29), (257, 64), (1000, 33), (1024, 2000), (4097, 40), (8192, 1100), (16000, 5)])
+def test_percentiles_radix_selection_bit_exact(cuda_dev, env_override, dtype, N, Q):
+    # exact selection by radix in shared memory (k_percentiles_select; the natural path of many medium-length columns
+    # with <= 4 quantiles, forced here onto every shape): histogram + compaction rounds, buckets too large for the
+    # compaction buffer (narrowed in place), ties, all-equal columns, infinities, signed zeros, NaN columns, keys that
+    # differ only in their low bits
+    env_override("ERTDIFF_PCTL_SELECT", 1)
+    rng = np.random.default_rng(N * 13 + Q)
+    a = rng.lognormal(sigma=2.0, size=(N, Q)).astype(dtype)
+    a[:, 0] = rng.integers(-2, 3, size=N)                         # heavy ties: one bucket holds a fifth of the column
+    if Q > 2:
+        a[:, 1] = 7.25                                            # all members equal
+        a[:, 2] = 1.0 + np.arange(N) * (1e-6 if dtype == np.float32 else 1e-13)     # only the low bits differ
+    if Q > 4 and N > 6:
+        a[[1, N // 2, N - 1], 3] = [np.inf, -np.inf, -0.0]
+        a[N // 3, 4] = np.nan
+    if Q > 5:
+        a[:, 5] = -a[:, 5]                                        # negative values: the key transform's other branch
+    for q in (50, [25, 50, 75], [0, 100], [2.5, 97.5, 33.3], np.float64(12.5), 99.9):
+        ref = np.percentile(a, q, axis=0)
+        got = eb.ensemble_percentile(a, q)
+        assert same(got, ref), (q, np.nonzero(~((got == ref) | (np.isnan(got) & np.isnan(ref)))))
