@@ -56,6 +56,9 @@
 #ifndef UC_PREFETCH_TABLE
 #define UC_PREFETCH_TABLE 1
 #endif
+#ifndef UC_RNG_ONEPASS
+#define UC_RNG_ONEPASS 1
+#endif
 #if UC_TIMING
 #define UC_T(...) __VA_ARGS__
 #else
@@ -290,6 +293,18 @@ __global__ void __launch_bounds__(UC_THREADS, CTAS) k_chain_umma(const ChainPara
             if (item >= UC_NSLOT) nb_sync(UC_NB_EMPTY + slot, cnt_ring);     // the slot's previous item was consumed
             UC_T(if (timed) { g1 = clock64(); tg[0] += g1 - g0; })
             const uint32_t draw = (item < first_item_step) ? 0u : (uint32_t)(d_first + item - first_item_step);
+            if (!REPLAY && CTAS == 1 && UC_RNG_ONEPASS) {
+                // one pass: eight Philox chains in flight (the one-CTA build has the registers for it)
+                float z[32];
+                philox_normal32(a.keys, a.offset, gmember, draw, z);
+#pragma unroll
+                for (int c = 0; c < 8; ++c) {
+                    float4 v = make_float4(z[4 * c], z[4 * c + 1], z[4 * c + 2], z[4 * c + 3]);
+                    if (4 * c + 3 >= P) { v.x = (4 * c < P) ? v.x : 0.f; v.y = (4 * c + 1 < P) ? v.y : 0.f;
+                                          v.z = (4 * c + 2 < P) ? v.z : 0.f; v.w = 0.f; }
+                    sts128(zrow + (uint32_t)slot * SLOT_BYTES + (uint32_t)((c ^ (m & 7)) * 16), v);
+                }
+            } else {
 #pragma unroll 1
             for (int u = 0; u < 4; u += 2) {                  // 16 draws per pass: four Philox chains in flight
                 float z[16];
@@ -307,6 +322,7 @@ __global__ void __launch_bounds__(UC_THREADS, CTAS) k_chain_umma(const ChainPara
                 for (int c = 0; c < 4; ++c)
                     sts128(zrow + (uint32_t)slot * SLOT_BYTES + (uint32_t)(((2 * u + c) ^ (m & 7)) * 16),
                            make_float4(z[4 * c], z[4 * c + 1], z[4 * c + 2], z[4 * c + 3]));
+            }
             }
             nb_arrive(UC_NB_FULL + slot, cnt_ring);
             UC_T(if (timed) tg[1] += clock64() - g1;)

@@ -230,6 +230,33 @@ __device__ __forceinline__ void philox_normal8(const PhiloxKeys& ks, uint64_t of
     box_muller(rb.z, rb.w, out[6], out[7]);
 }
 
+// all 32 draws of one (member, draw) at once: eight independent Philox chains advance round by round, so that the
+// multiply / xor latency of one chain is covered by the seven others (the noise warps of the tensor-core chain are
+// bound by this latency, not by issue slots)
+__device__ __forceinline__ void philox_normal32(const PhiloxKeys& ks, uint64_t offset, int64_t member, uint32_t draw,
+                                                float out[32]) {
+    const uint32_t M0 = 0xD2511F53u, M1 = 0xCD9E8D57u;
+    const uint32_t cy = (uint32_t)(offset >> 32) ^ (uint32_t)(member >> 32);
+    uint4 c[8];
+#pragma unroll
+    for (int q = 0; q < 8; ++q) c[q] = make_uint4((uint32_t)member, cy, (draw << 3) | (uint32_t)q, (uint32_t)offset);
+#pragma unroll
+    for (int r = 0; r < 10; ++r) {
+#pragma unroll
+        for (int q = 0; q < 8; ++q) {
+            uint32_t hi0, lo0, hi1, lo1;
+            mul_wide_u32(M0, c[q].x, hi0, lo0);
+            mul_wide_u32(M1, c[q].z, hi1, lo1);
+            c[q] = make_uint4(hi1 ^ c[q].y ^ ks.k[2 * r], lo1, hi0 ^ c[q].w ^ ks.k[2 * r + 1], lo0);
+        }
+    }
+#pragma unroll
+    for (int q = 0; q < 8; ++q) {
+        box_muller(c[q].x, c[q].y, out[4 * q], out[4 * q + 1]);
+        box_muller(c[q].z, c[q].w, out[4 * q + 2], out[4 * q + 3]);
+    }
+}
+
 // standalone generator with the chain's stream layout (tests compare the chain in device-RNG
 // mode against the oracle fed with these very draws): out[d][m][p], d = draw index.
 static __global__ void k_philox_fill(const PhiloxKeys keys, uint64_t offset, int64_t member_offset, int64_t B,

@@ -320,7 +320,7 @@ int ertdiff_ensemble_percentiles(const void* d_a, int dtype, int64_t N, int64_t 
     // many medium-length columns, few quantiles (maps of 1024 .. 16K members, 25/50/75): exact radix selection, no sort
     const bool select_forced = std::getenv("ERTDIFF_PCTL_SELECT") != nullptr;
     if (!std::getenv("ERTDIFF_PCTL_RUN_LEN") && !std::getenv("ERTDIFF_PCTL_NO_SELECT") && nq <= 4 && N < (int64_t(1) << 30) &&
-        (size_t)N * esz <= 128 * 1024 && (select_forced || (N > 256 && Q > 1024)))
+        (size_t)N * esz <= 128 * 1024 && (select_forced || (N > 512 && Q > 1024)))
         return percentiles_by_select(d_a, dtype, N, Q, qs, index_dtype, d_out, st);
     const int run_len = percentile_run_length(dtype, N, Q);
     if (run_len) return percentiles_by_runs(d_a, dtype, N, Q, qs, index_dtype, d_out, run_len, st);

@@ -475,22 +475,47 @@ template <> struct SortKey<double> {
 // Work per column ~ N (histogram) + ranks * N (one compaction pass each) + small rounds, against N log^2 N / 2
 // compare-exchanges for the bitonic sort: 8192 members x 65,702 pixels, float64: 43 ms -> a few ms.
 // The selected order statistics are the same keys a sort would deliver, so the results are bit-identical.
-constexpr int PS_CAP = 2048;        // candidates a compaction buffer holds
+constexpr int PS_CAP = 512;         // candidates a compaction buffer holds
+constexpr int PS_FINAL = 64;        // candidates left when the last step ranks them by counting
 
 template <typename K>
 struct SelectSmem {
     int hist[256];
     int wsum[8];
-    int bucket, before, count, counter;
-    K result, kmin[8], kmax[8];
+    int bucket, before, count, counter, have2;
+    K result, result2, kmin[8], kmax[8];
 };
 
+// one shared-memory atomic per distinct bin and warp instead of one per lane: a digit of floating-point keys is
+// often shared by most of a column (a binade holds a quarter of a lognormal sample), and 32 lanes hitting one
+// address serialise
+__device__ __forceinline__ void hist_add_aggregated(int* hist, int bin, bool active) {
+    const unsigned act = __ballot_sync(0xffffffffu, active);
+    if (active) {
+        const unsigned peers = __match_any_sync(act, bin);
+        if ((threadIdx.x & 31) == __ffs(peers) - 1) atomicAdd(&hist[bin], __popc(peers));
+    }
+}
+// append `key` of the lanes with `take` to dst, one atomic per warp
+template <typename K>
+__device__ __forceinline__ void append_aggregated(K* dst, int* counter, K key, bool take) {
+    const unsigned m = __ballot_sync(0xffffffffu, take);
+    if (m == 0) return;
+    const int lane = threadIdx.x & 31, leader = __ffs(m) - 1;
+    int base = 0;
+    if (lane == leader) base = atomicAdd(counter, __popc(m));
+    base = __shfl_sync(0xffffffffu, base, leader);
+    if (take) dst[base + __popc(m & ((1u << lane) - 1))] = key;
+}
+
 // exact k-th smallest (0-based) of keys[0..n): every thread of the 256-thread CTA calls; returns the key in all.
+// With `want_next` the (k+1)-th smallest is delivered in sm.result2 as well whenever it sits among the same final
+// candidates (sm.have2 = 1): the two order statistics numpy interpolates between are neighbours.
 // State: bits [shift, BITS) of the answer are decided and held in `prefix`; a key is a candidate when it agrees with
 // the prefix on those bits.  `cur` holds exactly the candidates (physical) or a superset that is prefix-tested.
 template <typename K, int BITS>
 __device__ K block_select(const K* __restrict__ keys, int n, int k, int shift0, const int* __restrict__ cum0 /* [257] */,
-                          K* bufA, K* bufB, SelectSmem<K>& sm) {
+                          K* bufA, K* bufB, SelectSmem<K>& sm, bool want_next = false) {
     const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
     // round 0 comes from the column's shared histogram of byte [shift0, shift0 + 8): thread t tests bucket t
     if (cum0[tid] <= k && k < cum0[tid + 1]) { sm.bucket = tid; sm.before = cum0[tid]; sm.count = cum0[tid + 1] - cum0[tid]; }
@@ -507,23 +532,29 @@ __device__ K block_select(const K* __restrict__ keys, int n, int k, int shift0, 
             K* dst = (cur == bufA) ? bufB : bufA;
             if (tid == 0) sm.counter = 0;
             __syncthreads();
-            for (int i = tid; i < n_cur; i += 256) {
-                const K key = cur[i];
-                if (((key ^ prefix) >> shift) == 0) dst[atomicAdd(&sm.counter, 1)] = key;
+            for (int i0 = 0; i0 < n_cur; i0 += 256) {           // (uniform trip count: warp-wide votes inside)
+                const int i = i0 + tid;
+                const K key = i < n_cur ? cur[i] : (K)0;
+                append_aggregated(dst, &sm.counter, key, i < n_cur && ((key ^ prefix) >> shift) == 0);
             }
             __syncthreads();
             cur = dst; n_cur = c; physical = true;
         }
-        if (physical && n_cur <= 256) break;
-        if (shift == 0) return prefix;          // every bit decided: all candidates equal the prefix
+        if (physical && n_cur <= PS_FINAL) break;
+        if (shift == 0) {                       // every bit decided: all candidates equal the prefix
+            if (tid == 0) { sm.have2 = (want_next && kk + 1 < c) ? 1 : 0; sm.result2 = prefix; }
+            __syncthreads();
+            return prefix;
+        }
         const int above = shift;                // candidates agree with the prefix on bits [above, BITS)
         shift -= 8;
         // ---- histogram of the next byte among the candidates ----------------------------------------------
         sm.hist[tid] = 0;
         __syncthreads();
-        for (int i = tid; i < n_cur; i += 256) {
-            const K key = cur[i];
-            if (physical || ((key ^ prefix) >> above) == 0) atomicAdd(&sm.hist[(int)((key >> shift) & 255)], 1);
+        for (int i0 = 0; i0 < n_cur; i0 += 256) {
+            const int i = i0 + tid;
+            const K key = i < n_cur ? cur[i] : (K)0;
+            hist_add_aggregated(sm.hist, (int)((key >> shift) & 255), i < n_cur && (physical || ((key ^ prefix) >> above) == 0));
         }
         __syncthreads();
         const int v = sm.hist[tid];             // inclusive scan of the 256 bins: thread t owns bin t
@@ -545,7 +576,7 @@ __device__ K block_select(const K* __restrict__ keys, int n, int k, int shift0, 
         physical = false;                       // the next round's candidates are a subset of cur
         __syncthreads();
     }
-    // ---- at most 256 candidates: thread t ranks candidate t by counting ------------------------------------
+    // ---- at most PS_FINAL candidates: thread t ranks candidate t by counting (two warps at most) -------------------
     if (tid < n_cur) {
         const K mine = cur[tid];
         int less = 0;
@@ -554,7 +585,9 @@ __device__ K block_select(const K* __restrict__ keys, int n, int k, int shift0, 
             less += (o < mine || (o == mine && j < tid)) ? 1 : 0;
         }
         if (less == kk) sm.result = mine;
+        if (want_next && less == kk + 1) sm.result2 = mine;
     }
+    if (tid == 0) sm.have2 = (want_next && kk + 1 < n_cur) ? 1 : 0;
     __syncthreads();
     const K r = sm.result;
     __syncthreads();
@@ -610,7 +643,10 @@ k_percentiles_select(const T* __restrict__ a, int64_t N, int64_t Q, int CT,
         int top = 0;                                              // highest differing bit (0 when all keys are equal)
         if (diff) top = BITS - 1 - (BITS == 64 ? __clzll((long long)diff) : __clz((int)diff));
         const int shift0 = (top / 8) * 8;
-        for (int i = tid; i < n; i += 256) atomicAdd(&sm.hist[(int)((col[i] >> shift0) & 255)], 1);
+        for (int i0 = 0; i0 < n; i0 += 256) {
+            const int i = i0 + tid;
+            hist_add_aggregated(sm.hist, i < n ? (int)((col[i] >> shift0) & 255) : 0, i < n);
+        }
         __syncthreads();
         {   // exclusive prefix of the 256 bins -> cum0[0..256]
             const int v = sm.hist[tid];
@@ -630,8 +666,14 @@ k_percentiles_select(const T* __restrict__ a, int64_t N, int64_t Q, int CT,
         __syncthreads();
         for (int k = 0; k < qs.n; ++k) {
             const PctlQuery qq = qs.q[k];
-            const K ka = block_select<K, BITS>(col, n, qq.lo, shift0, cum0, bufA, bufB, sm);
-            const K kb = qq.hi == qq.lo ? ka : block_select<K, BITS>(col, n, qq.hi, shift0, cum0, bufA, bufB, sm);
+            const K ka = block_select<K, BITS>(col, n, qq.lo, shift0, cum0, bufA, bufB, sm, qq.hi != qq.lo);
+            K kb = ka;
+            if (qq.hi != qq.lo) {               // usually the neighbour came with it; otherwise it heads the next bucket
+                const bool have = sm.have2 != 0;
+                const K k2 = sm.result2;
+                __syncthreads();
+                kb = have ? k2 : block_select<K, BITS>(col, n, qq.hi, shift0, cum0, bufA, bufB, sm);
+            }
             if (tid == 0) {
                 const T A = SortKey<T>::back(ka), Bv = SortKey<T>::back(kb);
                 O r;

@@ -39,7 +39,8 @@ jpath = os.path.join(out, f"{rnd}_ncu_kernels.json")
 summary = json.load(open(jpath)) if os.path.isfile(jpath) else {}      # captures arrive one per gpurun call
 for name, what in (("chain_fp32", "k_chain (two hidden units per thread), 256 members, T=1000 (chain_sweep.py)"),
                    ("moments", "k_moments<double>, maps (1024, 4693, 14) float64 (stats_bench.py)"),
-                   ("percentiles", "k_percentiles<double>, maps (1024, 4693, 14) float64 (stats_bench.py)"),
+                   ("percentiles", "k_percentiles_select<double> (exact radix selection), maps (1024, 4693, 14) float64 (stats_bench.py)"),
+                   ("percentiles_n50", "k_percentiles_warp<double> (one warp per column), maps (50, 4693, 14) float64: the reference's own shape (stats_bench.py)"),
                    ("kde_scan", "k_kde_scan32<double>, maps (1024, 4693, 14) float64 (stats_bench.py)"),
                    ("kde_select", "k_kde_select64<double>, maps (1024, 4693, 14) float64 (stats_bench.py)"),
                    ("posterior_update", "k_posterior_update, 2^26 elements (stats_bench.py)"),
