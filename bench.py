@@ -152,8 +152,8 @@ class Spec:
                                       "k_time_table in the first (warm-up) call after load_state_dict and reused; the "
                                       "(T,4) step-scalar table and the condition encoder run every step",
                "parallelism": f"members sharded over {world} GPU(s), one all-gather of (B/G,29) f32"
-                              + ("; statistics on the gathered fields: every rank all columns up to 4096 gathered members, columns "
-                                 "split over the ranks (one packed all-gather of the results) above" if world > 1 else "")}
+                              + ("; statistics columns split over the ranks (one library call per rank, one packed "
+                                 "all-gather of the results)" if world > 1 else "")}
         if self.note:
             cfg["note"] = self.note
         return cfg
@@ -319,8 +319,8 @@ class Runner:
         kw = dict(loop_mode=spec.loop_mode, precision=spec.precision)
 
         def stats(x):
-            # one library call per rank, packed float64 records; N > 1: columns split over the ranks (plus one packed
-            # all-gather of the results) above 4096 gathered members, every rank all columns below (see parallel.py)
+            # one library call per rank, packed float64 records; N > 1: columns split over the ranks plus one packed
+            # all-gather of the results (see parallel.py for the measured alternative)
             return eb.parallel.ensemble_statistics_distributed(x, PERCENTILES, KDE_GRID)
 
         def step_device(i):

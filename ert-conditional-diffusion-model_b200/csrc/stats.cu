@@ -28,14 +28,16 @@ struct Workspace {
     bool used = false;
     unsigned int* tickets = nullptr;  // persistent, self-cleaning per-column counters (last-CTA-done pattern of the KDE kernels)
 };
-static Workspace g_ws[64];
+// two independent regions per device: 0 = the KDE kernels, min/max and everything else, 1 = the sorted runs of the
+// percentile path -- so that the fused summary can run the percentiles beside the KDE kernels on another stream
+static Workspace g_ws[64][2];
 static std::recursive_mutex g_ws_mutex;
 
 class WorkspaceLease {
  public:
-    explicit WorkspaceLease(cudaStream_t st) : st_(st), lock_(g_ws_mutex) {
+    explicit WorkspaceLease(cudaStream_t st, int region = 0) : st_(st), lock_(g_ws_mutex) {
         int dev = 0;
-        if (cudaGetDevice(&dev) == cudaSuccess && dev >= 0 && dev < 64) w_ = &g_ws[dev];
+        if (cudaGetDevice(&dev) == cudaSuccess && dev >= 0 && dev < 64) w_ = &g_ws[dev][region];
         if (w_ && w_->used && w_->last != st_ && w_->done) cudaStreamWaitEvent(st_, w_->done, 0);
     }
     ~WorkspaceLease() {
@@ -117,7 +119,7 @@ static int percentiles_by_runs_t(const void* d_a, int64_t N, int64_t Q, const st
         ERT_CUDA(cudaFuncSetAttribute(k_select_runs<T, G, O>, cudaFuncAttributeMaxDynamicSharedMemorySize, 200 * 1024));
         attr_set = true;
     }
-    WorkspaceLease lease(st);
+    WorkspaceLease lease(st, 1);
     char* ws = nullptr;
     const size_t runs_bytes = ((size_t)qb * N * sizeof(K) + 255) & ~(size_t)255;
     if (int rc = lease.get(runs_bytes + (size_t)qb * sizeof(int), (void**)&ws)) return rc;
@@ -418,7 +420,10 @@ int ertdiff_ensemble_kde_mode(const void* d_a, int dtype, int64_t N, int64_t Q,
     const size_t cols_bytes = ((size_t)Q * sizeof(KdeColumn) + 255) & ~(size_t)255;
     // the float64 selection of a column is shared by several CTAs when there are few columns and many
     // members (one CTA would re-evaluate ~100 candidates x N members alone)
-    const int sel_parts = (qb <= 4096 && N >= 1024) ? (qb * 8 <= 4 * kNumSMs ? 8 : (qb * 2 <= 4 * kNumSMs ? 2 : 1)) : 1;
+    int sel_parts = (qb <= 4096 && N >= 1024) ? (qb * 8 <= 4 * kNumSMs ? 8 : (qb * 2 <= 4 * kNumSMs ? 2 : 1)) : 1;
+    // a handful of long columns (a rank's share of a big ensemble): more parts, so that the candidates' float64
+    // sums spread over the whole machine
+    while (sel_parts >= 8 && sel_parts < 32 && qb * sel_parts * 2 <= 4 * kNumSMs && N >= 16384) sel_parts *= 2;
     const size_t part_bytes = (size_t)qb * sel_parts * 2 * sizeof(double);
     if (int rc = lease.get(cols_bytes + part_bytes + (size_t)qb * G * sizeof(float), &ws)) return rc;
     unsigned int* tk = nullptr;
@@ -473,11 +478,15 @@ int ertdiff_ensemble_kde_mode(const void* d_a, int dtype, int64_t N, int64_t Q,
             // is left of 200 KB after one float64 accumulator per candidate (or per grid point of this part, should
             // the scan be flat)
             const int stile = tile_override ? tile_override : (ms > 1 ? 16 * 1024 : 48 * 1024);
-            const int n_acc = std::max(KDE_MAX_CAND, (G + sel_parts - 1) / sel_parts);
-            ERT_REQUIRE((size_t)n_acc * 8 + 64 * 8 <= 200 * 1024, "ensemble_kde_mode: n_grid too large");
-            int dtile = (int)((200 * 1024 - (size_t)n_acc * 8) / 8) / 32 * 32;
+            // running sums: one per candidate of this part and warp.  Candidates are consecutive grid indices dealt
+            // round-robin to the parts, so a part holds at most ceil(KDE_MAX_CAND / parts) + 1 of them -- or, should
+            // the scan be flat, its share of the grid
+            const int n_acc = std::max((KDE_MAX_CAND + sel_parts - 1) / sel_parts + 1, (G + sel_parts - 1) / sel_parts);
+            ERT_REQUIRE((size_t)8 * n_acc * 8 + 64 * 8 <= 160 * 1024, "ensemble_kde_mode: n_grid too large");
+            int dtile = (int)((200 * 1024 - (size_t)8 * n_acc * 8) / 8) / 32 * 32;
+            if (dtile > 8192) dtile = 8192;                      // 64 KB tiles: three CTAs per SM
             if (tile_override && tile_override < dtile) dtile = tile_override;
-            const size_t dsmem = ((size_t)dtile + n_acc) * 8;
+            const size_t dsmem = ((size_t)dtile + 8 * (size_t)n_acc) * 8;
             if (f32in) {
                 k_kde_scan32_tiled<float><<<grid, threads, (size_t)stile * 4, st>>>((const float*)d_a, N, Q, c0, d_lohi, G, cols, s32, stile, ms);
                 ERT_LAUNCH_CHECK("k_kde_scan32_tiled");
@@ -655,9 +664,8 @@ int ertdiff_ensemble_summary(const void* d_a, int dtype, int64_t N, int64_t Q, i
     // stream beside the percentile and KDE kernels and are joined before the packing launch
     // the three statistics are independent per-column reductions.  The moments are a dependent add chain per column
     // (numpy's order; 170 us at 18,944 members): they run on a side stream beside the percentile and KDE kernels.  The
-    // percentiles join them on a second side stream whenever they go through a kernel that needs no scratch (the
-    // run path shares the per-device scratch with the KDE kernels, so it stays on the caller's stream).  Both are
-    // joined before the packing launch.
+    // percentiles join them on a second side stream (their run path has its own scratch region).  Both are joined
+    // before the packing launch.
     static cudaStream_t side[64][2] = {};
     static cudaEvent_t ev_fork[64] = {}, ev_join[64][2] = {};
     if (!side[dev][0]) {
@@ -671,7 +679,7 @@ int ertdiff_ensemble_summary(const void* d_a, int dtype, int64_t N, int64_t Q, i
     ERT_CUDA(cudaStreamWaitEvent(side[dev][0], ev_fork[dev], 0));
     if (int rc = ertdiff_ensemble_moments(cols, dtype, N, ncols, p_mean, p_std, p_var, side[dev][0])) return rc;
     ERT_CUDA(cudaEventRecord(ev_join[dev][0], side[dev][0]));
-    const bool pct_beside = nq > 0 && percentile_run_length(dtype, N, ncols) == 0;
+    const bool pct_beside = nq > 0;      // (the run path has its own scratch region: it, too, runs beside the KDE kernels)
     if (pct_beside) {
         ERT_CUDA(cudaStreamWaitEvent(side[dev][1], ev_fork[dev], 0));
         if (int rc = ertdiff_ensemble_percentiles(cols, dtype, N, ncols, h_q, nq, ERTDIFF_F64, p_pct, side[dev][1])) return rc;

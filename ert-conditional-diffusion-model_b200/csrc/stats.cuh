@@ -1109,25 +1109,29 @@ __device__ __forceinline__ void kde_select_column(int64_t N, int64_t col, double
         g_first = g_lo + ((part - g_lo) % nparts + nparts) % nparts;      // first g >= g_lo with g % nparts == part
         n_eval = (degenerate || g_first > g_hi) ? 0 : (g_hi - g_first) / nparts + 1;
     }
+    // every candidate is summed by the whole CTA (thread t takes members t, t + 256, ...; a fixed shuffle tree, then the
+    // warps' partial sums in warp order), so that a part with two or three candidates still uses all its warps
     double best = -1.0;
     int besti = 0x7fffffff;
-    for (int k = warp; k < n_eval; k += nwarps) {
+    (void)redi;
+    for (int k = 0; k < n_eval; ++k) {
         const int g = all ? g_first + k * nparts : cand[k];
         const double gv = kde_grid_point(g, G, lo, hi, step);
         double acc = 0.0;
-        for (int64_t i = lane; i < N; i += 32) {
+        for (int64_t i = tid; i < N; i += nthr) {
             const double d = gv - xs[i];
             acc += exp(d * d * kc.neg_inv_2h2);
         }
 #pragma unroll
         for (int o = 16; o > 0; o >>= 1) acc += __shfl_xor_sync(0xffffffffu, acc, o);
-        if (acc > best || (acc == best && g < besti)) { best = acc; besti = g; }
+        __syncthreads();
+        if (lane == 0) redv[warp] = acc;
+        __syncthreads();
+        acc = redv[0];
+        for (int w = 1; w < nwarps; ++w) acc += redv[w];
+        if (acc > best || (acc == best && g < besti)) { best = acc; besti = g; }      // (identical in every thread)
     }
-    if (lane == 0) { redv[warp] = best; redi[warp] = besti; }
-    __syncthreads();
     if (tid == 0) {
-        for (int w = 1; w < nwarps; ++w)
-            if (redv[w] > best || (redv[w] == best && redi[w] < besti)) { best = redv[w]; besti = redi[w]; }
         if (nparts > 1) {
             double* mine = partials + (slot * nparts + part) * 2;
             mine[0] = best; mine[1] = (double)besti;
@@ -1284,7 +1288,7 @@ k_kde_scan32_tiled(const T* __restrict__ a, int64_t N, int64_t Q, int64_t col0,
     }
 }
 
-// grid = (columns of this batch, parts), 256 threads; dynamic shared memory: tile doubles + n_acc doubles
+// grid = (columns of this batch, parts), 256 threads; dynamic shared memory: tile doubles + 8 x n_acc doubles
 template <typename T>
 __global__ void __launch_bounds__(256)
 k_kde_select64_tiled(const T* __restrict__ a, int64_t N, int64_t Q, int64_t col0,
@@ -1294,7 +1298,7 @@ k_kde_select64_tiled(const T* __restrict__ a, int64_t N, int64_t Q, int64_t col0
                      unsigned int* __restrict__ tickets, int tile /* multiple of 32 */, int n_acc) {
     extern __shared__ __align__(16) unsigned char kde_smem_raw[];
     double* xs = reinterpret_cast<double*>(kde_smem_raw);      // [tile] members, float64
-    double* accs = xs + tile;                                  // [n_acc] one running sum per candidate
+    double* accs = xs + tile;                                  // [8 warps][n_acc] running sums per candidate
     __shared__ float redf[8];
     __shared__ double redv[8];
     __shared__ int redi[8];
@@ -1340,38 +1344,45 @@ k_kde_select64_tiled(const T* __restrict__ a, int64_t N, int64_t Q, int64_t col0
         g_first = g_lo + ((part - g_lo) % nparts + nparts) % nparts;
         n_eval = (degenerate || g_first > g_hi) ? 0 : (g_hi - g_first) / nparts + 1;
     }
-    for (int k = tid; k < n_eval && k < n_acc; k += nthr) accs[k] = 0.0;
-    for (int64_t t0 = 0; t0 < N; t0 += tile) {
-        const int n = (int)(N - t0 < tile ? N - t0 : tile);
-        __syncthreads();
-        for (int i = tid; i < n; i += nthr) xs[i] = (double)a[(t0 + i) * Q + col];
-        __syncthreads();
-        for (int k = warp; k < n_eval; k += nwarps) {           // candidate k belongs to warp k % nwarps throughout
-            const int g = all ? g_first + k * nparts : cand[k];
-            const double gv = kde_grid_point(g, G, lo, hi, step);
-            double acc = 0.0;
-            for (int i = lane; i < n; i += 32) {
-                const double d = gv - xs[i];
-                acc += exp(d * d * kc.neg_inv_2h2);
-            }
-#pragma unroll
-            for (int o = 16; o > 0; o >>= 1) acc += __shfl_xor_sync(0xffffffffu, acc, o);
-            if (lane == 0) accs[k] += acc;
-        }
-    }
-    __syncwarp();
+    // every warp sums its slice of the members (t, t + 256, ...) for EVERY candidate and keeps one running sum per
+    // candidate (accs[warp][k], no barrier inside a tile): a part with two or three candidates still uses all its
+    // warps.  Candidates are taken n_acc at a time (one batch unless they all fell to this part).
+    (void)redv; (void)redi;
     double best = -1.0;
     int besti = 0x7fffffff;
-    for (int k = warp; k < n_eval; k += nwarps) {
-        const int g = all ? g_first + k * nparts : cand[k];
-        const double acc = accs[k];
-        if (acc > best || (acc == best && g < besti)) { best = acc; besti = g; }
+    for (int k0 = 0; k0 < n_eval; k0 += n_acc) {
+        const int nb = n_eval - k0 < n_acc ? n_eval - k0 : n_acc;
+        __syncthreads();
+        for (int k = tid; k < nwarps * n_acc; k += nthr) accs[k] = 0.0;
+        for (int64_t t0 = 0; t0 < N; t0 += tile) {
+            const int n = (int)(N - t0 < tile ? N - t0 : tile);
+            __syncthreads();
+            for (int i = tid; i < n; i += nthr) xs[i] = (double)a[(t0 + i) * Q + col];
+            __syncthreads();
+            for (int k = 0; k < nb; ++k) {
+                const int g = all ? g_first + (k0 + k) * nparts : cand[k0 + k];
+                const double gv = kde_grid_point(g, G, lo, hi, step);
+                double acc = 0.0;
+                for (int i = tid; i < n; i += nthr) {
+                    const double d = gv - xs[i];
+                    acc += exp(d * d * kc.neg_inv_2h2);
+                }
+#pragma unroll
+                for (int o = 16; o > 0; o >>= 1) acc += __shfl_xor_sync(0xffffffffu, acc, o);
+                if (lane == 0) accs[warp * n_acc + k] += acc;
+            }
+        }
+        __syncthreads();
+        if (tid == 0) {
+            for (int k = 0; k < nb; ++k) {
+                const int g = all ? g_first + (k0 + k) * nparts : cand[k0 + k];
+                double acc = accs[k];
+                for (int w = 1; w < nwarps; ++w) acc += accs[w * n_acc + k];
+                if (acc > best || (acc == best && g < besti)) { best = acc; besti = g; }
+            }
+        }
     }
-    if (lane == 0) { redv[warp] = best; redi[warp] = besti; }
-    __syncthreads();
     if (tid == 0) {
-        for (int w = 1; w < nwarps; ++w)
-            if (redv[w] > best || (redv[w] == best && redi[w] < besti)) { best = redv[w]; besti = redi[w]; }
         if (nparts > 1) {
             double* mine = partials + (slot * nparts + part) * 2;
             mine[0] = best; mine[1] = (double)besti;
