@@ -476,6 +476,8 @@ def extra_specs(world):
     specs = [
         Spec("config3_bf16_1024_persistent", 1024, "bf16", baseline_config="BASELINE configs[2]"),
         Spec("config3_bf16_1024_graph", 1024, "bf16", loop_mode="graph", baseline_config="BASELINE configs[2] (CUDA-graph reverse loop)"),
+        Spec("fp32_1024", 1024, "fp32", note="config 3's ensemble through the fp32 CUDA-core chain: faster than the tensor-core "
+                                             "kernel up to ~1500 members, at fp32 accuracy"),
         Spec("bf16_8192", 8192, "bf16", note="BASELINE configs[3]'s whole ensemble on every GPU" if world == 1 else None),
         Spec("bf16_18944", 18944, "bf16", note="one full 128-member tile per SM (148 x 128)"),
         Spec("fp32_256_distinct_conditions", 256, "fp32", distinct=True, note="the encoder runs for 256 conditions every step"),

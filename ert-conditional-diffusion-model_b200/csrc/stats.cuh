@@ -490,10 +490,16 @@ struct SelectSmem {
 // often shared by most of a column (a binade holds a quarter of a lognormal sample), and 32 lanes hitting one
 // address serialise
 __device__ __forceinline__ void hist_add_aggregated(int* hist, int bin, bool active) {
+    // the lanes that share the first active lane's bin add once, together; the others add for themselves
+    // (a full match.any costs more than the conflicts it removes when most lanes hold different bins)
     const unsigned act = __ballot_sync(0xffffffffu, active);
+    if (act == 0) return;
+    const int leader = __ffs(act) - 1;
+    const int b0 = __shfl_sync(0xffffffffu, bin, leader);
+    const unsigned same = __ballot_sync(0xffffffffu, active && bin == b0);
     if (active) {
-        const unsigned peers = __match_any_sync(act, bin);
-        if ((threadIdx.x & 31) == __ffs(peers) - 1) atomicAdd(&hist[bin], __popc(peers));
+        if (bin != b0) atomicAdd(&hist[bin], 1);
+        else if ((int)(threadIdx.x & 31) == leader) atomicAdd(&hist[b0], __popc(same));
     }
 }
 // append `key` of the lanes with `take` to dst, one atomic per warp
@@ -1109,27 +1115,48 @@ __device__ __forceinline__ void kde_select_column(int64_t N, int64_t col, double
         g_first = g_lo + ((part - g_lo) % nparts + nparts) % nparts;      // first g >= g_lo with g % nparts == part
         n_eval = (degenerate || g_first > g_hi) ? 0 : (g_hi - g_first) / nparts + 1;
     }
-    // every candidate is summed by the whole CTA (thread t takes members t, t + 256, ...; a fixed shuffle tree, then the
-    // warps' partial sums in warp order), so that a part with two or three candidates still uses all its warps
+    // long columns: every candidate is summed by the whole CTA (thread t takes members t, t + 256, ...; a fixed shuffle
+    // tree, then the warps' partial sums in warp order), so that a part with two or three candidates uses all its warps
     double best = -1.0;
     int besti = 0x7fffffff;
-    (void)redi;
-    for (int k = 0; k < n_eval; ++k) {
-        const int g = all ? g_first + k * nparts : cand[k];
-        const double gv = kde_grid_point(g, G, lo, hi, step);
-        double acc = 0.0;
-        for (int64_t i = tid; i < N; i += nthr) {
-            const double d = gv - xs[i];
-            acc += exp(d * d * kc.neg_inv_2h2);
-        }
+    if (N >= 4096) {
+        for (int k = 0; k < n_eval; ++k) {
+            const int g = all ? g_first + k * nparts : cand[k];
+            const double gv = kde_grid_point(g, G, lo, hi, step);
+            double acc = 0.0;
+            for (int64_t i = tid; i < N; i += nthr) {
+                const double d = gv - xs[i];
+                acc += exp(d * d * kc.neg_inv_2h2);
+            }
 #pragma unroll
-        for (int o = 16; o > 0; o >>= 1) acc += __shfl_xor_sync(0xffffffffu, acc, o);
+            for (int o = 16; o > 0; o >>= 1) acc += __shfl_xor_sync(0xffffffffu, acc, o);
+            __syncthreads();
+            if (lane == 0) redv[warp] = acc;
+            __syncthreads();
+            acc = redv[0];
+            for (int w = 1; w < nwarps; ++w) acc += redv[w];
+            if (acc > best || (acc == best && g < besti)) { best = acc; besti = g; }      // (identical in every thread)
+        }
+    } else {
+        // short columns: one warp per candidate (eight candidates in flight hide the float64 exp latency that a
+        // single member per thread would expose)
+        for (int k = warp; k < n_eval; k += nwarps) {
+            const int g = all ? g_first + k * nparts : cand[k];
+            const double gv = kde_grid_point(g, G, lo, hi, step);
+            double acc = 0.0;
+            for (int64_t i = lane; i < N; i += 32) {
+                const double d = gv - xs[i];
+                acc += exp(d * d * kc.neg_inv_2h2);
+            }
+#pragma unroll
+            for (int o = 16; o > 0; o >>= 1) acc += __shfl_xor_sync(0xffffffffu, acc, o);
+            if (acc > best || (acc == best && g < besti)) { best = acc; besti = g; }
+        }
         __syncthreads();
-        if (lane == 0) redv[warp] = acc;
+        if (lane == 0) { redv[warp] = best; redi[warp] = besti; }
         __syncthreads();
-        acc = redv[0];
-        for (int w = 1; w < nwarps; ++w) acc += redv[w];
-        if (acc > best || (acc == best && g < besti)) { best = acc; besti = g; }      // (identical in every thread)
+        for (int w = 0; w < nwarps; ++w)
+            if (redv[w] > best || (redv[w] == best && redi[w] < besti)) { best = redv[w]; besti = redi[w]; }
     }
     if (tid == 0) {
         if (nparts > 1) {
