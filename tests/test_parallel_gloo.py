@@ -93,6 +93,11 @@ def _stats_worker(rank, world, port, n_members, n_cols, out_dir):
         return torch.from_numpy(np.stack(rows))
 
     out = sharded_statistics(x, qs, 64, stats_fn=numpy_stats)
+    from ertdiff_b200.parallel import ensemble_statistics_distributed
+    auto = ensemble_statistics_distributed(x, qs, 64, stats_fn=numpy_stats)           # world > 1: columns split
+    local = ensemble_statistics_distributed(x, qs, 64, shard=False, stats_fn=numpy_stats)   # every rank all columns
+    for k in ("mean", "std", "var", "pct", "mode", "mode_index", "packed"):
+        assert torch.equal(auto[k], out[k]) and torch.equal(local[k], out[k]), k
     np.savez(os.path.join(out_dir, f"stats_rank{rank}.npz"), **{k: v.numpy() for k, v in out.items()},
              slice=np.array(column_slice(n_cols, rank, world)))
     if rank == 0:
