@@ -317,18 +317,24 @@ class Runner:
         cond_dev_b = cond_dev if spec.distinct else cond_dev.expand(members, C, L)
         cond_pinned = cond_host.pin_memory()
         kw = dict(loop_mode=spec.loop_mode, precision=spec.precision)
+        # N > 1: the two latency-bound collectives of a step (the fields, the packed statistics records) go through the
+        # library's own NVLink peer-memory kernel; ERTDIFF_BENCH_NCCL=1 keeps them on NCCL for comparison
+        peer_x = peer_s = None
+        if world > 1 and not os.environ.get("ERTDIFF_BENCH_NCCL"):
+            peer_x = eb.parallel.PeerAllGather(members * P * 4, dev)
+            peer_s = eb.parallel.PeerAllGather(-(-P // world) * (5 + len(PERCENTILES)) * 8, dev)
 
         def stats(x):
             # one library call per rank, packed float64 records; N > 1: columns split over the ranks plus one packed
             # all-gather of the results (see parallel.py for the measured alternative)
-            return eb.parallel.ensemble_statistics_distributed(x, PERCENTILES, KDE_GRID)
+            return eb.parallel.ensemble_statistics_distributed(x, PERCENTILES, KDE_GRID, peer=peer_s)
 
         def step_device(i):
             """inputs resident in HBM"""
             x = eb.run_chain(model, cond_dev_b, T, *sched_dev, dev, seed=1234, offset=4 * i,
                              member_offset=rank * members, check_status=False, **kw)
             if world > 1:
-                x = eb.parallel.gather_members(x, total)
+                x = eb.parallel.gather_members(x, total, peer=peer_x)
             return x, stats(x)
 
         host_out = []
@@ -342,7 +348,7 @@ class Runner:
             else:
                 x = eb.run_chain(model, c, T, betas, alphas, alpha_bar, dev, seed=1234, offset=4 * i,
                                  member_offset=rank * members, check_status=False, **kw)
-                x = eb.parallel.gather_members(x, total)
+                x = eb.parallel.gather_members(x, total, peer=peer_x)
             st = stats(x)
             # D2H read of the step's results: fields + every statistic, straight into pinned host buffers
             # (no staging kernels), one stream synchronise at the end
@@ -420,6 +426,15 @@ class Runner:
                                             float(np.mean(floor_ms)) if floor_ms else None)
         if cpu_baseline_budget > 0 and world == 1 and rank == 0:
             rec["cpu_baseline"] = cpu_baselines(sd, cond_host, members, T, cpu_baseline_budget, ref_sample_steps)
+        if peer_x is not None:
+            if peer_x.status() or peer_s.status():
+                raise SystemExit("bench.py: a peer all-gather timed out")
+            rec["config"]["collectives"] = ("library kernel over NVLink peer memory (k_peer_all_gather: P2P stores + epoch "
+                                            "flags), 2 per step; NCCL only exchanges the IPC handles at set-up")
+            self.barrier()
+            peer_x.close(); peer_s.close()
+        elif world > 1:
+            rec["config"]["collectives"] = "NCCL all-gather, 2 per step"
         del model
         return rec
 

@@ -89,6 +89,11 @@ SIGNATURES = {
     "ertdiff_check_bounds": (C.c_int, [C.c_void_p, C.c_int, C.c_int64, C.c_int32, C.c_void_p, C.c_void_p, C.c_void_p,
                                        C.c_void_p, C.c_void_p]),
     "ertdiff_argsort_stable": (C.c_int, [C.c_void_p, C.c_int, C.c_int64, C.c_void_p, C.c_void_p]),
+    "ertdiff_peer_create": (C.c_int, [C.POINTER(C.c_void_p), C.c_int, C.c_int, C.c_int, C.c_size_t, C.c_void_p]),
+    "ertdiff_peer_connect": (C.c_int, [C.c_void_p, C.c_void_p]),
+    "ertdiff_peer_all_gather": (C.c_int, [C.c_void_p, C.c_void_p, C.c_size_t, C.c_size_t, C.POINTER(C.c_void_p), C.c_void_p]),
+    "ertdiff_peer_status": (C.c_int, [C.c_void_p, C.POINTER(C.c_int)]),
+    "ertdiff_peer_destroy": (C.c_int, [C.c_void_p]),
     "ertdiff_debug_umma_gemm": (C.c_int, [C.c_void_p, C.c_void_p, C.c_int32, C.c_int32, C.c_void_p, C.c_void_p]),
     "ertdiff_debug_chain_floor": (C.c_int, [C.c_void_p, C.c_int]),
     "ertdiff_debug_graph_stats": (C.c_int, [C.c_void_p, C.POINTER(C.c_int64)]),

@@ -657,9 +657,10 @@ int ertdiff_ensemble_summary(const void* d_a, int dtype, int64_t N, int64_t Q, i
     }
     // the KDE grid spans the min / max of the WHOLE array (ECD.py:749-751), not of this window.  Small ensembles: the
     // one-launch KDE kernel takes the range itself (every CTA scans the whole array: N*Q <= 64 K values)
-    // (a rank's window of a few columns keeps the one-launch form up to 4096 members: four dependent launches and
-    // their gaps cost more than the last CTA's lone float64 selection)
-    const bool kde_small = N * Q <= 65536 && (N < 1024 || (N < 4096 && ncols <= 8)) && ncols <= ertdiff::WorkspaceLease::kTicketSlots;
+    // (measured: beyond ~1000 members the staged kernels win even for a 4-column window -- 2048 x 4: 43 us of
+    // dependent launches against 90 us for the one-launch form, whose every CTA scans the whole array for the range
+    // and whose last CTA selects alone)
+    const bool kde_small = N * Q <= 65536 && N < 1024 && ncols <= ertdiff::WorkspaceLease::kTicketSlots;
     if (!kde_small)
         if (int rc = ertdiff_minmax(d_a, dtype, N * Q, p_lohi, stream)) return rc;
     // the moments are a dependent add chain per column (numpy's order; 170 us at 18,944 members): they run on a side

@@ -12,6 +12,79 @@ import torch
 import torch.distributed as dist
 
 
+class _RawCuda:
+    """A device allocation of the library seen as a CUDA array (zero-copy view for torch.as_tensor)."""
+
+    def __init__(self, ptr, nbytes):
+        self.__cuda_array_interface__ = {"shape": (nbytes,), "typestr": "|u1", "data": (int(ptr), False), "version": 3}
+
+
+class PeerAllGather:
+    """All-gather over NVLink peer memory through the library's own kernel (``ertdiff_peer_*``) instead of NCCL:
+    one launch stores this rank's slice into every peer's buffer (P2P stores), publishes an epoch flag and waits for
+    the peers' flags.  For the path's two latency-bound collectives (the final fields, the packed statistics
+    records) on the GPUs of one node, one process per GPU.  ``torch.distributed`` is used once, at set-up, to
+    exchange the CUDA IPC handles.
+
+    ``all_gather(src)`` returns a view of this rank's gathered buffer ``(world * slot,) + src.shape[1:]`` that stays
+    valid until the next-but-one call; every rank must call in the same order with equal shapes."""
+
+    def __init__(self, max_bytes_per_rank: int, device, group=None):
+        import ctypes as C
+        from . import _lib
+        self._lib, self._C = _lib, C
+        self.group = group
+        self.world = dist.get_world_size(group)
+        self.rank = dist.get_rank(group)
+        self.device = torch.device(device)
+        self.slot_cap = (int(max_bytes_per_rank) + 255) // 256 * 256
+        lib = _lib.load()
+        handle = (C.c_ubyte * 64)()
+        self._h = C.c_void_p()
+        index = self.device.index if self.device.index is not None else torch.cuda.current_device()
+        _lib.check(lib.ertdiff_peer_create(C.byref(self._h), index, self.rank, self.world, self.slot_cap * self.world, handle),
+                   "peer_create")
+        mine = torch.tensor(list(handle), dtype=torch.uint8, device=self.device)
+        every = torch.empty(self.world * 64, dtype=torch.uint8, device=self.device)
+        dist.all_gather_into_tensor(every, mine, group=group)
+        blob = bytes(every.cpu().numpy().tobytes())
+        _lib.check(lib.ertdiff_peer_connect(self._h, blob), "peer_connect")
+        dist.barrier(group)                 # every rank has mapped every buffer before the first store
+
+    def all_gather(self, src: torch.Tensor) -> torch.Tensor:
+        C, lib = self._C, self._lib.load()
+        src = src.contiguous()
+        nbytes = src.numel() * src.element_size()
+        if nbytes > self.slot_cap:
+            raise ValueError(f"slice of {nbytes} bytes exceeds the peer buffer's {self.slot_cap} per rank")
+        slot = (nbytes + 15) // 16 * 16
+        out = C.c_void_p()
+        with torch.cuda.device(self.device):
+            self._lib.check(lib.ertdiff_peer_all_gather(self._h, self._lib.ptr(src), nbytes, slot, C.byref(out),
+                                                        self._lib.stream_ptr(self.device)), "peer_all_gather")
+        raw = torch.as_tensor(_RawCuda(out.value, slot * self.world), device=self.device)
+        if slot == nbytes:
+            return raw.view(src.dtype).view((self.world * src.size(0),) + tuple(src.shape[1:]))
+        per = raw.view(self.world, slot)[:, :nbytes].contiguous()
+        return per.view(src.dtype).view((self.world * src.size(0),) + tuple(src.shape[1:]))
+
+    def status(self) -> int:
+        st = self._C.c_int()
+        self._lib.check(self._lib.load().ertdiff_peer_status(self._h, self._C.byref(st)), "peer_status")
+        return int(st.value)
+
+    def close(self):
+        if getattr(self, "_h", None) is not None and self._h:
+            self._lib.load().ertdiff_peer_destroy(self._h)
+            self._h = None
+
+    def __del__(self):
+        try:
+            self.close()
+        except Exception:
+            pass
+
+
 def member_slice(n_members: int, rank: int, world_size: int, multiple_of: int = 1):
     """Contiguous ``[start, stop)`` of rank's members; slice sizes are multiples of
     ``multiple_of`` (the number of distinct conditions, so ``member % n_cond`` is preserved)."""
@@ -25,7 +98,7 @@ def member_slice(n_members: int, rank: int, world_size: int, multiple_of: int = 
 
 
 def gather_members(x_local: torch.Tensor, n_members: int, multiple_of: int = 1,
-                   group=None) -> torch.Tensor:
+                   group=None, peer: "PeerAllGather | None" = None) -> torch.Tensor:
     """All-gather ``(B_local, P)`` slices into ``(n_members, P)`` in rank (= member) order.
     Slices may differ in length by one group: each rank pads to the longest slice, one
     equal-sized all-gather runs, and the padding is dropped."""
@@ -41,6 +114,8 @@ def gather_members(x_local: torch.Tensor, n_members: int, multiple_of: int = 1,
         pad = torch.zeros((longest - x_local.size(0),) + tuple(x_local.shape[1:]),
                           device=x_local.device, dtype=x_local.dtype)
         x_local = torch.cat([x_local, pad], dim=0)
+    if even and x_local.is_cuda and peer is not None:
+        return peer.all_gather(x_local)                                # the library's own NVLink kernel
     if even and x_local.is_cuda:
         out = torch.empty((n_members,) + tuple(x_local.shape[1:]), device=x_local.device,
                           dtype=x_local.dtype)
@@ -74,7 +149,7 @@ _UNPAD_INDEX = {}      # (Q, world, device) -> row indices that drop the padding
 
 
 def ensemble_statistics_distributed(x: torch.Tensor, percentiles=(25, 50, 75), n_grid: int = 5000, group=None, shard=None,
-                                    stats_fn=None):
+                                    stats_fn=None, peer: "PeerAllGather | None" = None):
     """Statistics of the gathered fields ``x (N, Q)`` on every rank: with more than one rank the columns are split over
     the ranks (``sharded_statistics``), otherwise the one-call summary runs on the whole array.  ``shard=False`` makes
     every rank compute all columns itself (no second collective) -- measured SLOWER on 8 GPUs even for 2048
@@ -85,14 +160,14 @@ def ensemble_statistics_distributed(x: torch.Tensor, percentiles=(25, 50, 75), n
     if shard is None:
         shard = world > 1
     if shard:
-        return sharded_statistics(x, percentiles, n_grid, group, stats_fn)
+        return sharded_statistics(x, percentiles, n_grid, group, stats_fn, peer)
     if stats_fn is not None:            # (CPU tests)
         return st.summary_views(stats_fn(x, None).t().contiguous(), len(percentiles))
     return st.ensemble_summary(x, percentiles, n_grid)
 
 
 def sharded_statistics(x: torch.Tensor, percentiles=(25, 50, 75), n_grid: int = 5000, group=None,
-                       stats_fn=None):
+                       stats_fn=None, peer: "PeerAllGather | None" = None):
     """Ensemble statistics of the gathered fields ``x (N, Q)`` with the COLUMNS split over the ranks:
     every statistic of the path is per column (ECD.py:747-762, 867-872), so rank r computes columns
     ``column_slice(Q, r, world)`` over all N members and one small all-gather returns every map to
@@ -121,8 +196,11 @@ def sharded_statistics(x: torch.Tensor, percentiles=(25, 50, 75), n_grid: int = 
         else:
             block[:b - a].copy_(stats_fn(x[:, a:b].contiguous(), None).t())
     if world > 1:
-        gathered = torch.empty(world * q_max, rows, device=x.device, dtype=torch.float64)
-        if x.is_cuda:
+        gathered = None
+        if x.is_cuda and peer is not None:
+            gathered = peer.all_gather(block)                              # the library's own NVLink kernel
+        elif x.is_cuda:
+            gathered = torch.empty(world * q_max, rows, device=x.device, dtype=torch.float64)
             dist.all_gather_into_tensor(gathered, block, group=group)      # one NCCL all-gather
         else:
             parts = [torch.empty_like(block) for _ in range(world)]

@@ -28,6 +28,7 @@
 #ifndef ERTDIFF_B200_H
 #define ERTDIFF_B200_H
 
+#include <stddef.h>
 #include <stdint.h>
 
 #ifdef __cplusplus
@@ -276,6 +277,25 @@ int ertdiff_check_bounds(const void* d_v, int dtype, int64_t B, int32_t P, const
 /* Stable ascending argsort of a device vector (n values, dtype ERTDIFF_F32 / F64), NaN last: the ranking
  * `np.argsort(WSSE_sim_total)` of ECD.py:786.  d_order[k] = index of the k-th smallest value. */
 int ertdiff_argsort_stable(const void* d_v, int dtype, int64_t n, int64_t* d_order, void* stream);
+
+/* ---- all-gather over NVLink peer memory (one process per GPU on one node) ----------------------------
+ * The path's collectives -- the final fields, (B/G, 29) fp32 per rank, and the packed statistics records -- are
+ * latency-bound.  A peer group replaces the NCCL call by ONE kernel: it stores this rank's slice straight into every
+ * peer's buffer (P2P stores over NVLink), publishes an epoch flag to every peer and waits for theirs.
+ *   create : allocates this rank's buffer (room for `bytes` = all ranks' slices, double-buffered) and returns its
+ *            64-byte CUDA IPC handle in h_ipc_handle64; the caller exchanges the handles (e.g. one
+ *            torch.distributed all-gather at set-up) and passes all `world` of them, in rank order, to connect.
+ *   all_gather : d_src (nbytes <= slot_bytes) lands at offset rank * slot_bytes of every rank's buffer;
+ *            *d_gathered = this rank's buffer for this call, valid until the next-but-one call.  Every rank must call
+ *            in the same order.  A peer that never arrives sets the status word after ~2 s instead of hanging.
+ * world <= 16.  Not thread-safe; one stream at a time. */
+typedef struct ertdiff_peer ertdiff_peer;
+int ertdiff_peer_create(ertdiff_peer** out, int device, int rank, int world, size_t bytes, void* h_ipc_handle64);
+int ertdiff_peer_connect(ertdiff_peer* p, const void* h_all_handles);
+int ertdiff_peer_all_gather(ertdiff_peer* p, const void* d_src, size_t nbytes, size_t slot_bytes, void** d_gathered,
+                            void* stream);
+int ertdiff_peer_status(ertdiff_peer* p, int* h_status);
+int ertdiff_peer_destroy(ertdiff_peer* p);
 
 /* ---- self-test of the tcgen05 building blocks -------------------------------------------------
  * D (128,N) = A (128,K) @ B (N,K)^T on the tensor cores (bf16 operands, fp32 accumulate in TMEM),

@@ -39,13 +39,17 @@ model.to(dev).eval()
 sched = [t.to(dev) for t in eb.get_diffusion_schedule(a.T)]
 cond_b = cond.to(dev).expand(a.members, bench.C, spec.L)
 total = a.members * world
+peer_x = peer_s = None
+if not os.environ.get("ERTDIFF_BENCH_NCCL"):
+    peer_x = eb.parallel.PeerAllGather(a.members * bench.P * 4, dev)
+    peer_s = eb.parallel.PeerAllGather(-(-bench.P // world) * (5 + len(bench.PERCENTILES)) * 8, dev)
 
 
 def step(i):
     x = eb.run_chain(model, cond_b, a.T, *sched, dev, seed=1234, offset=4 * i, member_offset=rank * a.members,
                      precision=a.precision, check_status=False)
-    x = eb.parallel.gather_members(x, total)
-    return eb.parallel.ensemble_statistics_distributed(x, bench.PERCENTILES, bench.KDE_GRID, shard=SHARD)
+    x = eb.parallel.gather_members(x, total, peer=peer_x)
+    return eb.parallel.ensemble_statistics_distributed(x, bench.PERCENTILES, bench.KDE_GRID, shard=SHARD, peer=peer_s)
 
 
 for i in range(3):

@@ -26,6 +26,8 @@ torch.manual_seed(1)
 cond1 = torch.rand(1, C, L)
 model.to(dev).eval()
 sched = eb.get_diffusion_schedule(T)
+peer_x = eb.parallel.PeerAllGather(600 * P * 4, dev)
+peer_s = eb.parallel.PeerAllGather(32 * 16 * 8, dev)
 ok = True
 for prec in ("fp32", "bf16"):
     for B in (512, 515):                      # even and uneven splits
@@ -33,6 +35,9 @@ for prec in ("fp32", "bf16"):
         x_loc = eb.run_chain(model, cond1.to(dev).expand(b - a, C, L), T, *sched, dev, seed=99, offset=0,
                              member_offset=a, precision=prec)
         x_all = eb.parallel.gather_members(x_loc, B)
+        if B % world == 0:                      # the library's own NVLink all-gather must deliver the same bytes as NCCL
+            x_peer = peer_x.all_gather(x_loc)
+            assert torch.equal(x_peer, x_all), "peer all-gather differs from NCCL"
         x_one = eb.run_chain(model, cond1.to(dev).expand(B, C, L), T, *sched, dev, seed=99, offset=0,
                              precision=prec)
         same = torch.equal(x_all, x_one)
@@ -40,6 +45,8 @@ for prec in ("fp32", "bf16"):
         st_one = eb.ensemble_statistics(x_one, percentiles=(), n_grid=512)
         pct_one = eb.ensemble_percentile(x_one, list(qs))                        # list q: float64 index arithmetic
         st_sh = eb.parallel.sharded_statistics(x_all, qs, 512)                   # columns split over the ranks
+        st_pp = eb.parallel.sharded_statistics(x_all, qs, 512, peer=peer_s)      # same, results through the peer kernel
+        assert torch.equal(st_pp["packed"], st_sh["packed"]), "peer-gathered statistics differ"
         bad = [k for k in ("mean", "std", "var", "mode", "mode_index")
                if not torch.equal(st_sh[k].to(st_one[k].dtype), st_one[k])]
         if not torch.equal(st_sh["pct"], pct_one.double()):
@@ -52,6 +59,8 @@ for prec in ("fp32", "bf16"):
         if rank == 0:
             print(f"{prec} B={B} world={world}: gathered == single-GPU: {bool(flag.item())}", flush=True)
         ok = ok and bool(flag.item())
+ok = ok and peer_x.status() == 0 and peer_s.status() == 0
 dist.barrier()
+peer_x.close(); peer_s.close()
 dist.destroy_process_group()
 sys.exit(0 if ok else 1)
