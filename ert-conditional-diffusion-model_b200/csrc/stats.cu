@@ -230,6 +230,12 @@ static int percentiles_by_runs(const void* d_a, int dtype, int64_t N, int64_t Q,
     return percentiles_by_runs_t<double, double, double>(d_a, N, Q, qs, d_out, CH, st);
 }
 
+// members below which the one-launch KDE kernel (k_kde_small) is used (ERTDIFF_KDE_SMALL_MAX overrides, for sweeps)
+static int64_t kde_small_max_members() {
+    if (const char* e = std::getenv("ERTDIFF_KDE_SMALL_MAX")) return std::atoll(e);
+    return 1024;
+}
+
 // Run length of the sorted-runs percentile path for an (N, Q) array, or 0 when a shared-memory kernel serves it
 // (those need no scratch, so the fused summary can run them beside the KDE kernels).
 static int percentile_run_length(int dtype, int64_t N, int64_t Q) {
@@ -518,7 +524,7 @@ int ertdiff_ensemble_kde_mode_auto(const void* d_a, int dtype, int64_t N, int64_
     ERT_REQUIRE(dtype == ERTDIFF_F32 || dtype == ERTDIFF_F64, "ensemble_kde_mode_auto: bad dtype");
     cudaStream_t st = (cudaStream_t)stream;
     // (from ~1000 members on, the staged kernels win: their float64 selection is shared by 8 CTAs per column)
-    const bool small = N * Q <= 65536 && N < 1024 && Q <= 4096;
+    const bool small = N * Q <= 65536 && N < kde_small_max_members() && Q <= 4096;
     if (!small) {
         if (int rc = ertdiff_minmax(d_a, dtype, N * Q, d_lohi, stream)) return rc;
         return ertdiff_ensemble_kde_mode(d_a, dtype, N, Q, d_lohi, n_grid, d_mode, d_index, stream);
@@ -660,7 +666,7 @@ int ertdiff_ensemble_summary(const void* d_a, int dtype, int64_t N, int64_t Q, i
     // (measured: beyond ~1000 members the staged kernels win even for a 4-column window -- 2048 x 4: 43 us of
     // dependent launches against 90 us for the one-launch form, whose every CTA scans the whole array for the range
     // and whose last CTA selects alone)
-    const bool kde_small = N * Q <= 65536 && N < 1024 && ncols <= ertdiff::WorkspaceLease::kTicketSlots;
+    const bool kde_small = N * Q <= 65536 && N < kde_small_max_members() && ncols <= ertdiff::WorkspaceLease::kTicketSlots;
     if (!kde_small)
         if (int rc = ertdiff_minmax(d_a, dtype, N * Q, p_lohi, stream)) return rc;
     // the moments are a dependent add chain per column (numpy's order; 170 us at 18,944 members): they run on a side

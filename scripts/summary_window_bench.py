@@ -17,6 +17,7 @@ import ertdiff_b200 as eb  # noqa: E402
 ap = argparse.ArgumentParser()
 ap.add_argument("--cases", default="2048x4,8192x4,151552x4,2048x29,8192x29,18944x29")
 ap.add_argument("--reps", type=int, default=5)
+ap.add_argument("--chain", action="store_true", help="use the fields of a real T=1000 bf16 chain (bench weights) instead of synthetic columns")
 a = ap.parse_args()
 dev = torch.device("cuda", 0)
 QS = [2.5, 25.0, 50.0, 75.0, 97.5]
@@ -27,6 +28,17 @@ for case in a.cases.split(","):
     scale = torch.linspace(150.0, 600.0, 29, device=dev)
     scale[5], scale[17] = 0.5, 5.0
     x = torch.randn(N, 29, device=dev, generator=torch.Generator(dev).manual_seed(N)) * scale
+    if a.chain:
+        import bench
+        spec = bench.Spec("w", N, "bf16")
+        sd, cond = bench.synthetic_inputs(spec)
+        model = eb.ConditionalDiffusionModel(29, 128)
+        model.load_state_dict(sd)
+        model.to(dev).eval()
+        sched = [t.to(dev) for t in eb.get_diffusion_schedule(1000)]
+        x = eb.run_chain(model, cond.to(dev).expand(N, 14, 4693), 1000, *sched, dev, seed=1234, offset=0, precision="bf16")
+        sdv = x.std(dim=0)
+        print(f"   chain fields: |x|max {x.abs().max().item():.0f}, column std min/median/max {sdv.min().item():.1f}/{sdv.median().item():.1f}/{sdv.max().item():.1f}")
     for _ in range(2):
         eb.ensemble_summary_packed(x, QS, 5000, col0=0, ncols=ncols)
     best = 1e30
