@@ -964,8 +964,8 @@ __device__ __forceinline__ void kde_scan_column(const float* __restrict__ xs, in
     const int g_begin = ga + part * chunk;
     const int g_end = min(gb + 1, g_begin + chunk);
     const float c2 = (float)(kc.neg_inv_2h2 * 1.4426950408889634);   // exponent in base 2
-    // `ms` adjacent lanes share a grid point and split the members between them (lane `sub` takes members sub,
-    // sub + ms, ...); their partial sums meet in a fixed xor-shuffle tree.  ms = 1 is one thread per grid
+    // `ms` adjacent lanes share a grid point and split the members between them in blocks of 64 (lane `sub` takes
+    // blocks sub, sub + ms, ...); their partial sums meet in a fixed xor-shuffle tree.  ms = 1 is one thread per grid
     // point; few columns of a long ensemble (a rank's share of the chain's output) use ms > 1 to fill the machine.
     const int sub = tid & (ms - 1), slot = tid / ms, slots = nthr / ms;
     for (int gbase = g_begin; gbase < g_end; gbase += 2 * slots) {        // (uniform trip count: shuffles inside)
@@ -973,14 +973,12 @@ __device__ __forceinline__ void kde_scan_column(const float* __restrict__ xs, in
         const bool has0 = g0 < g_end, has1 = g1 < g_end;
         const float va = has0 ? (float)(kde_grid_point(g0, G, lo, hi, step) - kc.mean) : 0.f;
         double sa = 0.0, sb = 0.0;
-        // (lane `sub` takes members sub, sub + ms, sub + 2 ms, ...: the ms lanes of a group read consecutive words --
-        // no bank conflict -- and the groups of a warp read the same words -- a broadcast; 64 terms per fp32 partial)
         if (has1) {                                // two grid points per thread: one shared-memory read feeds both
             const float vb = (float)(kde_grid_point(g1, G, lo, hi, step) - kc.mean);
-            for (int64_t i0 = sub; i0 < N; i0 += 64 * ms) {
-                const int64_t i1 = (i0 + 64 * ms < N) ? i0 + 64 * ms : N;
+            for (int64_t i0 = 64 * sub; i0 < N; i0 += 64 * ms) {
+                const int64_t i1 = (i0 + 64 < N) ? i0 + 64 : N;
                 float pa = 0.f, pb = 0.f;
-                for (int64_t i = i0; i < i1; i += ms) {
+                for (int64_t i = i0; i < i1; ++i) {
                     const float xi = xs[i];
                     const float da = va - xi, db = vb - xi;
                     pa += ex2_approx(da * da * c2);
@@ -990,10 +988,10 @@ __device__ __forceinline__ void kde_scan_column(const float* __restrict__ xs, in
                 sb += (double)pb;
             }
         } else if (has0) {                         // the tail of a chunk: no wasted second evaluation
-            for (int64_t i0 = sub; i0 < N; i0 += 64 * ms) {
-                const int64_t i1 = (i0 + 64 * ms < N) ? i0 + 64 * ms : N;
+            for (int64_t i0 = 64 * sub; i0 < N; i0 += 64 * ms) {
+                const int64_t i1 = (i0 + 64 < N) ? i0 + 64 : N;
                 float pa = 0.f;
-                for (int64_t i = i0; i < i1; i += ms) {
+                for (int64_t i = i0; i < i1; ++i) {
                     const float da = va - xs[i];
                     pa += ex2_approx(da * da * c2);
                 }
@@ -1282,10 +1280,10 @@ k_kde_scan32_tiled(const T* __restrict__ a, int64_t N, int64_t Q, int64_t col0,
             for (int i = tid; i < n; i += nthr) xs[i] = (float)((double)a[(t0 + i) * Q + col] - kc.mean);
             __syncthreads();
             if (has1) {
-                for (int i0 = sub; i0 < n; i0 += 64 * ms) {
-                    const int i1 = (i0 + 64 * ms < n) ? i0 + 64 * ms : n;
+                for (int i0 = 64 * sub; i0 < n; i0 += 64 * ms) {
+                    const int i1 = (i0 + 64 < n) ? i0 + 64 : n;
                     float pa = 0.f, pb = 0.f;
-                    for (int i = i0; i < i1; i += ms) {
+                    for (int i = i0; i < i1; ++i) {
                         const float xi = xs[i];
                         const float da = va - xi, db = vb - xi;
                         pa += ex2_approx(da * da * c2);
@@ -1295,10 +1293,10 @@ k_kde_scan32_tiled(const T* __restrict__ a, int64_t N, int64_t Q, int64_t col0,
                     sb += (double)pb;
                 }
             } else if (has0) {
-                for (int i0 = sub; i0 < n; i0 += 64 * ms) {
-                    const int i1 = (i0 + 64 * ms < n) ? i0 + 64 * ms : n;
+                for (int i0 = 64 * sub; i0 < n; i0 += 64 * ms) {
+                    const int i1 = (i0 + 64 < n) ? i0 + 64 : n;
                     float pa = 0.f;
-                    for (int i = i0; i < i1; i += ms) {
+                    for (int i = i0; i < i1; ++i) {
                         const float da = va - xs[i];
                         pa += ex2_approx(da * da * c2);
                     }
