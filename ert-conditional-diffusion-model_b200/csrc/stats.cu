@@ -480,10 +480,10 @@ int ertdiff_ensemble_kde_mode(const void* d_a, int dtype, int64_t N, int64_t Q,
         const dim3 grid((unsigned)nc, (unsigned)n_gchunks);
         const dim3 sgrid((unsigned)nc, (unsigned)sel_parts);
         if (tiled) {
-            // scan: 48 K fp32 members per tile (16 K when lanes share grid points: more CTAs per SM); selection: what
+            // scan: 44 K fp32 members per tile (16 K when lanes share grid points: more CTAs per SM); selection: what
             // is left of 200 KB after one float64 accumulator per candidate (or per grid point of this part, should
             // the scan be flat)
-            const int stile = tile_override ? tile_override : (ms > 1 ? 16 * 1024 : 48 * 1024);
+            const int stile = tile_override ? tile_override : (ms > 1 ? 16 * 1024 : 44 * 1024);
             // running sums: one per candidate of this part and warp.  Candidates are consecutive grid indices dealt
             // round-robin to the parts, so a part holds at most ceil(KDE_MAX_CAND / parts) + 1 of them -- or, should
             // the scan be flat, its share of the grid
@@ -494,22 +494,22 @@ int ertdiff_ensemble_kde_mode(const void* d_a, int dtype, int64_t N, int64_t Q,
             if (tile_override && tile_override < dtile) dtile = tile_override;
             const size_t dsmem = ((size_t)dtile + 8 * (size_t)n_acc) * 8;
             if (f32in) {
-                k_kde_scan32_tiled<float><<<grid, threads, (size_t)stile * 4, st>>>((const float*)d_a, N, Q, c0, d_lohi, G, cols, s32, stile, ms);
+                k_kde_scan32_tiled<float><<<grid, threads, (size_t)kde_padded(stile) * 4, st>>>((const float*)d_a, N, Q, c0, d_lohi, G, cols, s32, stile, ms);
                 ERT_LAUNCH_CHECK("k_kde_scan32_tiled");
                 k_kde_select64_tiled<float><<<sgrid, 256, dsmem, st>>>((const float*)d_a, N, Q, c0, d_lohi, G, cols, s32, d_mode, d_index, partials, tk, dtile, n_acc);
             } else {
-                k_kde_scan32_tiled<double><<<grid, threads, (size_t)stile * 4, st>>>((const double*)d_a, N, Q, c0, d_lohi, G, cols, s32, stile, ms);
+                k_kde_scan32_tiled<double><<<grid, threads, (size_t)kde_padded(stile) * 4, st>>>((const double*)d_a, N, Q, c0, d_lohi, G, cols, s32, stile, ms);
                 ERT_LAUNCH_CHECK("k_kde_scan32_tiled");
                 k_kde_select64_tiled<double><<<sgrid, 256, dsmem, st>>>((const double*)d_a, N, Q, c0, d_lohi, G, cols, s32, d_mode, d_index, partials, tk, dtile, n_acc);
             }
             ERT_LAUNCH_CHECK("k_kde_select64_tiled");
         } else if (f32in) {
-            k_kde_scan32<float><<<grid, threads, (size_t)N * 4, st>>>((const float*)d_a, N, Q, c0, d_lohi, G, ms, cols, s32);
+            k_kde_scan32<float><<<grid, threads, (size_t)kde_padded(N) * 4, st>>>((const float*)d_a, N, Q, c0, d_lohi, G, ms, cols, s32);
             ERT_LAUNCH_CHECK("k_kde_scan32");
             k_kde_select64<float><<<sgrid, 256, (size_t)N * 8, st>>>((const float*)d_a, N, Q, c0, d_lohi, G, cols, s32, d_mode, d_index, partials, tk);
             ERT_LAUNCH_CHECK("k_kde_select64");
         } else {
-            k_kde_scan32<double><<<grid, threads, (size_t)N * 4, st>>>((const double*)d_a, N, Q, c0, d_lohi, G, ms, cols, s32);
+            k_kde_scan32<double><<<grid, threads, (size_t)kde_padded(N) * 4, st>>>((const double*)d_a, N, Q, c0, d_lohi, G, ms, cols, s32);
             ERT_LAUNCH_CHECK("k_kde_scan32");
             k_kde_select64<double><<<sgrid, 256, (size_t)N * 8, st>>>((const double*)d_a, N, Q, c0, d_lohi, G, cols, s32, d_mode, d_index, partials, tk);
             ERT_LAUNCH_CHECK("k_kde_select64");
@@ -546,7 +546,7 @@ int ertdiff_ensemble_kde_mode_auto(const void* d_a, int dtype, int64_t N, int64_
     const int gchunk = (G + n_gchunks - 1) / n_gchunks;
     const double factor = std::pow((double)N, -1.0 / 5.0);
     const dim3 grid((unsigned)Q, (unsigned)n_gchunks);
-    const size_t smem = (size_t)N * 12;
+    const size_t smem = (size_t)N * 8 + (size_t)kde_padded(N) * 4;
     if (dtype == ERTDIFF_F32)
         k_kde_small<float><<<grid, 256, smem, st>>>((const float*)d_a, N, Q, 0, 1, d_lohi, G, gchunk, factor * factor,
                                                     (float*)ws, tk, d_mode, d_index);
@@ -570,7 +570,7 @@ static int kde_small_window(const void* d_a, int dtype, int64_t N, int64_t Q, in
     const int gchunk = (G + n_gchunks - 1) / n_gchunks;
     const double factor = std::pow((double)N, -1.0 / 5.0);
     const dim3 grid((unsigned)ncols, (unsigned)n_gchunks);
-    const size_t smem = (size_t)N * 12;
+    const size_t smem = (size_t)N * 8 + (size_t)kde_padded(N) * 4;
     if (dtype == ERTDIFF_F32)
         k_kde_small<float><<<grid, 256, smem, st>>>((const float*)d_a, N, Q, col0, 1, d_lohi, G, gchunk, factor * factor,
                                                     (float*)ws, tk, d_mode, d_index);

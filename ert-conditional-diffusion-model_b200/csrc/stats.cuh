@@ -890,6 +890,12 @@ __device__ __forceinline__ double kde_grid_point(int g, int G, double lo, double
     return (g == G - 1) ? hi : __dadd_rn(__dmul_rn((double)g, step), lo);
 }
 
+// Shared-memory layout of a column's centred members for the fp32 scan: 4 words of padding after every 64 members, so
+// that lanes working on neighbouring 64-member blocks (the member-split scan) hit different banks with their 128-bit
+// loads.  kde_pad(i) = word index of member i; kde_padded(n) = words for n members.
+__host__ __device__ __forceinline__ int64_t kde_pad(int64_t i) { return i + ((i >> 6) << 2); }
+__host__ __device__ __forceinline__ int64_t kde_padded(int64_t n) { return n + (((n + 63) >> 6) << 2); }
+
 // How far from the column's members the fp32 scan has to look (in data units).
 //  * Always: a term ex2.approx.ftz(d^2 * c2) is EXACTLY +0 once d^2/(2h^2) * log2(e) > 126, i.e. |d| > 13.22 h, so a
 //    grid point further than 14 h from every member has a scan value of exactly zero -- skipping it changes
@@ -924,7 +930,7 @@ __device__ __forceinline__ void kde_scan_column(const float* __restrict__ xs, in
     int inside = 0;
     const float glo = (float)(lo - kc.mean), ghi = (float)(hi - kc.mean);
     for (int64_t i = tid; i < N; i += nthr) {
-        const float v = xs[i];
+        const float v = xs[kde_pad(i)];
         mn = fminf(mn, v); mx = fmaxf(mx, v);
         inside |= (v >= glo && v <= ghi);
     }
@@ -976,10 +982,11 @@ __device__ __forceinline__ void kde_scan_column(const float* __restrict__ xs, in
         if (has1) {                                // two grid points per thread: one shared-memory read feeds both
             const float vb = (float)(kde_grid_point(g1, G, lo, hi, step) - kc.mean);
             for (int64_t i0 = 64 * sub; i0 < N; i0 += 64 * ms) {
-                const int64_t i1 = (i0 + 64 < N) ? i0 + 64 : N;
+                const int len = (int)((i0 + 64 < N) ? 64 : N - i0);
+                const float* __restrict__ blk = xs + kde_pad(i0);
                 float pa = 0.f, pb = 0.f;
-                for (int64_t i = i0; i < i1; ++i) {
-                    const float xi = xs[i];
+                for (int i = 0; i < len; ++i) {
+                    const float xi = blk[i];
                     const float da = va - xi, db = vb - xi;
                     pa += ex2_approx(da * da * c2);
                     pb += ex2_approx(db * db * c2);
@@ -989,10 +996,11 @@ __device__ __forceinline__ void kde_scan_column(const float* __restrict__ xs, in
             }
         } else if (has0) {                         // the tail of a chunk: no wasted second evaluation
             for (int64_t i0 = 64 * sub; i0 < N; i0 += 64 * ms) {
-                const int64_t i1 = (i0 + 64 < N) ? i0 + 64 : N;
+                const int len = (int)((i0 + 64 < N) ? 64 : N - i0);
+                const float* __restrict__ blk = xs + kde_pad(i0);
                 float pa = 0.f;
-                for (int64_t i = i0; i < i1; ++i) {
-                    const float da = va - xs[i];
+                for (int i = 0; i < len; ++i) {
+                    const float da = va - blk[i];
                     pa += ex2_approx(da * da * c2);
                 }
                 sa += (double)pa;
@@ -1021,7 +1029,7 @@ k_kde_scan32(const T* __restrict__ a, int64_t N, int64_t Q, int64_t col0,
     const int tid = threadIdx.x, nthr = blockDim.x;
     const int64_t col = col0 + blockIdx.x;
     const KdeColumn kc = cols[col];
-    for (int64_t i = tid; i < N; i += nthr) xs[i] = (float)((double)a[i * Q + col] - kc.mean);
+    for (int64_t i = tid; i < N; i += nthr) xs[kde_pad(i)] = (float)((double)a[i * Q + col] - kc.mean);
     __syncthreads();
     kde_scan_column(xs, N, kc, lohi[0], lohi[1], G, (int)blockIdx.y, (int)gridDim.y, s32 + (int64_t)blockIdx.x * G, ms);
 }
@@ -1277,14 +1285,15 @@ k_kde_scan32_tiled(const T* __restrict__ a, int64_t N, int64_t Q, int64_t col0,
         for (int64_t t0 = 0; t0 < N; t0 += tile) {
             const int n = (int)(N - t0 < tile ? N - t0 : tile);
             __syncthreads();
-            for (int i = tid; i < n; i += nthr) xs[i] = (float)((double)a[(t0 + i) * Q + col] - kc.mean);
+            for (int i = tid; i < n; i += nthr) xs[kde_pad(i)] = (float)((double)a[(t0 + i) * Q + col] - kc.mean);
             __syncthreads();
             if (has1) {
                 for (int i0 = 64 * sub; i0 < n; i0 += 64 * ms) {
-                    const int i1 = (i0 + 64 < n) ? i0 + 64 : n;
+                    const int len = (i0 + 64 < n) ? 64 : n - i0;
+                    const float* __restrict__ blk = xs + kde_pad(i0);
                     float pa = 0.f, pb = 0.f;
-                    for (int i = i0; i < i1; ++i) {
-                        const float xi = xs[i];
+                    for (int i = 0; i < len; ++i) {
+                        const float xi = blk[i];
                         const float da = va - xi, db = vb - xi;
                         pa += ex2_approx(da * da * c2);
                         pb += ex2_approx(db * db * c2);
@@ -1294,10 +1303,11 @@ k_kde_scan32_tiled(const T* __restrict__ a, int64_t N, int64_t Q, int64_t col0,
                 }
             } else if (has0) {
                 for (int i0 = 64 * sub; i0 < n; i0 += 64 * ms) {
-                    const int i1 = (i0 + 64 < n) ? i0 + 64 : n;
+                    const int len = (i0 + 64 < n) ? 64 : n - i0;
+                    const float* __restrict__ blk = xs + kde_pad(i0);
                     float pa = 0.f;
-                    for (int i = i0; i < i1; ++i) {
-                        const float da = va - xs[i];
+                    for (int i = 0; i < len; ++i) {
+                        const float da = va - blk[i];
                         pa += ex2_approx(da * da * c2);
                     }
                     sa += (double)pa;
@@ -1498,7 +1508,7 @@ k_kde_small(const T* __restrict__ a, int64_t N, int64_t Q, int64_t col0, int com
     for (int w = 0; w < 8; ++w) sum += rsum[w];
     const double mean = sum / (double)N;
     double ss = 0.0;
-    for (int64_t i = tid; i < N; i += 256) { const double d = xs[i] - mean; ss += d * d; xc[i] = (float)d; }
+    for (int64_t i = tid; i < N; i += 256) { const double d = xs[i] - mean; ss += d * d; xc[kde_pad(i)] = (float)d; }
 #pragma unroll
     for (int o = 16; o > 0; o >>= 1) ss += __shfl_xor_sync(0xffffffffu, ss, o);
     __syncthreads();
