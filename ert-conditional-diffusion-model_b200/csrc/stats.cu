@@ -476,6 +476,12 @@ int ertdiff_ensemble_kde_mode(const void* d_a, int dtype, int64_t N, int64_t Q,
         // ms lanes share a grid point and split the members, with ms times as many CTAs per column
         int ms = 1;
         while (ms < 32 && nc * n_gchunks * 2 <= 4 * kNumSMs && N / (2 * ms) >= 512) { ms *= 2; n_gchunks *= 2; }
+        if (ms > 1) {
+            // whole CTAs per SM: 320 CTAs on 148 SMs would leave a third of them with one CTA more than the others
+            const int64_t per_sm = tiled ? 3 : 4;
+            const int64_t even = per_sm * kNumSMs / nc;
+            if (even > n_gchunks && even <= 2 * n_gchunks) n_gchunks = (int)even;
+        }
         const int threads = 256;
         const dim3 grid((unsigned)nc, (unsigned)n_gchunks);
         const dim3 sgrid((unsigned)nc, (unsigned)sel_parts);
