@@ -476,12 +476,8 @@ int ertdiff_ensemble_kde_mode(const void* d_a, int dtype, int64_t N, int64_t Q,
         // ms lanes share a grid point and split the members, with ms times as many CTAs per column
         int ms = 1;
         while (ms < 32 && nc * n_gchunks * 2 <= 4 * kNumSMs && N / (2 * ms) >= 512) { ms *= 2; n_gchunks *= 2; }
-        if (ms > 1) {
-            // whole CTAs per SM: 320 CTAs on 148 SMs would leave a third of them with one CTA more than the others
-            const int64_t per_sm = tiled ? 3 : 4;
-            const int64_t even = per_sm * kNumSMs / nc;
-            if (even > n_gchunks && even <= 2 * n_gchunks) n_gchunks = (int)even;
-        }
+        // (evening the CTA count out to whole CTAs per SM -- 444 instead of 320 -- was measured slower: every CTA
+        // streams its whole column, so more CTAs cost more than the imbalance they remove)
         const int threads = 256;
         const dim3 grid((unsigned)nc, (unsigned)n_gchunks);
         const dim3 sgrid((unsigned)nc, (unsigned)sel_parts);
@@ -552,7 +548,7 @@ int ertdiff_ensemble_kde_mode_auto(const void* d_a, int dtype, int64_t N, int64_
     const int gchunk = (G + n_gchunks - 1) / n_gchunks;
     const double factor = std::pow((double)N, -1.0 / 5.0);
     const dim3 grid((unsigned)Q, (unsigned)n_gchunks);
-    const size_t smem = (size_t)N * 8 + (size_t)kde_padded(N) * 4;
+    const size_t smem = (((size_t)N * 8 + 15) & ~(size_t)15) + (size_t)kde_padded(N) * 4;
     if (dtype == ERTDIFF_F32)
         k_kde_small<float><<<grid, 256, smem, st>>>((const float*)d_a, N, Q, 0, 1, d_lohi, G, gchunk, factor * factor,
                                                     (float*)ws, tk, d_mode, d_index);
@@ -576,7 +572,7 @@ static int kde_small_window(const void* d_a, int dtype, int64_t N, int64_t Q, in
     const int gchunk = (G + n_gchunks - 1) / n_gchunks;
     const double factor = std::pow((double)N, -1.0 / 5.0);
     const dim3 grid((unsigned)ncols, (unsigned)n_gchunks);
-    const size_t smem = (size_t)N * 8 + (size_t)kde_padded(N) * 4;
+    const size_t smem = (((size_t)N * 8 + 15) & ~(size_t)15) + (size_t)kde_padded(N) * 4;
     if (dtype == ERTDIFF_F32)
         k_kde_small<float><<<grid, 256, smem, st>>>((const float*)d_a, N, Q, col0, 1, d_lohi, G, gchunk, factor * factor,
                                                     (float*)ws, tk, d_mode, d_index);

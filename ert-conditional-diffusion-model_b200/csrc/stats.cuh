@@ -910,6 +910,53 @@ __device__ __forceinline__ double kde_scan_reach(double h, double step, int64_t 
     return reach;
 }
 
+// fp32 partial sums of one block of <= 64 centred members (a padded block starts 16-byte aligned: full blocks are
+// read with 128-bit loads) for one / two grid points; the terms are added in member order
+__device__ __forceinline__ void kde_block_sum2(const float* __restrict__ blk, int len, float va, float vb, float c2,
+                                               float& pa, float& pb) {
+    pa = 0.f; pb = 0.f;
+    if (len == 64) {
+        const float4* __restrict__ b4 = reinterpret_cast<const float4*>(blk);
+#pragma unroll 4
+        for (int q = 0; q < 16; ++q) {
+            const float4 x4 = b4[q];
+            float d;
+            d = va - x4.x; pa += ex2_approx(d * d * c2); d = vb - x4.x; pb += ex2_approx(d * d * c2);
+            d = va - x4.y; pa += ex2_approx(d * d * c2); d = vb - x4.y; pb += ex2_approx(d * d * c2);
+            d = va - x4.z; pa += ex2_approx(d * d * c2); d = vb - x4.z; pb += ex2_approx(d * d * c2);
+            d = va - x4.w; pa += ex2_approx(d * d * c2); d = vb - x4.w; pb += ex2_approx(d * d * c2);
+        }
+    } else {
+        for (int i = 0; i < len; ++i) {
+            const float xi = blk[i];
+            const float da = va - xi, db = vb - xi;
+            pa += ex2_approx(da * da * c2);
+            pb += ex2_approx(db * db * c2);
+        }
+    }
+}
+__device__ __forceinline__ float kde_block_sum1(const float* __restrict__ blk, int len, float va, float c2) {
+    float pa = 0.f;
+    if (len == 64) {
+        const float4* __restrict__ b4 = reinterpret_cast<const float4*>(blk);
+#pragma unroll 4
+        for (int q = 0; q < 16; ++q) {
+            const float4 x4 = b4[q];
+            float d;
+            d = va - x4.x; pa += ex2_approx(d * d * c2);
+            d = va - x4.y; pa += ex2_approx(d * d * c2);
+            d = va - x4.z; pa += ex2_approx(d * d * c2);
+            d = va - x4.w; pa += ex2_approx(d * d * c2);
+        }
+    } else {
+        for (int i = 0; i < len; ++i) {
+            const float da = va - blk[i];
+            pa += ex2_approx(da * da * c2);
+        }
+    }
+    return pa;
+}
+
 // The fp32 scan of one column, split over `nparts` CTAs (this one is `part`).  `xs` = the column's N
 // members centred at kc.mean (fp32, shared memory).
 //
@@ -982,28 +1029,14 @@ __device__ __forceinline__ void kde_scan_column(const float* __restrict__ xs, in
         if (has1) {                                // two grid points per thread: one shared-memory read feeds both
             const float vb = (float)(kde_grid_point(g1, G, lo, hi, step) - kc.mean);
             for (int64_t i0 = 64 * sub; i0 < N; i0 += 64 * ms) {
-                const int len = (int)((i0 + 64 < N) ? 64 : N - i0);
-                const float* __restrict__ blk = xs + kde_pad(i0);
-                float pa = 0.f, pb = 0.f;
-                for (int i = 0; i < len; ++i) {
-                    const float xi = blk[i];
-                    const float da = va - xi, db = vb - xi;
-                    pa += ex2_approx(da * da * c2);
-                    pb += ex2_approx(db * db * c2);
-                }
+                float pa, pb;
+                kde_block_sum2(xs + kde_pad(i0), (int)((i0 + 64 <= N) ? 64 : N - i0), va, vb, c2, pa, pb);
                 sa += (double)pa;
                 sb += (double)pb;
             }
         } else if (has0) {                         // the tail of a chunk: no wasted second evaluation
             for (int64_t i0 = 64 * sub; i0 < N; i0 += 64 * ms) {
-                const int len = (int)((i0 + 64 < N) ? 64 : N - i0);
-                const float* __restrict__ blk = xs + kde_pad(i0);
-                float pa = 0.f;
-                for (int i = 0; i < len; ++i) {
-                    const float da = va - blk[i];
-                    pa += ex2_approx(da * da * c2);
-                }
-                sa += (double)pa;
+                sa += (double)kde_block_sum1(xs + kde_pad(i0), (int)((i0 + 64 <= N) ? 64 : N - i0), va, c2);
             }
         }
         for (int o = ms >> 1; o > 0; o >>= 1) {
@@ -1289,28 +1322,14 @@ k_kde_scan32_tiled(const T* __restrict__ a, int64_t N, int64_t Q, int64_t col0,
             __syncthreads();
             if (has1) {
                 for (int i0 = 64 * sub; i0 < n; i0 += 64 * ms) {
-                    const int len = (i0 + 64 < n) ? 64 : n - i0;
-                    const float* __restrict__ blk = xs + kde_pad(i0);
-                    float pa = 0.f, pb = 0.f;
-                    for (int i = 0; i < len; ++i) {
-                        const float xi = blk[i];
-                        const float da = va - xi, db = vb - xi;
-                        pa += ex2_approx(da * da * c2);
-                        pb += ex2_approx(db * db * c2);
-                    }
+                    float pa, pb;
+                    kde_block_sum2(xs + kde_pad(i0), (i0 + 64 <= n) ? 64 : n - i0, va, vb, c2, pa, pb);
                     sa += (double)pa;
                     sb += (double)pb;
                 }
             } else if (has0) {
                 for (int i0 = 64 * sub; i0 < n; i0 += 64 * ms) {
-                    const int len = (i0 + 64 < n) ? 64 : n - i0;
-                    const float* __restrict__ blk = xs + kde_pad(i0);
-                    float pa = 0.f;
-                    for (int i = 0; i < len; ++i) {
-                        const float da = va - blk[i];
-                        pa += ex2_approx(da * da * c2);
-                    }
-                    sa += (double)pa;
+                    sa += (double)kde_block_sum1(xs + kde_pad(i0), (i0 + 64 <= n) ? 64 : n - i0, va, c2);
                 }
             }
         }
@@ -1462,7 +1481,7 @@ k_kde_small(const T* __restrict__ a, int64_t N, int64_t Q, int64_t col0, int com
             unsigned int* __restrict__ tickets, double* __restrict__ mode_out, int64_t* __restrict__ index_out) {
     extern __shared__ __align__(16) unsigned char kde_smem_raw[];
     double* xs = reinterpret_cast<double*>(kde_smem_raw);                       // [N] members, float64
-    float* xc = reinterpret_cast<float*>(kde_smem_raw + (size_t)N * sizeof(double));   // [N] centred, fp32
+    float* xc = reinterpret_cast<float*>(kde_smem_raw + (((size_t)N * sizeof(double) + 15) & ~(size_t)15));   // [padded N] centred, fp32 (16-byte aligned)
     __shared__ double rlo[8], rhi[8], rsum[8];
     __shared__ int rnan[8];
     __shared__ int s_last;
