@@ -31,6 +31,16 @@ emit("r02_chain_fp32_variants.md",
       ("variants_h256.log", "hidden_dim 256, L = 9386")])
 emit("r02_chain_bf16_sweep.md", "r02 tensor-core chain (k_chain_umma), scripts/chain_sweep.py, T = 1000",
      [("sweep_bf16.log", None)])
+emit("r02_summary_window.md",
+     "r02 the fused statistics call (ertdiff_ensemble_summary) on a column window of the fields of a real T = 1000 bf16 chain "
+     "(scripts/summary_window_bench.py --chain; whole call by CUDA events, per kernel by torch.profiler; the side-stream "
+     "kernels -- k_colstats_smallq<.,0>, the percentile kernels -- overlap the KDE kernels)",
+     [("summary_window_chain.log", "real chain output (all 29 parameters spread over +-2000: every column covers most of the common grid)"),
+      ("summary_window_small.log", "one-launch KDE (k_kde_small) against the staged kernels below 1024 members: ERTDIFF_KDE_SMALL_MAX sweep")])
+emit("r02_multigpu_peer_vs_nccl.md",
+     "r02 the default bench workload (256 members per GPU) with the two per-step collectives through the library's NVLink "
+     "peer-memory kernel (k_peer_all_gather) and through NCCL (ERTDIFF_BENCH_NCCL=1); scripts/gpu_r2_peer.sh",
+     [(f"bench_peer_n{n}.json", f"{n} GPUs, peer kernel") for n in (2, 4, 8)] + [(f"bench_nccl_n{n}.json", f"{n} GPUs, NCCL") for n in (2, 4, 8)])
 emit("r02_stats_bench.md",
      "r02 statistics kernels on the reference's map-shaped workload and on the chain's own output (scripts/stats_bench.py; "
      "CUDA-event time of the whole library call, best of 3, L2 flushed; calls of a few microseconds are dominated by "
