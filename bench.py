@@ -321,8 +321,21 @@ class Runner:
         # library's own NVLink peer-memory kernel; ERTDIFF_BENCH_NCCL=1 keeps them on NCCL for comparison
         peer_x = peer_s = None
         if world > 1 and not os.environ.get("ERTDIFF_BENCH_NCCL"):
-            peer_x = eb.parallel.PeerAllGather(members * P * 4, dev)
-            peer_s = eb.parallel.PeerAllGather(-(-P // world) * (5 + len(PERCENTILES)) * 8, dev)
+            import torch.distributed as dist
+            try:
+                peer_x = eb.parallel.PeerAllGather(members * P * 4, dev)
+                peer_s = eb.parallel.PeerAllGather(-(-P // world) * (5 + len(PERCENTILES)) * 8, dev)
+                ok = torch.ones(1, device=dev)
+            except Exception as exc:            # CUDA IPC unavailable on this box: say so and use NCCL
+                if rank == 0:
+                    print(f"[bench] peer-memory all-gather unavailable ({exc}); using NCCL", file=sys.stderr)
+                ok = torch.zeros(1, device=dev)
+            dist.all_reduce(ok, op=dist.ReduceOp.MIN)          # every rank takes the same route
+            if ok.item() == 0:
+                for p_ in (peer_x, peer_s):
+                    if p_ is not None:
+                        p_.close()
+                peer_x = peer_s = None
 
         def stats(x):
             # one library call per rank, packed float64 records; N > 1: columns split over the ranks plus one packed

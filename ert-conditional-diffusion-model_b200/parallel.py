@@ -42,14 +42,32 @@ class PeerAllGather:
         handle = (C.c_ubyte * 64)()
         self._h = C.c_void_p()
         index = self.device.index if self.device.index is not None else torch.cuda.current_device()
-        _lib.check(lib.ertdiff_peer_create(C.byref(self._h), index, self.rank, self.world, self.slot_cap * self.world, handle),
-                   "peer_create")
+
+        def agree(err, what):
+            # set-up is collective: if a step fails on ANY rank, every rank raises (nobody is left waiting in the next one)
+            ok = torch.tensor([0.0 if err else 1.0], device=self.device)
+            dist.all_reduce(ok, op=dist.ReduceOp.MIN, group=group)
+            if ok.item() == 0:
+                self.close()
+                raise _lib.ErtdiffError(f"PeerAllGather: {what} failed on at least one rank"
+                                        + (f" (this rank: {err})" if err else ""))
+
+        err = None
+        try:
+            _lib.check(lib.ertdiff_peer_create(C.byref(self._h), index, self.rank, self.world,
+                                               self.slot_cap * self.world, handle), "peer_create")
+        except Exception as exc:
+            err = exc
+        agree(err, "allocating / exporting the peer buffer (CUDA IPC)")
         mine = torch.tensor(list(handle), dtype=torch.uint8, device=self.device)
         every = torch.empty(self.world * 64, dtype=torch.uint8, device=self.device)
         dist.all_gather_into_tensor(every, mine, group=group)
         blob = bytes(every.cpu().numpy().tobytes())
-        _lib.check(lib.ertdiff_peer_connect(self._h, blob), "peer_connect")
-        dist.barrier(group)                 # every rank has mapped every buffer before the first store
+        try:
+            _lib.check(lib.ertdiff_peer_connect(self._h, blob), "peer_connect")
+        except Exception as exc:
+            err = exc
+        agree(err, "mapping the peers' buffers (cudaIpcOpenMemHandle)")      # also: every buffer is mapped before the first store
 
     def all_gather(self, src: torch.Tensor) -> torch.Tensor:
         C, lib = self._C, self._lib.load()
