@@ -2,7 +2,7 @@
 """Benchmark of the ensemble posterior-sampling path (BASELINE.json metric).
 
     python bench.py [--gpus N] [--steps K] [--warmup W] [--impl ours|reference] [--members M]
-                    [--T T] [--loop-mode persistent|graph] [--precision fp32|bf16]
+                    [--T T] [--loop-mode persistent|graph] [--precision fp32|bf16|bf16x3]
                     [--distinct-conditions] [--no-extra-configs] [--no-cpu-baseline]
 
 One "step" = one pass of the hot path over one ensemble: condition encoder -> full DDPM reverse
@@ -377,7 +377,7 @@ class Runner:
             step_device(i)
             step_e2e(i)
         self.barrier()
-        if spec.precision == "bf16" and model.umma_status() != 0:
+        if spec.precision != "fp32" and model.umma_status() != 0:
             raise SystemExit("bench.py: a tensor-core chain tile timed out during warm-up")
 
         if rank == 0 and self.sampler:
@@ -409,7 +409,7 @@ class Runner:
                     model.chain_floor(False)
         model.profile_chain(False)
         ms_e2e, wall_e2e = self.timed(step_e2e, steps)
-        if spec.precision == "bf16" and model.umma_status() != 0:
+        if spec.precision != "fp32" and model.umma_status() != 0:
             raise SystemExit("bench.py: a tensor-core chain tile timed out")
         clocks = self.sampler.window() if (rank == 0 and self.sampler) else None
 
@@ -420,7 +420,7 @@ class Runner:
         rec = {
             "name": spec.name, "metric": METRIC, "value": value, "unit": "samples/s",
             "n_gpus": world, "steps": steps, "warmup": warmup,
-            "ms_per_step": ms_dev / steps, "dtype": "f32" if spec.precision == "fp32" else "bf16",
+            "ms_per_step": ms_dev / steps, "dtype": {"fp32": "f32", "bf16": "bf16", "bf16x3": "bf16x3 (bf16 hi + residual operands, fp32 accumulate)"}[spec.precision],
             "config": spec.config(world),
             "ms_per_denoiser_step": (float(np.mean(chain_ms)) / T) if chain_ms else ms_dev / steps / T,
             "e2e": {"value": e2e_value, "unit": "samples/s", "h2d_bytes_per_step": int(h2d),
@@ -461,13 +461,14 @@ class Runner:
         fp32_peak = 148 * 128 * 2 * sm_mhz * 1e6 / 1e12
         r = {
             "kernel": "k_chain (persistent reverse loop, fp32 FFMA2)" if fp32
-                      else "k_chain_umma (persistent reverse loop, tcgen05 bf16, TMEM accumulators)",
+                      else ("k_chain_umma (persistent reverse loop, tcgen05 bf16, TMEM accumulators)" if spec.precision == "bf16"
+                            else "k_chain_umma<SPLIT> (persistent reverse loop, tcgen05, split-precision bf16 hi+lo operands)"),
             # T dependent steps per member with ~15 KFLOP each and no HBM traffic beyond the tables: neither the
             # tensor pipe nor HBM bounds this kernel, the per-step latency of its hand-off chain does.  `achieved`,
             # `peak` and `frac` are still the FLOP rate against the measured bf16 tensor peak, as the contract asks.
             "bound": "latency",
             "achieved": achieved, "peak": peak, "unit": "TFLOP/s", "frac": achieved / peak,
-            "traffic": ncu_traffic("chain_fp32" if fp32 else "chain_umma") if (H == H_REF) else None,
+            "traffic": ncu_traffic("chain_fp32" if fp32 else "chain_umma") if (H == H_REF and spec.precision != "bf16x3") else None,
             "peak_source": self.peaks["source"] + ", sustained bf16",
             "kernel_ms": k_ms, "us_per_denoiser_step": k_ms / T * 1e3, "flop_per_launch": flops,
             "share_of_step": k_ms / step_ms,
@@ -508,6 +509,9 @@ def extra_specs(world):
                                              "kernel up to ~1500 members, at fp32 accuracy"),
         Spec("bf16_8192", 8192, "bf16", note="BASELINE configs[3]'s whole ensemble on every GPU" if world == 1 else None),
         Spec("bf16_18944", 18944, "bf16", note="one full 128-member tile per SM (148 x 128)"),
+        Spec("bf16x3_18944", 18944, "bf16x3", note="the same ensemble through the split-precision tensor-core chain "
+                                                   "(bf16 hi + residual operands, three products per projection): "
+                                                   "fp32-class fields, see bf16_vs_fp32.bf16x3_*"),
         Spec("fp32_256_distinct_conditions", 256, "fp32", distinct=True, note="the encoder runs for 256 conditions every step"),
         Spec("config5_h256_L9386_bf16", 4096 // world if world > 1 else 4096, "bf16", hidden=256, L=2 * L_REF,
              baseline_config="BASELINE configs[4]",
@@ -535,6 +539,10 @@ def bf16_vs_fp32(dev, members=1024, T=1000):
     c = cond.to(dev).expand(members, C, L_REF)
     x32 = eb.run_chain(model, c, T, *sched, dev, seed=99, offset=0)
     x16 = eb.run_chain(model, c, T, *sched, dev, seed=99, offset=0, precision="bf16")
+    x3 = eb.run_chain(model, c, T, *sched, dev, seed=99, offset=0, precision="bf16x3")
+    d3 = (x3 - x32).abs()
+    rel3 = d3.max(dim=1).values / x32.abs().max(dim=1).values
+    m3 = eb.ensemble_moments(x3)
     d = (x16 - x32).abs()
     scale = x32.abs().max().item()
     rel = d.max(dim=1).values / x32.abs().max(dim=1).values
@@ -543,7 +551,12 @@ def bf16_vs_fp32(dev, members=1024, T=1000):
             "bf16_vs_fp32_rel_of_scale": d.max().item() / scale,
             "per_member_rel_median": rel.median().item(), "per_member_rel_max": rel.max().item(),
             "ensemble_mean_max_abs_diff": (m16["mean"] - m32["mean"]).abs().max().item(),
-            "ensemble_std_max_abs_diff": (m16["std"] - m32["std"]).abs().max().item()}
+            "ensemble_std_max_abs_diff": (m16["std"] - m32["std"]).abs().max().item(),
+            # the split-precision tensor-core chain against the same fp32 fields
+            "bf16x3_vs_fp32_rel_of_scale": d3.max().item() / scale,
+            "bf16x3_per_member_rel_median": rel3.median().item(), "bf16x3_per_member_rel_max": rel3.max().item(),
+            "bf16x3_ensemble_mean_max_abs_diff": (m3["mean"] - m32["mean"]).abs().max().item(),
+            "bf16x3_ensemble_std_max_abs_diff": (m3["std"] - m32["std"]).abs().max().item()}
 
 
 def run_ours(args):
@@ -607,8 +620,9 @@ def main():
     ap.add_argument("--L", type=int, default=L_REF)
     ap.add_argument("--loop-mode", default="persistent", choices=["persistent", "graph", "stream"])
     ap.add_argument("--distinct-conditions", action="store_true")
-    ap.add_argument("--precision", default="fp32", choices=["fp32", "bf16"],
-                    help="fp32 = CUDA-core FFMA chain (BASELINE config 2); bf16 = tcgen05 chain (configs 3/4)")
+    ap.add_argument("--precision", default="fp32", choices=["fp32", "bf16", "bf16x3"],
+                    help="fp32 = CUDA-core FFMA chain (BASELINE config 2); bf16 = tcgen05 chain (configs 3/4); "
+                         "bf16x3 = tcgen05 chain with split-precision operands (fp32-class fields)")
     ap.add_argument("--ref-sample-steps", type=int, default=250,
                     help="steps of the T-step chain the CPU arm actually runs per sample")
     ap.add_argument("--no-cpu-baseline", action="store_true")

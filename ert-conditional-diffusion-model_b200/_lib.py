@@ -14,9 +14,9 @@ LIB_PATH = os.environ.get("ERTDIFF_B200_LIB") or os.path.join(_HERE, "libertdiff
 
 F32, F64 = 0, 1
 LOOP_PERSISTENT, LOOP_GRAPH, LOOP_STREAM = 0, 1, 2
-PREC_FP32, PREC_BF16 = 0, 1
+PREC_FP32, PREC_BF16, PREC_BF16X3 = 0, 1, 2
 LOOP_MODES = {"persistent": LOOP_PERSISTENT, "graph": LOOP_GRAPH, "stream": LOOP_STREAM}
-PRECISIONS = {"fp32": PREC_FP32, "bf16": PREC_BF16}
+PRECISIONS = {"fp32": PREC_FP32, "bf16": PREC_BF16, "bf16x3": PREC_BF16X3}
 
 
 class ErtdiffError(RuntimeError):

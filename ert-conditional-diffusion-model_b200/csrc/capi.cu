@@ -33,8 +33,11 @@ static int run_chain(ertdiff_model* m, const ertdiff_chain_args* a, const float*
     ERT_REQUIRE(d_cond_bias, "sample_chain: cond_bias is NULL");
     ERT_REQUIRE(a->d_x_out, "sample_chain: x_out is NULL");
     ERT_REQUIRE(!(a->d_noise && !a->d_x_T), "sample_chain: injected noise needs d_x_T as well (row 0 of the draws)");
-    const bool use_umma = a->precision == ERTDIFF_PREC_BF16;
+    const bool split = a->precision == ERTDIFF_PREC_BF16X3;
+    const bool use_umma = a->precision == ERTDIFF_PREC_BF16 || split;
     if (a->precision != ERTDIFF_PREC_FP32 && !use_umma) return fail(ERTDIFF_ERR_ARG, "sample_chain: bad precision");
+    if (split && !(chain_umma_split_supported(m->H, m->P) && m->w1_pk))
+        return fail(ERTDIFF_ERR_UNSUPPORTED, "sample_chain: the split-precision tensor-core chain is built for hidden_dim 128, param_dim <= 29");
     if (use_umma && !(chain_umma_supported(m->H, m->P) && m->w1_pk))
         return fail(ERTDIFF_ERR_UNSUPPORTED, "sample_chain: the bf16 tensor-core chain is built for hidden_dim 128 or 256, param_dim <= 29");
     const int S = a->num_steps, H = m->H, P = m->P;
@@ -75,7 +78,7 @@ static int run_chain(ertdiff_model* m, const ertdiff_chain_args* a, const float*
         }
         UmmaChainExtra ex{reinterpret_cast<const uint4*>(m->w1_pk), reinterpret_cast<const uint4*>(m->w2_pk), m->umma_status,
                           m->umma_timing_on ? m->umma_timing : nullptr, UC_M};
-        return launch_chain_umma(H, q, ex, s2);
+        return launch_chain_umma(H, q, ex, split, s2);
     };
 
     if (a->loop_mode == ERTDIFF_LOOP_PERSISTENT) {
@@ -195,7 +198,7 @@ int ertdiff_model_create(ertdiff_model** out, int device, int param_dim, int hid
     if (ok && !m->umma_status) ok = cudaMalloc(&m->umma_status, sizeof(int)) == cudaSuccess &&
                                     cudaMalloc(&m->umma_timing, 16 * sizeof(long long)) == cudaSuccess;
     if (ok && chain_umma_supported(H, m->P)) {
-        ok = cudaMalloc(&m->w1_pk, (size_t)H * UC_K1 * 2) == cudaSuccess && cudaMalloc(&m->w2_pk, (size_t)UC_N2 * H * 2) == cudaSuccess;
+        ok = cudaMalloc(&m->w1_pk, (size_t)2 * H * UC_K1 * 2) == cudaSuccess && cudaMalloc(&m->w2_pk, (size_t)2 * UC_N2 * H * 2) == cudaSuccess;   // operand + residual tiles
     }
     if (!ok) {
         ertdiff_model_destroy(m);
@@ -317,7 +320,9 @@ int ertdiff_encode_condition_prec(ertdiff_model* m, const float* d_condition, in
     if (precision == ERTDIFF_PREC_BF16)
         return run_encoder_umma(m, d_condition, n_cond, L, cond_member_stride, d_cond_emb, d_cond_bias,
                                 (cudaStream_t)stream);
-    if (precision != ERTDIFF_PREC_FP32) return fail(ERTDIFF_ERR_ARG, "encode_condition: bad precision");
+    // (ERTDIFF_PREC_BF16X3 keeps the fp32 encoder: the mode exists to return fp32-class fields, and the encoder runs
+    // once per condition, not once per step)
+    if (precision != ERTDIFF_PREC_FP32 && precision != ERTDIFF_PREC_BF16X3) return fail(ERTDIFF_ERR_ARG, "encode_condition: bad precision");
     return run_encoder(m, d_condition, n_cond, L, cond_member_stride, d_cond_emb, d_cond_bias,
                        (cudaStream_t)stream);
 }

@@ -48,8 +48,8 @@ struct ChainParams {
 };
 
 struct UmmaChainExtra {
-    const uint4* w1_pk;     // bf16 B operand of GEMM1 (W0x augmented), H x 32
-    const uint4* w2_pk;     // bf16 B operand(s) of GEMM2 (W2 padded), 32 x H
+    const uint4* w1_pk;     // bf16 B operand of GEMM1 (W0x augmented), H x 32, followed by the tile of its bf16 residuals
+    const uint4* w2_pk;     // bf16 B operand of GEMM2 (W2 padded), 32 x H, followed by the tile of its bf16 residuals
     int* status;            // [0] = 1 when an mbarrier wait timed out
     long long* timing;      // optional (16 int64): phase cycle sums of CTA 0, see ertdiff_debug_umma_timing
     int mpc;                // members per CTA: 32, 64 or 128 rows of the 128-row tile are in use, so that a
@@ -73,7 +73,9 @@ int launch_chain_fp32_floor(int H, const ChainParams& p, int mpb, int upt, cudaS
 // ---- chain_umma.cu -----------------------------------------------------------------------------
 bool chain_umma_supported(int H, int P);
 int chain_umma_mpc(int64_t B);
-int launch_chain_umma(int H, const ChainParams& q, UmmaChainExtra ex, cudaStream_t st);
+bool chain_umma_split_supported(int H, int P);      // the split-precision build (ERTDIFF_PREC_BF16X3)
+int launch_chain_umma(int H, const ChainParams& q, UmmaChainExtra ex, bool split, cudaStream_t st);
+// (each packed buffer holds two tiles: the bf16 operand and its bf16 residual)
 int pack_chain_umma_weights(int H, const float* w0xT, const float* w2p, int P, unsigned short* w1_pk,
                             unsigned short* w2_pk, cudaStream_t st);
 int umma_selftest(const float* A, const float* B, int N, int K, float* D, cudaStream_t st);

@@ -30,17 +30,21 @@ int pack_chain_umma_weights(int H, const float* w0xT, const float* w2p, int P, u
 
 using Kern = void (*)(const ChainParams, const UmmaChainExtra);
 
-template <int H, int CTAS>
+template <int H, int CTAS, bool SPLIT = false>
 static Kern pick_kernel(int variant) {
     static const Kern kerns[8] = {
-        k_chain_umma<H, false, false, false, CTAS>, k_chain_umma<H, false, false, true, CTAS>,
-        k_chain_umma<H, false, true, false, CTAS>,  k_chain_umma<H, false, true, true, CTAS>,
-        k_chain_umma<H, true, false, false, CTAS>,  k_chain_umma<H, true, false, true, CTAS>,
-        k_chain_umma<H, true, true, false, CTAS>,   k_chain_umma<H, true, true, true, CTAS>};
+        k_chain_umma<H, false, false, false, CTAS, SPLIT>, k_chain_umma<H, false, false, true, CTAS, SPLIT>,
+        k_chain_umma<H, false, true, false, CTAS, SPLIT>,  k_chain_umma<H, false, true, true, CTAS, SPLIT>,
+        k_chain_umma<H, true, false, false, CTAS, SPLIT>,  k_chain_umma<H, true, false, true, CTAS, SPLIT>,
+        k_chain_umma<H, true, true, false, CTAS, SPLIT>,   k_chain_umma<H, true, true, true, CTAS, SPLIT>};
     return kerns[variant];
 }
 
-int launch_chain_umma(int H, const ChainParams& q, UmmaChainExtra ex, cudaStream_t st) {
+bool chain_umma_split_supported(int H, int P) { return H == 128 && P <= UC_AUG; }
+
+int launch_chain_umma(int H, const ChainParams& q, UmmaChainExtra ex, bool split, cudaStream_t st) {
+    if (split && !chain_umma_split_supported(H, q.P))
+        return fail(ERTDIFF_ERR_UNSUPPORTED, "sample_chain: the split-precision tensor-core chain is built for hidden_dim 128, param_dim <= 29");
     if (!chain_umma_supported(H, q.P))
         return fail(ERTDIFF_ERR_UNSUPPORTED, "sample_chain: the bf16 tensor-core chain is built for hidden_dim 128 or 256, param_dim <= 29");
     // members per CTA: the fewest rows per tile that still fit one wave of CTAs, so that a mid-size
@@ -49,15 +53,17 @@ int launch_chain_umma(int H, const ChainParams& q, UmmaChainExtra ex, cudaStream
     const unsigned grid = (unsigned)((q.B + ex.mpc - 1) / ex.mpc);
     // more tiles than SMs: the build that keeps two CTAs resident per SM (H = 128 only: at H = 256 one CTA's
     // operands take 172 KB of shared memory)
-    const bool two = H == 128 && grid > (unsigned)kNumSMs && !std::getenv("ERTDIFF_UMMA_ONE_CTA");
+    // (the split-precision build holds two tiles per operand: 177 KB, one CTA per SM)
+    const bool two = H == 128 && !split && grid > (unsigned)kNumSMs && !std::getenv("ERTDIFF_UMMA_ONE_CTA");
     const int variant = (q.noise != nullptr ? 4 : 0) | (q.eps_trace != nullptr ? 2 : 0) | (q.n_cond == 1 ? 1 : 0);
     Kern k;
     size_t smem;
-    if (H == 256) { k = pick_kernel<256, 1>(variant); smem = sizeof(UmmaChainSmem<uc_nslot(1), 256>); }
+    if (split) { k = pick_kernel<128, 1, true>(variant); smem = sizeof(UmmaChainSmem<uc_nslot(1), 128, 2>); }
+    else if (H == 256) { k = pick_kernel<256, 1>(variant); smem = sizeof(UmmaChainSmem<uc_nslot(1), 256>); }
     else if (two) { k = pick_kernel<128, 2>(variant); smem = sizeof(UmmaChainSmem<uc_nslot(2), 128>); }
     else { k = pick_kernel<128, 1>(variant); smem = sizeof(UmmaChainSmem<uc_nslot(1), 128>); }
-    static PerDeviceOnce once[3][8];
-    bool& attr_set = *once[H == 256 ? 2 : (two ? 1 : 0)][variant].slot();
+    static PerDeviceOnce once[4][8];
+    bool& attr_set = *once[split ? 3 : (H == 256 ? 2 : (two ? 1 : 0))][variant].slot();
     if (!attr_set) {
         ERT_CUDA(cudaFuncSetAttribute(k, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
         attr_set = true;

@@ -42,6 +42,15 @@
 // the epilogue warps stop waiting on the mbarriers but keep every named-barrier operation (the tile's
 // output is then poisoned and the status word set).
 // TMEM: D columns 0..127, E 128..159, c_b 256..383 (distinct conditions only).
+//
+// Split precision (template parameter SPLIT; precision = ERTDIFF_PREC_BF16X3; H = 128, one CTA per SM).  Every
+// fp32 operand is carried as TWO bf16 terms, v = v_hi + v_lo with v_hi = bf16(v), v_lo = bf16(v - v_hi) (the
+// residual is exact in fp32, so v_hi + v_lo carries 16-17 mantissa bits), and each projection becomes three
+// accumulating products  A_hi B_hi + A_lo B_hi + A_hi B_lo  (the lo x lo term, 2^-18 of a product, is dropped):
+// the same kernel, three times the MMAs (24 + 6 per step, still a few per cent of the tensor pipe), a second copy
+// of every operand tile in shared memory, and the split arithmetic (max, cvt, shift/mask, subtract, cvt per pair)
+// in both epilogues.  The tensor cores then return the fp32 kernel's projections to ~1e-5 of their scale instead
+// of bf16's 3e-3 -- see DESIGN.md section 5 for the measured figures.
 // Algorithmic work: 14,848 FLOP per member-step, as in the fp32 kernel (the K/N padding to
 // 32/32 is not counted).
 #pragma once
@@ -89,12 +98,14 @@ constexpr int UC_AUG = 29;      // first augmentation column (param_dim <= 29)
 __host__ __device__ constexpr int uc_nslot(int ctas) { return ctas == 2 ? 2 : 4; }        // depth of the noise ring (steps)
 __host__ __device__ constexpr int uc_epi_chunk(int ctas) { return ctas == 2 ? 32 : 64; }
 
-template <int NSLOT, int H>
+// NT = bf16 terms per operand: 1, or 2 for the split-precision build ([hi tile | lo tile], each a complete
+// canonical K-major tile)
+template <int NSLOT, int H, int NT = 1>
 struct UmmaChainSmem {
-    unsigned char x[UC_M * UC_K1 * 2];      // A of GEMM1
-    unsigned char h[UC_M * H * 2];          // A of GEMM2
-    unsigned char w1[H * UC_K1 * 2];        // B of GEMM1 (W0x augmented)
-    unsigned char w2[UC_N2 * H * 2];        // B of GEMM2 (W2 padded)
+    unsigned char x[NT * UC_M * UC_K1 * 2];      // A of GEMM1
+    unsigned char h[NT * UC_M * H * 2];          // A of GEMM2
+    unsigned char w1[NT * H * UC_K1 * 2];        // B of GEMM1 (W0x augmented | its bf16 residual, augmentation columns 0)
+    unsigned char w2[NT * UC_N2 * H * 2];        // B of GEMM2 (W2 padded | its bf16 residual)
     float zring[NSLOT][UC_M][kPPad];     // noise ring; 16-byte chunk c of member m sits at chunk c ^ (m & 7)
     unsigned long long bar_d, bar_e;
     alignas(16) float b2[kPPad];
@@ -102,7 +113,8 @@ struct UmmaChainSmem {
     int timeout;
 };
 
-// pack the bf16 B operands once per load_state_dict: byte layout = umma::elem_offset
+// pack the bf16 B operands once per load_state_dict: byte layout = umma::elem_offset; each buffer holds the tile
+// of bf16(w) followed by the tile of the residuals bf16(w - bf16(w)) (read by the split-precision build only)
 static __global__ void k_pack_umma_weights(const float* __restrict__ w0xT /*(32,H)*/,
                                            const float* __restrict__ w2p /*(32,H)*/, int P, int H,
                                            unsigned short* __restrict__ w1_pk, unsigned short* __restrict__ w2_pk) {
@@ -111,12 +123,17 @@ static __global__ void k_pack_umma_weights(const float* __restrict__ w0xT /*(32,
         const int j = i / UC_K1, k = i % UC_K1;
         const float v = (k < P) ? w0xT[k * H + j] : 0.f;      // columns P..31 start as zero
         const __nv_bfloat16 b = __float2bfloat16_rn(v);
+        const __nv_bfloat16 r = __float2bfloat16_rn(v - __bfloat162float(b));
         w1_pk[umma::elem_offset(j, k, UC_K1) / 2] = *reinterpret_cast<const unsigned short*>(&b);
+        w1_pk[H * UC_K1 + umma::elem_offset(j, k, UC_K1) / 2] = *reinterpret_cast<const unsigned short*>(&r);
     }
     if (i < UC_N2 * H) {
         const int p = i / H, k = i % H;
-        const __nv_bfloat16 b = __float2bfloat16_rn(w2p[p * H + k]);
+        const float v = w2p[p * H + k];
+        const __nv_bfloat16 b = __float2bfloat16_rn(v);
+        const __nv_bfloat16 r = __float2bfloat16_rn(v - __bfloat162float(b));
         w2_pk[umma::elem_offset(p, k, H) / 2] = *reinterpret_cast<const unsigned short*>(&b);
+        w2_pk[UC_N2 * H + umma::elem_offset(p, k, H) / 2] = *reinterpret_cast<const unsigned short*>(&r);
     }
 }
 
@@ -126,16 +143,26 @@ static_assert(UC_NB_H + UC_TPM <= UC_NB_FULL && UC_NB_EMPTY + 4 <= 16, "named ba
 __device__ __forceinline__ void nb_sync(uint32_t id, uint32_t n) { asm volatile("bar.sync %0, %1;" ::"r"(id), "r"(n) : "memory"); }
 __device__ __forceinline__ void nb_arrive(uint32_t id, uint32_t n) { asm volatile("bar.arrive %0, %1;" ::"r"(id), "r"(n) : "memory"); }
 
-template <int H, bool REPLAY, bool TRACE, bool SHARED, int CTAS>
+// (a, b) as two packed bf16 pairs: hi = bf16(a), bf16(b); lo = bf16 of the (exact) fp32 residuals
+__device__ __forceinline__ void split_bf16_pair(float a, float b, uint32_t& hi, uint32_t& lo) {
+    hi = umma::pack_bf16(a, b);
+    lo = umma::pack_bf16(a - __uint_as_float(hi << 16), b - __uint_as_float(hi & 0xffff0000u));
+}
+
+template <int H, bool REPLAY, bool TRACE, bool SHARED, int CTAS, bool SPLIT = false>
 __global__ void __launch_bounds__(UC_THREADS, CTAS) k_chain_umma(const ChainParams a, const UmmaChainExtra ex) {
     static_assert(CTAS == 1 || CTAS == 2, "one or two CTAs per SM");
     static_assert(H == 128 || (H == 256 && CTAS == 1), "hidden_dim 128, or 256 with one CTA per SM");
+    static_assert(!SPLIT || (H == 128 && CTAS == 1), "split precision: hidden_dim 128, one CTA per SM");
     constexpr int UC_H = H;
+    constexpr int NT = SPLIT ? 2 : 1;
+    // byte offsets of the lo tiles behind the hi tiles
+    constexpr uint32_t X_LO = UC_M * UC_K1 * 2, H_LO = UC_M * H * 2, W1_LO = H * UC_K1 * 2, W2_LO = UC_N2 * H * 2;
     constexpr int UC_NSLOT = uc_nslot(CTAS);
     constexpr int UC_EPI_CHUNK = uc_epi_chunk(CTAS);
     using namespace umma;
     extern __shared__ __align__(128) unsigned char uc_smem_raw[];
-    UmmaChainSmem<UC_NSLOT, H>& s = *reinterpret_cast<UmmaChainSmem<UC_NSLOT, H>*>(uc_smem_raw);
+    UmmaChainSmem<UC_NSLOT, H, NT>& s = *reinterpret_cast<UmmaChainSmem<UC_NSLOT, H, NT>*>(uc_smem_raw);
     const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
     const uint32_t sX_ = smem_u32(s.x), sH_ = smem_u32(s.h), sW1_ = smem_u32(s.w1), sW2_ = smem_u32(s.w2);
     const uint32_t sZ_ = smem_u32(&s.zring[0][0][0]);
@@ -159,8 +186,8 @@ __global__ void __launch_bounds__(UC_THREADS, CTAS) k_chain_umma(const ChainPara
     {
         uint4* d1 = reinterpret_cast<uint4*>(s.w1);
         uint4* d2 = reinterpret_cast<uint4*>(s.w2);
-        for (int i = tid; i < UC_H * UC_K1 * 2 / 16; i += UC_THREADS) d1[i] = ex.w1_pk[i];
-        for (int i = tid; i < UC_N2 * UC_H * 2 / 16; i += UC_THREADS) d2[i] = ex.w2_pk[i];
+        for (int i = tid; i < NT * UC_H * UC_K1 * 2 / 16; i += UC_THREADS) d1[i] = ex.w1_pk[i];
+        for (int i = tid; i < NT * UC_N2 * UC_H * 2 / 16; i += UC_THREADS) d2[i] = ex.w2_pk[i];
         if (tid < kPPad) s.b2[tid] = a.b2p[tid];
         if (tid == 0) s.timeout = 0;
     }
@@ -246,6 +273,13 @@ __global__ void __launch_bounds__(UC_THREADS, CTAS) k_chain_umma(const ChainPara
                 mma_bf16_first(tmem, dA1[0], dB1[0], IDESC1);
 #pragma unroll
                 for (int k = 1; k < UC_K1 / 16; ++k) mma_bf16_acc(tmem, dA1[k], dB1[k], IDESC1);
+                if (SPLIT) {       // + x_lo W_hi + x_hi W_lo (the start-address field of a descriptor counts 16-byte units)
+#pragma unroll
+                    for (int k = 0; k < UC_K1 / 16; ++k) {
+                        mma_bf16_acc(tmem, dA1[k] + (X_LO >> 4), dB1[k], IDESC1);
+                        mma_bf16_acc(tmem, dA1[k], dB1[k] + (W1_LO >> 4), IDESC1);
+                    }
+                }
                 mma_commit(bar_d);
             }
             __syncwarp();
@@ -260,6 +294,10 @@ __global__ void __launch_bounds__(UC_THREADS, CTAS) k_chain_umma(const ChainPara
                         const int k = UC_H / 16 / UC_TPM * part + kk;
                         if (k == 0) mma_bf16_first(tmemE, dA2[0], dB2[0], IDESC2);
                         else mma_bf16_acc(tmemE, dA2[k], dB2[k], IDESC2);
+                        if (SPLIT) {
+                            mma_bf16_acc(tmemE, dA2[k] + (H_LO >> 4), dB2[k], IDESC2);
+                            mma_bf16_acc(tmemE, dA2[k], dB2[k] + (W2_LO >> 4), IDESC2);
+                        }
                     }
                     if (part == UC_TPM - 1) mma_commit(bar_e);
                 }
@@ -438,6 +476,16 @@ __global__ void __launch_bounds__(UC_THREADS, CTAS) k_chain_umma(const ChainPara
 #pragma unroll
             for (int c = 0; c < PW / 8; ++c) {
                 const bool last = (PW / 8 * part + c) == 3;   // parameters 24..28 + three constant-one columns (bf16 1.0 = 0x3F80)
+                if (SPLIT) {      // the residual tile carries zeros under the constant-one columns
+                    uint32_t hi[4], lo[4];
+                    split_bf16_pair(x[4 * c].x, x[4 * c].y, hi[0], lo[0]);
+                    split_bf16_pair(x[4 * c + 1].x, x[4 * c + 1].y, hi[1], lo[1]);
+                    split_bf16_pair(x[4 * c + 2].x, last ? 1.0f : x[4 * c + 2].y, hi[2], lo[2]);
+                    split_bf16_pair(last ? 1.0f : x[4 * c + 3].x, last ? 1.0f : x[4 * c + 3].y, hi[3], lo[3]);
+                    sts_u4(xchunk + (uint32_t)c * kLBO, hi[0], hi[1], hi[2], hi[3]);
+                    sts_u4(xchunk + X_LO + (uint32_t)c * kLBO, lo[0], lo[1], lo[2], lo[3]);
+                    continue;
+                }
                 const uint32_t w2 = last ? pack_bf16(x[4 * c + 2].x, 1.0f) : pack_bf16(x[4 * c + 2].x, x[4 * c + 2].y);
                 const uint32_t w3 = last ? 0x3F803F80u : pack_bf16(x[4 * c + 3].x, x[4 * c + 3].y);
                 sts_u4(xchunk + (uint32_t)c * kLBO, pack_bf16(x[4 * c].x, x[4 * c].y), pack_bf16(x[4 * c + 1].x, x[4 * c + 1].y), w2, w3);
@@ -488,12 +536,24 @@ __global__ void __launch_bounds__(UC_THREADS, CTAS) k_chain_umma(const ChainPara
                         tmem_ld16(tD + UC_EPI_CHUNK * half2 + 16 * hh, *reinterpret_cast<uint32_t(*)[16]>(&dv[16 * hh]));
                     tmem_ld_wait();
 #pragma unroll
-                    for (int q = 0; q < UC_EPI_CHUNK / 8; ++q)
+                    for (int q = 0; q < UC_EPI_CHUNK / 8; ++q) {
+                        if (SPLIT) {
+                            uint32_t hi[4], lo[4];
+#pragma unroll
+                            for (int i = 0; i < 4; ++i)
+                                split_bf16_pair(fmaxf(__uint_as_float(dv[8 * q + 2 * i]), 0.f),
+                                                fmaxf(__uint_as_float(dv[8 * q + 2 * i + 1]), 0.f), hi[i], lo[i]);
+                            const uint32_t dst = hrow + (uint32_t)(half2 * (UC_EPI_CHUNK / 8) + q) * kLBO;
+                            sts_u4(dst, hi[0], hi[1], hi[2], hi[3]);
+                            sts_u4(dst + H_LO, lo[0], lo[1], lo[2], lo[3]);
+                            continue;
+                        }
                         sts_u4(hrow + (uint32_t)(half2 * (UC_EPI_CHUNK / 8) + q) * kLBO,
                                pack_bf16_relu(__uint_as_float(dv[8 * q]), __uint_as_float(dv[8 * q + 1])),
                                pack_bf16_relu(__uint_as_float(dv[8 * q + 2]), __uint_as_float(dv[8 * q + 3])),
                                pack_bf16_relu(__uint_as_float(dv[8 * q + 4]), __uint_as_float(dv[8 * q + 5])),
                                pack_bf16_relu(__uint_as_float(dv[8 * q + 6]), __uint_as_float(dv[8 * q + 7])));
+                    }
                 }
             } else {
 #pragma unroll
@@ -502,15 +562,20 @@ __global__ void __launch_bounds__(UC_THREADS, CTAS) k_chain_umma(const ChainPara
                     tmem_ld16(tD + 16 * hh, dv);
                     tmem_ld16(tCB + 16 * hh, cv);
                     tmem_ld_wait();
-                    uint32_t pk[8];
+                    uint32_t pk[8], pl[8];
 #pragma unroll
                     for (int i = 0; i < 8; ++i) {
                         const float2 hsum = fadd2(make_float2(__uint_as_float(dv[2 * i]), __uint_as_float(dv[2 * i + 1])),
                                                   make_float2(__uint_as_float(cv[2 * i]), __uint_as_float(cv[2 * i + 1])));
-                        pk[i] = pack_bf16_relu(hsum.x, hsum.y);
+                        if (SPLIT) split_bf16_pair(fmaxf(hsum.x, 0.f), fmaxf(hsum.y, 0.f), pk[i], pl[i]);
+                        else pk[i] = pack_bf16_relu(hsum.x, hsum.y);
                     }
                     sts_u4(hrow + (uint32_t)(2 * hh) * kLBO, pk[0], pk[1], pk[2], pk[3]);
                     sts_u4(hrow + (uint32_t)(2 * hh + 1) * kLBO, pk[4], pk[5], pk[6], pk[7]);
+                    if (SPLIT) {
+                        sts_u4(hrow + H_LO + (uint32_t)(2 * hh) * kLBO, pl[0], pl[1], pl[2], pl[3]);
+                        sts_u4(hrow + H_LO + (uint32_t)(2 * hh + 1) * kLBO, pl[4], pl[5], pl[6], pl[7]);
+                    }
                 }
             }
             UC_T(long long f0 = 0; if (timed) f0 = clock64();)

@@ -24,8 +24,8 @@ struct ertdiff_model {
     float* w2p = nullptr;      // [32][H]      mlp.2.weight, rows >= P zero
     float* b2p = nullptr;      // [32]         mlp.2.bias padded
     float* freq = nullptr;     // [H/2]        timestep-embedding frequencies (from the host)
-    unsigned short* w1_pk = nullptr;   // bf16 B operand of GEMM1 (tcgen05 chain, H == 128): 8 KB
-    unsigned short* w2_pk = nullptr;   // bf16 B operand of GEMM2: 8 KB
+    unsigned short* w1_pk = nullptr;   // bf16 B operand of GEMM1 (tcgen05 chain) + the tile of its bf16 residuals (split precision)
+    unsigned short* w2_pk = nullptr;   // the same pair for GEMM2
     unsigned short* enc_w1_pk = nullptr;   // bf16 B operands of the tensor-core encoder (conv1: 3 KB, conv2: 12 KB)
     unsigned short* enc_w2_pk = nullptr;
     int* umma_status = nullptr;        // device flag: a tcgen05 chain tile timed out

@@ -911,8 +911,14 @@ __device__ __forceinline__ double kde_scan_reach(double h, double step, int64_t 
 }
 
 // fp32 partial sums of one block of <= 64 centred members (a padded block starts 16-byte aligned: full blocks are
-// read with 128-bit loads) for one / two grid points; the terms are added in member order
-__device__ __forceinline__ void kde_block_sum2(const float* __restrict__ blk, int len, float va, float vb, float c2,
+// read with 128-bit loads) for one / two grid points; the terms are added in member order.  A term is
+// ex2(-(v*sc - x*sc)^2) with sc = sqrt(log2(e) / (2 h^2)): one FFMA, one FMUL, the MUFU and the accumulating FADD --
+// four issue slots per term (va, vb arrive pre-multiplied by sc; nsc = -sc)
+__device__ __forceinline__ float kde_term(float vs, float x, float nsc) {
+    const float d = fmaf(x, nsc, vs);
+    return ex2_approx(-d * d);
+}
+__device__ __forceinline__ void kde_block_sum2(const float* __restrict__ blk, int len, float va, float vb, float nsc,
                                                float& pa, float& pb) {
     pa = 0.f; pb = 0.f;
     if (len == 64) {
@@ -920,39 +926,33 @@ __device__ __forceinline__ void kde_block_sum2(const float* __restrict__ blk, in
 #pragma unroll 4
         for (int q = 0; q < 16; ++q) {
             const float4 x4 = b4[q];
-            float d;
-            d = va - x4.x; pa += ex2_approx(d * d * c2); d = vb - x4.x; pb += ex2_approx(d * d * c2);
-            d = va - x4.y; pa += ex2_approx(d * d * c2); d = vb - x4.y; pb += ex2_approx(d * d * c2);
-            d = va - x4.z; pa += ex2_approx(d * d * c2); d = vb - x4.z; pb += ex2_approx(d * d * c2);
-            d = va - x4.w; pa += ex2_approx(d * d * c2); d = vb - x4.w; pb += ex2_approx(d * d * c2);
+            pa += kde_term(va, x4.x, nsc); pb += kde_term(vb, x4.x, nsc);
+            pa += kde_term(va, x4.y, nsc); pb += kde_term(vb, x4.y, nsc);
+            pa += kde_term(va, x4.z, nsc); pb += kde_term(vb, x4.z, nsc);
+            pa += kde_term(va, x4.w, nsc); pb += kde_term(vb, x4.w, nsc);
         }
     } else {
         for (int i = 0; i < len; ++i) {
             const float xi = blk[i];
-            const float da = va - xi, db = vb - xi;
-            pa += ex2_approx(da * da * c2);
-            pb += ex2_approx(db * db * c2);
+            pa += kde_term(va, xi, nsc);
+            pb += kde_term(vb, xi, nsc);
         }
     }
 }
-__device__ __forceinline__ float kde_block_sum1(const float* __restrict__ blk, int len, float va, float c2) {
+__device__ __forceinline__ float kde_block_sum1(const float* __restrict__ blk, int len, float va, float nsc) {
     float pa = 0.f;
     if (len == 64) {
         const float4* __restrict__ b4 = reinterpret_cast<const float4*>(blk);
 #pragma unroll 4
         for (int q = 0; q < 16; ++q) {
             const float4 x4 = b4[q];
-            float d;
-            d = va - x4.x; pa += ex2_approx(d * d * c2);
-            d = va - x4.y; pa += ex2_approx(d * d * c2);
-            d = va - x4.z; pa += ex2_approx(d * d * c2);
-            d = va - x4.w; pa += ex2_approx(d * d * c2);
+            pa += kde_term(va, x4.x, nsc);
+            pa += kde_term(va, x4.y, nsc);
+            pa += kde_term(va, x4.z, nsc);
+            pa += kde_term(va, x4.w, nsc);
         }
     } else {
-        for (int i = 0; i < len; ++i) {
-            const float da = va - blk[i];
-            pa += ex2_approx(da * da * c2);
-        }
+        for (int i = 0; i < len; ++i) pa += kde_term(va, blk[i], nsc);
     }
     return pa;
 }
@@ -1016,7 +1016,8 @@ __device__ __forceinline__ void kde_scan_column(const float* __restrict__ xs, in
     const int chunk = (n_act + nparts - 1) / nparts;
     const int g_begin = ga + part * chunk;
     const int g_end = min(gb + 1, g_begin + chunk);
-    const float c2 = (float)(kc.neg_inv_2h2 * 1.4426950408889634);   // exponent in base 2
+    // exponent in base 2: -(g - x)^2 log2(e) / (2 h^2) = -((g - x) sc)^2
+    const float sc = (float)sqrt(-kc.neg_inv_2h2 * 1.4426950408889634), nsc = -sc;
     // `ms` adjacent lanes share a grid point and split the members between them in blocks of 64 (lane `sub` takes
     // blocks sub, sub + ms, ...); their partial sums meet in a fixed xor-shuffle tree.  ms = 1 is one thread per grid
     // point; few columns of a long ensemble (a rank's share of the chain's output) use ms > 1 to fill the machine.
@@ -1024,19 +1025,19 @@ __device__ __forceinline__ void kde_scan_column(const float* __restrict__ xs, in
     for (int gbase = g_begin; gbase < g_end; gbase += 2 * slots) {        // (uniform trip count: shuffles inside)
         const int g0 = gbase + slot, g1 = g0 + slots;
         const bool has0 = g0 < g_end, has1 = g1 < g_end;
-        const float va = has0 ? (float)(kde_grid_point(g0, G, lo, hi, step) - kc.mean) : 0.f;
+        const float va = has0 ? (float)(kde_grid_point(g0, G, lo, hi, step) - kc.mean) * sc : 0.f;
         double sa = 0.0, sb = 0.0;
         if (has1) {                                // two grid points per thread: one shared-memory read feeds both
-            const float vb = (float)(kde_grid_point(g1, G, lo, hi, step) - kc.mean);
+            const float vb = (float)(kde_grid_point(g1, G, lo, hi, step) - kc.mean) * sc;
             for (int64_t i0 = 64 * sub; i0 < N; i0 += 64 * ms) {
                 float pa, pb;
-                kde_block_sum2(xs + kde_pad(i0), (int)((i0 + 64 <= N) ? 64 : N - i0), va, vb, c2, pa, pb);
+                kde_block_sum2(xs + kde_pad(i0), (int)((i0 + 64 <= N) ? 64 : N - i0), va, vb, nsc, pa, pb);
                 sa += (double)pa;
                 sb += (double)pb;
             }
         } else if (has0) {                         // the tail of a chunk: no wasted second evaluation
             for (int64_t i0 = 64 * sub; i0 < N; i0 += 64 * ms) {
-                sa += (double)kde_block_sum1(xs + kde_pad(i0), (int)((i0 + 64 <= N) ? 64 : N - i0), va, c2);
+                sa += (double)kde_block_sum1(xs + kde_pad(i0), (int)((i0 + 64 <= N) ? 64 : N - i0), va, nsc);
             }
         }
         for (int o = ms >> 1; o > 0; o >>= 1) {
@@ -1307,13 +1308,14 @@ k_kde_scan32_tiled(const T* __restrict__ a, int64_t N, int64_t Q, int64_t col0,
     const int chunk = (n_act + nparts - 1) / nparts;
     const int g_begin = ga + part * chunk;
     const int g_end = min(gb + 1, g_begin + chunk);
-    const float c2 = (float)(kc.neg_inv_2h2 * 1.4426950408889634);
+    // exponent in base 2: -(g - x)^2 log2(e) / (2 h^2) = -((g - x) sc)^2
+    const float sc = (float)sqrt(-kc.neg_inv_2h2 * 1.4426950408889634), nsc = -sc;
     const int sub = tid & (ms - 1), slot = tid / ms, slots = nthr / ms;     // see kde_scan_column
     for (int gbase = g_begin; gbase < g_end; gbase += 2 * slots) {          // uniform trip count: barriers inside
         const int g0 = gbase + slot, g1 = g0 + slots;
         const bool has0 = g0 < g_end, has1 = g1 < g_end;
-        const float va = has0 ? (float)(kde_grid_point(g0, G, lo, hi, step) - kc.mean) : 0.f;
-        const float vb = has1 ? (float)(kde_grid_point(g1, G, lo, hi, step) - kc.mean) : 0.f;
+        const float va = has0 ? (float)(kde_grid_point(g0, G, lo, hi, step) - kc.mean) * sc : 0.f;
+        const float vb = has1 ? (float)(kde_grid_point(g1, G, lo, hi, step) - kc.mean) * sc : 0.f;
         double sa = 0.0, sb = 0.0;
         for (int64_t t0 = 0; t0 < N; t0 += tile) {
             const int n = (int)(N - t0 < tile ? N - t0 : tile);
@@ -1323,13 +1325,13 @@ k_kde_scan32_tiled(const T* __restrict__ a, int64_t N, int64_t Q, int64_t col0,
             if (has1) {
                 for (int i0 = 64 * sub; i0 < n; i0 += 64 * ms) {
                     float pa, pb;
-                    kde_block_sum2(xs + kde_pad(i0), (i0 + 64 <= n) ? 64 : n - i0, va, vb, c2, pa, pb);
+                    kde_block_sum2(xs + kde_pad(i0), (i0 + 64 <= n) ? 64 : n - i0, va, vb, nsc, pa, pb);
                     sa += (double)pa;
                     sb += (double)pb;
                 }
             } else if (has0) {
                 for (int i0 = 64 * sub; i0 < n; i0 += 64 * ms) {
-                    sa += (double)kde_block_sum1(xs + kde_pad(i0), (i0 + 64 <= n) ? 64 : n - i0, va, c2);
+                    sa += (double)kde_block_sum1(xs + kde_pad(i0), (i0 + 64 <= n) ? 64 : n - i0, va, nsc);
                 }
             }
         }

@@ -90,7 +90,10 @@ def run_chain(model, condition, T, betas, alphas, alpha_bar, device, num_steps=N
     Returns ``x_0 (n_members, P)`` on ``device`` (and the per-step predicted noise
     ``(num_steps, n_members, P)`` indexed by t when ``return_eps``).
 
-    ``precision="bf16"``: a tile of the tensor-core chain whose MMA never completes (a hardware or
+    ``precision``: ``"fp32"`` (CUDA-core FFMA, pinned to the reference), ``"bf16"`` (tensor cores, bf16 operands,
+    fp32 accumulation; hidden_dim 128 or 256) or ``"bf16x3"`` (tensor cores, every operand as two bf16 terms and
+    three accumulating products per projection: fp32-class fields at tensor-core speed; hidden_dim 128; the
+    condition encoder stays in fp32).  Tensor-core modes: a tile whose MMA never completes (a hardware or
     driver fault; the waits are bounded) poisons its members with NaN and raises the handle's status
     word.  With ``check_status`` (default) that word is read after the launch -- one 4-byte D2H copy,
     which waits for the chain -- and ``ErtdiffError`` is raised; a caller that pipelines several
@@ -167,7 +170,7 @@ def run_chain(model, condition, T, betas, alphas, alpha_bar, device, num_steps=N
                                             C.byref(args), _lib.stream_ptr(device)),
                    "sample_model")
     del keep
-    if check_status and precision == "bf16" and model.umma_status() != 0:
+    if check_status and precision in ("bf16", "bf16x3") and model.umma_status() != 0:
         raise _lib.ErtdiffError("tensor-core chain: an MMA completion wait timed out; the affected members are NaN")
     return (x_out, eps) if return_eps else x_out
 

@@ -57,8 +57,13 @@ typedef enum ertdiff_loop_mode {
 /* arithmetic of the denoiser contractions */
 typedef enum ertdiff_precision {
     ERTDIFF_PREC_FP32 = 0,        /* fp32 FFMA everywhere (BASELINE config 2)               */
-    ERTDIFF_PREC_BF16 = 1         /* bf16 operands, fp32 accumulate on tcgen05 (configs 3/4); */
-                                  /* hidden_dim = 128, param_dim <= 29                        */
+    ERTDIFF_PREC_BF16 = 1,        /* bf16 operands, fp32 accumulate on tcgen05 (configs 3/4); */
+                                  /* hidden_dim = 128 or 256, param_dim <= 29                 */
+    ERTDIFF_PREC_BF16X3 = 2       /* split precision on tcgen05: every operand as two bf16    */
+                                  /* terms (hi + residual), three accumulating products per   */
+                                  /* projection -- fp32-class fields at tensor-core speed;    */
+                                  /* hidden_dim = 128, param_dim <= 29; the condition encoder */
+                                  /* stays in fp32                                            */
 } ertdiff_precision;
 
 typedef struct ertdiff_model ertdiff_model;

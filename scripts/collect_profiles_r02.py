@@ -31,6 +31,12 @@ emit("r02_chain_fp32_variants.md",
       ("variants_h256.log", "hidden_dim 256, L = 9386")])
 emit("r02_chain_bf16_sweep.md", "r02 tensor-core chain (k_chain_umma), scripts/chain_sweep.py, T = 1000",
      [("sweep_bf16.log", None)])
+emit("r02_chain_split_precision.md",
+     "r02 the three chain kernels side by side (scripts/chain_sweep.py; kernel duration by CUDA events): fp32 CUDA-core, "
+     "bf16 tensor-core, and the split-precision tensor-core build (precision=\"bf16x3\": bf16 hi + residual operands, "
+     "three accumulating products per projection); accuracy of the three against the reference goldens is in "
+     "r02_parity_measured.md",
+     [("chain_sweep_h.log", "T = 200 (first block) and T = 1000 (last four lines)")])
 emit("r02_summary_window.md",
      "r02 the fused statistics call (ertdiff_ensemble_summary) on a column window of the fields of a real T = 1000 bf16 chain "
      "(scripts/summary_window_bench.py --chain; whole call by CUDA events, per kernel by torch.profiler; the side-stream "

@@ -40,7 +40,7 @@ c1 = np.load(os.path.join(G, "chain_cfg1.npz"))
 cond1 = torch.from_numpy(c1["condition"]).to(dev)
 noise = torch.from_numpy(c1["noise"]).to(dev)
 b, a, ab = eb.get_diffusion_schedule(50)
-for prec in ("fp32", "bf16"):
+for prec in ("fp32", "bf16", "bf16x3"):
     x, eps = eb.run_chain(m, cond1.expand(16, C, L), 50, b, a, ab, dev, noise=noise, return_eps=True, precision=prec)
     for t in (49, 25, 0):
         report(f"cfg1 {prec} eps t={t}", eps[t].cpu(), c1[f"eps_t{t}"])
@@ -56,7 +56,7 @@ for name, (B, T, ns) in {"T1000_B4": (4, 1000, None), "T500_B3_steps120": (3, 50
     torch.manual_seed(2)
     nz = torch.randn(T if ns is None else ns, B, P)
     bb = eb.get_diffusion_schedule(T)
-    for prec in ("fp32", "bf16"):
+    for prec in ("fp32", "bf16", "bf16x3"):
         x = eb.sample_model(m, cond1.expand(B, C, L), T, *bb, P, dev, num_steps=ns, noise=nz.to(dev), precision=prec)
         report(f"long {name} {prec}", x.cpu(), g[name])
 g2 = np.load(os.path.join(G, "chain_cfg2.npz"))
@@ -65,7 +65,7 @@ for name, B in (("cfg2_B256_T1000", 256), ("B64_T1000", 64)):
     torch.manual_seed(2)
     nz = torch.randn(1000, B, P)
     assert np.array_equal(nz[:2].numpy(), g2[name + "_noise_head"])
-    for prec in ("fp32", "bf16"):
+    for prec in ("fp32", "bf16", "bf16x3"):
         for upt in ("1", "2") if prec == "fp32" else ("",):
             if upt:
                 os.environ["ERTDIFF_CHAIN_UPT"] = upt
@@ -83,10 +83,11 @@ for label, damp in (("random-init", 1.0), ("damped (mlp.2 x 0.25)", 0.25)):
         sd["mlp.2.weight"] = sd["mlp.2.weight"] * damp
         sd["mlp.2.bias"] = sd["mlp.2.bias"] * damp
         mm.load_state_dict(sd)
-    xs = {p_: eb.run_chain(mm, cond1.expand(1024, C, L), 1000, *bb, dev, seed=5, offset=0, precision=p_) for p_ in ("fp32", "bf16")}
-    report(f"bf16 vs fp32, 1024 x T1000, {label}", xs["bf16"].cpu(), xs["fp32"].cpu())
-    d = (xs["bf16"] - xs["fp32"]).abs().max(dim=1).values / xs["fp32"].abs().max(dim=1).values
-    print(f"    per-member max|d|/max|x|: median {d.median().item():.3e}  p99 {d.quantile(0.99).item():.3e}  max {d.max().item():.3e}")
+    xs = {p_: eb.run_chain(mm, cond1.expand(1024, C, L), 1000, *bb, dev, seed=5, offset=0, precision=p_) for p_ in ("fp32", "bf16", "bf16x3")}
+    for p_ in ("bf16", "bf16x3"):
+        report(f"{p_} vs fp32, 1024 x T1000, {label}", xs[p_].cpu(), xs["fp32"].cpu())
+        d = (xs[p_] - xs["fp32"]).abs().max(dim=1).values / xs["fp32"].abs().max(dim=1).values
+        print(f"    per-member max|d|/max|x|: median {d.median().item():.3e}  p99 {d.quantile(0.99).item():.3e}  max {d.max().item():.3e}")
 # hidden_dim = 256, L = 9386
 h = np.load(os.path.join(G, "model_h256_case.npz"))
 m256 = model_from(h, "sd.", 256)

@@ -32,8 +32,26 @@ def split3(v):
     return hi.double() + mid.double() + lo.double()
 
 
+def split2(t):
+    """t (fp32) as bf16 hi + bf16 residual -- the operands of the split-precision build."""
+    hi = t.to(torch.bfloat16).float()
+    lo = (t - hi).to(torch.bfloat16).float()
+    return hi.double(), lo.double()
+
+
+def mm_bf16(a, w):
+    return bf(a) @ bf(w).t()
+
+
+def mm_bf16x3(a, w):
+    """a w^T the way precision="bf16x3" forms it: hi hi + lo hi + hi lo (lo lo dropped)."""
+    ah, al = split2(a)
+    wh, wl = split2(w)
+    return ah @ wh.t() + al @ wh.t() + ah @ wl.t()
+
+
 def emulate_bf16_chain(sd, cond, T, betas, alphas, alpha_bar, noise, num_steps=None, temperature=1.0,
-                       shared=False):
+                       shared=False, split=False):
     """The chain with the tensor-core kernel's rounding points, in float64 arithmetic.
     shared=True: one condition for all members -- c_b is added to c_t in fp32 and rides through the
     MMA with it; otherwise c_b is added to the fp32 accumulator in the epilogue."""
@@ -41,7 +59,9 @@ def emulate_bf16_chain(sd, cond, T, betas, alphas, alpha_bar, noise, num_steps=N
     H = sd["time_embed.0.weight"].shape[1]
     W0 = sd["mlp.0.weight"]
     W0x, W0t, W0c = W0[:, :P], W0[:, P:P + H], W0[:, P + H:]
-    cemb = emulate_encoder(sd, cond)          # precision="bf16" also selects the tensor-core encoder
+    # precision="bf16" also selects the tensor-core encoder; "bf16x3" keeps the fp32 one
+    cemb = do.encode_condition(sd, cond) if split else emulate_encoder(sd, cond)
+    mm = mm_bf16x3 if split else mm_bf16
     cb = F.linear(cemb, W0c) + sd["mlp.0.bias"]
     x = noise[0].clone()
     draw = 1
@@ -51,11 +71,11 @@ def emulate_bf16_chain(sd, cond, T, betas, alphas, alpha_bar, noise, num_steps=N
                                sd["time_embed.0.bias"]))
         ct = F.linear(temb, W0t)[0]
         if shared:
-            pre = (bf(x) @ bf(W0x).t() + split3(ct + cb[0])).float()
+            pre = (mm(x, W0x) + split3(ct + cb[0])).float()
         else:
-            pre = (bf(x) @ bf(W0x).t() + split3(ct)).float() + cb
+            pre = (mm(x, W0x) + split3(ct)).float() + cb
         h = torch.relu(pre)
-        eps = (bf(h) @ bf(sd["mlp.2.weight"]).t()).float() + sd["mlp.2.bias"]
+        eps = mm(h, sd["mlp.2.weight"]).float() + sd["mlp.2.bias"]
         eps_trace[t_] = eps
         coef, c1, sigma = do.step_coefficients(betas, alphas, alpha_bar, t_, temperature)
         z = None
@@ -288,3 +308,99 @@ def test_bf16_config3_T1000_vs_fp32_same_streams(gpu_model, cuda_dev):
     m32, m16 = eb.ensemble_moments(x32), eb.ensemble_moments(x16)
     scale = x32.abs().max().item()
     assert (m16["mean"] - m32["mean"]).abs().max().item() <= 0.25 * BF16_T1000_OF_SCALE * scale
+
+
+# ---- split precision on the tensor cores: precision="bf16x3" ------------------------------------------------------
+# Every operand as bf16 hi + bf16 residual, three accumulating products per projection.  Two references again: the
+# emulation of the kernel's own rounding points (validates the data flow: operand tiles, the extra MMAs) and the
+# fp32 oracle / the reference's goldens (the accuracy the mode exists for).
+# Measured on a B200 (scripts/measure_parity.py, profiles/r02_parity_measured.md), bounds at about ten times that:
+X3_EPS_OF_SCALE = 5e-5         # predicted noise of one step, of its scale: measured 5.2e-6 (bf16: 3.0e-3)
+X3_T50_OF_SCALE = 1e-5         # final fields after 50 steps against the reference golden: measured 7.0e-7 (bf16: 1.8e-4)
+X3_T1000_OF_SCALE = 7e-5       # per member after 1000 steps: measured 6.6e-6 (fp32 kernel: 8.4e-7, bf16: 2.6e-3)
+
+
+@pytest.mark.parametrize("B,distinct", [(128, False), (200, False), (37, True), (300, True)])
+def test_bf16x3_chain_matches_its_emulation(gpu_model, ref_state_dict, cuda_dev, monkeypatch, B, distinct):
+    T = 24
+    g = torch.Generator().manual_seed(B)
+    cond = torch.rand(B if distinct else 1, C, 400, generator=g)
+    cond_b = cond if distinct else cond.expand(B, C, 400)
+    noise = torch.randn(T, B, P, generator=g)
+    b, a, ab = do.diffusion_schedule(T)
+    x_gpu, eps_gpu = eb.run_chain(gpu_model, cond_b.to(cuda_dev), T, b, a, ab, cuda_dev, noise=noise.to(cuda_dev),
+                                  precision="bf16x3", return_eps=True)
+    assert gpu_model.umma_status() == 0
+    x_emu, eps_emu = emulate_bf16_chain(ref_state_dict, cond_b, T, b, a, ab, noise, shared=not distinct, split=True)
+    e0 = eps_gpu[T - 1].cpu()
+    assert (e0 - eps_emu[T - 1]).abs().max() <= 2e-5 * eps_emu[T - 1].abs().max() + 2e-6
+    scale = x_emu.abs().max().item()
+    assert (x_gpu.cpu() - x_emu).abs().max().item() <= 1e-4 * scale, (x_gpu.cpu() - x_emu).abs().max().item() / scale
+    # and the fp32 oracle itself, step by step: this is what the mode is for
+    x_ref, tr = do.sample_chain(ref_state_dict, cond_b, T, b, a, ab, P, noise, trace_eps_at=(T - 1,))
+    e_ref = tr[T - 1]
+    assert (e0 - e_ref).abs().max() <= X3_EPS_OF_SCALE * e_ref.abs().max(), (e0 - e_ref).abs().max() / e_ref.abs().max()
+    assert (x_gpu.cpu() - x_ref).abs().max().item() <= X3_T50_OF_SCALE * x_ref.abs().max().item()
+    # rows per tile in use do not change a member's result
+    for mpc in ("32", "64", "128"):
+        monkeypatch.setenv("ERTDIFF_UMMA_MPC", mpc)
+        xm = eb.run_chain(gpu_model, cond_b.to(cuda_dev), T, b, a, ab, cuda_dev, noise=noise.to(cuda_dev), precision="bf16x3")
+        assert torch.equal(xm, x_gpu), mpc
+
+
+def test_bf16x3_chain_vs_reference_golden(gpu_model, cuda_dev, golden):
+    # BASELINE config 1 inputs, the reference's own outputs
+    c = golden("chain_cfg1.npz")
+    cond = torch.from_numpy(c["condition"]).to(cuda_dev).expand(16, C, 4693)
+    noise = torch.from_numpy(c["noise"]).to(cuda_dev)
+    b, a, ab = eb.get_diffusion_schedule(50)
+    x, eps = eb.run_chain(gpu_model, cond, 50, b, a, ab, cuda_dev, noise=noise, precision="bf16x3", return_eps=True)
+    assert gpu_model.umma_status() == 0
+    e49 = eps[49].cpu().numpy()
+    assert np.abs(e49 - c["eps_t49"]).max() <= X3_EPS_OF_SCALE * np.abs(c["eps_t49"]).max()
+    for t in (25, 0):
+        assert np.abs(eps[t].cpu().numpy() - c[f"eps_t{t}"]).max() <= X3_EPS_OF_SCALE * np.abs(c[f"eps_t{t}"]).max(), t
+    assert np.abs(x.cpu().numpy() - c["x0"]).max() <= X3_T50_OF_SCALE * np.abs(c["x0"]).max()
+
+
+def test_bf16x3_T1000_against_the_reference_golden(gpu_model, golden, cuda_dev):
+    g = golden("chain_cfg2.npz")
+    cond1 = torch.from_numpy(golden("chain_cfg1.npz")["condition"]).to(cuda_dev)
+    B, T = 64, 1000
+    torch.manual_seed(2)
+    nz = torch.randn(T, B, P)
+    b, a, ab = eb.get_diffusion_schedule(T)
+    x = eb.sample_model(gpu_model, cond1.expand(B, C, 4693), T, b, a, ab, P, cuda_dev, noise=nz.to(cuda_dev), precision="bf16x3")
+    want = g["B64_T1000"]
+    rel = np.abs(x.cpu().numpy() - want).max(axis=1) / np.abs(want).max(axis=1)
+    assert rel.max() <= X3_T1000_OF_SCALE, (rel.max(), np.median(rel))
+
+
+def test_bf16x3_rng_loop_modes_shards_and_waves(gpu_model, cuda_dev):
+    B, T = 260, 21
+    cond = torch.rand(1, C, 300, generator=torch.Generator().manual_seed(3)).to(cuda_dev).expand(B, C, 300)
+    b, a, ab = eb.get_diffusion_schedule(T)
+    x_rng = eb.run_chain(gpu_model, cond, T, b, a, ab, cuda_dev, seed=11, offset=0, precision="bf16x3")
+    draws = eb.philox_normal(11, 0, B, P, T, cuda_dev)
+    assert torch.equal(x_rng, eb.run_chain(gpu_model, cond, T, b, a, ab, cuda_dev, noise=draws, precision="bf16x3"))
+    for mode in ("graph", "stream"):
+        assert torch.equal(x_rng, eb.run_chain(gpu_model, cond, T, b, a, ab, cuda_dev, seed=11, offset=0,
+                                               precision="bf16x3", loop_mode=mode)), mode
+    part = eb.run_chain(gpu_model, cond[:100], T, b, a, ab, cuda_dev, seed=11, offset=0, precision="bf16x3", member_offset=160)
+    assert torch.equal(part, x_rng[160:260])
+    # more tiles than SMs: several waves of one CTA per SM
+    big = eb.run_chain(gpu_model, cond[:1].expand(148 * 128 + 77, C, 300), 5, b, a, ab, cuda_dev, seed=4, offset=0, precision="bf16x3")
+    tail = eb.run_chain(gpu_model, cond[:1].expand(77, C, 300), 5, b, a, ab, cuda_dev, seed=4, offset=0, precision="bf16x3",
+                        member_offset=148 * 128)
+    assert torch.equal(tail, big[148 * 128:])
+    # close to the fp32 kernel on the same streams
+    x32 = eb.run_chain(gpu_model, cond, T, b, a, ab, cuda_dev, seed=11, offset=0)
+    assert (x_rng - x32).abs().max().item() <= X3_T50_OF_SCALE * x32.abs().max().item()
+    assert gpu_model.umma_status() == 0
+
+
+def test_bf16x3_unsupported_hidden_dim_fails_loudly(cuda_dev):
+    m = eb.ConditionalDiffusionModel(29, 256).to(cuda_dev)
+    b, a, ab = eb.get_diffusion_schedule(5)
+    with pytest.raises(eb.ErtdiffError, match="split-precision"):
+        eb.run_chain(m, torch.rand(2, C, 50, device=cuda_dev), 5, b, a, ab, cuda_dev, seed=1, precision="bf16x3")
