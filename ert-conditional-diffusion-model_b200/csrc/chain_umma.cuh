@@ -47,12 +47,21 @@
 // fp32 operand is carried as TWO bf16 terms, v = v_hi + v_lo with v_hi = bf16(v), v_lo = bf16(v - v_hi) (the
 // residual is exact in fp32, so v_hi + v_lo carries 16-17 mantissa bits), and each projection becomes three
 // accumulating products  A_hi B_hi + A_lo B_hi + A_hi B_lo  (the lo x lo term, 2^-18 of a product, is dropped):
-// the same kernel, three times the MMAs (24 + 6 per step, still a few per cent of the tensor pipe), a second copy
-// of every operand tile in shared memory, and the split arithmetic (max, cvt, shift/mask, subtract, cvt per pair)
-// in both epilogues.  The tensor cores then return the fp32 kernel's projections to ~1e-5 of their scale instead
-// of bf16's 3e-3 -- see DESIGN.md section 5 for the measured figures.
-// Algorithmic work: 14,848 FLOP per member-step, as in the fp32 kernel (the K/N padding to
-// 32/32 is not counted).
+// the same kernel with a second copy of every operand tile in shared memory and the split arithmetic (cvt,
+// shift/mask, subtract, cvt per pair) in both epilogues.  The tensor cores then return the fp32 kernel's
+// projections to ~5e-6 of their scale instead of bf16's 3e-3 -- DESIGN.md section 5 has the measured figures.
+// What the step costs is shared-memory traffic (every MMA re-reads its A tile: ~44 cycles per K=16 slice of H)
+// and epilogue issue slots, not tensor-pipe time, so:
+//   * GEMM2 reads H_hi once: its B operand is [W2_hi ; W2_lo] as ONE 64-row tile (the residual tile sits right
+//     behind the operand tile, which is exactly rows 32..63 of the canonical layout), giving E1 = H_hi W_hi and
+//     E2 = H_hi W_lo in adjacent TMEM columns; H_lo W_hi accumulates into E1; epilogue 2 adds E1 + E2.
+//     16 MMAs instead of 24.  (GEMM1 keeps three products into one accumulator: it is off the critical path.)
+//   * H is handed to the MMA warp in four pieces (two per column part, named barriers 12/13 for the second
+//     halves), so that most of GEMM2 runs under the rest of epilogue 1.
+//   * h >= 0: hi = cvt.rz.relu (truncation), so that the residual of a positive h is never negative and
+//     cvt.rn.relu of (h - hi) is both the residual's rounding and the ReLU of a negative h -- no max().
+// Measured (18,944 members, T = 1000): 1.78 us per step against 1.24 (bf16) and 11.4 (fp32 kernel); epilogue 1 --
+// twice the conversions and shared-memory stores -- is what the extra time is.
 #pragma once
 #include "denoiser.cuh"
 #include "umma.cuh"
@@ -138,8 +147,8 @@ static __global__ void k_pack_umma_weights(const float* __restrict__ w0xT /*(32,
 }
 
 // named-barrier ids of the chain kernel (0 is __syncthreads)
-constexpr uint32_t UC_NB_X = 1, UC_NB_H = 2, UC_NB_FULL = 4, UC_NB_EMPTY = 8;
-static_assert(UC_NB_H + UC_TPM <= UC_NB_FULL && UC_NB_EMPTY + 4 <= 16, "named barrier ids");
+constexpr uint32_t UC_NB_X = 1, UC_NB_H = 2, UC_NB_FULL = 4, UC_NB_EMPTY = 8, UC_NB_H2 = 12;   // H2: second halves (split build)
+static_assert(UC_NB_H + UC_TPM <= UC_NB_FULL && UC_NB_EMPTY + 4 <= UC_NB_H2 && UC_NB_H2 + UC_TPM <= 16, "named barrier ids");
 __device__ __forceinline__ void nb_sync(uint32_t id, uint32_t n) { asm volatile("bar.sync %0, %1;" ::"r"(id), "r"(n) : "memory"); }
 __device__ __forceinline__ void nb_arrive(uint32_t id, uint32_t n) { asm volatile("bar.arrive %0, %1;" ::"r"(id), "r"(n) : "memory"); }
 
@@ -147,6 +156,15 @@ __device__ __forceinline__ void nb_arrive(uint32_t id, uint32_t n) { asm volatil
 __device__ __forceinline__ void split_bf16_pair(float a, float b, uint32_t& hi, uint32_t& lo) {
     hi = umma::pack_bf16(a, b);
     lo = umma::pack_bf16(a - __uint_as_float(hi << 16), b - __uint_as_float(hi & 0xffff0000u));
+}
+// the same of (max(a,0), max(b,0)): hi truncated toward zero (cvt.rz.relu), so the residual of a positive value is
+// >= 0 and the .relu of the second conversion only ever clears the residual (= a itself) of a negative one -- no
+// max().  (Measured alternative: hi as a byte permute of the fp32 words' upper halves after max(), which moves one
+// conversion per pair from the XU pipe to the ALU pipe, is SLOWER -- epilogue 1: 1490 -> 1920 cycles per step --
+// because the noise warps' Philox rounds already load the ALU pipe.)
+__device__ __forceinline__ void split_bf16_pair_relu(float a, float b, uint32_t& hi, uint32_t& lo) {
+    asm("cvt.rz.relu.bf16x2.f32 %0, %1, %2;" : "=r"(hi) : "f"(b), "f"(a));
+    lo = umma::pack_bf16_relu(a - __uint_as_float(hi << 16), b - __uint_as_float(hi & 0xffff0000u));
 }
 
 template <int H, bool REPLAY, bool TRACE, bool SHARED, int CTAS, bool SPLIT = false>
@@ -232,6 +250,7 @@ __global__ void __launch_bounds__(UC_THREADS, CTAS) k_chain_umma(const ChainPara
         // ===== MMA-issue warp: the whole warp walks the loop (converged), one elected lane issues ==========
         constexpr uint32_t IDESC1 = idesc_bf16_f32(UC_M, UC_H);
         constexpr uint32_t IDESC2 = idesc_bf16_f32(UC_M, UC_N2);
+        constexpr uint32_t IDESC2W = idesc_bf16_f32(UC_M, 2 * UC_N2);     // split build: B = [W2_hi ; W2_lo], 64 rows
         // all operand descriptors are loop-invariant: build them once, so that a step costs this
         // (single, latency-bound) thread little more than the ten MMA issues themselves
         uint64_t dA1[UC_K1 / 16], dB1[UC_K1 / 16], dA2[UC_H / 16], dB2[UC_H / 16];
@@ -284,24 +303,31 @@ __global__ void __launch_bounds__(UC_THREADS, CTAS) k_chain_umma(const ChainPara
             }
             __syncwarp();
             UC_T(if (timed) { c0 = clock64(); tm[1] += c0 - c1; })
+            // each part's K columns as soon as they are written (split build: each half of each part)
+            constexpr int NSUB = SPLIT ? 2 : 1, KPP = UC_H / 16 / UC_TPM, KPS = KPP / NSUB;
 #pragma unroll
-            for (int part = 0; part < UC_TPM; ++part) {      // each part's K columns as soon as they are written
-                nb_sync(UC_NB_H + part, cnt_h);
-                tc_fence_after();
-                if (elect_one()) {
+            for (int sub = 0; sub < NSUB; ++sub) {
 #pragma unroll
-                    for (int kk = 0; kk < UC_H / 16 / UC_TPM; ++kk) {
-                        const int k = UC_H / 16 / UC_TPM * part + kk;
-                        if (k == 0) mma_bf16_first(tmemE, dA2[0], dB2[0], IDESC2);
-                        else mma_bf16_acc(tmemE, dA2[k], dB2[k], IDESC2);
-                        if (SPLIT) {
-                            mma_bf16_acc(tmemE, dA2[k] + (H_LO >> 4), dB2[k], IDESC2);
-                            mma_bf16_acc(tmemE, dA2[k], dB2[k] + (W2_LO >> 4), IDESC2);
+                for (int part = 0; part < UC_TPM; ++part) {
+                    nb_sync((sub == 0 ? UC_NB_H : UC_NB_H2) + part, cnt_h);
+                    tc_fence_after();
+                    if (elect_one()) {
+#pragma unroll
+                        for (int kk = 0; kk < KPS; ++kk) {
+                            const int k = KPP * part + KPS * sub + kk;
+                            if (SPLIT) {      // [E1 | E2] (+)= H_hi [W_hi ; W_lo]^T,  E1 += H_lo W_hi^T
+                                if (k == 0) mma_bf16_first(tmemE, dA2[0], dB2[0], IDESC2W);
+                                else mma_bf16_acc(tmemE, dA2[k], dB2[k], IDESC2W);
+                                mma_bf16_acc(tmemE, dA2[k] + (H_LO >> 4), dB2[k], IDESC2);
+                            } else {
+                                if (k == 0) mma_bf16_first(tmemE, dA2[0], dB2[0], IDESC2);
+                                else mma_bf16_acc(tmemE, dA2[k], dB2[k], IDESC2);
+                            }
                         }
+                        if (sub == NSUB - 1 && part == UC_TPM - 1) mma_commit(bar_e);
                     }
-                    if (part == UC_TPM - 1) mma_commit(bar_e);
+                    __syncwarp();
                 }
-                __syncwarp();
             }
             UC_T(if (timed) { c1 = clock64(); tm[2] += c1 - c0; })
         }
@@ -380,7 +406,12 @@ __global__ void __launch_bounds__(UC_THREADS, CTAS) k_chain_umma(const ChainPara
         const uint32_t tD = tlane + CW * part;           // this thread's hidden columns of D
         const uint32_t tE = tlane + E_COL + PW * part;   // this thread's parameter columns of E
         const uint32_t tCB = tlane + CB_COL + CW * part; // c_b of this member (distinct conditions)
-        const uint32_t nb_h = UC_NB_H + (uint32_t)part;
+        // H columns written so far -> the MMA warp (split build: the first half of this thread's columns early)
+        auto h_arrive = [&](uint32_t base) {
+            fence_proxy_async();
+            tc_fence_before();
+            nb_arrive(base + (uint32_t)part, cnt_h);
+        };
         const uint32_t zrow = sZ + (uint32_t)row * (kPPad * 4);
         const uint32_t zsw = (uint32_t)(row & 7);
 
@@ -541,11 +572,11 @@ __global__ void __launch_bounds__(UC_THREADS, CTAS) k_chain_umma(const ChainPara
                             uint32_t hi[4], lo[4];
 #pragma unroll
                             for (int i = 0; i < 4; ++i)
-                                split_bf16_pair(fmaxf(__uint_as_float(dv[8 * q + 2 * i]), 0.f),
-                                                fmaxf(__uint_as_float(dv[8 * q + 2 * i + 1]), 0.f), hi[i], lo[i]);
+                                split_bf16_pair_relu(__uint_as_float(dv[8 * q + 2 * i]), __uint_as_float(dv[8 * q + 2 * i + 1]), hi[i], lo[i]);
                             const uint32_t dst = hrow + (uint32_t)(half2 * (UC_EPI_CHUNK / 8) + q) * kLBO;
                             sts_u4(dst, hi[0], hi[1], hi[2], hi[3]);
                             sts_u4(dst + H_LO, lo[0], lo[1], lo[2], lo[3]);
+                            if (q == UC_EPI_CHUNK / 16 - 1) h_arrive(UC_NB_H);      // first half of this thread's columns
                             continue;
                         }
                         sts_u4(hrow + (uint32_t)(half2 * (UC_EPI_CHUNK / 8) + q) * kLBO,
@@ -567,7 +598,7 @@ __global__ void __launch_bounds__(UC_THREADS, CTAS) k_chain_umma(const ChainPara
                     for (int i = 0; i < 8; ++i) {
                         const float2 hsum = fadd2(make_float2(__uint_as_float(dv[2 * i]), __uint_as_float(dv[2 * i + 1])),
                                                   make_float2(__uint_as_float(cv[2 * i]), __uint_as_float(cv[2 * i + 1])));
-                        if (SPLIT) split_bf16_pair(fmaxf(hsum.x, 0.f), fmaxf(hsum.y, 0.f), pk[i], pl[i]);
+                        if (SPLIT) split_bf16_pair_relu(hsum.x, hsum.y, pk[i], pl[i]);
                         else pk[i] = pack_bf16_relu(hsum.x, hsum.y);
                     }
                     sts_u4(hrow + (uint32_t)(2 * hh) * kLBO, pk[0], pk[1], pk[2], pk[3]);
@@ -575,6 +606,7 @@ __global__ void __launch_bounds__(UC_THREADS, CTAS) k_chain_umma(const ChainPara
                     if (SPLIT) {
                         sts_u4(hrow + H_LO + (uint32_t)(2 * hh) * kLBO, pl[0], pl[1], pl[2], pl[3]);
                         sts_u4(hrow + H_LO + (uint32_t)(2 * hh + 1) * kLBO, pl[4], pl[5], pl[6], pl[7]);
+                        if (hh == CW / 32 - 1) h_arrive(UC_NB_H);
                     }
                 }
             }
@@ -582,7 +614,7 @@ __global__ void __launch_bounds__(UC_THREADS, CTAS) k_chain_umma(const ChainPara
             fence_proxy_async();
             UC_T(if (timed) { const long long f1 = clock64(); tf[0] += f1 - f0; f0 = f1; })
             tc_fence_before();
-            nb_arrive(nb_h, cnt_h);
+            nb_arrive((SPLIT ? UC_NB_H2 : UC_NB_H) + (uint32_t)part, cnt_h);
             UC_T(if (timed) tf[1] += clock64() - f0;)
             // GEMM1 of this step has long read W1aug: write the next step's v while GEMM2 runs (made visible
             // to the tensor core by the proxy fence of the publish below, before the next NB_X arrival)
@@ -596,10 +628,22 @@ __global__ void __launch_bounds__(UC_THREADS, CTAS) k_chain_umma(const ChainPara
             tc_fence_after();
             // ---- epilogue 2: eps -> posterior update of this thread's parameters ----------------
             {
-                uint32_t ev[PW];
+                uint32_t ev[PW], ev2[SPLIT ? PW : 1];
                 if (PW == 16) tmem_ld16(tE, *reinterpret_cast<uint32_t(*)[16]>(&ev[0]));
                 else tmem_ld8(tE, *reinterpret_cast<uint32_t(*)[8]>(&ev[0]));
+                if (SPLIT) {      // E2 = H_hi W_lo^T, 32 columns further
+                    if (PW == 16) tmem_ld16(tE + UC_N2, *reinterpret_cast<uint32_t(*)[16]>(&ev2[0]));
+                    else tmem_ld8(tE + UC_N2, *reinterpret_cast<uint32_t(*)[8]>(&ev2[0]));
+                }
                 tmem_ld_wait();
+                if (SPLIT) {
+#pragma unroll
+                    for (int i = 0; i < PW / 2; ++i) {
+                        const float2 e12 = fadd2(make_float2(__uint_as_float(ev[2 * i]), __uint_as_float(ev[2 * i + 1])),
+                                                 make_float2(__uint_as_float(ev2[2 * i]), __uint_as_float(ev2[2 * i + 1])));
+                        ev[2 * i] = __float_as_uint(e12.x); ev[2 * i + 1] = __float_as_uint(e12.y);
+                    }
+                }
                 // ECD.py:111-118: u = coef*eps ; v = x - u ; x' = c1*v ; [ w = sigma*z ; x' = x' + w ]
                 // in packed fp32 (x - u formed as x + (-coef)*eps; the assembler is free to contract
                 // these, the bf16 path's contract is its tolerance, not bit-exactness of the update)

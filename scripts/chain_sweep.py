@@ -48,7 +48,7 @@ for B in [int(v) for v in a.members.split(",")]:
             ms.append(model.last_chain_ms())
         assert torch.isfinite(x).all()
         best = min(ms[1:])
-        if prec == "bf16" and a.timing:
+        if prec in ("bf16", "bf16x3") and a.timing:
             model.umma_timing(True)
             eb.run_chain(model, cond_b, a.T, *sched, dev, seed=7, offset=0, precision=prec, n_members=B)
             tm = model.umma_timing(False)
