@@ -420,7 +420,7 @@ class Runner:
         rec = {
             "name": spec.name, "metric": METRIC, "value": value, "unit": "samples/s",
             "n_gpus": world, "steps": steps, "warmup": warmup,
-            "ms_per_step": ms_dev / steps, "dtype": {"fp32": "f32", "bf16": "bf16", "bf16x3": "bf16x3 (bf16 hi + residual operands, fp32 accumulate)"}[spec.precision],
+            "ms_per_step": ms_dev / steps, "dtype": {"fp32": "f32", "bf16": "bf16", "bf16x3": "bf16x3"}[spec.precision],      # bf16x3: bf16 hi + residual operands, fp32 accumulate
             "config": spec.config(world),
             "ms_per_denoiser_step": (float(np.mean(chain_ms)) / T) if chain_ms else ms_dev / steps / T,
             "e2e": {"value": e2e_value, "unit": "samples/s", "h2d_bytes_per_step": int(h2d),

@@ -33,7 +33,10 @@ KEYS = ["gpu__time_duration.sum", "dram__bytes_read.sum", "dram__bytes_write.sum
         "sm__inst_executed.sum.per_cycle_active", "sm__warps_active.avg.pct_of_peak_sustained_active",
         "smsp__issue_active.avg.pct_of_peak_sustained_active", "launch__registers_per_thread",
         "launch__grid_size", "launch__block_size", "dram__throughput.avg.pct_of_peak_sustained_elapsed",
-        "sm__throughput.avg.pct_of_peak_sustained_elapsed", "l1tex__data_bank_conflicts_pipe_lsu_mem_shared.sum"]
+        "sm__throughput.avg.pct_of_peak_sustained_elapsed", "l1tex__data_bank_conflicts_pipe_lsu_mem_shared.sum",
+        # per-pipe instruction rates: XU = MUFU + conversions, the pipe the KDE scan and the chain's noise warps live on
+        "sm__inst_executed_pipe_xu.avg.pct_of_peak_sustained_active", "sm__inst_executed_pipe_fma.avg.pct_of_peak_sustained_active",
+        "sm__inst_executed_pipe_alu.avg.pct_of_peak_sustained_active", "l1tex__data_pipe_lsu_wavefronts_mem_shared.sum.pct_of_peak_sustained_elapsed"]
 SCALE = {"byte": 1, "Kbyte": 1e3, "Mbyte": 1e6, "Gbyte": 1e9, "ns": 1e-3, "us": 1, "ms": 1e3}
 jpath = os.path.join(out, f"{rnd}_ncu_kernels.json")
 summary = json.load(open(jpath)) if os.path.isfile(jpath) else {}      # captures arrive one per gpurun call
@@ -47,6 +50,7 @@ for name, what in (("chain_fp32", "k_chain (two hidden units per thread), 256 me
                    ("sort_runs", "k_sort_runs<float>, fields (151552, 29) float32 (stats_bench.py)"),
                    ("select_runs", "k_select_runs<float>, fields (151552, 29) float32 (stats_bench.py)"),
                    ("chain_umma", "k_chain_umma, 18,944 members, T=200 (chain_sweep.py)"),
+                   ("chain_umma_split", "k_chain_umma<SPLIT> (precision bf16x3: bf16 hi + residual operands), 18,944 members, T=200 (chain_sweep.py)"),
                    ("chain_umma2", "k_chain_umma, two CTAs per SM build, 37,888 members, T=200 (chain_sweep.py)"),
                    ("encoder_umma", "k_encoder_umma, 1024 conditions of 14x4693 (encoder_bench.py)")):
     rep = os.path.join(go, f"prof_{name}.ncu-rep")

@@ -41,6 +41,15 @@ def test_chain_args_layout_matches_header():
     assert ctypes.sizeof(_lib.ChainArgs) == 136
 
 
+def test_enum_values_match_header():
+    # the host mirror's names for the loop modes and precisions carry the header's enum values
+    src = open(os.path.join(ROOT, "include", "ertdiff_b200.h")).read()
+    enum = {k: int(v) for k, v in re.findall(r"\b(ERTDIFF_(?:PREC|LOOP)_[A-Z0-9]+)\s*=\s*(\d+)", src)}
+    assert {k: enum["ERTDIFF_PREC_" + k.upper()] for k in _lib.PRECISIONS} == _lib.PRECISIONS
+    assert sorted(_lib.PRECISIONS) == ["bf16", "bf16x3", "fp32"]
+    assert {k: enum["ERTDIFF_LOOP_" + k.upper()] for k in _lib.LOOP_MODES} == _lib.LOOP_MODES
+
+
 def test_model_surface_and_seeded_init_equal_reference(golden):
     torch.manual_seed(0)
     m = eb.ConditionalDiffusionModel(29, 128)
