@@ -37,6 +37,15 @@ emit("r02_chain_split_precision.md",
      "three accumulating products per projection); accuracy of the three against the reference goldens is in "
      "r02_parity_measured.md",
      [("chain_sweep_h.log", "T = 200 (first block) and T = 1000 (last four lines)")])
+emit("r02_chain_umma_rng_variants.md",
+     "r02 tensor-core chain, noise-warp variants that were measured and NOT kept (scripts/chain_sweep.py, T = 1000; separately "
+     "built libraries).  `a` = the shipped kernel (four noise warps, one item at a time: Philox rounds, then Box-Muller).  "
+     "`main` = the noise warps skewed by one item, the next item's Philox rounds written between the current item's "
+     "Box-Muller pairs so that the FMA/ALU and XU pipes would overlap inside the warp: ptxas still emits the MUFU stream "
+     "as one cluster, and the extra live registers cost more than the overlap gives (bf16, 18,944 members: 1.237 -> 1.356 us "
+     "per step); the code was reverted.  `b` = eight noise warps, two per scheduler (-DUC_RNG_WARPS_N=8; 544 threads, 96 "
+     "registers): no gain for bf16, slower for bf16x3 (64 bytes of spills).  `c` = both.",
+     [("rng_variants.log", None)])
 emit("r02_summary_window.md",
      "r02 the fused statistics call (ertdiff_ensemble_summary) on a column window of the fields of a real T = 1000 bf16 chain "
      "(scripts/summary_window_bench.py --chain; whole call by CUDA events, per kernel by torch.profiler; the side-stream "
