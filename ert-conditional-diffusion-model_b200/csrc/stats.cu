@@ -27,6 +27,8 @@ struct Workspace {
     cudaStream_t last = nullptr;
     bool used = false;
     unsigned int* tickets = nullptr;  // persistent, self-cleaning per-column counters (last-CTA-done pattern of the KDE kernels)
+    unsigned long long* kde_cells = nullptr;   // per column of a scan launch: (launch epoch << 32 | running fp32 maximum)
+    unsigned int kde_epoch = 0;
 };
 // two independent regions per device: 0 = the KDE kernels, min/max and everything else, 1 = the sorted runs of the
 // percentile path -- so that the fused summary can run the percentiles beside the KDE kernels on another stream
@@ -66,6 +68,24 @@ class WorkspaceLease {
             ERT_CUDA(cudaMemset(w_->tickets, 0, kTicketSlots * sizeof(unsigned int)));
         }
         *out = w_->tickets;
+        return 0;
+    }
+    // the coarse-to-fine KDE scan's per-column cells and a fresh tag for the launch that is about to use them (a
+    // cell tagged by an earlier launch is ignored by the kernel, so nothing is ever reset -- except when the 32-bit
+    // tag wraps)
+    int kde_cells(unsigned long long** out, unsigned int* epoch) {
+        if (!w_) return fail(ERTDIFF_ERR_ARG, "kde: device index out of range");
+        touched_ = true;
+        if (!w_->kde_cells) {
+            ERT_CUDA(cudaMalloc(&w_->kde_cells, kTicketSlots * sizeof(unsigned long long)));
+            ERT_CUDA(cudaMemset(w_->kde_cells, 0, kTicketSlots * sizeof(unsigned long long)));
+        }
+        if (++w_->kde_epoch == 0) {
+            ERT_CUDA(cudaMemsetAsync(w_->kde_cells, 0, kTicketSlots * sizeof(unsigned long long), st_));
+            w_->kde_epoch = 1;
+        }
+        *out = w_->kde_cells;
+        *epoch = w_->kde_epoch;
         return 0;
     }
     static constexpr int kTicketSlots = 4096;
@@ -479,6 +499,16 @@ int ertdiff_ensemble_kde_mode(const void* d_a, int dtype, int64_t N, int64_t Q,
         // (evening the CTA count out to whole CTAs per SM -- 444 instead of 320 -- was measured slower: every CTA
         // streams its whole column, so more CTAs cost more than the imbalance they remove)
         const int threads = 256;
+        // coarse-to-fine scan (stats.cuh): largest coarse stride (ERTDIFF_KDE_COARSE: 1 scans every point), and the
+        // cells through which the CTAs of a column share its running maximum
+        int max_stride = 32;
+        if (const char* e = std::getenv("ERTDIFF_KDE_COARSE")) { const int v = std::atoi(e); max_stride = v >= 1 && v <= 64 ? v : 32; }
+        unsigned long long* cells = nullptr;
+        unsigned int epoch = 0;
+        if (n_gchunks > 1) {
+            ERT_REQUIRE(nc <= WorkspaceLease::kTicketSlots, "ensemble_kde_mode: internal: more shared columns than cells");
+            if (int rc = lease.kde_cells(&cells, &epoch)) return rc;
+        }
         const dim3 grid((unsigned)nc, (unsigned)n_gchunks);
         const dim3 sgrid((unsigned)nc, (unsigned)sel_parts);
         if (tiled) {
@@ -496,22 +526,22 @@ int ertdiff_ensemble_kde_mode(const void* d_a, int dtype, int64_t N, int64_t Q,
             if (tile_override && tile_override < dtile) dtile = tile_override;
             const size_t dsmem = ((size_t)dtile + 8 * (size_t)n_acc) * 8;
             if (f32in) {
-                k_kde_scan32_tiled<float><<<grid, threads, (size_t)kde_padded(stile) * 4, st>>>((const float*)d_a, N, Q, c0, d_lohi, G, cols, s32, stile, ms);
+                k_kde_scan32_tiled<float><<<grid, threads, (size_t)kde_padded(stile) * 4, st>>>((const float*)d_a, N, Q, c0, d_lohi, G, cols, s32, stile, ms, max_stride, cells, epoch);
                 ERT_LAUNCH_CHECK("k_kde_scan32_tiled");
                 k_kde_select64_tiled<float><<<sgrid, 256, dsmem, st>>>((const float*)d_a, N, Q, c0, d_lohi, G, cols, s32, d_mode, d_index, partials, tk, dtile, n_acc);
             } else {
-                k_kde_scan32_tiled<double><<<grid, threads, (size_t)kde_padded(stile) * 4, st>>>((const double*)d_a, N, Q, c0, d_lohi, G, cols, s32, stile, ms);
+                k_kde_scan32_tiled<double><<<grid, threads, (size_t)kde_padded(stile) * 4, st>>>((const double*)d_a, N, Q, c0, d_lohi, G, cols, s32, stile, ms, max_stride, cells, epoch);
                 ERT_LAUNCH_CHECK("k_kde_scan32_tiled");
                 k_kde_select64_tiled<double><<<sgrid, 256, dsmem, st>>>((const double*)d_a, N, Q, c0, d_lohi, G, cols, s32, d_mode, d_index, partials, tk, dtile, n_acc);
             }
             ERT_LAUNCH_CHECK("k_kde_select64_tiled");
         } else if (f32in) {
-            k_kde_scan32<float><<<grid, threads, (size_t)kde_padded(N) * 4, st>>>((const float*)d_a, N, Q, c0, d_lohi, G, ms, cols, s32);
+            k_kde_scan32<float><<<grid, threads, (size_t)kde_padded(N) * 4, st>>>((const float*)d_a, N, Q, c0, d_lohi, G, ms, cols, s32, max_stride, cells, epoch);
             ERT_LAUNCH_CHECK("k_kde_scan32");
             k_kde_select64<float><<<sgrid, 256, (size_t)N * 8, st>>>((const float*)d_a, N, Q, c0, d_lohi, G, cols, s32, d_mode, d_index, partials, tk);
             ERT_LAUNCH_CHECK("k_kde_select64");
         } else {
-            k_kde_scan32<double><<<grid, threads, (size_t)kde_padded(N) * 4, st>>>((const double*)d_a, N, Q, c0, d_lohi, G, ms, cols, s32);
+            k_kde_scan32<double><<<grid, threads, (size_t)kde_padded(N) * 4, st>>>((const double*)d_a, N, Q, c0, d_lohi, G, ms, cols, s32, max_stride, cells, epoch);
             ERT_LAUNCH_CHECK("k_kde_scan32");
             k_kde_select64<double><<<sgrid, 256, (size_t)N * 8, st>>>((const double*)d_a, N, Q, c0, d_lohi, G, cols, s32, d_mode, d_index, partials, tk);
             ERT_LAUNCH_CHECK("k_kde_select64");

@@ -957,19 +957,200 @@ __device__ __forceinline__ float kde_block_sum1(const float* __restrict__ blk, i
     return pa;
 }
 
+// ---- coarse-to-fine scan ---------------------------------------------------------------------------------
+// The scan only has to deliver, exactly, the grid points whose value reaches (1 - KDE_TOL) of the column's maximum
+// (k_kde_select64 re-evaluates those in float64); everything else may be written as zero.  The sum of kernels
+// S(x) = sum_i 2^-((x - x_i) sc)^2 has a bounded second derivative, |S''(x)| <= 2 ln 2 N sc^2 (each term's is
+// largest at its centre), so between two evaluated points c < c' = c + s step it cannot rise above their larger
+// value by more than (c' - c)^2 / 8 times that bound (the error of linear interpolation).  Where the grid is fine
+// against the bandwidth a CTA therefore first evaluates every s-th point of its chunk ("coarse" points, plus the
+// chunk's end), takes M = the largest value seen so far for the column -- its own coarse maximum and, when several
+// CTAs share the column, a global cell they all atomicMax into: whatever is in the cell is an evaluated value, i.e.
+// a valid lower bound of the maximum, no matter how far the other CTAs have got (the cell is (launch epoch << 32 |
+// float bits): a value left by an earlier launch is ignored, nothing needs resetting) -- and skips every interval with
+//       max(S(c), S(c')) + 0.17329 N (sc s step)^2  <  M (1 - 2 KDE_TOL)
+// because no point inside it can then reach the candidates' threshold (the factor 2 covers the fp32 scan's own
+// error, <= 2e-5 relative).  An evaluated point is the same sum of the same 64-term fp32 blocks as in a full scan
+// (how many lanes share it only regroups the float64 additions of the block sums); which of the NON-candidate
+// points are evaluated may vary from run to run (the cell), the candidates -- and the mode -- never do.
+// s = the largest power of two <= max_stride with 3 s step <= h: the bound then costs <= 1.4 % of N in height; a
+// unimodal column of the chain's output (step / h ~ 0.01 .. 0.02) evaluates 1/16 .. 1/32 of its active range plus the
+// band around the mode -- about a tenth of the points of the full scan (numerical check of the rule on normal,
+// bimodal, log-normal, uniform and tied samples: oracle/stats_oracle.py:kde_coarse_to_fine_check).
+constexpr int KDE_MAX_COARSE = 2560;       // coarse values of one CTA's grid chunk, in shared memory
+
+__device__ __forceinline__ int kde_coarse_stride(double h, double step, int max_stride) {
+    int s = 1;
+    while (2 * s <= max_stride && 6.0 * (double)s * step <= h) s *= 2;
+    return s;
+}
+
+// lanes per grid point for a pass over `npoints` points: all of a CTA's threads on the points there are (a coarse
+// pass of a dozen points, or the few fine points around the mode, would otherwise leave most threads idle while a
+// few walk all N members), never fewer than the launch's own `ms`, never more than there are 64-member blocks
+__device__ __forceinline__ int kde_lanes_for(int npoints, int nthr, int ms_launch, int64_t N) {
+    int ms = ms_launch;
+    while (ms < 32 && (int64_t)npoints * (2 * ms) <= nthr && (int64_t)64 * (2 * ms) <= N + 63) ms *= 2;
+    return ms;
+}
+
+// This CTA's (`part` of `nparts`) share of the scan of one column's active grid range [ga, gb].
+// accumulate(va, vb, has0, has1, sa, sb, sub, ms): member sums of up to two grid points (scaled coordinates va / vb)
+// into sa / sb, by lane `sub` of the `ms` lanes that share the points (lane `sub` takes the 64-member blocks sub,
+// sub + ms, ...; the partial sums meet in a fixed xor-shuffle tree).  cta_uniform: accumulate contains block barriers
+// (the tiled form) and must be called by every thread.
+// Without a coarse pass (s = 1) a part takes a contiguous chunk of the range.  With one, the unit of work is the
+// interval between two coarse points, dealt to the parts ROUND-ROBIN: the intervals that need their interior evaluated
+// are neighbours on the grid (the band around the mode), and contiguous chunks would leave them all to one or two
+// CTAs.  A part evaluates both ends of each of its intervals (the right end is also the next part's left end: the
+// coarse pass is done twice, it is a sixteenth or less of the points); alone on the column it shares the ends.
+template <typename Acc>
+__device__ __forceinline__ void kde_scan_points(Acc&& accumulate, bool cta_uniform, int ga, int gb, int part, int nparts, int s,
+                                                int64_t N, const KdeColumn kc, double lo, double hi, double step, int G,
+                                                float sc, int ms_launch, unsigned long long* cell, unsigned int epoch,
+                                                float* __restrict__ out) {
+    __shared__ float cv[KDE_MAX_COARSE];       // coarse values of this part's intervals
+    __shared__ int ivl[KDE_MAX_COARSE];        // (local) intervals that may hold a candidate
+    __shared__ float s_red[8];
+    __shared__ float s_thr;
+    __shared__ int s_nact;
+    (void)cta_uniform;
+    const int tid = threadIdx.x, nthr = blockDim.x, lane = tid & 31, warp = tid >> 5, nwarps = nthr >> 5;
+    auto coord = [&](int g) { return (float)(kde_grid_point(g, G, lo, hi, step) - kc.mean) * sc; };
+    auto reduce_lanes = [&](double& sa, double& sb, int ms) {
+        for (int o = ms >> 1; o > 0; o >>= 1) {
+            sa += __shfl_xor_sync(0xffffffffu, sa, o);
+            sb += __shfl_xor_sync(0xffffffffu, sb, o);
+        }
+    };
+    // intervals of the active range: k = 0 .. n_iv - 1, interval k = [ga + k s, min(ga + (k + 1) s, gb)]
+    const int n_iv = (s > 1 && ga < gb) ? (gb - ga + s - 1) / s : 0;
+    const int n_own = n_iv > part ? (n_iv - part + nparts - 1) / nparts : 0;          // this part's: k = part + i nparts
+    const bool shared_ends = nparts == 1;
+    const int n_pts = shared_ends ? n_own + 1 : 2 * n_own;                            // coarse points this part evaluates
+    // (the same decision in every CTA of the column: taken on the largest share, not on this part's)
+    const bool coarse = n_iv > 0 && (shared_ends ? n_iv + 1 : 2 * ((n_iv + nparts - 1) / nparts)) <= KDE_MAX_COARSE;
+    if (!coarse) {
+        // ---- every point of a contiguous chunk ----------------------------------------------------------------
+        const int n_act = gb - ga + 1;
+        const int chunk = (n_act + nparts - 1) / nparts;
+        const int g_begin = ga + part * chunk;
+        const int g_end = min(gb + 1, g_begin + chunk);
+        const int ms = kde_lanes_for(g_end - g_begin, nthr, ms_launch, N);
+        const int sub = tid & (ms - 1), slot = tid / ms, slots = nthr / ms;
+        for (int gbase = g_begin; gbase < g_end; gbase += 2 * slots) {        // (uniform trip count: shuffles inside)
+            const int g0 = gbase + slot, g1 = g0 + slots;
+            const bool has0 = g0 < g_end, has1 = g1 < g_end;
+            const float va = has0 ? coord(g0) : 0.f, vb = has1 ? coord(g1) : 0.f;
+            double sa = 0.0, sb = 0.0;
+            accumulate(va, vb, has0, has1, sa, sb, sub, ms);
+            reduce_lanes(sa, sb, ms);
+            if (sub == 0) {
+                if (has1) out[g1] = (float)sb;
+                if (has0) out[g0] = (float)sa;
+            }
+        }
+        return;
+    }
+    // coarse point j of this part -> grid point; who writes it; the ends of local interval i
+    auto point_g = [&](int j) {
+        const int k = shared_ends ? j : part + (j >> 1) * nparts + (j & 1);           // index of the coarse point in the range
+        return min(ga + k * s, gb);
+    };
+    auto point_written_here = [&](int j, int g) { return shared_ends || !(j & 1) || g == gb; };
+    auto left_of = [&](int i) { return shared_ends ? i : 2 * i; };
+    // ---- coarse pass ------------------------------------------------------------------------------------------
+    {
+        const int ms = kde_lanes_for(n_pts, nthr, ms_launch, N);
+        const int sub = tid & (ms - 1), slot = tid / ms, slots = nthr / ms;
+        for (int jb = 0; jb < n_pts; jb += 2 * slots) {                  // (uniform trip count)
+            const int j0 = jb + slot, j1 = j0 + slots;
+            const bool has0 = j0 < n_pts, has1 = j1 < n_pts;
+            const int g0 = has0 ? point_g(j0) : 0, g1 = has1 ? point_g(j1) : 0;
+            const float va = has0 ? coord(g0) : 0.f, vb = has1 ? coord(g1) : 0.f;
+            double sa = 0.0, sb = 0.0;
+            accumulate(va, vb, has0, has1, sa, sb, sub, ms);
+            reduce_lanes(sa, sb, ms);
+            if (sub == 0) {
+                if (has0) { cv[j0] = (float)sa; if (point_written_here(j0, g0)) out[g0] = (float)sa; }
+                if (has1) { cv[j1] = (float)sb; if (point_written_here(j1, g1)) out[g1] = (float)sb; }
+            }
+        }
+    }
+    if (tid == 0) s_nact = 0;
+    __syncthreads();
+    float m = 0.f;
+    for (int j = tid; j < n_pts; j += nthr) m = fmaxf(m, cv[j]);
+#pragma unroll
+    for (int o = 16; o > 0; o >>= 1) m = fmaxf(m, __shfl_xor_sync(0xffffffffu, m, o));
+    if (lane == 0) s_red[warp] = m;
+    __syncthreads();
+    if (tid == 0) {
+        for (int w = 1; w < nwarps; ++w) m = fmaxf(m, s_red[w]);
+        if (cell) {                           // sums are >= 0: their bit patterns order as integers
+            const unsigned long long old = atomicMax(cell, ((unsigned long long)epoch << 32) | __float_as_uint(m));
+            if ((unsigned int)(old >> 32) == epoch) m = fmaxf(m, __uint_as_float((unsigned int)old));
+        }
+        const double w = (double)sc * (double)s * step;
+        const float add = (float)(0.17329 * (double)N * w * w) * 1.001f;          // (s step)^2 / 8 * max |S''|
+        s_thr = m * (1.0f - 2.0f * KDE_TOL) - add;
+    }
+    __syncthreads();
+    const float thr = s_thr;
+    // ---- the intervals that may hold a candidate are listed, the others' interior points written as zero --------
+    for (int i = tid; i < n_own; i += nthr) {
+        const int k = part + i * nparts;
+        const int c0 = ga + k * s, c1 = min(c0 + s, gb);
+        const int l = left_of(i);
+        if (fmaxf(cv[l], cv[l + 1]) < thr) {                                      // (a NaN never compares below)
+            for (int g = c0 + 1; g < c1; ++g) out[g] = 0.f;
+        } else if (c1 - c0 > 1) {
+            ivl[atomicAdd(&s_nact, 1)] = i;
+        }
+    }
+    __syncthreads();
+    // ---- fine pass over the listed intervals' interior points, densely mapped onto the threads -----------------
+    const int n_fine = s_nact * (s - 1);             // (the range's last interval may be shorter: its surplus slots idle)
+    if (n_fine == 0) return;
+    const int ms = kde_lanes_for(n_fine, nthr, ms_launch, N);
+    const int sub = tid & (ms - 1), slot = tid / ms, slots = nthr / ms;
+    auto fine_g = [&](int p, bool& has) {
+        const int k = part + ivl[p / (s - 1)] * nparts;
+        const int g = ga + k * s + 1 + p % (s - 1);
+        has = g < min(ga + (k + 1) * s, gb);
+        return g;
+    };
+    for (int pb = 0; pb < n_fine; pb += 2 * slots) {                     // (uniform trip count)
+        const int p0 = pb + slot, p1 = p0 + slots;
+        bool has0 = p0 < n_fine, has1 = p1 < n_fine;
+        const int g0 = has0 ? fine_g(p0, has0) : 0, g1 = has1 ? fine_g(p1, has1) : 0;
+        const float va = has0 ? coord(g0) : 0.f, vb = has1 ? coord(g1) : 0.f;
+        double sa = 0.0, sb = 0.0;
+        accumulate(va, vb, has0, has1, sa, sb, sub, ms);
+        reduce_lanes(sa, sb, ms);
+        if (sub == 0) {
+            if (has1) out[g1] = (float)sb;
+            if (has0) out[g0] = (float)sa;
+        }
+    }
+}
+
 // The fp32 scan of one column, split over `nparts` CTAs (this one is `part`).  `xs` = the column's N
 // members centred at kc.mean (fp32, shared memory).
 //
 // Grid points further than `kde_scan_reach` from every member are written as zero and only the "active" range
 // [x_min - reach, x_max + reach] is evaluated, split evenly over the parts: a column that occupies a
 // small part of the common grid (ECD.py:749-751 spans the GLOBAL min..max) costs proportionally less.
-// Inside the active range every member is summed, so the values equal the full scan's bit for bit.
+// Inside the active range every member is summed for every evaluated point, so the values equal the full scan's bit
+// for bit; with max_stride > 1 the range is scanned coarse to fine (above), `cell` = the column's shared maximum
+// (nullptr when this CTA scans the column alone), `epoch` = this launch's tag.
 __device__ __forceinline__ void kde_scan_column(const float* __restrict__ xs, int64_t N, const KdeColumn kc,
                                                 double lo, double hi, int G, int part, int nparts,
-                                                float* __restrict__ out, int ms = 1) {
+                                                float* __restrict__ out, int ms = 1, int max_stride = 1,
+                                                unsigned long long* cell = nullptr, unsigned int epoch = 0) {
     __shared__ float s_mn[8], s_mx[8];
     __shared__ int s_in[8];
-    __shared__ int s_range[2];
+    __shared__ int s_range[3];
     const int tid = threadIdx.x, nthr = blockDim.x, lane = tid & 31, warp = tid >> 5, nwarps = nthr >> 5;
     const double step = (hi - lo) / (double)(G - 1);
     // ---- the column's extent and whether a member lies inside the grid ------------------------------
@@ -991,7 +1172,7 @@ __device__ __forceinline__ void kde_scan_column(const float* __restrict__ xs, in
     __syncthreads();
     if (tid == 0) {
         for (int w = 1; w < nwarps; ++w) { mn = fminf(mn, s_mn[w]); mx = fmaxf(mx, s_mx[w]); inside |= s_in[w]; }
-        int ga = 0, gb = G - 1;
+        int ga = 0, gb = G - 1, stride = 1;
         const double h = sqrt(-0.5 / kc.neg_inv_2h2);               // 0 for a constant column, NaN for NaN data
         if (h > 0.0 && step > 0.0) {
             const double reach = kde_scan_reach(h, step, N, inside != 0);
@@ -1000,11 +1181,12 @@ __device__ __forceinline__ void kde_scan_column(const float* __restrict__ xs, in
             if (a > 1.0) ga = (int)fmin(a - 1.0, (double)(G - 1));  // one grid point of slack on both sides
             if (b < (double)(G - 2)) gb = (int)fmax(b + 1.0, 0.0);
             if (gb < ga) { ga = 0; gb = G - 1; }
+            stride = kde_coarse_stride(h, step, max_stride);
         }
-        s_range[0] = ga; s_range[1] = gb;
+        s_range[0] = ga; s_range[1] = gb; s_range[2] = stride;
     }
     __syncthreads();
-    const int ga = s_range[0], gb = s_range[1];
+    const int ga = s_range[0], gb = s_range[1], stride = s_range[2];
     // ---- zeros outside the active range (each part clears its static slice of the row) --------------
     {
         const int z0 = (int)((int64_t)G * part / nparts), z1 = (int)((int64_t)G * (part + 1) / nparts);
@@ -1012,43 +1194,25 @@ __device__ __forceinline__ void kde_scan_column(const float* __restrict__ xs, in
             if (g < ga || g > gb) out[g] = 0.f;
     }
     // ---- this part's share of the active range ---------------------------------------------------------
-    const int n_act = gb - ga + 1;
-    const int chunk = (n_act + nparts - 1) / nparts;
-    const int g_begin = ga + part * chunk;
-    const int g_end = min(gb + 1, g_begin + chunk);
     // exponent in base 2: -(g - x)^2 log2(e) / (2 h^2) = -((g - x) sc)^2
     const float sc = (float)sqrt(-kc.neg_inv_2h2 * 1.4426950408889634), nsc = -sc;
-    // `ms` adjacent lanes share a grid point and split the members between them in blocks of 64 (lane `sub` takes
-    // blocks sub, sub + ms, ...); their partial sums meet in a fixed xor-shuffle tree.  ms = 1 is one thread per grid
-    // point; few columns of a long ensemble (a rank's share of the chain's output) use ms > 1 to fill the machine.
-    const int sub = tid & (ms - 1), slot = tid / ms, slots = nthr / ms;
-    for (int gbase = g_begin; gbase < g_end; gbase += 2 * slots) {        // (uniform trip count: shuffles inside)
-        const int g0 = gbase + slot, g1 = g0 + slots;
-        const bool has0 = g0 < g_end, has1 = g1 < g_end;
-        const float va = has0 ? (float)(kde_grid_point(g0, G, lo, hi, step) - kc.mean) * sc : 0.f;
-        double sa = 0.0, sb = 0.0;
-        if (has1) {                                // two grid points per thread: one shared-memory read feeds both
-            const float vb = (float)(kde_grid_point(g1, G, lo, hi, step) - kc.mean) * sc;
+    auto accumulate = [&](float va, float vb, bool has0, bool has1, double& sa, double& sb, int sub, int ms) {
+        if (has0 && has1) {                        // two grid points per thread: one shared-memory read feeds both
             for (int64_t i0 = 64 * sub; i0 < N; i0 += 64 * ms) {
                 float pa, pb;
                 kde_block_sum2(xs + kde_pad(i0), (int)((i0 + 64 <= N) ? 64 : N - i0), va, vb, nsc, pa, pb);
                 sa += (double)pa;
                 sb += (double)pb;
             }
-        } else if (has0) {                         // the tail of a chunk: no wasted second evaluation
-            for (int64_t i0 = 64 * sub; i0 < N; i0 += 64 * ms) {
-                sa += (double)kde_block_sum1(xs + kde_pad(i0), (int)((i0 + 64 <= N) ? 64 : N - i0), va, nsc);
-            }
+        } else if (has0 || has1) {                 // a single point: no wasted second evaluation
+            const float v = has0 ? va : vb;
+            double t = 0.0;
+            for (int64_t i0 = 64 * sub; i0 < N; i0 += 64 * ms)
+                t += (double)kde_block_sum1(xs + kde_pad(i0), (int)((i0 + 64 <= N) ? 64 : N - i0), v, nsc);
+            if (has0) sa = t; else sb = t;
         }
-        for (int o = ms >> 1; o > 0; o >>= 1) {
-            sa += __shfl_xor_sync(0xffffffffu, sa, o);
-            sb += __shfl_xor_sync(0xffffffffu, sb, o);
-        }
-        if (sub == 0) {
-            if (has1) out[g1] = (float)sb;
-            if (has0) out[g0] = (float)sa;
-        }
-    }
+    };
+    kde_scan_points(accumulate, false, ga, gb, part, nparts, stride, N, kc, lo, hi, step, G, sc, ms, cell, epoch, out);
 }
 
 // grid = (columns of this batch, n_gchunks); CTA (c, gc) scans grid points
@@ -1057,7 +1221,10 @@ template <typename T>
 __global__ void __launch_bounds__(256)
 k_kde_scan32(const T* __restrict__ a, int64_t N, int64_t Q, int64_t col0,
              const double* __restrict__ lohi, int G, int ms /* lanes per grid point, a power of two <= 32 */,
-             const KdeColumn* __restrict__ cols, float* __restrict__ s32) {
+             const KdeColumn* __restrict__ cols, float* __restrict__ s32,
+             int max_stride /* coarse-to-fine: largest coarse stride, 1 = scan every point */,
+             unsigned long long* __restrict__ cells /* per column of the launch: shared maximum (gridDim.y > 1) */,
+             unsigned int epoch /* tag of this launch in the cells */) {
     extern __shared__ __align__(16) unsigned char kde_smem_raw[];
     float* xs = reinterpret_cast<float*>(kde_smem_raw);        // [N] centred members, fp32
     const int tid = threadIdx.x, nthr = blockDim.x;
@@ -1065,7 +1232,8 @@ k_kde_scan32(const T* __restrict__ a, int64_t N, int64_t Q, int64_t col0,
     const KdeColumn kc = cols[col];
     for (int64_t i = tid; i < N; i += nthr) xs[kde_pad(i)] = (float)((double)a[i * Q + col] - kc.mean);
     __syncthreads();
-    kde_scan_column(xs, N, kc, lohi[0], lohi[1], G, (int)blockIdx.y, (int)gridDim.y, s32 + (int64_t)blockIdx.x * G, ms);
+    kde_scan_column(xs, N, kc, lohi[0], lohi[1], G, (int)blockIdx.y, (int)gridDim.y, s32 + (int64_t)blockIdx.x * G, ms,
+                    max_stride, gridDim.y > 1 ? cells + blockIdx.x : nullptr, epoch);
 }
 
 // All-grid fallback of the float64 decision: exp(-d^2/(2h^2)) is exactly 0 in float64 once d^2/(2h^2) > 745.2
@@ -1253,12 +1421,13 @@ template <typename T>
 __global__ void __launch_bounds__(256)
 k_kde_scan32_tiled(const T* __restrict__ a, int64_t N, int64_t Q, int64_t col0,
                    const double* __restrict__ lohi, int G, const KdeColumn* __restrict__ cols,
-                   float* __restrict__ s32, int tile /* members per tile, multiple of 64 */, int ms /* lanes per grid point */) {
+                   float* __restrict__ s32, int tile /* members per tile, multiple of 64 */, int ms /* lanes per grid point */,
+                   int max_stride, unsigned long long* __restrict__ cells, unsigned int epoch /* as in k_kde_scan32 */) {
     extern __shared__ __align__(16) unsigned char kde_smem_raw[];
     float* xs = reinterpret_cast<float*>(kde_smem_raw);        // [tile] centred members, fp32
     __shared__ float s_mn[8], s_mx[8];
     __shared__ int s_in[8];
-    __shared__ int s_range[2];
+    __shared__ int s_range[3];
     const int tid = threadIdx.x, nthr = blockDim.x, lane = tid & 31, warp = tid >> 5, nwarps = nthr >> 5;
     const int64_t col = col0 + blockIdx.x;
     const int part = blockIdx.y, nparts = gridDim.y;
@@ -1285,9 +1454,10 @@ k_kde_scan32_tiled(const T* __restrict__ a, int64_t N, int64_t Q, int64_t col0,
     __syncthreads();
     if (tid == 0) {
         for (int w = 1; w < nwarps; ++w) { mn = fminf(mn, s_mn[w]); mx = fmaxf(mx, s_mx[w]); inside |= s_in[w]; }
-        int ga = 0, gb = G - 1;
+        int ga = 0, gb = G - 1, stride = 1;
         const double h = sqrt(-0.5 / kc.neg_inv_2h2);
         if (h > 0.0 && step > 0.0) {                                    // see kde_scan_column
+            stride = kde_coarse_stride(h, step, max_stride);
             const double reach = kde_scan_reach(h, step, N, inside != 0);
             const double aa = ((kc.mean + (double)mn - reach) - lo) / step;
             const double bb = ((kc.mean + (double)mx + reach) - lo) / step;
@@ -1295,55 +1465,43 @@ k_kde_scan32_tiled(const T* __restrict__ a, int64_t N, int64_t Q, int64_t col0,
             if (bb < (double)(G - 2)) gb = (int)fmax(bb + 1.0, 0.0);
             if (gb < ga) { ga = 0; gb = G - 1; }
         }
-        s_range[0] = ga; s_range[1] = gb;
+        s_range[0] = ga; s_range[1] = gb; s_range[2] = stride;
     }
     __syncthreads();
-    const int ga = s_range[0], gb = s_range[1];
+    const int ga = s_range[0], gb = s_range[1], stride = s_range[2];
     {
         const int z0 = (int)((int64_t)G * part / nparts), z1 = (int)((int64_t)G * (part + 1) / nparts);
         for (int g = z0 + tid; g < z1; g += nthr)
             if (g < ga || g > gb) out[g] = 0.f;
     }
-    const int n_act = gb - ga + 1;
-    const int chunk = (n_act + nparts - 1) / nparts;
-    const int g_begin = ga + part * chunk;
-    const int g_end = min(gb + 1, g_begin + chunk);
     // exponent in base 2: -(g - x)^2 log2(e) / (2 h^2) = -((g - x) sc)^2
     const float sc = (float)sqrt(-kc.neg_inv_2h2 * 1.4426950408889634), nsc = -sc;
-    const int sub = tid & (ms - 1), slot = tid / ms, slots = nthr / ms;     // see kde_scan_column
-    for (int gbase = g_begin; gbase < g_end; gbase += 2 * slots) {          // uniform trip count: barriers inside
-        const int g0 = gbase + slot, g1 = g0 + slots;
-        const bool has0 = g0 < g_end, has1 = g1 < g_end;
-        const float va = has0 ? (float)(kde_grid_point(g0, G, lo, hi, step) - kc.mean) * sc : 0.f;
-        const float vb = has1 ? (float)(kde_grid_point(g1, G, lo, hi, step) - kc.mean) * sc : 0.f;
-        double sa = 0.0, sb = 0.0;
+    // the members stream through shared memory once per pass of up to two grid points per slot: block barriers inside,
+    // so every thread calls it
+    auto accumulate = [&](float va, float vb, bool has0, bool has1, double& sa, double& sb, int sub, int ms) {
+        const float v1 = has0 ? va : vb;
+        double t = 0.0;
         for (int64_t t0 = 0; t0 < N; t0 += tile) {
             const int n = (int)(N - t0 < tile ? N - t0 : tile);
             __syncthreads();
             for (int i = tid; i < n; i += nthr) xs[kde_pad(i)] = (float)((double)a[(t0 + i) * Q + col] - kc.mean);
             __syncthreads();
-            if (has1) {
+            if (has0 && has1) {
                 for (int i0 = 64 * sub; i0 < n; i0 += 64 * ms) {
                     float pa, pb;
                     kde_block_sum2(xs + kde_pad(i0), (i0 + 64 <= n) ? 64 : n - i0, va, vb, nsc, pa, pb);
                     sa += (double)pa;
                     sb += (double)pb;
                 }
-            } else if (has0) {
-                for (int i0 = 64 * sub; i0 < n; i0 += 64 * ms) {
-                    sa += (double)kde_block_sum1(xs + kde_pad(i0), (i0 + 64 <= n) ? 64 : n - i0, va, nsc);
-                }
+            } else if (has0 || has1) {
+                for (int i0 = 64 * sub; i0 < n; i0 += 64 * ms)
+                    t += (double)kde_block_sum1(xs + kde_pad(i0), (i0 + 64 <= n) ? 64 : n - i0, v1, nsc);
             }
         }
-        for (int o = ms >> 1; o > 0; o >>= 1) {
-            sa += __shfl_xor_sync(0xffffffffu, sa, o);
-            sb += __shfl_xor_sync(0xffffffffu, sb, o);
-        }
-        if (sub == 0) {
-            if (has1) out[g1] = (float)sb;
-            if (has0) out[g0] = (float)sa;
-        }
-    }
+        if (has0 != has1) { if (has0) sa = t; else sb = t; }
+    };
+    kde_scan_points(accumulate, true, ga, gb, part, nparts, stride, N, kc, lo, hi, step, G, sc, ms,
+                    nparts > 1 ? cells + blockIdx.x : nullptr, epoch, out);
 }
 
 // grid = (columns of this batch, parts), 256 threads; dynamic shared memory: tile doubles + 8 x n_acc doubles

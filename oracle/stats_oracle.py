@@ -150,6 +150,43 @@ def kde_mode_scipy(a: np.ndarray, grid: np.ndarray | None = None, n_grid: int = 
     return grid[idx].reshape(a.shape[1:]), idx.reshape(a.shape[1:]), np.stack(pdfs, axis=1)
 
 
+def kde_coarse_to_fine_check(col: np.ndarray, grid: np.ndarray, max_stride: int = 32, tol: float = 1e-3):
+    """Numpy restatement of the CUDA scan's coarse-to-fine skip rule (csrc/stats.cuh, "coarse-to-fine scan"), used by the
+    CPU tests to check the RULE, not the kernel: every ``s``-th grid point is evaluated; an interval between two
+    evaluated points is skipped when ``max(S(c), S(c')) + 0.17329 N (sc s step)^2 < M (1 - 2 tol)``, ``M`` the largest
+    coarse value.  Returns ``(stride, evaluated_fraction, worst)`` with ``worst`` = the largest skipped value divided by
+    the candidates' threshold ``max(S) (1 - tol)``: the rule is sound iff ``worst < 1`` (and the argmax is never
+    skipped)."""
+    col = np.asarray(col, dtype=np.float64)
+    N, G = col.shape[0], grid.shape[0]
+    step = (grid[-1] - grid[0]) / (G - 1)
+    h = np.sqrt(np.var(col, ddof=1)) * float(N) ** (-0.2)
+    s = 1
+    while 2 * s <= max_stride and 6.0 * s * step <= h:
+        s *= 2
+    sc = np.sqrt(np.log2(np.e) / (2.0 * h * h))
+    S = np.zeros(G)
+    for i in range(0, N, 256):
+        S += np.exp2(-((grid[:, None] - col[None, i:i + 256]) * sc) ** 2).sum(axis=1)
+    if s == 1:
+        return 1, 1.0, 0.0
+    cidx = np.arange(0, G, s)
+    if cidx[-1] != G - 1:
+        cidx = np.append(cidx, G - 1)
+    cv = S[cidx]
+    M = cv.max()
+    thr = M * (1.0 - 2.0 * tol) - 0.17329 * N * (sc * s * step) ** 2 * 1.001
+    evaluated, worst = len(cidx), 0.0
+    for k in range(len(cidx) - 1):
+        a, b = cidx[k], cidx[k + 1]
+        if max(cv[k], cv[k + 1]) < thr:
+            if b - a > 1:
+                worst = max(worst, S[a + 1:b].max() / (S.max() * (1.0 - tol)))
+        else:
+            evaluated += b - a - 1
+    return s, evaluated / G, worst
+
+
 # ---------------------------------------------------------------------------------------------
 # UQ calibration metrics (ECD.py:1089-1137 for all parameters pooled, ECD.py:1191-1214 per
 # parameter).  `generated` is (N realisations, M conditions, P) -- Uncertainty_params.npy at

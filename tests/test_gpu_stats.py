@@ -346,3 +346,50 @@ def test_percentiles_radix_selection_bit_exact(cuda_dev, env_override, dtype, N,
         ref = np.percentile(a, q, axis=0)
         got = eb.ensemble_percentile(a, q)
         assert same(got, ref), (q, np.nonzero(~((got == ref) | (np.isnan(got) & np.isnan(ref)))))
+
+
+def _mixture_columns(rng, N, Q, dtype):
+    """Columns of different shapes on one common grid: normal, bimodal (equal and unequal heights), log-normal, uniform,
+    heavy ties, a narrow spike far from a broad bulk -- the shapes the coarse-to-fine scan has to get right."""
+    cols = []
+    for j in range(Q):
+        k = j % 7
+        if k == 0:
+            c = rng.normal(0.0, 1.0 + j, N)
+        elif k == 1:
+            c = np.concatenate([rng.normal(-4.0, 0.5, N // 2), rng.normal(3.0, 0.5, N - N // 2)])
+        elif k == 2:
+            c = np.concatenate([rng.normal(-6.0, 1.5, (2 * N) // 3), rng.normal(5.0, 0.4, N - (2 * N) // 3)])
+        elif k == 3:
+            c = rng.lognormal(0.0, 0.7, N)
+        elif k == 4:
+            c = rng.uniform(-8.0, 8.0, N)
+        elif k == 5:
+            c = np.concatenate([rng.normal(0.0, 2.0, N - N // 8), np.full(N // 8, 1.25)])
+        else:
+            c = np.concatenate([rng.normal(0.0, 3.0, N - N // 5), rng.normal(25.0, 0.02, N // 5)])
+        cols.append(c[:N])
+    return np.stack(cols, axis=1).astype(dtype)
+
+
+@pytest.mark.parametrize("N,Q,tile", [(1024, 29, 0), (3000, 7, 0), (2048, 4, 0), (2500, 700, 0), (6000, 14, 448), (30000, 3, 0), (70000, 2, 0)])
+def test_kde_coarse_to_fine_scan_equals_full_scan(cuda_dev, env_override, N, Q, tile):
+    # the scan evaluates every s-th grid point first and skips the intervals that provably hold no candidate
+    # (ERTDIFF_KDE_COARSE=1 scans every point): same argmax index for every column shape, one or many CTAs per
+    # column, members split between lanes, resident and tiled kernels -- and scipy's index
+    a = _mixture_columns(np.random.default_rng(N + Q), N, Q, np.float32 if Q % 2 else np.float64)
+    if tile:
+        env_override("ERTDIFF_KDE_TILE", tile)
+    env_override("ERTDIFF_KDE_COARSE", 1)
+    m_full, i_full = eb.ensemble_kde_mode(a, 5000, return_index=True)
+    for stride in (4, 32, 64):
+        env_override("ERTDIFF_KDE_COARSE", stride)
+        for rep in range(2):                   # (the shared-maximum cells are tagged per launch: a second call must not see the first's)
+            m, i = eb.ensemble_kde_mode(a, 5000, return_index=True)
+            assert np.array_equal(i, i_full) and np.array_equal(m, m_full), (stride, rep, np.nonzero(i != i_full)[0])
+    if N <= 6000 and Q <= 29:
+        grid = so.kde_grid(a, 5000)
+        _, idx_sp, pdfs = so.kde_mode_scipy(a.astype(np.float64), grid)
+        for j in np.nonzero(i_full != idx_sp)[0]:
+            p = pdfs[:, j]
+            assert abs(p[i_full[j]] - p[idx_sp[j]]) <= 1e-13 * p[idx_sp[j]], (j, i_full[j], idx_sp[j])

@@ -67,3 +67,28 @@ def test_golden_maps(golden):
     mode, idx = so.kde_mode(sim)
     assert np.array_equal(idx, g["mode_index"])
     assert np.array_equal(mode, g["mode"])
+
+
+@pytest.mark.parametrize("N", [50, 256, 2048, 20000])
+def test_kde_coarse_to_fine_rule_never_skips_a_candidate(N):
+    # the CUDA scan evaluates every s-th grid point first and skips intervals that provably hold no candidate of the
+    # float64 selection (csrc/stats.cuh); this checks the RULE on seeded samples: no skipped point reaches the
+    # candidates' threshold, and a useful share of the grid is skipped
+    rng = np.random.default_rng(N)
+    samples = {
+        "normal": rng.normal(0.0, 270.0, N),
+        "bimodal": np.concatenate([rng.normal(-2.0, 0.3, N // 2), rng.normal(1.5, 0.6, N - N // 2)]),
+        "lognormal": rng.lognormal(0.0, 0.8, N),
+        "uniform": rng.uniform(-1.0, 1.0, N),
+        "ties": np.concatenate([rng.normal(0.0, 1.0, N - 5), np.full(5, 0.25)]),
+        "two far clusters": np.concatenate([rng.normal(0.0, 1.0, N - N // 4), rng.normal(40.0, 0.05, N // 4)]),
+    }
+    fractions = []
+    for name, col in samples.items():
+        span = col.max() - col.min()
+        grid = np.linspace(col.min() - 0.3 * span, col.max() + 0.2 * span, 5000)      # the common grid is wider than a column
+        s, frac, worst = so.kde_coarse_to_fine_check(col, grid)
+        assert worst < 1.0, (name, s, worst)
+        if s > 1:
+            fractions.append(frac)
+    assert fractions and np.median(fractions) < 0.5
