@@ -46,6 +46,11 @@ emit("r02_chain_umma_rng_variants.md",
      "per step); the code was reverted.  `b` = eight noise warps, two per scheduler (-DUC_RNG_WARPS_N=8; 544 threads, 96 "
      "registers): no gain for bf16, slower for bf16x3 (64 bytes of spills).  `c` = both.",
      [("rng_variants.log", None)])
+emit("r02_kde_coarse_to_fine.md",
+     "r02 the coarse-to-fine KDE scan against the full scan (ERTDIFF_KDE_COARSE=1 evaluates every grid point; the default "
+     "largest coarse stride is 32): scripts/stats_bench.py --only kde, then the fused statistics call on real chain output "
+     "(scripts/summary_window_bench.py --chain; whole call by CUDA events, per kernel by torch.profiler).  scripts/gpu_r2_j.sh",
+     [("kde_coarse_ab.log", None)])
 emit("r02_summary_window.md",
      "r02 the fused statistics call (ertdiff_ensemble_summary) on a column window of the fields of a real T = 1000 bf16 chain "
      "(scripts/summary_window_bench.py --chain; whole call by CUDA events, per kernel by torch.profiler; the side-stream "
