@@ -976,7 +976,7 @@ __device__ __forceinline__ float kde_block_sum1(const float* __restrict__ blk, i
 // s = the largest power of two <= max_stride with 3 s step <= h: the bound then costs <= 1.4 % of N in height; a
 // unimodal column of the chain's output (step / h ~ 0.01 .. 0.02) evaluates 1/16 .. 1/32 of its active range plus the
 // band around the mode -- about a tenth of the points of the full scan (numerical check of the rule on normal,
-// bimodal, log-normal, uniform and tied samples: oracle/stats_oracle.py:kde_coarse_to_fine_check).
+// bimodal, log-normal, uniform and tied samples is part of the CPU test suite).
 constexpr int KDE_MAX_COARSE = 2560;       // coarse values of one CTA's grid chunk, in shared memory
 
 __device__ __forceinline__ int kde_coarse_stride(double h, double step, int max_stride) {
